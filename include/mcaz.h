@@ -1,0 +1,223 @@
+/* mcaz.h -- C ABI of the B200-native MinitChess AlphaZero self-play engine (libmcaz.so).
+ *
+ * This is the drop-in boundary for the reference's self-play hot path.  The reference is pure
+ * Python, so the "FFI" a maintainer binds is ctypes; the entry points
+ * below replace, one for one, the Python call sites named beside them (paths relative to the
+ * reference tree):
+ *
+ *   mc_*   stateless MinitChess rules on packed positions  -> exp/environment.py:34-50 (legal
+ *          moves, result), :68-82 (step), and the python-chess fork calls at :25,36,39,48,76
+ *   az_*   batched AlphaZero search over GPU-resident trees -> exp/agent.py:24-88
+ *          (MonteCarloTreeSearch), :110-119 (select_action), exp/policy.py:71-80 (Network
+ *          forward), :96-105 (process_observation), :115-122 (get_distribution)
+ *
+ * Conventions: plain pointers and sizes only.  Unless a parameter says otherwise, every buffer
+ * may be a host pointer (pageable or pinned) or a device pointer; the library inspects it with
+ * cudaPointerGetAttributes and stages host buffers through its own device scratch.  All
+ * functions return 0 on success or a negative MCAZ_E* code; mcaz_last_error() gives the text.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * MCAZ_ENODEV.
+ */
+#ifndef MCAZ_H
+#define MCAZ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCAZ_ABI_VERSION 1
+
+/* ---- geometry and action indexing (exp/generate_moves_list.py:5-57, exp/moves_dict.json) */
+#define MC_FILES 5
+#define MC_RANKS 6
+#define MC_SQUARES 30
+#define MC_NUM_ACTIONS 554   /* 430 queen-like (from,dir,dist) + 124 knight moves          */
+#define MC_MAX_MOVES 96      /* safe upper bound on legal moves in one position (<= 78)     */
+#define MC_TOKENS 60         /* Network input: 2 channels x 6 x 5 (exp/policy.py:82-95)     */
+
+/* ---- error codes */
+#define MCAZ_OK 0
+#define MCAZ_EINVAL (-1)     /* bad argument                                               */
+#define MCAZ_ENODEV (-2)     /* no usable CUDA device                                      */
+#define MCAZ_ECUDA (-3)      /* a CUDA call failed; see mcaz_last_error()                  */
+#define MCAZ_ECAPACITY (-4)  /* a tree arena or hash table overflowed                      */
+#define MCAZ_ESTATE (-5)     /* call made in the wrong phase (e.g. backup before select)   */
+
+/* ---- packed position: everything the 4-field FEN holds (exp/environment.py:6)
+ * Piece type of square s = bit s of (pl0 | pl1<<1 | pl2<<2), numbered like the reference
+ * tokeniser alphabet '0prbnqk' (exp/policy.py:7): 0 empty, 1 pawn, 2 rook, 3 bishop,
+ * 4 knight, 5 queen, 6 king.  Square s = 5*rank + file (a1 = 0 ... e6 = 29).               */
+typedef struct mc_state {
+    uint32_t pl0, pl1, pl2; /* piece-type bit planes over the 30 squares                   */
+    uint32_t white;         /* squares holding white pieces                                */
+    uint32_t meta;          /* bit 0: 1 = white to move; bits 8-15 halfmove clock;
+                               bits 16-23 fullmove number                                  */
+} mc_state;
+
+#define MC_META(turn_white, halfmove, fullmove) \
+    ((uint32_t)((turn_white) ? 1u : 0u) | ((uint32_t)(halfmove) << 8) | ((uint32_t)(fullmove) << 16))
+
+/* ---- game result of a position, as exp/environment.py:39-45 reads board.result()        */
+#define MC_ONGOING 0         /* '*'                                                        */
+#define MC_WHITE_WINS 1      /* '1-0'                                                      */
+#define MC_BLACK_WINS 2      /* '0-1'                                                      */
+#define MC_DRAW 3            /* '1/2-1/2'                                                  */
+
+/* ---- switches for the rules the reference does not pin (SURVEY.md §8c ledger).  Passing
+ * NULL where a `const mc_rules*` is expected selects mc_default_rules().                   */
+typedef struct mc_rules {
+    int32_t pawn_double_step;      /* default 0                                            */
+    int32_t promo_multiplicity;    /* default 1 (queen only); 4 = q,r,b,n share one code   */
+    int32_t max_fullmoves;         /* default 30: draw once fullmove number > this         */
+    int32_t insufficient_material; /* default 1                                            */
+    int32_t fivefold_repetition;   /* default 1 (episode-level only: needs history)        */
+} mc_rules;
+
+void mc_default_rules(mc_rules* out);
+
+/* ---- library */
+int mcaz_abi_version(void);
+const char* mcaz_last_error(void);
+int mcaz_device_count(void);         /* 0 when no CUDA device is usable                    */
+int mcaz_set_device(int device);
+
+/* ---- host helpers (string <-> packed; no GPU work) */
+int mc_state_from_fen(const char* fen, mc_state* out);
+int mc_state_to_fen(const mc_state* s, char* buf, size_t buflen);
+/* code -> (from,to) squares as seen on the real board for the given side (1 = white):
+ * exp/environment.py:19 MOVES_DICT_INV.  Returns MCAZ_EINVAL for code >= 554.             */
+int mc_code_squares(int code, int white_to_move, int* from_sq, int* to_sq);
+int mc_squares_code(int from_sq, int to_sq, int white_to_move);   /* -1 if not a move shape */
+
+/* ---- stateless rules kernels (replace python-chess on the path) ------------------------
+ * mc_legal_moves: for each of n positions, the sorted legal action codes
+ * (codes[i*MC_MAX_MOVES + k], k < counts[i]) and the MC_* result; a finished position
+ * still lists its legal moves exactly like exp/environment.py:47-50 does.                  */
+int mc_legal_moves(const mc_state* states, int n, const mc_rules* rules,
+                   uint16_t* codes, int32_t* counts, int8_t* results);
+/* mc_apply: out[i] = states[i] after action codes[i] (pawn reaching the last rank queens,
+ * exp/environment.py:72-74).  status[i] = 0 ok, 1 illegal move (out[i] = states[i]),
+ * 2 position already finished (exp/environment.py:69-70).                                  */
+int mc_apply(const mc_state* states, const uint16_t* codes, int n, const mc_rules* rules,
+             mc_state* out, int8_t* status);
+/* mc_perft: number of legal move sequences of length `depth` from each root, finished
+ * positions having no successors.                                                          */
+int mc_perft(const mc_state* roots, int n, int depth, const mc_rules* rules, uint64_t* nodes);
+/* mc_tokenize: Network.process_observation (exp/policy.py:82-105): 60 tokens per position in
+ * the mover's view (channel 0 = mover's pieces, channel 1 = opponent's) and the clock
+ * (fullmove + 0.5*[black to move]) / 30 as float32.                                        */
+int mc_tokenize(const mc_state* states, int n, uint8_t* tokens, float* clocks);
+
+/* ---- AlphaZero engine -------------------------------------------------------------------*/
+typedef struct az_engine az_engine;
+
+typedef struct az_config {
+    int32_t n_games;           /* concurrent games; 2 trees per game (one per colour's agent,
+                                  app/base.py:113, exp/agent.py:105-108)                    */
+    int32_t max_sims_per_move; /* sizes the per-tree arenas: <= 1 new node per simulation   */
+    int32_t node_capacity;     /* nodes per tree; 0 = derive from max_sims_per_move         */
+    int32_t edge_capacity;     /* edges per tree; 0 = derive                                */
+    float cpuct;               /* exp/agent.py:96 (default 1)                               */
+    int32_t tau_change;        /* exp/agent.py:97 (default 6)                               */
+    float dirichlet_alpha;     /* exp/agent.py:82 (0.6)                                     */
+    float dirichlet_epsilon;   /* exp/agent.py:82 (0.25); 0 disables root noise             */
+    int32_t numpy1_dtype_flow; /* Q6: 1 = round P*sqrt(sumN) to f32 as numpy 1.x did        */
+    int32_t device_rng;        /* 1 = Philox Dirichlet/sampling on device (throughput mode);
+                                  0 = caller supplies noise / picks moves (parity mode)     */
+    uint64_t seed;
+    mc_rules rules;
+    int32_t network;           /* 0 = external evaluator only; 1 = built-in bf16 tcgen05 net */
+} az_config;
+
+void az_default_config(az_config* out);
+int az_create(const az_config* cfg, az_engine** out);
+int az_destroy(az_engine* e);
+
+/* Network weights, fp32, flattened in Network.state_dict() order without the
+ * num_batches_tracked counters (exp/policy.py:53-69).  n must be AZ_NUM_WEIGHT_FLOATS.
+ * Replaces SimulatePuppet.load_weights (app/base.py:126-129).                              */
+#define AZ_NUM_PARAMS 10693458
+#define AZ_NUM_BN_STATS 9734
+#define AZ_NUM_WEIGHT_FLOATS (AZ_NUM_PARAMS + AZ_NUM_BN_STATS)
+int az_set_weights(az_engine* e, const float* flat, size_t n);
+
+/* (Re)start games: game_ids[i] gets position states[i] (NULL = STARTING_FEN) and two empty
+ * trees -- MonteCarloInit.on_episode_begin (exp/callbacks.py:57-62).                        */
+int az_reset_games(az_engine* e, const int32_t* game_ids, int n, const mc_state* states);
+/* Overwrite the current position of running games without touching their trees (used by the
+ * per-agent facade, where the environment owns the game line).                              */
+int az_set_positions(az_engine* e, const int32_t* game_ids, int n, const mc_state* states,
+                     const int32_t* tree_of_game);
+
+/* -- one simulation, split at the evaluate phase (external evaluator / parity mode) --------
+ * az_select_expand: for every active game, one descent from the current root of the tree of
+ * the side to move: PUCT select (exp/agent.py:75-88) down to an unvisited or terminal
+ * position, expansion of that position (exp/agent.py:57-66).  root_noise is NULL or, per
+ * game, MC_MAX_MOVES doubles of Dirichlet noise used if the root is already expanded
+ * (exp/agent.py:81-82); noise_used[g] (optional) reports whether it was consumed.
+ * Leaves needing a network evaluation are written to the leaf batch.                        */
+int az_select_expand(az_engine* e, const double* root_noise, uint8_t* noise_used);
+/* The leaf batch of the last az_select_expand: slot i belongs to game i.  needs_eval[i] = 1
+ * when (tokens, clock) hold a position to evaluate.  Device pointers owned by the engine.   */
+int az_leaf_batch(az_engine* e, const uint8_t** tokens, const float** clocks,
+                  const uint8_t** needs_eval, const mc_state** leaf_states, int* n_slots);
+/* az_backup: softmax of the legal logits into the new node's priors (exp/agent.py:67-71) and
+ * the value backup along the path (exp/agent.py:47-52).  logits [n_slots x 554] and values
+ * [n_slots] are float32.  If priors != NULL it supplies per-slot priors [n_slots x
+ * MC_MAX_MOVES] directly instead of logits (bit-exact injection for tree-logic parity).     */
+int az_backup(az_engine* e, const float* logits, const float* values, const float* priors);
+
+/* -- whole searches with the built-in network (throughput mode) ---------------------------*/
+int az_search(az_engine* e, int n_sims);
+
+/* Root statistics of the tree of the side to move (exp/policy.py:118-121): sorted legal
+ * codes, visit counts N and Q per edge; pi = N / sum(N) is left to the caller.              */
+int az_root_stats(az_engine* e, const int32_t* game_ids, int n, uint16_t* codes,
+                  uint32_t* visits, double* q, int32_t* n_legal);
+/* Statistics of an arbitrary visited position in one tree (MonteCarloTreeSearch.__getitem__,
+ * exp/agent.py:38-39): returns 1 in *found when present.  priors may be NULL.               */
+int az_node_stats(az_engine* e, int game_id, int tree, const mc_state* state, int* found,
+                  uint16_t* codes, uint32_t* visits, double* q, float* priors, int32_t* n_legal,
+                  int* is_terminal, double* terminal_value);
+
+/* Play one move in each listed game (exp/environment.py:68-82 on the real game line; fivefold
+ * repetition is tracked here).  results[i] is the MC_* result after the move.               */
+int az_play(az_engine* e, const int32_t* game_ids, const uint16_t* codes, int n, int8_t* results);
+/* Throughput mode: choose (sample while fullmove < tau_change, else argmax with random
+ * tie-break, exp/agent.py:113-118), record the replay tuple, play, and restart finished
+ * games -- all on device.                                                                   */
+int az_play_device(az_engine* e);
+
+int az_game_states(az_engine* e, const int32_t* game_ids, int n, mc_state* states, int8_t* results);
+
+/* Replay tuples (exp/callbacks.py:31-54 -> exp/learner.py:23-41), packed per ply.           */
+typedef struct az_replay_tuple {
+    mc_state observation;            /* position before the move                            */
+    uint16_t n_legal;
+    uint16_t action;
+    int8_t reward;                   /* +1 / 0 / -1 from the mover's point of view, back-filled */
+    uint8_t pad[3];
+    uint16_t codes[MC_MAX_MOVES];
+    float pi[MC_MAX_MOVES];
+} az_replay_tuple;
+/* Moves up to `max` finished-game tuples into out (host or device); *n_out = count.         */
+int az_drain_replay(az_engine* e, az_replay_tuple* out, int max, int* n_out);
+
+/* Counters since creation: [0] simulations, [1] network evaluations, [2] terminal leaves,
+ * [3] moves played, [4] games finished, [5] nodes allocated, [6] edges allocated,
+ * [7] kernels launched by this library.                                                     */
+#define AZ_NUM_COUNTERS 8
+int az_counters(az_engine* e, uint64_t* out);
+
+/* Stand-alone network forward (exp/policy.py:71-80) on n positions with the engine's weights:
+ * logits [n x 554], values [n].  Used by the parity tests.                                  */
+int az_network_forward(az_engine* e, const uint8_t* tokens, const float* clocks, int n,
+                       float* logits, float* values);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCAZ_H */
