@@ -1,0 +1,30 @@
+// Host build of csrc/minitchess.cuh for CPU-only tests (no GPU in the build container).
+// TEST INFRASTRUCTURE: lets `pytest -m "not gpu"` drive the very same bitboard rules the CUDA
+// kernels compile, against the mailbox oracle.  The product never loads this library.
+#include <cstring>
+#include "minitchess.cuh"
+
+static mc_rules rules_or_default(const mc_rules* r) {
+    mc_rules d = {0, 1, 30, 1, 1};
+    return r ? *r : d;
+}
+
+extern "C" {
+void hh_legal_moves(const mc_state* s, int n, const mc_rules* rules, uint16_t* codes, int32_t* counts, int8_t* results) {
+    mc_rules R = rules_or_default(rules);
+    for (int i = 0; i < n; ++i) {
+        int res;
+        counts[i] = mc::generate(s[i], R, codes + (size_t)i * MC_MAX_MOVES, &res);
+        results[i] = (int8_t)res;
+    }
+}
+void hh_apply(const mc_state* s, const uint16_t* codes, int n, const mc_rules* rules, mc_state* out, int8_t* status) {
+    mc_rules R = rules_or_default(rules);
+    for (int i = 0; i < n; ++i) status[i] = (int8_t)mc::step(s[i], codes[i], R, &out[i]);
+}
+void hh_tokenize(const mc_state* s, int n, uint8_t* tokens, float* clocks) {
+    for (int i = 0; i < n; ++i) mc::tokenize(s[i], tokens + (size_t)i * 60, clocks + i);
+}
+int hh_view_to_code(int fv, int tv) { return mc::view_to_code(fv, tv); }
+int hh_code_to_view(int code, int* fv, int* tv) { return mc::code_to_view(code, *fv, *tv) ? 0 : -1; }
+}
