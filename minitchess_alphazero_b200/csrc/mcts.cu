@@ -1,0 +1,661 @@
+// mcts.cu -- kernels and az_* entry points of the batched AlphaZero search engine (sm_100a).
+//
+// Kernels (one warp per game/tree, grid-stride over games, grid sized to the SM count):
+//   select_expand_kernel  PUCT descent + expansion of the leaf (exp/agent.py:54-66,75-88)
+//   backup_kernel         legal-logit softmax -> priors, value backup (exp/agent.py:47-52,67-72)
+//   play_kernel / play_device_kernel   the real game line (exp/environment.py:68-82,
+//                         exp/agent.py:110-119, exp/callbacks.py:31-54)
+//   root_stats_kernel / node_stats_kernel   what exp/policy.py:118-121 reads back
+#include <algorithm>
+#include <cstring>
+
+#include "engine.cuh"
+
+using namespace mcaz;
+using az::View;
+
+namespace mcaz {
+int num_sms();
+
+// ---- device RNG (throughput mode): Philox4x32-10 ------------------------------------------------
+struct Philox {
+    uint32_t key[2];
+    uint32_t ctr[4];
+    uint32_t out[4];
+    int have;
+    __device__ Philox(unsigned long long seed, uint32_t a, uint32_t b, uint32_t c) : have(0) {
+        key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
+        ctr[0] = 0; ctr[1] = a; ctr[2] = b; ctr[3] = c;
+    }
+    __device__ void round(uint32_t* c, const uint32_t* k) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    __device__ void refill() {
+        uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]}, k[2] = {key[0], key[1]};
+#pragma unroll
+        for (int r = 0; r < 10; ++r) { round(c, k); k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u; }
+        out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+        ctr[0] += 1;
+        have = 4;
+    }
+    __device__ uint32_t next() { if (!have) refill(); return out[--have]; }
+    __device__ double uniform() {  // (0,1)
+        uint32_t a = next() >> 5, b = next() >> 6;
+        return ((double)a * 67108864.0 + (double)b + 0.5) * (1.0 / 9007199254740992.0);
+    }
+    __device__ double normal() {
+        double u1 = uniform(), u2 = uniform();
+        return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    }
+    // Marsaglia-Tsang; shape < 1 via gamma(shape+1) * U^(1/shape)
+    __device__ double gamma(double shape) {
+        double boost = 1.0;
+        if (shape < 1.0) { boost = pow(uniform(), 1.0 / shape); shape += 1.0; }
+        double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+        for (int it = 0; it < 64; ++it) {
+            double x = normal(), v = 1.0 + c * x;
+            if (v <= 0.0) continue;
+            v = v * v * v;
+            double u = uniform();
+            if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return boost * d * v;
+        }
+        return boost * d;
+    }
+};
+
+__global__ void __launch_bounds__(128) dirichlet_kernel(View V, unsigned long long sim_counter, double* noise) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < V.G; g += warps) {
+        if (V.game_result[g] != MC_ONGOING) continue;
+        const int t = 2 * g + (V.game_ply[g] & 1);
+        const uint32_t root = V.tree_root[t];
+        if (root == az::NONE) continue;
+        const int E = (int)(V.node_info[(size_t)t * V.NC + root] & 0xffffu);
+        double gam[3] = {0, 0, 0}, sum = 0;
+        for (int i = lane, k = 0; i < E; i += 32, ++k) {
+            Philox rng(V.seed, (uint32_t)g, (uint32_t)sim_counter, (uint32_t)(sim_counter >> 32) ^ ((uint32_t)i << 16));
+            gam[k] = rng.gamma((double)V.alpha);
+            sum += gam[k];
+        }
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        for (int i = lane, k = 0; i < E; i += 32, ++k) noise[(size_t)g * MC_MAX_MOVES + i] = gam[k] / sum;
+    }
+}
+
+__global__ void __launch_bounds__(128) select_expand_kernel(View V, const double* noise, uint8_t* noise_used) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < V.G; g += warps)
+        az::select_expand_one(V, g, lane, noise, noise_used);
+}
+
+__global__ void __launch_bounds__(128) backup_kernel(View V, const float* logits, const float* values, const float* priors) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < V.G; g += warps)
+        az::backup_one(V, g, lane, logits, values, priors);
+}
+
+// (re)start games: position, history, both trees emptied (block per listed game)
+__global__ void __launch_bounds__(256) reset_games_kernel(View V, const int32_t* game_ids, int n, const mc_state* states,
+                                                          mc_state start) {
+    for (int k = blockIdx.x; k < n; k += gridDim.x) {
+        const int g = game_ids ? game_ids[k] : k;
+        if (g < 0 || g >= V.G) continue;
+        uint32_t* tab = V.ht + (size_t)(2 * g) * V.HC;
+        for (int i = threadIdx.x; i < 2 * V.HC; i += blockDim.x) tab[i] = 0u;
+        if (threadIdx.x == 0) {
+            mc_state s = states ? states[k] : start;
+            V.game_state[g] = s;
+            V.game_ply[g] = mc::white_to_move(s) ? 0 : 1;   // white's agent owns tree 0
+            V.game_start_ply[g] = V.game_ply[g];
+            az::hist_reset(V, g, s);
+            V.game_result[g] = (int8_t)az::game_result_of(V, g, s);
+            for (int t = 2 * g; t < 2 * g + 2; ++t) { V.tree_nodes[t] = 0; V.tree_edges[t] = 0; V.tree_root[t] = az::NONE; }
+            V.leaf_kind[g] = az::LEAF_NONE;
+            V.needs_eval[g] = 0;
+            V.path_len[g] = 0;
+        }
+    }
+}
+
+__global__ void set_positions_kernel(View V, const int32_t* game_ids, int n, const mc_state* states, const int32_t* tree_of_game) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int g = game_ids ? game_ids[k] : k;
+        if (g < 0 || g >= V.G) continue;
+        mc_state s = states[k];
+        V.game_state[g] = s;
+        V.game_ply[g] = tree_of_game ? (tree_of_game[k] & 1) : (mc::white_to_move(s) ? 0 : 1);
+        V.game_start_ply[g] = V.game_ply[g];
+        az::hist_reset(V, g, s);   // a fresh Board(fen) has no history (exp/agent.py:43)
+        V.game_result[g] = (int8_t)az::game_result_of(V, g, s);
+        V.tree_root[2 * g] = az::NONE;
+        V.tree_root[2 * g + 1] = az::NONE;
+        V.leaf_kind[g] = az::LEAF_NONE;
+    }
+}
+
+__global__ void play_kernel(View V, const int32_t* game_ids, const uint16_t* codes, int n, int8_t* results) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int g = game_ids ? game_ids[k] : k;
+        if (g < 0 || g >= V.G) { az::raise(V, az::ERR_ILLEGAL); continue; }
+        int st = az::play_one(V, g, codes[k]);
+        if (st == 1) az::raise(V, az::ERR_ILLEGAL);
+        if (results) results[k] = V.game_result[g];
+    }
+}
+
+__global__ void game_states_kernel(View V, const int32_t* game_ids, int n, mc_state* states, int8_t* results) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int g = game_ids ? game_ids[k] : k;
+        if (g < 0 || g >= V.G) continue;
+        if (states) states[k] = V.game_state[g];
+        if (results) results[k] = V.game_result[g];
+    }
+}
+
+// Root statistics (exp/policy.py:118-121): codes, N, Q of the current position in the active tree.
+__global__ void __launch_bounds__(128) root_stats_kernel(View V, const int32_t* game_ids, int n, uint16_t* codes,
+                                                         uint32_t* visits, double* q, int32_t* n_legal) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += warps) {
+        const int g = game_ids ? game_ids[k] : k;
+        if (g < 0 || g >= V.G) { if (lane == 0) n_legal[k] = -1; continue; }
+        const int t = 2 * g + (V.game_ply[g] & 1);
+        uint32_t root = V.tree_root[t];
+        if (root == az::NONE) root = az::ht_find(V, t, V.game_state[g]);
+        if (root == az::NONE) { if (lane == 0) n_legal[k] = -1; continue; }
+        const size_t gi = (size_t)t * V.NC + root;
+        const uint32_t info = V.node_info[gi];
+        const int E = (info & az::INFO_TERMINAL) ? 0 : (int)(info & 0xffffu);
+        const size_t e0 = (size_t)t * V.EC + V.node_edge_off[gi];
+        for (int i = lane; i < E; i += 32) {
+            codes[(size_t)k * MC_MAX_MOVES + i] = V.edge_code[e0 + i];
+            visits[(size_t)k * MC_MAX_MOVES + i] = V.edge_N[e0 + i];
+            if (q) q[(size_t)k * MC_MAX_MOVES + i] = V.edge_Q[e0 + i];
+        }
+        if (lane == 0) n_legal[k] = E;
+    }
+}
+
+struct NodeStatsOut {
+    int found, n_legal, is_terminal;
+    double terminal_value;
+};
+
+__global__ void node_stats_kernel(View V, int g, int tree, mc_state s, NodeStatsOut* out, uint16_t* codes, uint32_t* visits,
+                                  double* q, float* priors) {
+    const int lane = threadIdx.x & 31;
+    const int t = 2 * g + (tree & 1);
+    uint32_t node = az::ht_find(V, t, s);
+    if (node == az::NONE) { if (lane == 0) { out->found = 0; out->n_legal = 0; out->is_terminal = 0; out->terminal_value = 0; } return; }
+    const size_t gi = (size_t)t * V.NC + node;
+    const uint32_t info = V.node_info[gi];
+    const bool term = (info & az::INFO_TERMINAL) != 0;
+    const int E = term ? 0 : (int)(info & 0xffffu);
+    const size_t e0 = (size_t)t * V.EC + V.node_edge_off[gi];
+    for (int i = lane; i < E; i += 32) {
+        codes[i] = V.edge_code[e0 + i];
+        visits[i] = V.edge_N[e0 + i];
+        q[i] = V.edge_Q[e0 + i];
+        priors[i] = V.edge_P[e0 + i];
+    }
+    if (lane == 0) {
+        out->found = 1; out->n_legal = E; out->is_terminal = term ? 1 : 0;
+        out->terminal_value = term ? ((info & az::INFO_DECISIVE) ? -1.0 : -0.0) : 0.0;
+    }
+}
+
+// Throughput mode: pick a move from the root visit counts, record the replay tuple, play it,
+// back-fill rewards and restart finished games (exp/agent.py:110-119, exp/callbacks.py:31-54).
+__global__ void __launch_bounds__(128) play_device_kernel(View V, az_replay_tuple* record, az_replay_tuple* replay,
+                                                          unsigned long long* replay_count, unsigned long long replay_cap,
+                                                          unsigned long long move_counter, mc_state start) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < V.G; g += warps) {
+        if (V.game_result[g] != MC_ONGOING) continue;
+        const int ply = V.game_ply[g];
+        const int t = 2 * g + (ply & 1);
+        uint32_t root = V.tree_root[t];
+        if (root == az::NONE) root = az::ht_find(V, t, V.game_state[g]);
+        if (root == az::NONE) continue;
+        const size_t gi = (size_t)t * V.NC + root;
+        const int E = (int)(V.node_info[gi] & 0xffffu);
+        const size_t e0 = (size_t)t * V.EC + V.node_edge_off[gi];
+        const mc_state s = V.game_state[g];
+        unsigned int nsum = 0, nmax = 0;
+        for (int i = lane; i < E; i += 32) { unsigned int c = V.edge_N[e0 + i]; nsum += c; nmax = max(nmax, c); }
+        for (int o = 16; o > 0; o >>= 1) { nsum += __shfl_xor_sync(0xffffffffu, nsum, o); nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o)); }
+        if (nsum == 0) continue;
+        Philox rng(V.seed ^ 0xA5A5A5A5DEADBEEFull, (uint32_t)g, (uint32_t)move_counter, (uint32_t)(move_counter >> 32));
+        const double u = rng.uniform();     // same on every lane
+        int choice = -1;
+        if (mc::fullmove(s) < V.tau_change) {
+            // sample proportionally to N (np.random.choice(legal, p=pi))
+            const double target = u * (double)nsum;
+            double acc = 0;
+            for (int i = 0; i < E && choice < 0; ++i) { acc += (double)V.edge_N[e0 + i]; if (target < acc) choice = i; }
+            if (choice < 0) choice = E - 1;
+        } else {
+            int n_best = 0;
+            for (int i = 0; i < E; ++i) n_best += (V.edge_N[e0 + i] == nmax);
+            int pick = min((int)(u * n_best), n_best - 1);
+            for (int i = 0; i < E; ++i) if (V.edge_N[e0 + i] == nmax) { if (pick == 0) { choice = i; break; } --pick; }
+        }
+        const int code = V.edge_code[e0 + choice];
+        // replay tuple of this ply
+        az_replay_tuple* rec = record + (size_t)g * az::MAX_DEPTH + min(ply - V.game_start_ply[g], az::MAX_DEPTH - 1);
+        for (int i = lane; i < E; i += 32) { rec->codes[i] = V.edge_code[e0 + i]; rec->pi[i] = (float)((double)V.edge_N[e0 + i] / (double)nsum); }
+        if (lane == 0) { rec->observation = s; rec->n_legal = (uint16_t)E; rec->action = (uint16_t)code; rec->reward = 0; }
+        __syncwarp();
+        if (lane == 0) {
+            az::play_one(V, g, code);
+            const int res = V.game_result[g];
+            if (res != MC_ONGOING) {
+                // exp/callbacks.py:49-53: the side that moved last gets +reward, alternating backwards
+                const int n_rec = min(V.game_ply[g] - V.game_start_ply[g], az::MAX_DEPTH);
+                unsigned long long base = atomicAdd(replay_count, (unsigned long long)n_rec);
+                int reward = (res == MC_DRAW) ? 0 : 1;
+                for (int p = n_rec - 1; p >= 0; --p) {
+                    az_replay_tuple* r = record + (size_t)g * az::MAX_DEPTH + p;
+                    r->reward = (int8_t)reward;
+                    reward = -reward;
+                    unsigned long long dst = base + (unsigned long long)p;
+                    if (dst < replay_cap) replay[dst] = *r;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// restart every finished game from the start position (block per game; clears both hash tables)
+__global__ void __launch_bounds__(256) restart_finished_kernel(View V, mc_state start) {
+    for (int g = blockIdx.x; g < V.G; g += gridDim.x) {
+        if (V.game_result[g] == MC_ONGOING) continue;
+        uint32_t* tab = V.ht + (size_t)(2 * g) * V.HC;
+        for (int i = threadIdx.x; i < 2 * V.HC; i += blockDim.x) tab[i] = 0u;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            V.game_state[g] = start;
+            V.game_ply[g] = mc::white_to_move(start) ? 0 : 1;
+            V.game_start_ply[g] = V.game_ply[g];
+            az::hist_reset(V, g, start);
+            for (int t = 2 * g; t < 2 * g + 2; ++t) { V.tree_nodes[t] = 0; V.tree_edges[t] = 0; V.tree_root[t] = az::NONE; }
+            V.leaf_kind[g] = az::LEAF_NONE;
+            V.game_result[g] = MC_ONGOING;
+        }
+        __syncthreads();
+    }
+}
+
+int warp_grid(int n_warps, int block) {
+    int per = block / 32;
+    int want = (n_warps + per - 1) / per;
+    return std::max(1, std::min(want, num_sms() * 16));
+}
+
+int engine_check_errors(az_engine* e) {
+    int flag = 0;
+    MCAZ_CUDA(cudaMemcpyAsync(&flag, e->v.error_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    MCAZ_CUDA(cudaStreamSynchronize(e->stream));
+    if (flag == 0) return MCAZ_OK;
+    cudaMemsetAsync(e->v.error_flag, 0, sizeof(int), e->stream);
+    std::string msg = "engine error flags:";
+    if (flag & az::ERR_NODE_CAP) msg += " node arena full";
+    if (flag & az::ERR_EDGE_CAP) msg += " edge arena full";
+    if (flag & az::ERR_HASH_CAP) msg += " hash table full";
+    if (flag & az::ERR_DEPTH) msg += " path deeper than MAX_DEPTH";
+    if (flag & az::ERR_ILLEGAL) msg += " illegal move or bad game id in az_play";
+    return fail((flag & az::ERR_ILLEGAL) && !(flag & 7) ? MCAZ_EINVAL : MCAZ_ECAPACITY, msg);
+}
+
+static mc_state start_state() {
+    mc_state s;
+    mc_state_from_fen("2nbk/2ppp/5/5/PPP2/KBN2 w 0 1", &s);
+    return s;
+}
+
+template <typename T>
+static int dev_alloc(az_engine* e, T** p, size_t n, bool zero = true) {
+    void* q = nullptr;
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    MCAZ_CUDA(cudaMalloc(&q, bytes));
+    if (zero) MCAZ_CUDA(cudaMemset(q, 0, bytes));
+    e->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return MCAZ_OK;
+}
+
+}  // namespace mcaz
+
+extern "C" {
+
+void az_default_config(az_config* c) {
+    if (!c) return;
+    std::memset(c, 0, sizeof(*c));
+    c->n_games = 1;
+    c->max_sims_per_move = 36;      // app/base.py:25
+    c->cpuct = 1.0f;                // exp/agent.py:96
+    c->tau_change = 6;              // exp/agent.py:97
+    c->dirichlet_alpha = 0.6f;      // exp/agent.py:82
+    c->dirichlet_epsilon = 0.25f;
+    c->numpy1_dtype_flow = 0;
+    c->device_rng = 0;
+    c->seed = 0;
+    mc_default_rules(&c->rules);
+    c->network = 0;
+}
+
+int az_create(const az_config* cfg, az_engine** out) {
+    if (!cfg || !out) return fail(MCAZ_EINVAL, "az_create: null argument");
+    if (cfg->n_games <= 0 || cfg->max_sims_per_move <= 0) return fail(MCAZ_EINVAL, "az_create: n_games and max_sims_per_move must be positive");
+    if (int rc = require_device()) return rc;
+    az_engine* e = new az_engine();
+    e->cfg = *cfg;
+    cudaGetDevice(&e->device);
+    View& V = e->v;
+    V.G = cfg->n_games;
+    // <= 1 new node per simulation, <= 31 searches per tree under the 30-move cap (+ roots)
+    long long nc = cfg->node_capacity > 0 ? cfg->node_capacity : (long long)cfg->max_sims_per_move * 31 + 64;
+    long long ec = cfg->edge_capacity > 0 ? cfg->edge_capacity : nc * 14;
+    if (nc > 0x3fffffff || ec > 0x7fffffff) { delete e; return fail(MCAZ_EINVAL, "az_create: arena too large"); }
+    V.NC = (int)nc;
+    V.EC = (int)ec;
+    int hc = 64;
+    while (hc < 2 * V.NC) hc <<= 1;
+    V.HC = hc;
+    V.cpuct = cfg->cpuct; V.eps = cfg->dirichlet_epsilon; V.alpha = cfg->dirichlet_alpha;
+    V.numpy1 = cfg->numpy1_dtype_flow; V.tau_change = cfg->tau_change; V.rules = cfg->rules; V.seed = cfg->seed;
+    const size_t G = V.G, T = 2 * G, N = T * V.NC, E = T * V.EC;
+    int rc = MCAZ_OK;
+#define A(ptr, n) if (!rc) rc = dev_alloc(e, &ptr, (n))
+    A(V.game_state, G); A(V.game_result, G); A(V.game_ply, G); A(V.game_hist, G * az::HIST); A(V.game_hist_len, G); A(V.game_start_ply, G);
+    A(V.tree_nodes, T); A(V.tree_edges, T); A(V.tree_root, T);
+    A(V.node_board, N); A(V.node_meta, N); A(V.node_edge_off, N); A(V.node_info, N);
+    A(V.edge_Q, E); A(V.edge_N, E); A(V.edge_P, E); A(V.edge_child, E); A(V.edge_code, E);
+    A(V.ht, T * V.HC);
+    A(V.path_len, G); A(V.path_edge, G * az::MAX_DEPTH); A(V.path_node, G * az::MAX_DEPTH);
+    A(V.leaf_node, G); A(V.leaf_kind, G); A(V.leaf_value, G);
+    A(V.tokens, G * MC_TOKENS); A(V.clocks, G); A(V.needs_eval, G); A(V.leaf_states, G);
+    A(V.counters, AZ_NUM_COUNTERS); A(V.error_flag, 1);
+    A(e->d_noise, G * MC_MAX_MOVES); A(e->d_noise_used, G);
+    A(e->d_logits, G * MC_NUM_ACTIONS); A(e->d_values, G); A(e->d_priors, G * MC_MAX_MOVES);
+    A(e->d_record, G * az::MAX_DEPTH);
+    e->replay_capacity = G * az::MAX_DEPTH;
+    A(e->d_replay, e->replay_capacity); A(e->d_replay_count, 1);
+#undef A
+    if (!rc && cfg->network) rc = network_create(e);
+    if (rc) { az_destroy(e); return rc; }
+    *out = e;
+    return az_reset_games(e, nullptr, V.G, nullptr);
+}
+
+int az_destroy(az_engine* e) {
+    if (!e) return MCAZ_OK;
+    cudaDeviceSynchronize();
+    if (e->net) network_destroy(e);
+    for (void* p : e->allocs) cudaFree(p);
+    delete e;
+    return MCAZ_OK;
+}
+
+int az_set_weights(az_engine* e, const float* flat, size_t n) {
+    if (!e || !flat) return fail(MCAZ_EINVAL, "az_set_weights: null argument");
+    if (n != (size_t)AZ_NUM_WEIGHT_FLOATS) return fail(MCAZ_EINVAL, "az_set_weights: expected AZ_NUM_WEIGHT_FLOATS floats");
+    if (!e->net) return fail(MCAZ_ESTATE, "az_set_weights: engine was created with network = 0");
+    In<float> in;
+    if (int rc = in.init(flat, n, e->stream)) return rc;
+    int rc = network_set_weights(e, in.ptr);
+    if (!rc) MCAZ_CUDA(cudaStreamSynchronize(e->stream));
+    return rc;
+}
+
+int az_reset_games(az_engine* e, const int32_t* game_ids, int n, const mc_state* states) {
+    if (!e || n < 0) return fail(MCAZ_EINVAL, "az_reset_games: bad argument");
+    if (n == 0) return MCAZ_OK;
+    In<int32_t> ids; In<mc_state> st;
+    if (int rc = ids.init(game_ids, n, e->stream)) return rc;
+    if (int rc = st.init(states, n, e->stream)) return rc;
+    reset_games_kernel<<<std::min(n, num_sms() * 8), 256, 0, e->stream>>>(e->v, ids.ptr, n, st.ptr, start_state());
+    MCAZ_CHECK_LAUNCH();
+    e->launches++;
+    e->leaf_pending = false;
+    MCAZ_CUDA(cudaStreamSynchronize(e->stream));
+    return MCAZ_OK;
+}
+
+int az_set_positions(az_engine* e, const int32_t* game_ids, int n, const mc_state* states, const int32_t* tree_of_game) {
+    if (!e || n < 0 || (n > 0 && !states)) return fail(MCAZ_EINVAL, "az_set_positions: bad argument");
+    if (n == 0) return MCAZ_OK;
+    In<int32_t> ids; In<mc_state> st; In<int32_t> tg;
+    if (int rc = ids.init(game_ids, n, e->stream)) return rc;
+    if (int rc = st.init(states, n, e->stream)) return rc;
+    if (int rc = tg.init(tree_of_game, n, e->stream)) return rc;
+    set_positions_kernel<<<std::max(1, std::min((n + 127) / 128, num_sms() * 8)), 128, 0, e->stream>>>(e->v, ids.ptr, n, st.ptr, tg.ptr);
+    MCAZ_CHECK_LAUNCH();
+    e->launches++;
+    e->leaf_pending = false;
+    MCAZ_CUDA(cudaStreamSynchronize(e->stream));
+    return MCAZ_OK;
+}
+
+int az_select_expand(az_engine* e, const double* root_noise, uint8_t* noise_used) {
+    if (!e) return fail(MCAZ_EINVAL, "az_select_expand: null engine");
+    if (e->leaf_pending) return fail(MCAZ_ESTATE, "az_select_expand: previous simulation not backed up");
+    const View& V = e->v;
+    const double* noise = nullptr;
+    if (root_noise) {
+        if (is_device_pointer(root_noise)) noise = root_noise;
+        else {
+            MCAZ_CUDA(cudaMemcpyAsync(e->d_noise, root_noise, (size_t)V.G * MC_MAX_MOVES * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+            noise = e->d_noise;
+        }
+    } else if (e->cfg.device_rng && V.eps > 0.0f) {
+        dirichlet_kernel<<<warp_grid(V.G, 128), 128, 0, e->stream>>>(V, e->sim_counter, e->d_noise);
+        MCAZ_CHECK_LAUNCH();
+        e->launches++;
+        noise = e->d_noise;
+    }
+    e->sim_counter++;
+    select_expand_kernel<<<warp_grid(V.G, 128), 128, 0, e->stream>>>(V, noise, e->d_noise_used);
+    MCAZ_CHECK_LAUNCH();
+    e->launches++;
+    e->leaf_pending = true;
+    if (noise_used) {
+        if (is_device_pointer(noise_used)) MCAZ_CUDA(cudaMemcpyAsync(noise_used, e->d_noise_used, V.G, cudaMemcpyDeviceToDevice, e->stream));
+        else { MCAZ_CUDA(cudaMemcpyAsync(noise_used, e->d_noise_used, V.G, cudaMemcpyDeviceToHost, e->stream)); MCAZ_CUDA(cudaStreamSynchronize(e->stream)); }
+    }
+    return MCAZ_OK;
+}
+
+int az_leaf_batch(az_engine* e, const uint8_t** tokens, const float** clocks, const uint8_t** needs_eval,
+                  const mc_state** leaf_states, int* n_slots) {
+    if (!e) return fail(MCAZ_EINVAL, "az_leaf_batch: null engine");
+    if (tokens) *tokens = e->v.tokens;
+    if (clocks) *clocks = e->v.clocks;
+    if (needs_eval) *needs_eval = e->v.needs_eval;
+    if (leaf_states) *leaf_states = e->v.leaf_states;
+    if (n_slots) *n_slots = e->v.G;
+    return MCAZ_OK;
+}
+
+int az_backup(az_engine* e, const float* logits, const float* values, const float* priors) {
+    if (!e) return fail(MCAZ_EINVAL, "az_backup: null engine");
+    if (!e->leaf_pending) return fail(MCAZ_ESTATE, "az_backup: no simulation pending (call az_select_expand first)");
+    if (!values || (!logits && !priors)) return fail(MCAZ_EINVAL, "az_backup: values and one of logits/priors are required");
+    const View& V = e->v;
+    const float *lg = logits, *vl = values, *pr = priors;
+    if (logits && !is_device_pointer(logits)) {
+        MCAZ_CUDA(cudaMemcpyAsync(e->d_logits, logits, (size_t)V.G * MC_NUM_ACTIONS * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        lg = e->d_logits;
+    }
+    if (!is_device_pointer(values)) {
+        MCAZ_CUDA(cudaMemcpyAsync(e->d_values, values, (size_t)V.G * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        vl = e->d_values;
+    }
+    if (priors && !is_device_pointer(priors)) {
+        MCAZ_CUDA(cudaMemcpyAsync(e->d_priors, priors, (size_t)V.G * MC_MAX_MOVES * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        pr = e->d_priors;
+    }
+    backup_kernel<<<warp_grid(V.G, 128), 128, 0, e->stream>>>(V, lg, vl, pr);
+    MCAZ_CHECK_LAUNCH();
+    e->launches++;
+    e->leaf_pending = false;
+    return MCAZ_OK;
+}
+
+int az_search(az_engine* e, int n_sims) {
+    if (!e || n_sims < 0) return fail(MCAZ_EINVAL, "az_search: bad argument");
+    if (!e->net) return fail(MCAZ_ESTATE, "az_search: engine was created with network = 0 (use az_select_expand / az_backup)");
+    const View& V = e->v;
+    for (int s = 0; s < n_sims; ++s) {
+        if (int rc = az_select_expand(e, nullptr, nullptr)) return rc;
+        if (int rc = network_forward(e, V.tokens, V.clocks, V.needs_eval, V.G, e->d_logits, e->d_values)) return rc;
+        if (int rc = az_backup(e, e->d_logits, e->d_values, nullptr)) return rc;
+    }
+    return engine_check_errors(e);
+}
+
+int az_root_stats(az_engine* e, const int32_t* game_ids, int n, uint16_t* codes, uint32_t* visits, double* q, int32_t* n_legal) {
+    if (!e || n < 0 || (n > 0 && (!codes || !visits || !n_legal))) return fail(MCAZ_EINVAL, "az_root_stats: bad argument");
+    if (n == 0) return MCAZ_OK;
+    In<int32_t> ids; Out<uint16_t> oc; Out<uint32_t> ov; Out<double> oq; Out<int32_t> on;
+    if (int rc = ids.init(game_ids, n, e->stream)) return rc;
+    if (int rc = oc.init(codes, (size_t)n * MC_MAX_MOVES, e->stream, true)) return rc;
+    if (int rc = ov.init(visits, (size_t)n * MC_MAX_MOVES, e->stream, true)) return rc;
+    if (int rc = oq.init(q, q ? (size_t)n * MC_MAX_MOVES : 0, e->stream, true)) return rc;
+    if (int rc = on.init(n_legal, n, e->stream)) return rc;
+    root_stats_kernel<<<warp_grid(n, 128), 128, 0, e->stream>>>(e->v, ids.ptr, n, oc.ptr, ov.ptr, oq.ptr, on.ptr);
+    MCAZ_CHECK_LAUNCH();
+    e->launches++;
+    if (int rc = oc.finish(e->stream)) return rc;
+    if (int rc = ov.finish(e->stream)) return rc;
+    if (int rc = oq.finish(e->stream)) return rc;
+    if (int rc = on.finish(e->stream)) return rc;
+    return engine_check_errors(e);
+}
+
+int az_node_stats(az_engine* e, int game_id, int tree, const mc_state* state, int* found, uint16_t* codes, uint32_t* visits,
+                  double* q, float* priors, int32_t* n_legal, int* is_terminal, double* terminal_value) {
+    if (!e || !state || !found || game_id < 0 || game_id >= e->v.G) return fail(MCAZ_EINVAL, "az_node_stats: bad argument");
+    NodeStatsOut* d_out = nullptr;
+    uint16_t* d_codes = nullptr; uint32_t* d_vis = nullptr; double* d_q = nullptr; float* d_p = nullptr;
+    MCAZ_CUDA(cudaMalloc(&d_out, sizeof(NodeStatsOut)));
+    MCAZ_CUDA(cudaMalloc(&d_codes, MC_MAX_MOVES * sizeof(uint16_t)));
+    MCAZ_CUDA(cudaMalloc(&d_vis, MC_MAX_MOVES * sizeof(uint32_t)));
+    MCAZ_CUDA(cudaMalloc(&d_q, MC_MAX_MOVES * sizeof(double)));
+    MCAZ_CUDA(cudaMalloc(&d_p, MC_MAX_MOVES * sizeof(float)));
+    node_stats_kernel<<<1, 32, 0, e->stream>>>(e->v, game_id, tree, *state, d_out, d_codes, d_vis, d_q, d_p);
+    g_launches.fetch_add(1);
+    e->launches++;
+    NodeStatsOut h;
+    cudaMemcpyAsync(&h, d_out, sizeof(h), cudaMemcpyDeviceToHost, e->stream);
+    if (codes) cudaMemcpyAsync(codes, d_codes, MC_MAX_MOVES * sizeof(uint16_t), cudaMemcpyDeviceToHost, e->stream);
+    if (visits) cudaMemcpyAsync(visits, d_vis, MC_MAX_MOVES * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream);
+    if (q) cudaMemcpyAsync(q, d_q, MC_MAX_MOVES * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+    if (priors) cudaMemcpyAsync(priors, d_p, MC_MAX_MOVES * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+    cudaError_t err = cudaStreamSynchronize(e->stream);
+    cudaFree(d_out); cudaFree(d_codes); cudaFree(d_vis); cudaFree(d_q); cudaFree(d_p);
+    if (err != cudaSuccess) return fail(MCAZ_ECUDA, std::string("az_node_stats: ") + cudaGetErrorString(err));
+    *found = h.found;
+    if (n_legal) *n_legal = h.n_legal;
+    if (is_terminal) *is_terminal = h.is_terminal;
+    if (terminal_value) *terminal_value = h.terminal_value;
+    return MCAZ_OK;
+}
+
+int az_play(az_engine* e, const int32_t* game_ids, const uint16_t* codes, int n, int8_t* results) {
+    if (!e || n < 0 || (n > 0 && !codes)) return fail(MCAZ_EINVAL, "az_play: bad argument");
+    if (e->leaf_pending) return fail(MCAZ_ESTATE, "az_play: a simulation is pending (call az_backup first)");
+    if (n == 0) return MCAZ_OK;
+    In<int32_t> ids; In<uint16_t> ic; Out<int8_t> orr;
+    if (int rc = ids.init(game_ids, n, e->stream)) return rc;
+    if (int rc = ic.init(codes, n, e->stream)) return rc;
+    if (int rc = orr.init(results, results ? n : 0, e->stream)) return rc;
+    play_kernel<<<std::max(1, std::min((n + 127) / 128, num_sms() * 8)), 128, 0, e->stream>>>(e->v, ids.ptr, ic.ptr, n, orr.ptr);
+    MCAZ_CHECK_LAUNCH();
+    e->launches++;
+    if (int rc = orr.finish(e->stream)) return rc;
+    return engine_check_errors(e);
+}
+
+int az_play_device(az_engine* e) {
+    if (!e) return fail(MCAZ_EINVAL, "az_play_device: null engine");
+    if (e->leaf_pending) return fail(MCAZ_ESTATE, "az_play_device: a simulation is pending");
+    const View& V = e->v;
+    static unsigned long long move_counter = 0;
+    play_device_kernel<<<warp_grid(V.G, 128), 128, 0, e->stream>>>(V, e->d_record, e->d_replay, e->d_replay_count,
+                                                                   (unsigned long long)e->replay_capacity, ++move_counter, start_state());
+    MCAZ_CHECK_LAUNCH();
+    restart_finished_kernel<<<std::min(V.G, num_sms() * 8), 256, 0, e->stream>>>(V, start_state());
+    MCAZ_CHECK_LAUNCH();
+    e->launches += 2;
+    return MCAZ_OK;
+}
+
+int az_game_states(az_engine* e, const int32_t* game_ids, int n, mc_state* states, int8_t* results) {
+    if (!e || n < 0) return fail(MCAZ_EINVAL, "az_game_states: bad argument");
+    if (n == 0) return MCAZ_OK;
+    In<int32_t> ids; Out<mc_state> os; Out<int8_t> orr;
+    if (int rc = ids.init(game_ids, n, e->stream)) return rc;
+    if (int rc = os.init(states, states ? n : 0, e->stream)) return rc;
+    if (int rc = orr.init(results, results ? n : 0, e->stream)) return rc;
+    game_states_kernel<<<std::max(1, std::min((n + 127) / 128, num_sms() * 8)), 128, 0, e->stream>>>(e->v, ids.ptr, n, os.ptr, orr.ptr);
+    MCAZ_CHECK_LAUNCH();
+    e->launches++;
+    if (int rc = os.finish(e->stream)) return rc;
+    if (int rc = orr.finish(e->stream)) return rc;
+    MCAZ_CUDA(cudaStreamSynchronize(e->stream));
+    return MCAZ_OK;
+}
+
+int az_drain_replay(az_engine* e, az_replay_tuple* out, int max, int* n_out) {
+    if (!e || !n_out || max < 0) return fail(MCAZ_EINVAL, "az_drain_replay: bad argument");
+    unsigned long long count = 0;
+    MCAZ_CUDA(cudaMemcpyAsync(&count, e->d_replay_count, sizeof(count), cudaMemcpyDeviceToHost, e->stream));
+    MCAZ_CUDA(cudaStreamSynchronize(e->stream));
+    size_t have = (size_t)std::min<unsigned long long>(count, e->replay_capacity);
+    size_t take = std::min<size_t>(have, (size_t)max);
+    if (take && out)
+        MCAZ_CUDA(cudaMemcpyAsync(out, e->d_replay, take * sizeof(az_replay_tuple),
+                                  is_device_pointer(out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
+    MCAZ_CUDA(cudaMemsetAsync(e->d_replay_count, 0, sizeof(unsigned long long), e->stream));
+    MCAZ_CUDA(cudaStreamSynchronize(e->stream));
+    *n_out = (int)take;
+    return MCAZ_OK;
+}
+
+int az_counters(az_engine* e, uint64_t* out) {
+    if (!e || !out) return fail(MCAZ_EINVAL, "az_counters: bad argument");
+    unsigned long long h[AZ_NUM_COUNTERS];
+    MCAZ_CUDA(cudaMemcpyAsync(h, e->v.counters, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+    MCAZ_CUDA(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < AZ_NUM_COUNTERS; ++i) out[i] = h[i];
+    out[az::C_LAUNCHES] = e->launches;
+    return MCAZ_OK;
+}
+
+int az_network_forward(az_engine* e, const uint8_t* tokens, const float* clocks, int n, float* logits, float* values) {
+    if (!e || n < 0 || (n > 0 && (!tokens || !clocks || !logits || !values))) return fail(MCAZ_EINVAL, "az_network_forward: bad argument");
+    if (!e->net) return fail(MCAZ_ESTATE, "az_network_forward: engine was created with network = 0");
+    if (n == 0) return MCAZ_OK;
+    In<uint8_t> it; In<float> ic; Out<float> ol; Out<float> ov;
+    if (int rc = it.init(tokens, (size_t)n * MC_TOKENS, e->stream)) return rc;
+    if (int rc = ic.init(clocks, n, e->stream)) return rc;
+    if (int rc = ol.init(logits, (size_t)n * MC_NUM_ACTIONS, e->stream)) return rc;
+    if (int rc = ov.init(values, n, e->stream)) return rc;
+    if (int rc = network_forward(e, it.ptr, ic.ptr, nullptr, n, ol.ptr, ov.ptr)) return rc;
+    if (int rc = ol.finish(e->stream)) return rc;
+    if (int rc = ov.finish(e->stream)) return rc;
+    MCAZ_CUDA(cudaStreamSynchronize(e->stream));
+    return MCAZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,419 @@
+// mcts_core.cuh -- AlphaZero tree search over GPU-resident structure-of-arrays trees.
+//
+// Restates, with the reference's exact arithmetic, exp/agent.py:24-88 (MonteCarloTreeSearch):
+//   select   :75-88  u = Q + cpuct*P*sqrt(sum N)/(1+N), first-max argmax, root Dirichlet mix
+//   expand   :57-66  unseen position -> terminal record or zeroed Q/N + legal codes
+//   evaluate :67-71  softmax of the legal logits -> priors, value
+//   backup   :47-52  value = -value; Q = (N*Q + value)/(N+1); N += 1   (float64, this order)
+// One warp walks one tree; lanes split the edges of a node.  The same source compiles for the
+// host with one "lane" so CPU tests can drive it; the product only launches the kernels.
+//
+// Layout in HBM (per engine; T = 2*G trees, fixed per-tree arenas of NC nodes / EC edges):
+//   node_board[T*NC] 16 B  piece planes + colour plane      node_meta[T*NC] 4 B  turn/clocks
+//   node_edge_off[T*NC] 4 B first edge (tree-relative)      node_info[T*NC] 4 B  n_edges | flags
+//   edge_Q[T*EC] f64, edge_N[T*EC] u32, edge_P[T*EC] f32, edge_child[T*EC] u32, edge_code[T*EC] u16
+//   ht[T*HC] u32  open-addressing table: position -> node (the reference keys its dicts by the
+//                 FEN string, so one position reached by two paths is ONE node: a DAG)
+// A node's edges are contiguous in every edge array, so a warp reads them coalesced.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "minitchess.cuh"
+
+namespace az {
+
+constexpr uint32_t NONE = 0xffffffffu;
+constexpr int MAX_DEPTH = 64;        // a path cannot be longer than the plies left to the 30-move cap
+constexpr int HIST = 64;             // reversible-position history per game (fivefold repetition)
+constexpr uint32_t INFO_TERMINAL = 1u << 16;
+constexpr uint32_t INFO_DECISIVE = 1u << 17;  // terminal with reward 1.0 (else draw, reward 0.0)
+
+enum LeafKind : uint8_t { LEAF_NONE = 0, LEAF_EVAL = 1, LEAF_TERMINAL = 2 };
+enum Counter : int { C_SIMS = 0, C_EVALS, C_TERMINAL, C_MOVES, C_GAMES, C_NODES, C_EDGES, C_LAUNCHES };
+enum ErrorBit : int { ERR_NODE_CAP = 1, ERR_EDGE_CAP = 2, ERR_HASH_CAP = 4, ERR_DEPTH = 8, ERR_ILLEGAL = 16 };
+
+struct alignas(16) Board4 { uint32_t x, y, z, w; };
+
+struct View {
+    int G, NC, EC, HC;
+    // real games
+    mc_state* game_state; int8_t* game_result; int32_t* game_ply; int32_t* game_start_ply;
+    Board4* game_hist; int32_t* game_hist_len;     // [G*HIST] positions since the last irreversible move
+    // trees
+    uint32_t* tree_nodes; uint32_t* tree_edges; uint32_t* tree_root;
+    Board4* node_board; uint32_t* node_meta; uint32_t* node_edge_off; uint32_t* node_info;
+    double* edge_Q; uint32_t* edge_N; float* edge_P; uint32_t* edge_child; uint16_t* edge_code;
+    uint32_t* ht;
+    // per-game simulation scratch
+    int32_t* path_len; uint32_t* path_edge; uint32_t* path_node;   // [G*MAX_DEPTH]
+    uint32_t* leaf_node; uint8_t* leaf_kind; double* leaf_value;
+    // leaf batch (slot = game)
+    uint8_t* tokens; float* clocks; uint8_t* needs_eval; mc_state* leaf_states;
+    unsigned long long* counters; int* error_flag;
+    // parameters
+    float cpuct; float eps; float alpha; int numpy1; int tau_change; mc_rules rules;
+    unsigned long long seed;
+};
+
+#if defined(__CUDA_ARCH__)
+#define AZ_LANES 32
+#define AZ_SYNCWARP() __syncwarp()
+#else
+#define AZ_LANES 1
+#define AZ_SYNCWARP() ((void)0)
+#endif
+
+MC_HD double dmul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+MC_HD double dadd(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+MC_HD double ddiv(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __ddiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+MC_HD double dsqrt(double a) {
+#if defined(__CUDA_ARCH__)
+    return __dsqrt_rn(a);
+#else
+    return sqrt(a);
+#endif
+}
+MC_HD float fmul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+
+MC_HD void raise(const View& V, int bit) {
+#if defined(__CUDA_ARCH__)
+    atomicOr(V.error_flag, bit);
+#else
+    *V.error_flag |= bit;
+#endif
+}
+MC_HD void count(const View& V, int which, unsigned long long n) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(&V.counters[which], n);
+#else
+    V.counters[which] += n;
+#endif
+}
+
+MC_HD Board4 board_of(const mc_state& s) { return Board4{s.pl0, s.pl1, s.pl2, s.white}; }
+MC_HD mc_state state_of(const Board4& b, uint32_t meta) { return mc_state{b.x, b.y, b.z, b.w, meta}; }
+
+MC_HD uint32_t hash_state(const mc_state& s) {
+    uint32_t h = s.pl0 * 0x9E3779B1u;
+    h = (h ^ (h >> 15)) + s.pl1 * 0x85EBCA77u;
+    h = (h ^ (h >> 13)) + s.pl2 * 0xC2B2AE3Du;
+    h = (h ^ (h >> 16)) + s.white * 0x27D4EB2Fu;
+    h = (h ^ (h >> 15)) + s.meta * 0x165667B1u;
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return h;
+}
+
+// Position -> node of tree t, or NONE.  Scalar: every lane computes the same answer.
+MC_HD uint32_t ht_find(const View& V, int t, const mc_state& s) {
+    const uint32_t* tab = V.ht + (size_t)t * V.HC;
+    uint32_t mask = (uint32_t)V.HC - 1u, h = hash_state(s) & mask;
+    for (int probe = 0; probe < V.HC; ++probe) {
+        uint32_t e = tab[h];
+        if (e == 0) return NONE;
+        uint32_t n = e - 1;
+        size_t gi = (size_t)t * V.NC + n;
+        Board4 b = V.node_board[gi];
+        if (b.x == s.pl0 && b.y == s.pl1 && b.z == s.pl2 && b.w == s.white && V.node_meta[gi] == s.meta) return n;
+        h = (h + 1) & mask;
+    }
+    return NONE;
+}
+// Single writer (lane 0 of the tree's warp).
+MC_HD void ht_insert(const View& V, int t, const mc_state& s, uint32_t node) {
+    uint32_t* tab = V.ht + (size_t)t * V.HC;
+    uint32_t mask = (uint32_t)V.HC - 1u, h = hash_state(s) & mask;
+    for (int probe = 0; probe < V.HC; ++probe) {
+        if (tab[h] == 0) { tab[h] = node + 1; return; }
+        h = (h + 1) & mask;
+    }
+    raise(V, ERR_HASH_CAP);
+}
+
+// Create the node for an unvisited position (exp/agent.py:57-66).  Lane 0 writes; every lane
+// gets the node index, its kind and, for a finished position, the value to back up.
+MC_HD uint32_t expand(const View& V, int g, int t, int lane, const mc_state& s, uint8_t* kind, double* value) {
+    uint32_t node = NONE;
+    int is_terminal = 0, decisive = 0;
+#if defined(__CUDA_ARCH__)
+    if (lane == 0)
+#endif
+    {
+        uint32_t n = V.tree_nodes[t];
+        if (n >= (uint32_t)V.NC) {
+            raise(V, ERR_NODE_CAP);
+        } else {
+            uint16_t codes[MC_MAX_MOVES];
+            int res;
+            int E = mc::generate(s, V.rules, codes, &res);
+            uint32_t off = V.tree_edges[t];
+            size_t gi = (size_t)t * V.NC + n;
+            if (res != MC_ONGOING) {
+                is_terminal = 1;
+                decisive = (res != MC_DRAW);
+                E = 0;
+            } else if (off + (uint32_t)E > (uint32_t)V.EC) {
+                raise(V, ERR_EDGE_CAP);
+                E = 0;
+                is_terminal = 1;  // keeps the tree consistent; the error flag fails the call
+            }
+            V.node_board[gi] = board_of(s);
+            V.node_meta[gi] = s.meta;
+            V.node_edge_off[gi] = off;
+            V.node_info[gi] = (uint32_t)E | (is_terminal ? INFO_TERMINAL : 0u) | (decisive ? INFO_DECISIVE : 0u);
+            size_t ge = (size_t)t * V.EC + off;
+            for (int k = 0; k < E; ++k) {
+                V.edge_Q[ge + k] = 0.0;
+                V.edge_N[ge + k] = 0u;
+                V.edge_P[ge + k] = 0.0f;
+                V.edge_child[ge + k] = NONE;
+                V.edge_code[ge + k] = codes[k];
+            }
+            V.tree_nodes[t] = n + 1;
+            V.tree_edges[t] = off + (uint32_t)E;
+            ht_insert(V, t, s, n);
+            node = n;
+            if (!is_terminal) {
+                mc::tokenize(s, V.tokens + (size_t)g * MC_TOKENS, &V.clocks[g]);
+                V.leaf_states[g] = s;
+            }
+            count(V, C_NODES, 1);
+            count(V, C_EDGES, (unsigned long long)E);
+        }
+    }
+#if defined(__CUDA_ARCH__)
+    node = __shfl_sync(0xffffffffu, node, 0);
+    is_terminal = __shfl_sync(0xffffffffu, is_terminal, 0);
+    decisive = __shfl_sync(0xffffffffu, decisive, 0);
+    __syncwarp();
+#endif
+    if (node == NONE) { *kind = LEAF_TERMINAL; *value = 0.0; return NONE; }
+    if (is_terminal) {
+        *kind = LEAF_TERMINAL;
+        *value = decisive ? -1.0 : -0.0;  // value = -reward (exp/agent.py:60)
+    } else {
+        *kind = LEAF_EVAL;
+        *value = 0.0;
+    }
+    return node;
+}
+
+// One simulation of game g down to its leaf (exp/agent.py:54-88 without the backup).
+// `noise`: per-game Dirichlet sample [MC_MAX_MOVES] or nullptr.
+MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise, uint8_t* noise_used) {
+    if (lane == 0) {
+        V.leaf_kind[g] = LEAF_NONE;
+        V.needs_eval[g] = 0;
+        V.path_len[g] = 0;
+        if (noise_used) noise_used[g] = 0;
+    }
+    if (V.game_result[g] != MC_ONGOING) return;
+    const int t = 2 * g + (V.game_ply[g] & 1);
+    const size_t nbase = (size_t)t * V.NC, ebase = (size_t)t * V.EC;
+    uint32_t* pedge = V.path_edge + (size_t)g * MAX_DEPTH;
+    uint32_t* pnode = V.path_node + (size_t)g * MAX_DEPTH;
+
+    uint8_t kind = LEAF_NONE;
+    double value = 0.0;
+    uint32_t node = V.tree_root[t];
+    int depth = 0;
+    if (node == NONE) {
+        mc_state s = V.game_state[g];
+        node = ht_find(V, t, s);
+        if (node == NONE) node = expand(V, g, t, lane, s, &kind, &value);
+        if (lane == 0 && node != NONE) V.tree_root[t] = node;
+        AZ_SYNCWARP();
+    }
+    while (kind == LEAF_NONE) {
+        uint32_t info = V.node_info[nbase + node];
+        if (info & INFO_TERMINAL) {  // exp/agent.py:75-77: revisit backs up -terminal[node]
+            kind = LEAF_TERMINAL;
+            value = (info & INFO_DECISIVE) ? 1.0 : 0.0;
+            break;
+        }
+        const int E = (int)(info & 0xffffu);
+        const size_t e0 = ebase + V.node_edge_off[nbase + node];
+        // sum of visit counts (exact in float64: small integers)
+        unsigned int nsum_u = 0;
+        for (int i = lane; i < E; i += AZ_LANES) nsum_u += V.edge_N[e0 + i];
+#if defined(__CUDA_ARCH__)
+        for (int o = 16; o > 0; o >>= 1) nsum_u += __shfl_xor_sync(0xffffffffu, nsum_u, o);
+#endif
+        const double root_n = dsqrt((double)nsum_u);
+        const bool mix = (depth == 0) && (noise != nullptr) && (V.eps > 0.0f);
+        double best_u = 0.0;
+        int best_i = 0x7fffffff;
+        for (int i = lane; i < E; i += AZ_LANES) {
+            const float p = V.edge_P[e0 + i];
+            double x;
+            if (mix) {
+                // P = (1-eps)*P + eps*dirichlet: float32 product, float64 sum (exp/agent.py:82 under NEP 50)
+                double pn = dadd((double)fmul((float)(1.0 - (double)V.eps), p),
+                                 dmul((double)V.eps, noise[(size_t)g * MC_MAX_MOVES + i]));
+                x = dmul(dmul((double)V.cpuct, pn), root_n);
+            } else if (V.numpy1) {
+                // numpy 1.x value-based casting: float32 array * float64 scalar stays float32 (Q6)
+                x = (double)fmul(fmul(V.cpuct, p), (float)root_n);
+            } else {
+                x = dmul((double)fmul(V.cpuct, p), root_n);
+            }
+            const double u = dadd(V.edge_Q[e0 + i], ddiv(x, dadd(1.0, (double)V.edge_N[e0 + i])));
+            if (best_i == 0x7fffffff || u > best_u) { best_u = u; best_i = i; }  // first max within the lane
+        }
+#if defined(__CUDA_ARCH__)
+        for (int o = 16; o > 0; o >>= 1) {
+            double ou = __shfl_xor_sync(0xffffffffu, best_u, o);
+            int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+            if (oi != 0x7fffffff && (best_i == 0x7fffffff || ou > best_u || (ou == best_u && oi < best_i))) {
+                best_u = ou;
+                best_i = oi;
+            }
+        }
+#endif
+        if (mix && lane == 0 && noise_used) noise_used[g] = 1;
+        if (depth >= MAX_DEPTH) { raise(V, ERR_DEPTH); kind = LEAF_TERMINAL; value = 0.0; break; }
+        const size_t e = e0 + (size_t)best_i;
+        if (lane == 0) {
+            pedge[depth] = (uint32_t)(e - ebase);
+            pnode[depth] = node;
+        }
+        ++depth;
+        uint32_t child = V.edge_child[e];
+        if (child == NONE) {
+            // first traversal of this edge: apply the move and look the position up
+            mc_state ps = state_of(V.node_board[nbase + node], V.node_meta[nbase + node]);
+            int fv, tv;
+            mc::code_to_view(V.edge_code[e], fv, tv);
+            const bool white = mc::white_to_move(ps);
+            mc_state cs = mc::apply_move(ps, white ? fv : 29 - fv, white ? tv : 29 - tv);
+            child = ht_find(V, t, cs);
+            if (child == NONE) child = expand(V, g, t, lane, cs, &kind, &value);
+            if (lane == 0 && child != NONE) V.edge_child[e] = child;
+            AZ_SYNCWARP();
+            if (child == NONE) break;
+        }
+        node = child;
+    }
+    if (lane == 0) {
+        V.path_len[g] = depth;
+        V.leaf_node[g] = node;
+        V.leaf_kind[g] = kind;
+        V.leaf_value[g] = value;
+        V.needs_eval[g] = (kind == LEAF_EVAL) ? 1 : 0;
+    }
+}
+
+// Evaluate + backup for game g (exp/agent.py:67-72 and :47-52).
+// logits: [G x 554] float32 (softmax over the legal entries, float32) or priors: [G x MC_MAX_MOVES].
+MC_HD void backup_one(const View& V, int g, int lane, const float* logits, const float* values, const float* priors) {
+    const uint8_t kind = V.leaf_kind[g];
+    if (kind == LEAF_NONE) return;
+    const int t = 2 * g + (V.game_ply[g] & 1);
+    const size_t nbase = (size_t)t * V.NC, ebase = (size_t)t * V.EC;
+    double value = V.leaf_value[g];
+    if (kind == LEAF_EVAL) {
+        const uint32_t node = V.leaf_node[g];
+        const int E = (int)(V.node_info[nbase + node] & 0xffffu);
+        const size_t e0 = ebase + V.node_edge_off[nbase + node];
+        if (priors) {
+            for (int i = lane; i < E; i += AZ_LANES) V.edge_P[e0 + i] = priors[(size_t)g * MC_MAX_MOVES + i];
+        } else {
+            const float* lg = logits + (size_t)g * MC_NUM_ACTIONS;
+            float m = -INFINITY;
+            for (int i = lane; i < E; i += AZ_LANES) m = fmaxf(m, lg[V.edge_code[e0 + i]]);
+#if defined(__CUDA_ARCH__)
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+#endif
+            float sum = 0.f;
+            for (int i = lane; i < E; i += AZ_LANES) sum += expf(lg[V.edge_code[e0 + i]] - m);
+#if defined(__CUDA_ARCH__)
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#endif
+            for (int i = lane; i < E; i += AZ_LANES) V.edge_P[e0 + i] = expf(lg[V.edge_code[e0 + i]] - m) / sum;
+        }
+        value = (double)values[g];
+    }
+    if (lane == 0) {
+        const uint32_t* pedge = V.path_edge + (size_t)g * MAX_DEPTH;
+        for (int d = V.path_len[g] - 1; d >= 0; --d) {
+            value = -value;
+            const size_t e = ebase + pedge[d];
+            const double n = (double)V.edge_N[e];
+            V.edge_Q[e] = ddiv(dadd(dmul(n, V.edge_Q[e]), value), dadd(n, 1.0));
+            V.edge_N[e] += 1u;
+        }
+        count(V, C_SIMS, 1);
+        count(V, kind == LEAF_EVAL ? C_EVALS : C_TERMINAL, 1);
+        V.leaf_kind[g] = LEAF_NONE;
+    }
+}
+
+// ---- the real game line -----------------------------------------------------------------------
+MC_HD Board4 rep_key(const mc_state& s) { return Board4{s.pl0, s.pl1, s.pl2, s.white | ((s.meta & 1u) << 31)}; }
+
+// Result of the current position of game g including fivefold repetition over the game line
+// (python-chess is_fivefold_repetition over the move stack; exp/environment.py:39).
+MC_HD int game_result_of(const View& V, int g, const mc_state& s) {
+    uint16_t codes[MC_MAX_MOVES];
+    int res;
+    mc::generate(s, V.rules, codes, &res);
+    if (res == MC_ONGOING && V.rules.fivefold_repetition) {
+        const Board4 key = rep_key(s);
+        const Board4* h = V.game_hist + (size_t)g * HIST;
+        int same = 0, n = V.game_hist_len[g];
+        for (int i = 0; i < n; ++i) same += (h[i].x == key.x && h[i].y == key.y && h[i].z == key.z && h[i].w == key.w);
+        if (same >= 5) res = MC_DRAW;
+    }
+    return res;
+}
+
+MC_HD void hist_reset(const View& V, int g, const mc_state& s) {
+    V.game_hist[(size_t)g * HIST] = rep_key(s);
+    V.game_hist_len[g] = 1;
+}
+
+// Play `code` in game g (exp/environment.py:68-82).  Returns 0 ok, 1 illegal, 2 finished.  Scalar.
+MC_HD int play_one(const View& V, int g, int code) {
+    if (V.game_result[g] != MC_ONGOING) return 2;
+    mc_state s = V.game_state[g], o;
+    int st = mc::step(s, code, V.rules, &o);
+    if (st != 0) return st;
+    const bool zeroing = mc::halfmove(o) == 0;
+    if (zeroing) V.game_hist_len[g] = 0;
+    int n = V.game_hist_len[g];
+    if (n < HIST) { V.game_hist[(size_t)g * HIST + n] = rep_key(o); V.game_hist_len[g] = n + 1; }
+    V.game_state[g] = o;
+    V.game_ply[g] += 1;
+    V.tree_root[2 * g] = NONE;
+    V.tree_root[2 * g + 1] = NONE;
+    V.game_result[g] = (int8_t)game_result_of(V, g, o);
+    count(V, C_MOVES, 1);
+    if (V.game_result[g] != MC_ONGOING) count(V, C_GAMES, 1);
+    return 0;
+}
+
+}  // namespace az

@@ -1,0 +1,234 @@
+"""Python handle over the az_* entry points of include/mcaz.h: the batched AlphaZero search engine.
+
+One `Engine` owns `n_games` concurrent games with two GPU-resident trees each (one per colour's
+agent, like the two `SimpleAlphaZeroAgent`s of app/base.py:113).  Search runs either with the
+built-in network (`search`) or one simulation at a time around an external evaluator
+(`select_expand` -> evaluate the leaf batch -> `backup`), which is also how the parity tests feed
+the reference MCTS and the engine identical priors.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import (AZ_NUM_COUNTERS, AZ_NUM_WEIGHT_FLOATS, MC_MAX_MOVES, MC_NUM_ACTIONS, MC_TOKENS, STATE_DTYPE, Config,
+                   check, ptr)
+
+COUNTER_NAMES = ('simulations', 'evaluations', 'terminal_leaves', 'moves', 'games_finished', 'nodes', 'edges',
+                 'kernel_launches')
+
+REPLAY_DTYPE = np.dtype([('observation', STATE_DTYPE), ('n_legal', '<u2'), ('action', '<u2'), ('reward', 'i1'),
+                         ('pad', 'u1', 3), ('codes', '<u2', MC_MAX_MOVES), ('pi', '<f4', MC_MAX_MOVES)])
+
+
+class _CudaView:
+    """Engine-owned device memory exposed through __cuda_array_interface__ (zero copy into torch)."""
+
+    def __init__(self, address, shape, typestr):
+        self.__cuda_array_interface__ = {'data': (int(address), False), 'shape': tuple(shape), 'typestr': typestr,
+                                         'version': 2, 'strides': None}
+
+
+def default_config(**overrides):
+    cfg = Config()
+    _lib.lib().az_default_config(ctypes.byref(cfg))
+    for k, v in overrides.items():
+        if k == 'rules':
+            cfg.rules = v
+        else:
+            if not hasattr(cfg, k):
+                raise TypeError('unknown engine option %r' % k)
+            setattr(cfg, k, v)
+    return cfg
+
+
+class Engine:
+    def __init__(self, n_games=1, _backend=None, **options):
+        # `_backend` is a test hook: the CPU suite passes the host build of csrc/mcts_core.cuh
+        # (tests/host_harness).  The product always uses libmcaz.so.
+        self._L = _backend if _backend is not None else _lib.lib()
+        self._host = _backend is not None
+        cfg = Config()
+        self._L.az_default_config(ctypes.byref(cfg))
+        cfg.n_games = int(n_games)
+        for k, v in options.items():
+            if not hasattr(cfg, k):
+                raise TypeError('unknown engine option %r' % k)
+            setattr(cfg, k, v)
+        self.config = cfg
+        self.n_games = int(n_games)
+        self._h = ctypes.c_void_p()
+        self._check(self._L.az_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+        self._noise_used = np.zeros(self.n_games, dtype=np.uint8)
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._L.mcaz_last_error()
+            if isinstance(msg, int):
+                msg = ctypes.cast(msg, ctypes.c_char_p).value
+            raise _lib.McazError(rc, (msg or b'').decode(errors='replace'))
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self._L.az_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ games
+    @staticmethod
+    def _ids(game_ids):
+        return None if game_ids is None else np.ascontiguousarray(game_ids, dtype=np.int32)
+
+    def reset_games(self, game_ids=None, states=None):
+        """MonteCarloInit.on_episode_begin (exp/callbacks.py:57-62) + env.new_episode for the listed games."""
+        ids = self._ids(game_ids)
+        n = self.n_games if ids is None else len(ids)
+        st = None if states is None else np.ascontiguousarray(states, dtype=STATE_DTYPE)
+        self._check(self._L.az_reset_games(self._h, ptr(ids), n, ptr(st)))
+
+    def set_positions(self, states, game_ids=None, trees=None):
+        ids = self._ids(game_ids)
+        st = np.ascontiguousarray(np.atleast_1d(states), dtype=STATE_DTYPE)
+        tr = None if trees is None else np.ascontiguousarray(trees, dtype=np.int32)
+        self._check(self._L.az_set_positions(self._h, ptr(ids), len(st), ptr(st), ptr(tr)))
+
+    def play(self, codes, game_ids=None):
+        ids = self._ids(game_ids)
+        codes = np.ascontiguousarray(np.atleast_1d(codes), dtype=np.uint16)
+        results = np.zeros(len(codes), dtype=np.int8)
+        self._check(self._L.az_play(self._h, ptr(ids), ptr(codes), len(codes), ptr(results)))
+        return results
+
+    def play_device(self):
+        self._check(self._L.az_play_device(self._h))
+
+    def game_states(self, game_ids=None):
+        ids = self._ids(game_ids)
+        n = self.n_games if ids is None else len(ids)
+        states = np.zeros(n, dtype=STATE_DTYPE)
+        results = np.zeros(n, dtype=np.int8)
+        self._check(self._L.az_game_states(self._h, ptr(ids), n, ptr(states), ptr(results)))
+        return states, results
+
+    # ------------------------------------------------------------- simulation
+    def select_expand(self, noise=None, want_noise_used=False):
+        """One PUCT descent + expansion per active game.  `noise`: float64 [n_games, MC_MAX_MOVES] or None."""
+        if noise is not None and isinstance(noise, np.ndarray):
+            noise = np.ascontiguousarray(noise, dtype=np.float64)
+            assert noise.shape == (self.n_games, MC_MAX_MOVES)
+        used = self._noise_used if want_noise_used else None
+        self._check(self._L.az_select_expand(self._h, ptr(noise), ptr(used)))
+        return used
+
+    def _leaf_pointers(self):
+        tok, clk, need, st = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        n = ctypes.c_int()
+        self._check(self._L.az_leaf_batch(self._h, ctypes.byref(tok), ctypes.byref(clk), ctypes.byref(need),
+                                          ctypes.byref(st), ctypes.byref(n)))
+        return tok.value, clk.value, need.value, st.value, n.value
+
+    def leaf_batch_device(self):
+        """Zero-copy torch views of the leaf batch: tokens uint8[G,60], clocks float32[G], needs_eval uint8[G]."""
+        import torch
+        tok, clk, need, _st, n = self._leaf_pointers()
+        assert not self._host
+        return (torch.as_tensor(_CudaView(tok, (n, MC_TOKENS), '|u1'), device='cuda'),
+                torch.as_tensor(_CudaView(clk, (n,), '<f4'), device='cuda'),
+                torch.as_tensor(_CudaView(need, (n,), '|u1'), device='cuda'))
+
+    def leaf_batch(self):
+        """Host copies: tokens, clocks, needs_eval, leaf_states (numpy)."""
+        tok, clk, need, st, n = self._leaf_pointers()
+        if self._host:
+            def view(addr, dtype, shape):
+                count = int(np.prod(shape))
+                buf = (ctypes.c_char * (count * np.dtype(dtype).itemsize)).from_address(addr)
+                return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape).copy()
+            return (view(tok, np.uint8, (n, MC_TOKENS)), view(clk, np.float32, (n,)), view(need, np.uint8, (n,)),
+                    view(st, STATE_DTYPE, (n,)))
+        import torch
+        tokens = torch.as_tensor(_CudaView(tok, (n, MC_TOKENS), '|u1'), device='cuda').cpu().numpy()
+        clocks = torch.as_tensor(_CudaView(clk, (n,), '<f4'), device='cuda').cpu().numpy()
+        needs = torch.as_tensor(_CudaView(need, (n,), '|u1'), device='cuda').cpu().numpy()
+        raw = torch.as_tensor(_CudaView(st, (n, 5), '<i4'), device='cuda').cpu().numpy()
+        return tokens, clocks, needs, raw.view(np.uint32).reshape(-1).view(STATE_DTYPE)
+
+    def backup(self, values, logits=None, priors=None):
+        """exp/agent.py:67-72 + :47-52.  logits [G,554] / priors [G,MC_MAX_MOVES] / values [G], float32."""
+        def prep(x, shape):
+            if x is None:
+                return None
+            if isinstance(x, np.ndarray):
+                x = np.ascontiguousarray(x, dtype=np.float32)
+                assert x.shape == shape, (x.shape, shape)
+            return x
+        self._check(self._L.az_backup(self._h, ptr(prep(logits, (self.n_games, MC_NUM_ACTIONS))),
+                                      ptr(prep(values, (self.n_games,))),
+                                      ptr(prep(priors, (self.n_games, MC_MAX_MOVES)))))
+
+    def search(self, n_sims):
+        """n_sims simulations for every active game with the built-in network."""
+        self._check(self._L.az_search(self._h, int(n_sims)))
+
+    # ------------------------------------------------------------------ read-back
+    def root_stats(self, game_ids=None, want_q=True):
+        """-> codes uint16[n,M], visits uint32[n,M], q float64[n,M] or None, n_legal int32[n] (-1: not visited)."""
+        ids = self._ids(game_ids)
+        n = self.n_games if ids is None else len(ids)
+        codes = np.zeros((n, MC_MAX_MOVES), dtype=np.uint16)
+        visits = np.zeros((n, MC_MAX_MOVES), dtype=np.uint32)
+        q = np.zeros((n, MC_MAX_MOVES), dtype=np.float64) if want_q else None
+        n_legal = np.zeros(n, dtype=np.int32)
+        self._check(self._L.az_root_stats(self._h, ptr(ids), n, ptr(codes), ptr(visits), ptr(q), ptr(n_legal)))
+        return codes, visits, q, n_legal
+
+    def node_stats(self, game_id, tree, state):
+        """MonteCarloTreeSearch.__getitem__ for one position (exp/agent.py:38-39); None if never visited."""
+        st = np.ascontiguousarray(np.atleast_1d(state), dtype=STATE_DTYPE)
+        found, n_legal, term = ctypes.c_int(), ctypes.c_int32(), ctypes.c_int()
+        tval = ctypes.c_double()
+        codes = np.zeros(MC_MAX_MOVES, dtype=np.uint16)
+        visits = np.zeros(MC_MAX_MOVES, dtype=np.uint32)
+        q = np.zeros(MC_MAX_MOVES, dtype=np.float64)
+        pri = np.zeros(MC_MAX_MOVES, dtype=np.float32)
+        self._check(self._L.az_node_stats(self._h, int(game_id), int(tree), ptr(st), ctypes.byref(found), ptr(codes),
+                                          ptr(visits), ptr(q), ptr(pri), ctypes.byref(n_legal), ctypes.byref(term),
+                                          ctypes.byref(tval)))
+        if not found.value:
+            return None
+        E = n_legal.value
+        return {'legal_moves': codes[:E].astype(int).tolist(), 'N': visits[:E].astype(np.float64), 'Q': q[:E].copy(),
+                'P': pri[:E].copy(), 'terminal': tval.value if term.value else None}
+
+    def counters(self):
+        out = np.zeros(AZ_NUM_COUNTERS, dtype=np.uint64)
+        self._check(self._L.az_counters(self._h, ptr(out)))
+        return dict(zip(COUNTER_NAMES, (int(x) for x in out)))
+
+    # ------------------------------------------------------------------ network
+    def set_weights(self, flat):
+        """flat: float32 [AZ_NUM_WEIGHT_FLOATS] numpy array or CUDA tensor (policy.flatten_state_dict)."""
+        n = flat.numel() if hasattr(flat, 'numel') else flat.size
+        assert n == AZ_NUM_WEIGHT_FLOATS, n
+        self._check(self._L.az_set_weights(self._h, ptr(flat), ctypes.c_size_t(n)))
+
+    def network_forward(self, tokens, clocks):
+        tokens = np.ascontiguousarray(tokens, dtype=np.uint8).reshape(-1, MC_TOKENS)
+        clocks = np.ascontiguousarray(clocks, dtype=np.float32).reshape(-1)
+        n = len(tokens)
+        logits = np.zeros((n, MC_NUM_ACTIONS), dtype=np.float32)
+        values = np.zeros(n, dtype=np.float32)
+        self._check(self._L.az_network_forward(self._h, ptr(tokens), ptr(clocks), n, ptr(logits), ptr(values)))
+        return logits, values
+
+    def drain_replay(self, max_tuples=None):
+        cap = self.n_games * 64 if max_tuples is None else int(max_tuples)
+        out = np.zeros(cap, dtype=REPLAY_DTYPE)
+        n = ctypes.c_int()
+        self._check(self._L.az_drain_replay(self._h, ptr(out), cap, ctypes.byref(n)))
+        return out[:n.value]
