@@ -1,0 +1,170 @@
+"""Drop-in for exp/agent.py: `SimpleAlphaZeroAgent`, `MonteCarloTreeSearch`, `RoundRobinReferee`
+with the reference's signatures, the search itself running on the GPU engine.
+
+Per-agent use (one game at a time, like app/base.py:113-120) keeps the reference's semantics
+exactly: one tree per agent kept for the whole game, Dirichlet noise drawn from numpy's global
+RNG once per simulation whose root is expanded (exp/agent.py:81-82), move choice by
+`np.random.choice` (exp/agent.py:113-118).  For thousands of concurrent games use
+`selfplay.BatchedSelfPlay`.
+"""
+import numpy as np
+
+from . import rules
+from ._lib import MC_MAX_MOVES
+from .engine import Engine
+from .erlyx_compat import ActionData, BaseAgent, PolicyAgent
+from .policy import TorchEvaluator, weights_fingerprint
+
+
+class RoundRobinReferee(BaseAgent):                         # exp/agent.py:6-21
+    def __init__(self, agent_tuple):
+        self._agent_tuple = tuple(agent_tuple)
+        self._turn = False
+
+    def select_action(self, observation):
+        action = self._agent_tuple[int(self._turn)].select_action(observation)
+        self._turn = not self._turn
+        return action
+
+    def reset(self):
+        self._turn = False
+
+    @property
+    def turn(self):
+        return self._turn
+
+
+class _NodeField:
+    """`mcts['N'][fen]`-style access to one per-node array of the GPU tree."""
+
+    def __init__(self, tree, field):
+        self._tree, self._field = tree, field
+
+    def _fetch(self, fen):
+        st = self._tree._node(fen)
+        if st is None:
+            return None
+        if self._field == 'terminal':
+            return st['terminal']
+        if st['terminal'] is not None:
+            return None
+        return st[self._field]
+
+    def __getitem__(self, fen):
+        val = self._fetch(fen)
+        if val is None:
+            raise KeyError(fen)
+        return val
+
+    def get(self, fen, default=None):
+        val = self._fetch(fen)
+        return default if val is None else val
+
+    def __contains__(self, fen):
+        return self._fetch(fen) is not None
+
+    def keys(self):
+        raise NotImplementedError('the GPU tree is addressed by position; enumerate via Engine.node_stats')
+
+
+class _Visited:
+    def __init__(self, tree):
+        self._tree = tree
+
+    def __contains__(self, fen):
+        return self._tree._node(fen) is not None
+
+
+class MonteCarloTreeSearch:
+    """exp/agent.py:24-88 over one GPU-resident tree.  `model` is the torch `Network`
+    (`policy.model`); its weights are mirrored to the GPU evaluator and re-read whenever they change."""
+
+    def __init__(self, environment, model, cpuct, epsilon=0.25, alpha=0.6, evaluator=None, rules_switches=None):
+        self._environment = environment
+        self._model = model
+        self._cpuct = cpuct
+        self._epsilon, self._alpha = epsilon, alpha
+        self._rules = rules_switches
+        self._engine = None
+        self._capacity_sims = 0
+        self._evaluator = evaluator
+        self._fingerprint = None
+        self._fields = {k: _NodeField(self, k) for k in ('Q', 'N', 'P', 'legal_moves', 'terminal')}
+        self._fields['visited'] = _Visited(self)
+
+    def __getitem__(self, item):
+        return self._fields.get(item, None)
+
+    def _node(self, fen):
+        if self._engine is None:
+            return None
+        return self._engine.node_stats(0, 0, rules.state_from_fen(fen))
+
+    def _ensure(self, num_simulations):
+        if self._engine is None:
+            opts = dict(max_sims_per_move=max(int(num_simulations), 1), cpuct=float(self._cpuct),
+                        dirichlet_epsilon=float(self._epsilon), dirichlet_alpha=float(self._alpha))
+            if self._rules is not None:
+                opts['rules'] = self._rules
+            self._engine = Engine(1, **opts)
+            self._capacity_sims = int(num_simulations)
+        if self._evaluator is None:
+            self._evaluator = TorchEvaluator(self._model)
+            self._fingerprint = weights_fingerprint(self._model)
+        elif self._fingerprint is not None:
+            fp = weights_fingerprint(self._model)
+            if fp != self._fingerprint:          # load_state_dict / optimiser step happened
+                self._evaluator.load(self._model)
+                self._fingerprint = fp
+
+    def simulate(self, num_simulations, observation):       # exp/agent.py:41-45
+        self._ensure(num_simulations)
+        eng, ev = self._engine, self._evaluator
+        eng.set_positions(rules.state_from_fen(observation), trees=[0])
+        tokens, clocks, _needs = eng.leaf_batch_device()
+        for _ in range(num_simulations):
+            noise = None
+            if self._epsilon > 0:
+                _, _, _, n_legal = eng.root_stats(want_q=False)
+                if n_legal[0] > 0:                          # root already expanded: exp/agent.py:81-82
+                    noise = np.zeros((1, MC_MAX_MOVES))
+                    noise[0, :n_legal[0]] = np.random.dirichlet([self._alpha] * int(n_legal[0]))
+            eng.select_expand(noise)
+            logits, values = ev.forward(tokens, clocks)
+            eng.backup(values, logits=logits)
+        return self
+
+    @property
+    def engine(self):
+        return self._engine
+
+
+class SimpleAlphaZeroAgent(PolicyAgent):                    # exp/agent.py:91-119
+    def __init__(self, environment, policy, num_simulations, cpuct=1, tau_change=6):
+        super().__init__(policy)
+        self._environment = environment
+        self._num_simulations = num_simulations
+        self._cpuct = cpuct
+        self._tau_change = tau_change
+        self._evaluator = None
+        self.init_mcts()
+
+    def init_mcts(self):
+        old = getattr(self, '_mcts', None)
+        if old is not None and old._evaluator is not None:
+            self._evaluator = old._evaluator                # keep the GPU copy of the weights between games
+        self._mcts = MonteCarloTreeSearch(self._environment, self.policy.model, self._cpuct, evaluator=self._evaluator)
+        if self._evaluator is not None:
+            self._mcts._fingerprint = weights_fingerprint(self.policy.model)
+            self._evaluator.load(self.policy.model)
+        self._count = 0
+
+    def select_action(self, observation):
+        info = self.policy.get_distribution(observation, self._mcts, self._num_simulations)
+        num_moves = int(observation.split()[3])
+        if num_moves < self._tau_change:
+            action = np.random.choice(info['legal_moves'], p=info['pi'])
+        else:
+            maxima = np.where(info['pi'] == info['pi'].max())[0]
+            action = info['legal_moves'][np.random.choice(maxima)]
+        return ActionData(action=action, info=info)

@@ -1,0 +1,78 @@
+"""Batched self-play: thousands of concurrent MinitChess games on one GPU, the superset API the
+reference does not have (its actors play one game, one simulation, one batch-1 evaluation at a
+time: app/base.py:108-124).  Replay tuples come back in the reference's episode format
+(exp/callbacks.py:31-54) so `SimpleAlphaZeroDataset.push` / `collate_fn` run unchanged.
+"""
+import numpy as np
+import torch
+
+from . import rules
+from ._lib import MC_MAX_MOVES
+from .engine import Engine
+from .policy import TorchEvaluator, flatten_state_dict
+
+
+def replay_to_episode_dicts(tuples):
+    """Packed az_replay_tuple records -> the dicts InfoRecorder emits (exp/callbacks.py:40-53)."""
+    out = []
+    for t in tuples:
+        E = int(t['n_legal'])
+        out.append({'observation': rules.state_to_fen(t['observation']),
+                    'legal_moves': t['codes'][:E].astype(int).tolist(),
+                    'pi': t['pi'][:E].astype(np.float64).tolist(),
+                    'action': int(t['action']), 'reward': float(t['reward'])})
+    return out
+
+
+class BatchedSelfPlay:
+    """`n_games` concurrent games x `num_simulations` per move in throughput mode: Philox Dirichlet
+    noise, move sampling, replay recording and game restarts all on the device.
+
+    evaluator='builtin' uses the hand-written sm_100a network inside libmcaz.so (`az_search`);
+    evaluator='torch' evaluates the leaf batch with cuDNN/cuBLAS through PyTorch (library baseline).
+    """
+
+    def __init__(self, network, n_games, num_simulations, cpuct=1.0, tau_change=6, epsilon=0.25, alpha=0.6, seed=0,
+                 evaluator='builtin', dtype=torch.bfloat16, **engine_options):
+        self.n_games, self.num_simulations = int(n_games), int(num_simulations)
+        self.mode = evaluator
+        self.engine = Engine(n_games, max_sims_per_move=num_simulations, cpuct=float(cpuct), tau_change=int(tau_change),
+                             dirichlet_epsilon=float(epsilon), dirichlet_alpha=float(alpha), seed=int(seed),
+                             device_rng=1, network=1 if evaluator == 'builtin' else 0, **engine_options)
+        self.network = network
+        if evaluator == 'builtin':
+            self.sync_weights()
+        else:
+            self.evaluator = TorchEvaluator(network, dtype=dtype)
+            self._tokens, self._clocks, self._needs = self.engine.leaf_batch_device()
+            self.evaluator.capture(self._tokens, self._clocks)
+
+    def sync_weights(self, flat=None):
+        """Push the torch Network's weights to the engine (SimulatePuppet.load_weights, app/base.py:126-129)."""
+        if self.mode == 'builtin':
+            self.engine.set_weights(flatten_state_dict(self.network.state_dict(), device='cuda') if flat is None else flat)
+        else:
+            self.evaluator.load(self.network)
+            self.evaluator.capture(self._tokens, self._clocks)
+
+    def search(self):
+        if self.mode == 'builtin':
+            self.engine.search(self.num_simulations)
+        else:
+            eng, ev = self.engine, self.evaluator
+            for _ in range(self.num_simulations):
+                eng.select_expand()
+                logits, values = ev.replay()
+                eng.backup(values, logits=logits)
+
+    def step(self):
+        """One move in every game: search, choose, record, play, restart finished games."""
+        self.search()
+        self.engine.play_device()
+
+    def run(self, n_moves):
+        for _ in range(int(n_moves)):
+            self.step()
+
+    def drain(self):
+        return self.engine.drain_replay()
