@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- MCTS simulations/s of batched MinitChess AlphaZero self-play on B200.
+
+Contract:  python bench.py --gpus N --steps K --warmup W
+  * workload = BASELINE.json configs[2]: 4096 concurrent games x 200 simulations/move per GPU,
+    random-init reference-size network (seed 0), synthetic self-play from STARTING_FEN.
+  * one "step" = one move in every game: 200 simulations (select/expand -> network -> backup)
+    for each of the 4096 active trees, then move choice, replay recording, play, restarts.
+  * `value` = simulations/s of the whole job, everything resident in HBM (device RNG, device move
+    choice).  `e2e` = the same metric through the host-buffer API: per step the positions go up
+    from pinned host memory, root statistics come back, the host samples the moves.
+  * --impl reference : the reference's CPU self-play path (oracle port of exp/agent.py +
+    exp/policy.py + exp/environment.py) on the host cores, same sims/move.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+FLOP_PER_EVAL = 638245892           # 2 x 319 122 946 MAC per leaf evaluation
+METRIC = 'mcts_simulations_per_second'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=4)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--games', type=int, default=4096, help='concurrent games per GPU')
+    ap.add_argument('--sims', type=int, default=200, help='simulations per move')
+    ap.add_argument('--evaluator', default='builtin', choices=['builtin', 'torch'])
+    ap.add_argument('--cpu-seconds', type=float, default=15.0, help='budget of the CPU baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {'hbm_gbs': p['hbm_gbs'], 'tflops': p.get('bf16_tflops_sustained', p['bf16_tflops']), 'which': 'measured (sustained bf16)'}
+    return {'hbm_gbs': 6650.0, 'tflops': 1400.0, 'which': 'fallback'}
+
+
+# --------------------------------------------------------------------------- clocks sampling
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), parts[2:6]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU baseline (oracle port)
+def _cpu_worker(args):
+    seed, sims, seconds, threads = args
+    import numpy as np
+    import torch
+    torch.set_num_threads(threads)
+    from minitchess_alphazero_b200.policy import Network
+    from oracle import ref_selfplay as rs
+    torch.manual_seed(0)
+    net = rs.RefNetwork(Network().eval().state_dict())
+    rng = np.random.RandomState(seed)
+    trees = [rs.RefTree(net.evaluate, 1, rng=rng) for _ in range(2)]
+    ep = rs.RefEpisode(rs.STARTING_FEN)
+    t0 = time.perf_counter()
+    n_sims = n_moves = 0
+    turn = 0
+    while time.perf_counter() - t0 < seconds:
+        if ep.done:
+            trees = [rs.RefTree(net.evaluate, 1, rng=rng) for _ in range(2)]
+            ep = rs.RefEpisode(rs.STARTING_FEN)
+            turn = 0
+        action, _ = rs.ref_select_action(trees[turn], ep.fen, sims, rng=rng)
+        ep.step(action)
+        n_sims += sims
+        n_moves += 1
+        turn ^= 1
+    dt = time.perf_counter() - t0
+    return n_sims, n_moves, dt
+
+
+def cpu_reference_sample(sims, seconds, processes, threads):
+    """Runs the oracle port of the reference self-play on `processes` host processes for ~`seconds`."""
+    import multiprocessing as mp
+    if processes == 1:
+        res = [_cpu_worker((0, sims, seconds, threads))]
+    else:
+        with mp.get_context('spawn').Pool(processes) as pool:
+            res = pool.map(_cpu_worker, [(i, sims, seconds, threads) for i in range(processes)])
+    total_sims = sum(r[0] for r in res)
+    wall = max(r[2] for r in res)
+    return total_sims / wall, sum(r[1] for r in res) / wall, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    per_step = max(2.0, 2.0 * args.sims * 0.017)      # about two moves per process per step
+    per_step = min(per_step, 20.0)
+    for _ in range(args.warmup):
+        cpu_reference_sample(args.sims, min(per_step, 3.0), procs, 1)
+    t0 = time.perf_counter()
+    sims_s = []
+    for _ in range(args.steps):
+        s, _, _ = cpu_reference_sample(args.sims, per_step, procs, 1)
+        sims_s.append(s)
+    dt = time.perf_counter() - t0
+    value = sum(sims_s) / len(sims_s)
+    sample = '%d processes x 1 torch thread, each playing self-play moves at %d sims/move for %.1f s per step' % (procs, args.sims, per_step)
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'sims/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1000 * dt / max(args.steps, 1), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'reference self-play path (oracle port of exp/agent.py + exp/policy.py + exp/environment.py), '
+                               '%d sims/move, random-init net' % args.sims, 'sims_per_move': args.sims},
+        'cpu_baseline': {'value': value, 'unit': 'sims/s', 'cores': procs, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'sims/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the engine has no CPU fallback)')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from minitchess_alphazero_b200 import build, _lib
+    build.build()
+    _lib.check(_lib.lib().mcaz_set_device(local))
+    from minitchess_alphazero_b200.policy import Network
+    from minitchess_alphazero_b200.selfplay import BatchedSelfPlay
+    from minitchess_alphazero_b200.parallel import gather_replay
+
+    G, S = args.games, args.sims
+    torch.manual_seed(0)
+    net = Network().eval()
+    sp = BatchedSelfPlay(net, n_games=G, num_simulations=S, seed=1234 + rank, evaluator=args.evaluator)
+    eng = sp.engine
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        sp.step()
+        if world > 1:
+            gather_replay(eng, world, max_tuples=2 * G)     # replay gather of config 4 (NCCL all_gather)
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    c0 = eng.counters()
+    l0 = _lib.lib().mcaz_kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    net_ms = sp.reset_kernel_timer() if hasattr(sp, 'reset_kernel_timer') else None
+    ev0.record()
+    for _ in range(args.steps):
+        one_step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    c1 = eng.counters()
+    launches = int(_lib.lib().mcaz_kernel_launches() - l0)
+    sims = c1['simulations'] - c0['simulations']
+    evals = c1['evaluations'] - c0['evaluations']
+    moves = c1['moves'] - c0['moves']
+    tot = torch.tensor([sims, evals, moves], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(tot)
+    sims_all, evals_all, moves_all = (float(x) for x in tot.tolist())
+    value = sims_all / (ms / 1000.0)
+
+    # roofline of the dominant kernel: the network tower (tensor-bound)
+    pk = peaks()
+    prof = sp.kernel_profile() if hasattr(sp, 'kernel_profile') else None
+    if prof is None:
+        # library evaluator: time the whole forward over the resident leaf batch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            sp.evaluator.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        fwd_ms = e0.elapsed_time(e1) / 20
+        achieved = G * FLOP_PER_EVAL / (fwd_ms / 1000.0) / 1e12
+        roof = {'bound': 'tensor', 'kernel': 'network forward (cuDNN/cuBLAS via PyTorch, all layers)', 'achieved': achieved,
+                'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'], 'traffic': None, 'peak_source': pk['which'],
+                'ms_per_launch': fwd_ms}
+    else:
+        roof = prof
+        roof.update({'peak': pk['tflops'], 'frac': roof['achieved'] / pk['tflops'], 'peak_source': pk['which']})
+
+    # end to end through the host-buffer API
+    e2e = None
+    if not args.no_e2e:
+        e2e = measure_e2e(sp, args, world)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = torch.get_num_threads()
+        s, m, wall = cpu_reference_sample(36, args.cpu_seconds, 1, threads)
+        cpu = {'value': s, 'unit': 'sims/s', 'cores': threads, 'kind': 'port',
+               'sample': 'BASELINE.json configs[0]: one process, %d torch threads, self-play from STARTING_FEN at 36 sims/move for %.1f s '
+                         '(%.2f positions/s); oracle/ref_selfplay.py' % (threads, wall, m)}
+    if rank == 0:
+        out = {
+            'metric': METRIC, 'value': value, 'unit': 'sims/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / max(args.steps, 1), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16 network / f64 tree statistics', 'data': 'synthetic',
+            'config': {'workload': 'BASELINE.json configs[2]: batched self-play, %d concurrent games x %d sims/move per GPU, random-init '
+                                   'reference-size net' % (G, S), 'games_per_gpu': G, 'sims_per_move': S, 'evaluator': args.evaluator,
+                       'parallelism': 'games sharded over %d GPU(s), no data-path collective except replay all_gather' % world,
+                       'l2': 'inputs larger than L2 (tree arenas ~%d MB, activations %d MB per layer)' % (
+                           int(c1['edges'] * 22 / 1e6), int(G * 30 * 256 * 2 * 2 / 1e6))},
+            'positions_per_second': moves_all / (ms / 1000.0), 'evals_per_second': evals_all / (ms / 1000.0),
+            'roofline': roof, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_e2e(sp, args, world):
+    """Same metric through the host-buffer API: every step uploads the positions from pinned host
+    memory, searches, downloads the root statistics, samples moves on the host and plays them."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from minitchess_alphazero_b200._lib import MC_MAX_MOVES, STATE_DTYPE
+    eng, G, S = sp.engine, sp.n_games, sp.num_simulations
+    rng = np.random.RandomState(7)
+    pinned = torch.empty(G * 5, dtype=torch.int32).pin_memory()
+    host_states = pinned.numpy().view(np.uint32).view(STATE_DTYPE)
+    start = eng.game_states()[0]
+    eng.reset_games()
+    host_states[:] = eng.game_states()[0]
+    plies = np.zeros(G, dtype=np.int32)
+
+    def step():
+        eng.set_positions(host_states, trees=plies & 1)                    # H2D: positions
+        sp.search()
+        codes, visits, _, n_legal = eng.root_stats(want_q=False)           # D2H: root statistics
+        E = np.maximum(n_legal, 1)
+        w = visits.astype(np.float64)
+        cum = np.cumsum(w, axis=1)
+        u = rng.random_sample(G) * cum[np.arange(G), E - 1]
+        pick = np.minimum((cum <= u[:, None]).sum(1), E - 1)
+        greedy = w.argmax(1)
+        fullmove = (host_states['meta'] >> 16) & 0xff
+        pick = np.where(fullmove < 6, pick, greedy)
+        actions = codes[np.arange(G), pick]
+        results = eng.play(actions)                                         # H2D: moves, D2H: results
+        new_states, _ = eng.game_states()                                   # D2H: positions
+        host_states[:] = new_states
+        plies[:] += 1
+        done = np.nonzero(results != 0)[0].astype(np.int32)
+        if len(done):
+            eng.reset_games(game_ids=done)
+            host_states[done] = start[done]
+            plies[done] = 0
+        return G * 20 + G * 4 + G * 2, G * MC_MAX_MOVES * 6 + G * 4 + G + G * 21
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    steps = max(2, min(args.steps, 4))
+    c0 = eng.counters()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        h2d, d2h = step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    c1 = eng.counters()
+    t = torch.tensor([dt, float(c1['simulations'] - c0['simulations'])], dtype=torch.float64, device='cuda')
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t)
+        dt, sims = float(tmax[0]), float(t[1])
+    else:
+        sims = float(t[1])
+    return {'value': sims / dt, 'unit': 'sims/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h), 'steps': steps,
+            'api': 'Engine.set_positions / search / root_stats / play with host (pinned) buffers'}
+
+
+if __name__ == '__main__':
+    a = parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -151,6 +151,17 @@ class TorchEvaluator:
     @torch.no_grad()
     def forward(self, tokens_u8, clocks):
         """tokens uint8 [B,60], clocks float32 [B] (CUDA) -> logits float32 [B,554], values float32 [B]."""
+        if self.dtype == torch.float32:            # true fp32 (no TF32) when used as the parity reference
+            with torch.backends.cudnn.flags(enabled=True, benchmark=True, allow_tf32=False):
+                old = torch.backends.cuda.matmul.allow_tf32
+                torch.backends.cuda.matmul.allow_tf32 = False
+                try:
+                    return self._forward(tokens_u8, clocks)
+                finally:
+                    torch.backends.cuda.matmul.allow_tf32 = old
+        return self._forward(tokens_u8, clocks)
+
+    def _forward(self, tokens_u8, clocks):
         F = torch.nn.functional
         B = tokens_u8.shape[0]
         x = F.embedding(tokens_u8.long().view(B, 2, 6, 5), self.emb).permute(0, 1, 4, 2, 3).reshape(B, 8, 6, 5)
