@@ -217,6 +217,14 @@ int az_counters(az_engine* e, uint64_t* out);
 int az_network_forward(az_engine* e, const uint8_t* tokens, const float* clocks, int n,
                        float* logits, float* values);
 
+/* Profiling hook for bench.py: while on, every network forward is bracketed by CUDA events on the
+ * engine's stream around its 18 tower-convolution launches.  A call with a non-NULL
+ * avg_ms_per_conv_launch synchronises, reports the average since the previous call and resets.   */
+int az_profile_network(az_engine* e, int on, double* avg_ms_per_conv_launch, int* n_forwards);
+
+/* Kernels launched by this library in this process (all engines and mc_* calls).               */
+uint64_t mcaz_kernel_launches(void);
+
 #ifdef __cplusplus
 }
 #endif

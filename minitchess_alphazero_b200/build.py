@@ -33,7 +33,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO_PATH
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + sources() + ['-o', SO_PATH, '-lcuda']
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + sources() + ['-o', SO_PATH]
     subprocess.check_call(cmd)
     return SO_PATH
 

@@ -1,11 +1,645 @@
-// net.cu -- built-in policy/value network (placeholder until the tcgen05 tower lands).
+// net.cu -- the policy/value network of exp/policy.py:53-80 as hand-written sm_100a kernels.
+//
+//   stem_kernel        Embedding(7,4) + Conv3x3(8->256) + BN + ReLU as a table sum (no MACs)
+//   conv3x3_tc_kernel  the 18 tower convolutions 256->256: tcgen05.mma (UMMA 128x256x16, bf16 in,
+//                      fp32 accumulate in TMEM), operands staged by TMA (SWIZZLE_128B, K-major),
+//                      4-stage mbarrier pipeline, double-buffered TMEM accumulators, fused
+//                      bias(+BN) / residual / ReLU / bf16 epilogue
+//   heads_kernel       policy head (conv1x1 -> 61->554 linear) and value head (conv1x1 -> 31->256
+//                      -> 1, tanh), fp32
+//
+// Tower data layout in HBM: act[pos 30][board Bpad][channel 256] bf16 (two ping-pong buffers).
+// With boards as the GEMM M dimension a 3x3 tap is a plain shift of the *position* index, so the
+// implicit GEMM needs no im2col and no halo: for output position p,
+//     D[128 boards x 256 cout] = sum over valid taps t, cin:  act[p + t][boards][cin] * W[t][cout][cin]
+// and taps that fall off the 6x5 board are simply skipped (208 of 270 tap-positions remain).
+// Weights: W[layer 18][tap 9][cout 256][cin 256] bf16 with BatchNorm folded in, 21.2 MB, L2-resident.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
 #include "engine.cuh"
 
 namespace mcaz {
-int network_create(az_engine*) { return fail(MCAZ_ESTATE, "built-in network not available in this build"); }
-void network_destroy(az_engine*) {}
-int network_set_weights(az_engine*, const float*) { return fail(MCAZ_ESTATE, "built-in network not available"); }
-int network_forward(az_engine*, const uint8_t*, const float*, const uint8_t*, int, float*, float*) {
-    return fail(MCAZ_ESTATE, "built-in network not available");
+int num_sms();
+
+namespace {
+
+constexpr int C = 256;            // tower width
+constexpr int NPOS = 30;
+constexpr int NLAYERS = 18;       // 9 residual blocks x 2 convolutions
+constexpr int BLOCK_M = 128;      // boards per tile
+constexpr int BLOCK_K = 64;       // bf16 elements = one 128-byte swizzle row
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
+constexpr int B_BYTES = C * BLOCK_K * 2;         // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int CONV_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int CONV_THREADS = 256;
+
+// flat state_dict offsets (floats), exp/policy.py:56-69 order without num_batches_tracked
+constexpr size_t OFF_EMB = 0;
+constexpr size_t OFF_STEM = 28;                         // w[256][8][3][3], b, gamma, beta, mean, var
+constexpr size_t OFF_TOWER = 19740;
+constexpr size_t TOWER_STRIDE = 589824 + 5 * 256;
+constexpr size_t OFF_PCONV = 10659612;                  // w[2][256], b2, gamma2, beta2, mean2, var2
+constexpr size_t OFF_PLIN = 10660134;                   // w[554][61], b[554]
+constexpr size_t OFF_VCONV = 10694482;                  // w[256], b, gamma, beta, mean, var
+constexpr size_t OFF_V1 = 10694743;                     // w[256][31], b[256]
+constexpr size_t OFF_V2 = 10702935;                     // w[256], b
+constexpr float BN_EPS = 1e-5f;
+
+// ---------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar), ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start address >> 4 in [0,14), LBO in [16,30) (unused for swizzled K-major), SBO = 1024 B (8 rows x
+// 128 B) in [32,46), version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10),
+// both K-major, N >> 3 in [17,23), M >> 4 in [24,29).
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+
+struct ConvParams {
+    const float* bias;              // [256] folded conv bias + BatchNorm
+    const __nv_bfloat16* residual;  // same layout as out, or nullptr
+    __nv_bfloat16* out;
+    int n_tiles;                    // board tiles of 128
+    int bpad;                       // n_tiles * 128
+    int layer;
+    int relu;
+    uint8_t order[NPOS];            // positions, heaviest (most valid taps) first
+};
+
+__device__ __forceinline__ bool tap_valid(int pos, int tap, int& src) {
+    int row = pos / 5 + tap / 3 - 1, col = pos % 5 + tap % 3 - 1;
+    src = row * 5 + col;
+    return row >= 0 && row < 6 && col >= 0 && col < 5;
+}
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_w, const ConvParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = bars;                 // [STAGES]  TMA -> MMA
+    uint64_t* empty = bars + STAGES;       // [STAGES]  MMA -> TMA
+    uint64_t* acc_full = bars + 2 * STAGES;      // [2]  MMA -> epilogue
+    uint64_t* acc_empty = bars + 2 * STAGES + 2; // [2]  epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    __shared__ float s_bias[C];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = P.n_tiles * NPOS;
+
+    for (int i = threadIdx.x; i < C; i += CONV_THREADS) s_bias[i] = P.bias[i];
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------------------------------------------------------- TMA producer
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int pos = P.order[item / P.n_tiles], tile = item % P.n_tiles;
+            for (int tap = 0; tap < 9; ++tap) {
+                int src;
+                if (!tap_valid(pos, tap, src)) continue;
+                for (int kc = 0; kc < C / BLOCK_K; ++kc, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&full[s], STAGE_BYTES);
+                    uint8_t* a = smem + s * STAGE_BYTES;
+                    tma_load_3d(a, &map_act, &full[s], kc * BLOCK_K, tile * BLOCK_M, src);
+                    tma_load_3d(a + A_BYTES, &map_w, &full[s], kc * BLOCK_K, 0, P.layer * 9 + tap);
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------------------------------------------------------- MMA issuer
+        uint32_t it = 0, n = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+            const int pos = P.order[item / P.n_tiles];
+            const uint32_t acc = n & 1;
+            mbar_wait(&acc_empty[acc], ((n >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * C;
+            uint32_t accumulate = 0;
+            for (int tap = 0; tap < 9; ++tap) {
+                int src;
+                if (!tap_valid(pos, tap, src)) continue;
+                for (int kc = 0; kc < C / BLOCK_K; ++kc, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full[s], (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t da = umma_desc(a_addr), db = umma_desc(a_addr + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k) {
+                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, IDESC, accumulate);
+                        accumulate = 1;
+                    }
+                    umma_commit(&empty[s]);      // frees the smem stage when these MMAs retire
+                }
+            }
+            umma_commit(&acc_full[acc]);         // accumulator complete -> epilogue
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------------------- epilogue (TMEM -> HBM)
+        const int q = warp & 3;                  // TMEM lane quadrant this warp may read
+        uint32_t n = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+            const int pos = P.order[item / P.n_tiles], tile = item % P.n_tiles;
+            const uint32_t acc = n & 1;
+            mbar_wait(&acc_full[acc], (n >> 1) & 1);
+            tc_fence_after();
+            const size_t row_off = ((size_t)pos * P.bpad + (size_t)tile * BLOCK_M + q * 32 + lane) * C;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C;
+#pragma unroll 1
+            for (int c = 0; c < C / 32; ++c) {
+                uint32_t v[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr + c * 32)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                uint4 res[4];
+                if (P.residual) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(P.residual + row_off + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) res[j] = rp[j];
+                }
+                uint4 outv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t packed[4];
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const int e = j * 8 + h * 2;
+                        float x0 = __uint_as_float(v[e]) + s_bias[c * 32 + e];
+                        float x1 = __uint_as_float(v[e + 1]) + s_bias[c * 32 + e + 1];
+                        if (P.residual) {
+                            const uint32_t r = (&res[j].x)[h];
+                            x0 += __uint_as_float(r << 16);
+                            x1 += __uint_as_float(r & 0xffff0000u);
+                        }
+                        if (P.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(x0, x1);
+                        packed[h] = *reinterpret_cast<uint32_t*>(&b2);
+                    }
+                    outv[j] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                }
+                uint4* op = reinterpret_cast<uint4*>(P.out + row_off + c * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) op[j] = outv[j];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------- weight preparation
+__global__ void prep_tower_kernel(const float* __restrict__ flat, __nv_bfloat16* __restrict__ w, float* __restrict__ bias) {
+    // grid: (256 cout, 18 layers), block 256 (cin)
+    const int n = blockIdx.x, L = blockIdx.y, k = threadIdx.x;
+    const float* base = flat + OFF_TOWER + (size_t)L * TOWER_STRIDE;
+    const float *cw = base, *cb = base + 589824, *gamma = cb + 256, *beta = gamma + 256, *mean = beta + 256, *var = mean + 256;
+    const float scale = gamma[n] / sqrtf(var[n] + BN_EPS);
+    for (int t = 0; t < 9; ++t)
+        w[(((size_t)L * 9 + t) * C + n) * C + k] = __float2bfloat16(cw[((size_t)n * C + k) * 9 + t] * scale);
+    if (k == 0) bias[L * C + n] = (cb[n] - mean[n]) * scale + beta[n];
+}
+
+// stem table: T[tap][j][c], j < 7: token j in channel group 0 (mover), j >= 7: token j-7 in group 1
+__global__ void prep_stem_kernel(const float* __restrict__ flat, float* __restrict__ table, float* __restrict__ bias) {
+    const int c = threadIdx.x, j = blockIdx.x % 14, t = blockIdx.x / 14;
+    const float* sw = flat + OFF_STEM;
+    const float *sb = sw + 18432, *gamma = sb + 256, *beta = gamma + 256, *mean = beta + 256, *var = mean + 256;
+    const float* emb = flat + OFF_EMB;
+    const float scale = gamma[c] / sqrtf(var[c] + BN_EPS);
+    const int grp = j / 7, tok = j % 7;
+    float acc = 0.f;
+    for (int e = 0; e < 4; ++e) acc += sw[((size_t)c * 8 + grp * 4 + e) * 9 + t] * emb[tok * 4 + e];
+    table[((size_t)t * 14 + j) * C + c] = acc * scale;
+    if (blockIdx.x == 0) bias[c] = (sb[c] - mean[c]) * scale + beta[c];
+}
+
+struct HeadWeights {
+    float* pw;     // [2][256] folded policy conv
+    float* pb;     // [2]
+    float* vw;     // [256]
+    float* vb;     // [1]
+    float* plt;    // [61][554] plinear transposed
+    float* plb;    // [554]
+    float* v1t;    // [31][256] vlinear.0 transposed
+    float* v1b;    // [256]
+    float* v2;     // [256]
+    float* v2b;    // [1]
+};
+
+__global__ void prep_heads_kernel(const float* __restrict__ flat, HeadWeights H) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const float* pc = flat + OFF_PCONV;
+    const float *pcb = pc + 512, *pg = pcb + 2, *pbeta = pg + 2, *pm = pbeta + 2, *pv = pm + 2;
+    for (int i = tid; i < 512; i += nthr) {
+        const int o = i / 256;
+        H.pw[i] = pc[i] * (pg[o] / sqrtf(pv[o] + BN_EPS));
+    }
+    if (tid < 2) H.pb[tid] = (pcb[tid] - pm[tid]) * (pg[tid] / sqrtf(pv[tid] + BN_EPS)) + pbeta[tid];
+    const float* vc = flat + OFF_VCONV;
+    const float vscale = vc[257] / sqrtf(vc[260] + BN_EPS);
+    for (int i = tid; i < 256; i += nthr) H.vw[i] = vc[i] * vscale;
+    if (tid == 0) H.vb[0] = (vc[256] - vc[259]) * vscale + vc[258];
+    const float* pl = flat + OFF_PLIN;
+    for (int i = tid; i < 554 * 61; i += nthr) { const int o = i / 61, j = i % 61; H.plt[j * 554 + o] = pl[i]; }
+    for (int i = tid; i < 554; i += nthr) H.plb[i] = pl[554 * 61 + i];
+    const float* v1 = flat + OFF_V1;
+    for (int i = tid; i < 256 * 31; i += nthr) { const int o = i / 31, j = i % 31; H.v1t[j * 256 + o] = v1[i]; }
+    for (int i = tid; i < 256; i += nthr) H.v1b[i] = v1[256 * 31 + i];
+    const float* v2 = flat + OFF_V2;
+    for (int i = tid; i < 256; i += nthr) H.v2[i] = v2[i];
+    if (tid == 0) H.v2b[0] = v2[256];
+}
+
+// ---------------------------------------------------------------------------------- stem
+// One warp per (board, position): 32 lanes x 8 channels; <= 18 table rows summed.
+__global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ tokens, int n, int bpad,
+                                                   const float* __restrict__ table, const float* __restrict__ bias,
+                                                   __nv_bfloat16* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long total = (long long)bpad * NPOS;
+    for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
+        const int board = (int)(w / NPOS), pos = (int)(w % NPOS);
+        float acc[8];
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + lane * 8), b1 = *reinterpret_cast<const float4*>(bias + lane * 8 + 4);
+        acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+        if (board < n) {
+            const uint8_t* tk = tokens + (size_t)board * MC_TOKENS;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                int src;
+                if (!tap_valid(pos, t, src)) continue;
+                const int j0 = tk[src], j1 = 7 + tk[30 + src];
+                const float* r0 = table + ((size_t)t * 14 + j0) * C + lane * 8;
+                const float* r1 = table + ((size_t)t * 14 + j1) * C + lane * 8;
+                const float4 a0 = *reinterpret_cast<const float4*>(r0), a1 = *reinterpret_cast<const float4*>(r0 + 4);
+                const float4 c0 = *reinterpret_cast<const float4*>(r1), c1 = *reinterpret_cast<const float4*>(r1 + 4);
+                acc[0] += a0.x + c0.x; acc[1] += a0.y + c0.y; acc[2] += a0.z + c0.z; acc[3] += a0.w + c0.w;
+                acc[4] += a1.x + c1.x; acc[5] += a1.y + c1.y; acc[6] += a1.z + c1.z; acc[7] += a1.w + c1.w;
+            }
+        }
+        uint32_t pk[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(fmaxf(acc[2 * h], 0.f), fmaxf(acc[2 * h + 1], 0.f));
+            pk[h] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        *reinterpret_cast<uint4*>(out + ((size_t)pos * bpad + board) * C + lane * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------- heads
+// Persistent CTAs; plinear^T (135 KB) and vlinear.0^T (31 KB) staged in shared memory once per CTA,
+// one warp per board.
+constexpr int HEADS_THREADS = 256;
+constexpr int HEADS_SMEM = (61 * 554 + 554 + 31 * 256 + 256 + 256 + 3 * 256 + 8 + (HEADS_THREADS / 32) * 96) * 4;
+
+__global__ void __launch_bounds__(HEADS_THREADS, 1)
+heads_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ clocks, int n, int bpad, HeadWeights H,
+             float* __restrict__ logits, float* __restrict__ values) {
+    extern __shared__ float hs[];
+    float* s_plt = hs;                       // [61][554]
+    float* s_plb = s_plt + 61 * 554;         // [554]
+    float* s_v1t = s_plb + 554;              // [31][256]
+    float* s_v1b = s_v1t + 31 * 256;         // [256]
+    float* s_v2 = s_v1b + 256;               // [256]
+    float* s_cw = s_v2 + 256;                // [3][256]: policy conv rows 0,1 and value conv
+    float* s_cb = s_cw + 3 * 256;            // [8]: pb0, pb1, vb, v2b
+    float* s_in = s_cb + 8;                  // per warp [96]: px[60], clock, vx[30], clock
+    for (int i = threadIdx.x; i < 61 * 554; i += HEADS_THREADS) s_plt[i] = H.plt[i];
+    for (int i = threadIdx.x; i < 554; i += HEADS_THREADS) s_plb[i] = H.plb[i];
+    for (int i = threadIdx.x; i < 31 * 256; i += HEADS_THREADS) s_v1t[i] = H.v1t[i];
+    for (int i = threadIdx.x; i < 256; i += HEADS_THREADS) { s_v1b[i] = H.v1b[i]; s_v2[i] = H.v2[i]; s_cw[i] = H.pw[i]; s_cw[256 + i] = H.pw[256 + i]; s_cw[512 + i] = H.vw[i]; }
+    if (threadIdx.x == 0) { s_cb[0] = H.pb[0]; s_cb[1] = H.pb[1]; s_cb[2] = H.vb[0]; s_cb[3] = H.v2b[0]; }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* in = s_in + warp * 96;
+    float cw0[8], cw1[8], cw2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { cw0[k] = s_cw[lane * 8 + k]; cw1[k] = s_cw[256 + lane * 8 + k]; cw2[k] = s_cw[512 + lane * 8 + k]; }
+    for (int board = blockIdx.x * (HEADS_THREADS / 32) + warp; board < n; board += gridDim.x * (HEADS_THREADS / 32)) {
+        // 1x1 convolutions over 256 channels: lane holds 8 channels
+        for (int pos = 0; pos < NPOS; ++pos) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(act + ((size_t)pos * bpad + board) * C + lane * 8);
+            const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const float x0 = __uint_as_float(rw[h] << 16), x1 = __uint_as_float(rw[h] & 0xffff0000u);
+                d0 += x0 * cw0[2 * h] + x1 * cw0[2 * h + 1];
+                d1 += x0 * cw1[2 * h] + x1 * cw1[2 * h + 1];
+                d2 += x0 * cw2[2 * h] + x1 * cw2[2 * h + 1];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+                d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+                d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+            }
+            if (lane == 0) {
+                in[pos] = fmaxf(d0 + s_cb[0], 0.f);
+                in[30 + pos] = fmaxf(d1 + s_cb[1], 0.f);
+                in[61 + pos] = fmaxf(d2 + s_cb[2], 0.f);
+            }
+        }
+        if (lane == 0) { const float ck = clocks[board]; in[60] = ck; in[91] = ck; }
+        __syncwarp();
+        // policy: 554 logits = plinear([px, clock])
+        for (int o = lane; o < MC_NUM_ACTIONS; o += 32) {
+            float acc = s_plb[o];
+#pragma unroll 1
+            for (int j = 0; j < 61; ++j) acc += in[j] * s_plt[j * 554 + o];
+            logits[(size_t)board * MC_NUM_ACTIONS + o] = acc;
+        }
+        // value: tanh(v2 . relu(v1 [vx, clock] + b1) + b2)
+        float part = 0.f;
+        for (int o = lane; o < 256; o += 32) {
+            float acc = s_v1b[o];
+#pragma unroll 1
+            for (int j = 0; j < 31; ++j) acc += in[61 + j] * s_v1t[j * 256 + o];
+            part += fmaxf(acc, 0.f) * s_v2[o];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) values[board] = tanhf(part + s_cb[3]);
+        __syncwarp();
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map_3d(CUtensorMap* map, void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
+            return fail(MCAZ_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MCAZ_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return MCAZ_OK;
+}
+
+}  // namespace
+
+struct Network {
+    int capacity = 0;   // boards the activation buffers hold (multiple of 128)
+    __nv_bfloat16 *act[2] = {nullptr, nullptr};
+    __nv_bfloat16* w = nullptr;        // [18][9][256][256]
+    float* bias = nullptr;             // [18][256]
+    float *stem_table = nullptr, *stem_bias = nullptr;
+    float* head_pool = nullptr;
+    HeadWeights heads{};
+    CUtensorMap map_act[2], map_w;
+    bool have_weights = false;
+    uint8_t order[NPOS];
+    // profiling (az_profile_network)
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+    size_t events_used = 0;
+};
+
+static int net_alloc_acts(az_engine* e, int boards) {
+    Network* N = e->net;
+    int cap = ((boards + BLOCK_M - 1) / BLOCK_M) * BLOCK_M;
+    if (cap <= N->capacity) return MCAZ_OK;
+    for (int i = 0; i < 2; ++i) {
+        if (N->act[i]) cudaFree(N->act[i]);
+        N->act[i] = nullptr;
+        MCAZ_CUDA(cudaMalloc(&N->act[i], (size_t)NPOS * cap * C * sizeof(__nv_bfloat16)));
+        MCAZ_CUDA(cudaMemset(N->act[i], 0, (size_t)NPOS * cap * C * sizeof(__nv_bfloat16)));
+        if (int rc = make_map_3d(&N->map_act[i], N->act[i], C, cap, NPOS, BLOCK_K, BLOCK_M)) return rc;
+    }
+    N->capacity = cap;
+    return MCAZ_OK;
+}
+
+int network_create(az_engine* e) {
+    int dev = 0, major = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) return fail(MCAZ_ENODEV, "the built-in network needs an sm_100 GPU (tcgen05/TMEM/TMA)");
+    Network* N = new Network();
+    e->net = N;
+    MCAZ_CUDA(cudaMalloc(&N->w, (size_t)NLAYERS * 9 * C * C * sizeof(__nv_bfloat16)));
+    MCAZ_CUDA(cudaMalloc(&N->bias, (size_t)NLAYERS * C * sizeof(float)));
+    MCAZ_CUDA(cudaMalloc(&N->stem_table, (size_t)9 * 14 * C * sizeof(float)));
+    MCAZ_CUDA(cudaMalloc(&N->stem_bias, C * sizeof(float)));
+    const size_t head_floats = 512 + 2 + 256 + 1 + 61 * 554 + 554 + 31 * 256 + 256 + 256 + 1 + 16;
+    MCAZ_CUDA(cudaMalloc(&N->head_pool, head_floats * sizeof(float)));
+    float* p = N->head_pool;
+    N->heads.pw = p; p += 512;
+    N->heads.pb = p; p += 4;
+    N->heads.vw = p; p += 256;
+    N->heads.vb = p; p += 4;
+    N->heads.plt = p; p += 61 * 554;
+    N->heads.plb = p; p += 554;
+    N->heads.v1t = p; p += 31 * 256;
+    N->heads.v1b = p; p += 256;
+    N->heads.v2 = p; p += 256;
+    N->heads.v2b = p;
+    if (int rc = make_map_3d(&N->map_w, N->w, C, C, (uint64_t)NLAYERS * 9, BLOCK_K, C)) return rc;
+    // positions ordered by number of valid taps, heaviest first (static load balancing)
+    int idx = 0;
+    for (int want : {9, 6, 4})
+        for (int pos = 0; pos < NPOS; ++pos) {
+            int r = pos / 5, c = pos % 5;
+            int taps = ((r == 0 || r == 5) ? 2 : 3) * ((c == 0 || c == 4) ? 2 : 3);
+            if (taps == want) N->order[idx++] = (uint8_t)pos;
+        }
+    MCAZ_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
+    MCAZ_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_SMEM));
+    return net_alloc_acts(e, e->v.G);
+}
+
+void network_destroy(az_engine* e) {
+    Network* N = e->net;
+    if (!N) return;
+    for (int i = 0; i < 2; ++i) if (N->act[i]) cudaFree(N->act[i]);
+    if (N->w) cudaFree(N->w);
+    if (N->bias) cudaFree(N->bias);
+    if (N->stem_table) cudaFree(N->stem_table);
+    if (N->stem_bias) cudaFree(N->stem_bias);
+    if (N->head_pool) cudaFree(N->head_pool);
+    for (auto& ev : N->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    delete N;
+    e->net = nullptr;
+}
+
+int network_set_weights(az_engine* e, const float* flat) {
+    Network* N = e->net;
+    prep_tower_kernel<<<dim3(C, NLAYERS), C, 0, e->stream>>>(flat, N->w, N->bias);
+    MCAZ_CHECK_LAUNCH();
+    prep_stem_kernel<<<9 * 14, C, 0, e->stream>>>(flat, N->stem_table, N->stem_bias);
+    MCAZ_CHECK_LAUNCH();
+    prep_heads_kernel<<<64, 256, 0, e->stream>>>(flat, N->heads);
+    MCAZ_CHECK_LAUNCH();
+    e->launches += 3;
+    N->have_weights = true;
+    return MCAZ_OK;
+}
+
+int network_forward(az_engine* e, const uint8_t* tokens, const float* clocks, const uint8_t* /*active*/, int n, float* logits,
+                    float* values) {
+    Network* N = e->net;
+    if (!N->have_weights) return fail(MCAZ_ESTATE, "network weights have not been set (az_set_weights)");
+    if (int rc = net_alloc_acts(e, n)) return rc;
+    const int n_tiles = (n + BLOCK_M - 1) / BLOCK_M, bpad = N->capacity;
+    cudaStream_t st = e->stream;
+    {
+        long long warps = (long long)n_tiles * BLOCK_M * NPOS;
+        int grid = (int)std::min<long long>((warps * 32 + 255) / 256, (long long)num_sms() * 16);
+        stem_kernel<<<grid, 256, 0, st>>>(tokens, n, bpad, N->stem_table, N->stem_bias, N->act[0]);
+        MCAZ_CHECK_LAUNCH();
+    }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (N->profiling) {
+        if (N->events_used == N->events.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            N->events.emplace_back(a, b);
+        }
+        ev0 = N->events[N->events_used].first; ev1 = N->events[N->events_used].second;
+        N->events_used++;
+        cudaEventRecord(ev0, st);
+    }
+    ConvParams P;
+    P.n_tiles = n_tiles; P.bpad = bpad; P.relu = 1;
+    std::memcpy(P.order, N->order, NPOS);
+    const int grid = std::min(num_sms(), n_tiles * NPOS);
+    for (int L = 0; L < NLAYERS; ++L) {
+        const int src = L & 1, dst = src ^ 1;          // conv1: act0 -> act1, conv2: act1 -> act0 (+ residual act0)
+        P.layer = L;
+        P.bias = N->bias + L * C;
+        P.residual = (L & 1) ? N->act[dst] : nullptr;
+        P.out = N->act[dst];
+        conv3x3_tc_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(N->map_act[src], N->map_w, P);
+        MCAZ_CHECK_LAUNCH();
+    }
+    if (ev1) cudaEventRecord(ev1, st);
+    heads_kernel<<<num_sms(), HEADS_THREADS, HEADS_SMEM, st>>>(N->act[0], clocks, n, bpad, N->heads, logits, values);
+    MCAZ_CHECK_LAUNCH();
+    e->launches += NLAYERS + 2;
+    return MCAZ_OK;
+}
+
+int network_profile(az_engine* e, int on, double* avg_ms_per_conv_launch, int* n_forwards) {
+    Network* N = e->net;
+    if (!N) return fail(MCAZ_ESTATE, "engine has no built-in network");
+    if (avg_ms_per_conv_launch) {
+        cudaStreamSynchronize(e->stream);
+        double total = 0;
+        for (size_t i = 0; i < N->events_used; ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, N->events[i].first, N->events[i].second);
+            total += ms;
+        }
+        *avg_ms_per_conv_launch = N->events_used ? total / (double)N->events_used / NLAYERS : 0.0;
+        if (n_forwards) *n_forwards = (int)N->events_used;
+    }
+    N->events_used = 0;
+    N->profiling = on != 0;
+    return MCAZ_OK;
+}
+
 }  // namespace mcaz
+
+extern "C" int az_profile_network(az_engine* e, int on, double* avg_ms_per_conv_launch, int* n_forwards) {
+    if (!e) return mcaz::fail(MCAZ_EINVAL, "az_profile_network: null engine");
+    return mcaz::network_profile(e, on, avg_ms_per_conv_launch, n_forwards);
+}

@@ -232,3 +232,14 @@ class Engine:
         n = ctypes.c_int()
         self._check(self._L.az_drain_replay(self._h, ptr(out), cap, ctypes.byref(n)))
         return out[:n.value]
+
+
+def _profile_network(self, on=True, read=False):
+    """bench hook: (avg ms per tower-conv launch, forwards measured) since the last call."""
+    ms, n = ctypes.c_double(), ctypes.c_int()
+    self._check(self._L.az_profile_network(self._h, int(bool(on)), ctypes.byref(ms) if read else None,
+                                           ctypes.byref(n) if read else None))
+    return (ms.value, n.value) if read else None
+
+
+Engine.profile_network = _profile_network
