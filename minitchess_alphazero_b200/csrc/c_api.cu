@@ -17,6 +17,11 @@ int fail(int code, const std::string& msg) {
     return code;
 }
 
+Scratch& thread_scratch() {
+    static thread_local Scratch sc;
+    return sc;
+}
+
 int require_device() {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);

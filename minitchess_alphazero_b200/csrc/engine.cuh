@@ -16,6 +16,7 @@ struct az_engine {
     az::View v;                  // device pointers + parameters, passed to kernels by value
     cudaStream_t stream = 0;     // legacy default stream: orders with the caller's torch work
     std::vector<void*> allocs;
+    mcaz::Scratch scratch;       // staging for host-pointer arguments
     int device = 0;
     bool leaf_pending = false;   // az_select_expand done, az_backup not yet
     // external-evaluator scratch

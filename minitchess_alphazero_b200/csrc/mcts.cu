@@ -7,6 +7,8 @@
 //                         exp/agent.py:110-119, exp/callbacks.py:31-54)
 //   root_stats_kernel / node_stats_kernel   what exp/policy.py:118-121 reads back
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.cuh"
@@ -402,6 +404,7 @@ int az_destroy(az_engine* e) {
     cudaDeviceSynchronize();
     if (e->net) network_destroy(e);
     for (void* p : e->allocs) cudaFree(p);
+    e->scratch.release();
     delete e;
     return MCAZ_OK;
 }
@@ -410,8 +413,9 @@ int az_set_weights(az_engine* e, const float* flat, size_t n) {
     if (!e || !flat) return fail(MCAZ_EINVAL, "az_set_weights: null argument");
     if (n != (size_t)AZ_NUM_WEIGHT_FLOATS) return fail(MCAZ_EINVAL, "az_set_weights: expected AZ_NUM_WEIGHT_FLOATS floats");
     if (!e->net) return fail(MCAZ_ESTATE, "az_set_weights: engine was created with network = 0");
+    e->scratch.begin();
     In<float> in;
-    if (int rc = in.init(flat, n, e->stream)) return rc;
+    if (int rc = in.init(flat, n, e->stream, e->scratch)) return rc;
     int rc = network_set_weights(e, in.ptr);
     if (!rc) MCAZ_CUDA(cudaStreamSynchronize(e->stream));
     return rc;
@@ -420,9 +424,10 @@ int az_set_weights(az_engine* e, const float* flat, size_t n) {
 int az_reset_games(az_engine* e, const int32_t* game_ids, int n, const mc_state* states) {
     if (!e || n < 0) return fail(MCAZ_EINVAL, "az_reset_games: bad argument");
     if (n == 0) return MCAZ_OK;
+    e->scratch.begin();
     In<int32_t> ids; In<mc_state> st;
-    if (int rc = ids.init(game_ids, n, e->stream)) return rc;
-    if (int rc = st.init(states, n, e->stream)) return rc;
+    if (int rc = ids.init(game_ids, n, e->stream, e->scratch)) return rc;
+    if (int rc = st.init(states, n, e->stream, e->scratch)) return rc;
     reset_games_kernel<<<std::min(n, num_sms() * 8), 256, 0, e->stream>>>(e->v, ids.ptr, n, st.ptr, start_state());
     MCAZ_CHECK_LAUNCH();
     e->launches++;
@@ -434,10 +439,11 @@ int az_reset_games(az_engine* e, const int32_t* game_ids, int n, const mc_state*
 int az_set_positions(az_engine* e, const int32_t* game_ids, int n, const mc_state* states, const int32_t* tree_of_game) {
     if (!e || n < 0 || (n > 0 && !states)) return fail(MCAZ_EINVAL, "az_set_positions: bad argument");
     if (n == 0) return MCAZ_OK;
+    e->scratch.begin();
     In<int32_t> ids; In<mc_state> st; In<int32_t> tg;
-    if (int rc = ids.init(game_ids, n, e->stream)) return rc;
-    if (int rc = st.init(states, n, e->stream)) return rc;
-    if (int rc = tg.init(tree_of_game, n, e->stream)) return rc;
+    if (int rc = ids.init(game_ids, n, e->stream, e->scratch)) return rc;
+    if (int rc = st.init(states, n, e->stream, e->scratch)) return rc;
+    if (int rc = tg.init(tree_of_game, n, e->stream, e->scratch)) return rc;
     set_positions_kernel<<<std::max(1, std::min((n + 127) / 128, num_sms() * 8)), 128, 0, e->stream>>>(e->v, ids.ptr, n, st.ptr, tg.ptr);
     MCAZ_CHECK_LAUNCH();
     e->launches++;
@@ -526,32 +532,47 @@ int az_search(az_engine* e, int n_sims) {
 int az_root_stats(az_engine* e, const int32_t* game_ids, int n, uint16_t* codes, uint32_t* visits, double* q, int32_t* n_legal) {
     if (!e || n < 0 || (n > 0 && (!codes || !visits || !n_legal))) return fail(MCAZ_EINVAL, "az_root_stats: bad argument");
     if (n == 0) return MCAZ_OK;
+    const bool trace = getenv("MCAZ_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now();
+    e->scratch.begin();
     In<int32_t> ids; Out<uint16_t> oc; Out<uint32_t> ov; Out<double> oq; Out<int32_t> on;
-    if (int rc = ids.init(game_ids, n, e->stream)) return rc;
-    if (int rc = oc.init(codes, (size_t)n * MC_MAX_MOVES, e->stream, true)) return rc;
-    if (int rc = ov.init(visits, (size_t)n * MC_MAX_MOVES, e->stream, true)) return rc;
-    if (int rc = oq.init(q, q ? (size_t)n * MC_MAX_MOVES : 0, e->stream, true)) return rc;
-    if (int rc = on.init(n_legal, n, e->stream)) return rc;
+    if (int rc = ids.init(game_ids, n, e->stream, e->scratch)) return rc;
+    if (int rc = oc.init(codes, (size_t)n * MC_MAX_MOVES, e->stream, e->scratch, true)) return rc;
+    if (int rc = ov.init(visits, (size_t)n * MC_MAX_MOVES, e->stream, e->scratch, true)) return rc;
+    if (int rc = oq.init(q, q ? (size_t)n * MC_MAX_MOVES : 0, e->stream, e->scratch, true)) return rc;
+    if (int rc = on.init(n_legal, n, e->stream, e->scratch)) return rc;
+    double t1 = now();
     root_stats_kernel<<<warp_grid(n, 128), 128, 0, e->stream>>>(e->v, ids.ptr, n, oc.ptr, ov.ptr, oq.ptr, on.ptr);
     MCAZ_CHECK_LAUNCH();
     e->launches++;
+    if (trace) cudaStreamSynchronize(e->stream);
+    double t2 = now();
     if (int rc = oc.finish(e->stream)) return rc;
     if (int rc = ov.finish(e->stream)) return rc;
     if (int rc = oq.finish(e->stream)) return rc;
     if (int rc = on.finish(e->stream)) return rc;
-    return engine_check_errors(e);
+    int rc = engine_check_errors(e);
+    double t3 = now();
+    if (trace) fprintf(stderr, "[mcaz] root_stats n=%d: staging %.2f ms, kernel %.2f ms, copies+sync %.2f ms\n", n, t1 - t0, t2 - t1, t3 - t2);
+    return rc;
 }
 
 int az_node_stats(az_engine* e, int game_id, int tree, const mc_state* state, int* found, uint16_t* codes, uint32_t* visits,
                   double* q, float* priors, int32_t* n_legal, int* is_terminal, double* terminal_value) {
     if (!e || !state || !found || game_id < 0 || game_id >= e->v.G) return fail(MCAZ_EINVAL, "az_node_stats: bad argument");
-    NodeStatsOut* d_out = nullptr;
-    uint16_t* d_codes = nullptr; uint32_t* d_vis = nullptr; double* d_q = nullptr; float* d_p = nullptr;
-    MCAZ_CUDA(cudaMalloc(&d_out, sizeof(NodeStatsOut)));
-    MCAZ_CUDA(cudaMalloc(&d_codes, MC_MAX_MOVES * sizeof(uint16_t)));
-    MCAZ_CUDA(cudaMalloc(&d_vis, MC_MAX_MOVES * sizeof(uint32_t)));
-    MCAZ_CUDA(cudaMalloc(&d_q, MC_MAX_MOVES * sizeof(double)));
-    MCAZ_CUDA(cudaMalloc(&d_p, MC_MAX_MOVES * sizeof(float)));
+    e->scratch.begin();
+    void *p_out, *p_codes, *p_vis, *p_q, *p_p;
+    if (int rc = e->scratch.take(sizeof(NodeStatsOut), &p_out)) return rc;
+    if (int rc = e->scratch.take(MC_MAX_MOVES * sizeof(uint16_t), &p_codes)) return rc;
+    if (int rc = e->scratch.take(MC_MAX_MOVES * sizeof(uint32_t), &p_vis)) return rc;
+    if (int rc = e->scratch.take(MC_MAX_MOVES * sizeof(double), &p_q)) return rc;
+    if (int rc = e->scratch.take(MC_MAX_MOVES * sizeof(float), &p_p)) return rc;
+    NodeStatsOut* d_out = static_cast<NodeStatsOut*>(p_out);
+    uint16_t* d_codes = static_cast<uint16_t*>(p_codes);
+    uint32_t* d_vis = static_cast<uint32_t*>(p_vis);
+    double* d_q = static_cast<double*>(p_q);
+    float* d_p = static_cast<float*>(p_p);
     node_stats_kernel<<<1, 32, 0, e->stream>>>(e->v, game_id, tree, *state, d_out, d_codes, d_vis, d_q, d_p);
     g_launches.fetch_add(1);
     e->launches++;
@@ -562,7 +583,6 @@ int az_node_stats(az_engine* e, int game_id, int tree, const mc_state* state, in
     if (q) cudaMemcpyAsync(q, d_q, MC_MAX_MOVES * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
     if (priors) cudaMemcpyAsync(priors, d_p, MC_MAX_MOVES * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
     cudaError_t err = cudaStreamSynchronize(e->stream);
-    cudaFree(d_out); cudaFree(d_codes); cudaFree(d_vis); cudaFree(d_q); cudaFree(d_p);
     if (err != cudaSuccess) return fail(MCAZ_ECUDA, std::string("az_node_stats: ") + cudaGetErrorString(err));
     *found = h.found;
     if (n_legal) *n_legal = h.n_legal;
@@ -575,10 +595,11 @@ int az_play(az_engine* e, const int32_t* game_ids, const uint16_t* codes, int n,
     if (!e || n < 0 || (n > 0 && !codes)) return fail(MCAZ_EINVAL, "az_play: bad argument");
     if (e->leaf_pending) return fail(MCAZ_ESTATE, "az_play: a simulation is pending (call az_backup first)");
     if (n == 0) return MCAZ_OK;
+    e->scratch.begin();
     In<int32_t> ids; In<uint16_t> ic; Out<int8_t> orr;
-    if (int rc = ids.init(game_ids, n, e->stream)) return rc;
-    if (int rc = ic.init(codes, n, e->stream)) return rc;
-    if (int rc = orr.init(results, results ? n : 0, e->stream)) return rc;
+    if (int rc = ids.init(game_ids, n, e->stream, e->scratch)) return rc;
+    if (int rc = ic.init(codes, n, e->stream, e->scratch)) return rc;
+    if (int rc = orr.init(results, results ? n : 0, e->stream, e->scratch)) return rc;
     play_kernel<<<std::max(1, std::min((n + 127) / 128, num_sms() * 8)), 128, 0, e->stream>>>(e->v, ids.ptr, ic.ptr, n, orr.ptr);
     MCAZ_CHECK_LAUNCH();
     e->launches++;
@@ -603,10 +624,11 @@ int az_play_device(az_engine* e) {
 int az_game_states(az_engine* e, const int32_t* game_ids, int n, mc_state* states, int8_t* results) {
     if (!e || n < 0) return fail(MCAZ_EINVAL, "az_game_states: bad argument");
     if (n == 0) return MCAZ_OK;
+    e->scratch.begin();
     In<int32_t> ids; Out<mc_state> os; Out<int8_t> orr;
-    if (int rc = ids.init(game_ids, n, e->stream)) return rc;
-    if (int rc = os.init(states, states ? n : 0, e->stream)) return rc;
-    if (int rc = orr.init(results, results ? n : 0, e->stream)) return rc;
+    if (int rc = ids.init(game_ids, n, e->stream, e->scratch)) return rc;
+    if (int rc = os.init(states, states ? n : 0, e->stream, e->scratch)) return rc;
+    if (int rc = orr.init(results, results ? n : 0, e->stream, e->scratch)) return rc;
     game_states_kernel<<<std::max(1, std::min((n + 127) / 128, num_sms() * 8)), 128, 0, e->stream>>>(e->v, ids.ptr, n, os.ptr, orr.ptr);
     MCAZ_CHECK_LAUNCH();
     e->launches++;
@@ -646,11 +668,12 @@ int az_network_forward(az_engine* e, const uint8_t* tokens, const float* clocks,
     if (!e || n < 0 || (n > 0 && (!tokens || !clocks || !logits || !values))) return fail(MCAZ_EINVAL, "az_network_forward: bad argument");
     if (!e->net) return fail(MCAZ_ESTATE, "az_network_forward: engine was created with network = 0");
     if (n == 0) return MCAZ_OK;
+    e->scratch.begin();
     In<uint8_t> it; In<float> ic; Out<float> ol; Out<float> ov;
-    if (int rc = it.init(tokens, (size_t)n * MC_TOKENS, e->stream)) return rc;
-    if (int rc = ic.init(clocks, n, e->stream)) return rc;
-    if (int rc = ol.init(logits, (size_t)n * MC_NUM_ACTIONS, e->stream)) return rc;
-    if (int rc = ov.init(values, n, e->stream)) return rc;
+    if (int rc = it.init(tokens, (size_t)n * MC_TOKENS, e->stream, e->scratch)) return rc;
+    if (int rc = ic.init(clocks, n, e->stream, e->scratch)) return rc;
+    if (int rc = ol.init(logits, (size_t)n * MC_NUM_ACTIONS, e->stream, e->scratch)) return rc;
+    if (int rc = ov.init(values, n, e->stream, e->scratch)) return rc;
     if (int rc = network_forward(e, it.ptr, ic.ptr, nullptr, n, ol.ptr, ov.ptr)) return rc;
     if (int rc = ol.finish(e->stream)) return rc;
     if (int rc = ov.finish(e->stream)) return rc;

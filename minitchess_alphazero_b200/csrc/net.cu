@@ -33,12 +33,15 @@ constexpr int NPOS = 30;
 constexpr int NLAYERS = 18;       // 9 residual blocks x 2 convolutions
 constexpr int BLOCK_M = 128;      // boards per tile
 constexpr int BLOCK_K = 64;       // bf16 elements = one 128-byte swizzle row
-constexpr int STAGES = 4;
-constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
-constexpr int B_BYTES = C * BLOCK_K * 2;         // 32 KB
+constexpr int STAGES = 6;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB: this CTA's 128 boards x 64 input channels
+constexpr int B_BYTES = (C / 2) * BLOCK_K * 2;   // 16 KB: this CTA's half of the 256 output channels
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int CONV_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int CONV_THREADS = 256;
+constexpr int CONV_THREADS = 256;                // TMA, MMA, TMEM-alloc, spare + 4 epilogue warps
+constexpr int MAX_ITEMS_PER_CTA = 16;
+constexpr uint32_t SCHED_END = 0xffffffffu;
+constexpr int MAX_CHUNK_BOARDS = 8192;           // keeps the per-CTA schedule within MAX_ITEMS_PER_CTA
 
 // flat state_dict offsets (floats), exp/policy.py:56-69 order without num_batches_tracked
 constexpr size_t OFF_EMB = 0;
@@ -93,6 +96,46 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the even CTA of the pair
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
+// TMA load whose completion bytes are credited to the pair leader's mbarrier
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// commit: arrive on the barrier at this offset in both CTAs of the pair once the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -109,17 +152,17 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10),
 // both K-major, N >> 3 in [17,23), M >> 4 in [24,29).
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+// cta_group::2: one instruction spans the CTA pair, M = 256 boards (128 per CTA), N = 256.
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
 
 struct ConvParams {
     const float* bias;              // [256] folded conv bias + BatchNorm
     const __nv_bfloat16* residual;  // same layout as out, or nullptr
     __nv_bfloat16* out;
-    int n_tiles;                    // board tiles of 128
-    int bpad;                       // n_tiles * 128
+    const uint32_t* sched;          // [grid][MAX_ITEMS_PER_CTA] work items: pos | tile << 8 | n_tiles << 24
+    int bpad;                       // boards per position plane (multiple of 128)
     int layer;
     int relu;
-    uint8_t order[NPOS];            // positions, heaviest (most valid taps) first
 };
 
 __device__ __forceinline__ bool tap_valid(int pos, int tap, int& src) {
@@ -128,61 +171,73 @@ __device__ __forceinline__ bool tap_valid(int pos, int tap, int& src) {
     return row >= 0 && row < 6 && col >= 0 && col < 5;
 }
 
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+// One work item = one output position x a pair of 128-board tiles, computed by a CTA pair with
+// tcgen05.mma.cta_group::2: each CTA stages its own boards (A) and half of the output channels (B),
+// so every SM reads and writes half the weight bytes of the single-CTA form -- the shared-memory
+// port, not the tensor pipe, is what limits a 1-CTA 128x256 SS-mode MMA.  Roles per CTA: warp 0
+// lane 0 TMA producer, warp 1 lane 0 MMA issuer (leader CTA only), warp 2 TMEM allocator,
+// warps 4-7 epilogue of this CTA's 128 accumulator rows.  TMEM accumulators are double buffered.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_w, const ConvParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* full = bars;                 // [STAGES]  TMA -> MMA
-    uint64_t* empty = bars + STAGES;       // [STAGES]  MMA -> TMA
-    uint64_t* acc_full = bars + 2 * STAGES;      // [2]  MMA -> epilogue
-    uint64_t* acc_empty = bars + 2 * STAGES + 2; // [2]  epilogue -> MMA
+    uint64_t* full = bars;                           // [STAGES]  TMA (both CTAs) -> MMA, lives in the leader
+    uint64_t* empty = bars + STAGES;                 // [STAGES]  MMA -> TMA, one copy per CTA
+    uint64_t* acc_full = bars + 2 * STAGES;          // [2]  MMA -> epilogue, one copy per CTA
+    uint64_t* acc_empty = bars + 2 * STAGES + 2;     // [2]  epilogue (both CTAs) -> MMA, lives in the leader
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     __shared__ float s_bias[C];
+    __shared__ uint32_t s_sched[MAX_ITEMS_PER_CTA];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_items = P.n_tiles * NPOS;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
 
     for (int i = threadIdx.x; i < C; i += CONV_THREADS) s_bias[i] = P.bias[i];
+    if (threadIdx.x < MAX_ITEMS_PER_CTA) s_sched[threadIdx.x] = P.sched[(blockIdx.x >> 1) * MAX_ITEMS_PER_CTA + threadIdx.x];
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                              // the peer's barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0 && lane == 0) {
-        // ---------------------------------------------------------------- TMA producer
+        // ---------------------------------------------------------------- TMA producer (both CTAs)
         uint32_t it = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int pos = P.order[item / P.n_tiles], tile = item % P.n_tiles;
+        for (int k = 0; k < MAX_ITEMS_PER_CTA && s_sched[k] != SCHED_END; ++k) {
+            const uint32_t item = s_sched[k];
+            const int pos = item & 0xff, tile = 2 * (int)(item >> 8) + (int)rank;
             for (int tap = 0; tap < 9; ++tap) {
                 int src;
                 if (!tap_valid(pos, tap, src)) continue;
                 for (int kc = 0; kc < C / BLOCK_K; ++kc, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
-                    mbar_expect_tx(&full[s], STAGE_BYTES);
-                    uint8_t* a = smem + s * STAGE_BYTES;
-                    tma_load_3d(a, &map_act, &full[s], kc * BLOCK_K, tile * BLOCK_M, src);
-                    tma_load_3d(a + A_BYTES, &map_w, &full[s], kc * BLOCK_K, 0, P.layer * 9 + tap);
+                    if (leader) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
+                    else mbar_arrive_remote(&full[s], 0);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    tma_load_3d_2sm(st, &map_act, &full[s], kc * BLOCK_K, tile * BLOCK_M, src);
+                    tma_load_3d_2sm(st + A_BYTES, &map_w, &full[s], kc * BLOCK_K, (int)rank * (C / 2), P.layer * 9 + tap);
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ---------------------------------------------------------------- MMA issuer
-        uint32_t it = 0, n = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
-            const int pos = P.order[item / P.n_tiles];
-            const uint32_t acc = n & 1;
-            mbar_wait(&acc_empty[acc], ((n >> 1) & 1) ^ 1);
+    } else if (warp == 1 && lane == 0 && leader) {
+        // ---------------------------------------------------------------- MMA issuer (leader CTA)
+        uint32_t it = 0;
+        for (int k = 0; k < MAX_ITEMS_PER_CTA && s_sched[k] != SCHED_END; ++k) {
+            const int pos = s_sched[k] & 0xff;
+            const uint32_t acc = k & 1;
+            mbar_wait(&acc_empty[acc], ((k >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * C;
             uint32_t accumulate = 0;
@@ -196,27 +251,37 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_cons
                     const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
                     const uint64_t da = umma_desc(a_addr), db = umma_desc(a_addr + A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 16; ++k) {
-                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, IDESC, accumulate);
+                    for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
+                        umma_bf16_2sm(d_tmem, da + 2 * kk, db + 2 * kk, IDESC, accumulate);
                         accumulate = 1;
                     }
-                    umma_commit(&empty[s]);      // frees the smem stage when these MMAs retire
+                    umma_commit_2sm(&empty[s]);      // frees this stage in both CTAs when the MMAs retire
                 }
             }
-            umma_commit(&acc_full[acc]);         // accumulator complete -> epilogue
+            umma_commit_2sm(&acc_full[acc]);         // accumulators complete -> both epilogues
         }
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- epilogue (TMEM -> HBM)
-        const int q = warp & 3;                  // TMEM lane quadrant this warp may read
-        uint32_t n = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
-            const int pos = P.order[item / P.n_tiles], tile = item % P.n_tiles;
-            const uint32_t acc = n & 1;
-            mbar_wait(&acc_full[acc], (n >> 1) & 1);
-            tc_fence_after();
+        const int q = warp & 3;                      // TMEM lane quadrant this warp may read
+        for (int k = 0; k < MAX_ITEMS_PER_CTA && s_sched[k] != SCHED_END; ++k) {
+            const uint32_t item = s_sched[k];
+            const int pos = item & 0xff, tile = 2 * (int)(item >> 8) + (int)rank;
+            const uint32_t acc = k & 1;
             const size_t row_off = ((size_t)pos * P.bpad + (size_t)tile * BLOCK_M + q * 32 + lane) * C;
+            // residual rows are outputs of the previous layer: fetch them while the MMAs still run
+            uint4 res[4][4];
+            if (P.residual) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(P.residual + row_off + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) res[c][j] = rp[j];
+                }
+            }
+            mbar_wait(&acc_full[acc], (k >> 1) & 1);
+            tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C;
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < C / 32; ++c) {
                 uint32_t v[32];
                 asm volatile(
@@ -230,12 +295,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_cons
                     : "r"(taddr + c * 32)
                     : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                uint4 res[4];
-                if (P.residual) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(P.residual + row_off + c * 32);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) res[j] = rp[j];
-                }
                 uint4 outv[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -246,7 +305,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_cons
                         float x0 = __uint_as_float(v[e]) + s_bias[c * 32 + e];
                         float x1 = __uint_as_float(v[e + 1]) + s_bias[c * 32 + e + 1];
                         if (P.residual) {
-                            const uint32_t r = (&res[j].x)[h];
+                            const uint32_t r = (&res[c & 3][j].x)[h];
                             x0 += __uint_as_float(r << 16);
                             x1 += __uint_as_float(r & 0xffff0000u);
                         }
@@ -256,20 +315,29 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_cons
                     }
                     outv[j] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                 }
+                if (P.residual && c + 4 < C / 32) {      // refill the ring slot just consumed
+                    const uint4* rp = reinterpret_cast<const uint4*>(P.residual + row_off + (c + 4) * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) res[c & 3][j] = rp[j];
+                }
                 uint4* op = reinterpret_cast<uint4*>(P.out + row_off + c * 32);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) op[j] = outv[j];
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            if (lane == 0) {
+                if (leader) mbar_arrive(&acc_empty[acc]);
+                else mbar_arrive_remote(&acc_empty[acc], 0);
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                              // nobody tears down TMEM / exits while the peer still uses it
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -285,17 +353,20 @@ __global__ void prep_tower_kernel(const float* __restrict__ flat, __nv_bfloat16*
     if (k == 0) bias[L * C + n] = (cb[n] - mean[n]) * scale + beta[n];
 }
 
-// stem table: T[tap][j][c], j < 7: token j in channel group 0 (mover), j >= 7: token j-7 in group 1
+// stem table: T[tap][combo][c]; a square holds at most one piece, so the two token channels collapse into
+// 13 combinations: 0 = empty, 1..6 = mover's piece of that type, 7..12 = opponent's piece.  The entry is the
+// BatchNorm-folded contribution of that square through tap `t` to output channel c.
 __global__ void prep_stem_kernel(const float* __restrict__ flat, float* __restrict__ table, float* __restrict__ bias) {
-    const int c = threadIdx.x, j = blockIdx.x % 14, t = blockIdx.x / 14;
+    const int c = threadIdx.x, combo = blockIdx.x % 13, t = blockIdx.x / 13;
     const float* sw = flat + OFF_STEM;
     const float *sb = sw + 18432, *gamma = sb + 256, *beta = gamma + 256, *mean = beta + 256, *var = mean + 256;
     const float* emb = flat + OFF_EMB;
     const float scale = gamma[c] / sqrtf(var[c] + BN_EPS);
-    const int grp = j / 7, tok = j % 7;
+    const int tok0 = combo <= 6 ? combo : 0, tok1 = combo > 6 ? combo - 6 : 0;
     float acc = 0.f;
-    for (int e = 0; e < 4; ++e) acc += sw[((size_t)c * 8 + grp * 4 + e) * 9 + t] * emb[tok * 4 + e];
-    table[((size_t)t * 14 + j) * C + c] = acc * scale;
+    for (int e = 0; e < 4; ++e)
+        acc += sw[((size_t)c * 8 + e) * 9 + t] * emb[tok0 * 4 + e] + sw[((size_t)c * 8 + 4 + e) * 9 + t] * emb[tok1 * 4 + e];
+    table[((size_t)t * 13 + combo) * C + c] = acc * scale;
     if (blockIdx.x == 0) bias[c] = (sb[c] - mean[c]) * scale + beta[c];
 }
 
@@ -337,31 +408,29 @@ __global__ void prep_heads_kernel(const float* __restrict__ flat, HeadWeights H)
 }
 
 // ---------------------------------------------------------------------------------- stem
-// One warp per (board, position): 32 lanes x 8 channels; <= 18 table rows summed.
+// One warp per (board, position): 32 lanes x 8 channels; one 1 KB table row per valid tap.
 __global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ tokens, int n, int bpad,
                                                    const float* __restrict__ table, const float* __restrict__ bias,
                                                    __nv_bfloat16* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long total = (long long)bpad * NPOS;
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + lane * 8), b1 = *reinterpret_cast<const float4*>(bias + lane * 8 + 4);
     for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
         const int board = (int)(w / NPOS), pos = (int)(w % NPOS);
-        float acc[8];
-        const float4 b0 = *reinterpret_cast<const float4*>(bias + lane * 8), b1 = *reinterpret_cast<const float4*>(bias + lane * 8 + 4);
-        acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+        float acc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         if (board < n) {
             const uint8_t* tk = tokens + (size_t)board * MC_TOKENS;
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
                 int src;
                 if (!tap_valid(pos, t, src)) continue;
-                const int j0 = tk[src], j1 = 7 + tk[30 + src];
-                const float* r0 = table + ((size_t)t * 14 + j0) * C + lane * 8;
-                const float* r1 = table + ((size_t)t * 14 + j1) * C + lane * 8;
-                const float4 a0 = *reinterpret_cast<const float4*>(r0), a1 = *reinterpret_cast<const float4*>(r0 + 4);
-                const float4 c0 = *reinterpret_cast<const float4*>(r1), c1 = *reinterpret_cast<const float4*>(r1 + 4);
-                acc[0] += a0.x + c0.x; acc[1] += a0.y + c0.y; acc[2] += a0.z + c0.z; acc[3] += a0.w + c0.w;
-                acc[4] += a1.x + c1.x; acc[5] += a1.y + c1.y; acc[6] += a1.z + c1.z; acc[7] += a1.w + c1.w;
+                const int mine = tk[src], theirs = tk[30 + src];
+                const int combo = mine ? mine : (theirs ? 6 + theirs : 0);
+                const float* r = table + ((size_t)t * 13 + combo) * C + lane * 8;
+                const float4 a0 = *reinterpret_cast<const float4*>(r), a1 = *reinterpret_cast<const float4*>(r + 4);
+                acc[0] += a0.x; acc[1] += a0.y; acc[2] += a0.z; acc[3] += a0.w;
+                acc[4] += a1.x; acc[5] += a1.y; acc[6] += a1.z; acc[7] += a1.w;
             }
         }
         uint32_t pk[4];
@@ -375,10 +444,13 @@ __global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ t
 }
 
 // ---------------------------------------------------------------------------------- heads
-// Persistent CTAs; plinear^T (135 KB) and vlinear.0^T (31 KB) staged in shared memory once per CTA,
-// one warp per board.
-constexpr int HEADS_THREADS = 256;
-constexpr int HEADS_SMEM = (61 * 554 + 554 + 31 * 256 + 256 + 256 + 3 * 256 + 8 + (HEADS_THREADS / 32) * 96) * 4;
+// Persistent CTAs of 16 warps; plinear^T (135 KB) and vlinear.0^T (31 KB) staged in shared memory once
+// per CTA; one warp per board.  1x1 convolutions: lane = board position (30 of 32 lanes), each lane
+// walks its own 512-byte channel row; the dense layers keep 18 (policy) / 8 (value) independent
+// accumulators per lane so shared-memory latency is pipelined.
+constexpr int HEADS_THREADS = 512;
+constexpr int HEADS_WARPS = HEADS_THREADS / 32;
+constexpr int HEADS_SMEM = (61 * 554 + 554 + 31 * 256 + 256 + 256 + 3 * 256 + 8 + HEADS_WARPS * 96) * 4;
 
 __global__ void __launch_bounds__(HEADS_THREADS, 1)
 heads_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ clocks, int n, int bpad, HeadWeights H,
@@ -400,51 +472,69 @@ heads_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ cl
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* in = s_in + warp * 96;
-    float cw0[8], cw1[8], cw2[8];
+    const int pos = lane < NPOS ? lane : NPOS - 1;
+    for (int board = blockIdx.x * HEADS_WARPS + warp; board < n; board += gridDim.x * HEADS_WARPS) {
+        // ---- 1x1 convolutions 256 -> {2, 1} for this lane's position
+        const uint4* row = reinterpret_cast<const uint4*>(act + ((size_t)pos * bpad + board) * C);
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll 1
+        for (int c4 = 0; c4 < C / 8; c4 += 4) {
+            uint4 raw[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { cw0[k] = s_cw[lane * 8 + k]; cw1[k] = s_cw[256 + lane * 8 + k]; cw2[k] = s_cw[512 + lane * 8 + k]; }
-    for (int board = blockIdx.x * (HEADS_THREADS / 32) + warp; board < n; board += gridDim.x * (HEADS_THREADS / 32)) {
-        // 1x1 convolutions over 256 channels: lane holds 8 channels
-        for (int pos = 0; pos < NPOS; ++pos) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(act + ((size_t)pos * bpad + board) * C + lane * 8);
-            const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
-            float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+            for (int u = 0; u < 4; ++u) raw[u] = row[c4 + u];
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                const float x0 = __uint_as_float(rw[h] << 16), x1 = __uint_as_float(rw[h] & 0xffff0000u);
-                d0 += x0 * cw0[2 * h] + x1 * cw0[2 * h + 1];
-                d1 += x0 * cw1[2 * h] + x1 * cw1[2 * h + 1];
-                d2 += x0 * cw2[2 * h] + x1 * cw2[2 * h + 1];
-            }
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t rw[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+                const float* w0 = s_cw + (c4 + u) * 8;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                d0 += __shfl_xor_sync(0xffffffffu, d0, o);
-                d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-                d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-            }
-            if (lane == 0) {
-                in[pos] = fmaxf(d0 + s_cb[0], 0.f);
-                in[30 + pos] = fmaxf(d1 + s_cb[1], 0.f);
-                in[61 + pos] = fmaxf(d2 + s_cb[2], 0.f);
+                for (int h = 0; h < 4; ++h) {
+                    const float x0 = __uint_as_float(rw[h] << 16), x1 = __uint_as_float(rw[h] & 0xffff0000u);
+                    d0 += x0 * w0[2 * h] + x1 * w0[2 * h + 1];
+                    d1 += x0 * w0[256 + 2 * h] + x1 * w0[256 + 2 * h + 1];
+                    d2 += x0 * w0[512 + 2 * h] + x1 * w0[512 + 2 * h + 1];
+                }
             }
         }
-        if (lane == 0) { const float ck = clocks[board]; in[60] = ck; in[91] = ck; }
+        if (lane < NPOS) {
+            in[lane] = fmaxf(d0 + s_cb[0], 0.f);
+            in[30 + lane] = fmaxf(d1 + s_cb[1], 0.f);
+            in[61 + lane] = fmaxf(d2 + s_cb[2], 0.f);
+        } else if (lane == 30) {
+            const float ck = clocks[board];
+            in[60] = ck;
+            in[91] = ck;
+        }
         __syncwarp();
-        // policy: 554 logits = plinear([px, clock])
-        for (int o = lane; o < MC_NUM_ACTIONS; o += 32) {
-            float acc = s_plb[o];
+        // ---- policy: 554 logits = plinear([px, clock]); lane owns outputs lane + 32 k
+        float acc[18];
+#pragma unroll
+        for (int k = 0; k < 18; ++k) acc[k] = (lane + 32 * k < MC_NUM_ACTIONS) ? s_plb[lane + 32 * k] : 0.f;
 #pragma unroll 1
-            for (int j = 0; j < 61; ++j) acc += in[j] * s_plt[j * 554 + o];
-            logits[(size_t)board * MC_NUM_ACTIONS + o] = acc;
+        for (int j = 0; j < 61; ++j) {
+            const float xj = in[j];
+            const float* wr = s_plt + j * 554 + lane;
+#pragma unroll
+            for (int k = 0; k < 17; ++k) acc[k] += xj * wr[32 * k];
+            if (lane < MC_NUM_ACTIONS - 17 * 32) acc[17] += xj * wr[32 * 17];
         }
-        // value: tanh(v2 . relu(v1 [vx, clock] + b1) + b2)
+        float* lg = logits + (size_t)board * MC_NUM_ACTIONS + lane;
+#pragma unroll
+        for (int k = 0; k < 17; ++k) lg[32 * k] = acc[k];
+        if (lane < MC_NUM_ACTIONS - 17 * 32) lg[32 * 17] = acc[17];
+        // ---- value: tanh(v2 . relu(v1 [vx, clock] + b1) + b2)
+        float hv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hv[k] = s_v1b[lane + 32 * k];
+#pragma unroll 1
+        for (int j = 0; j < 31; ++j) {
+            const float xj = in[61 + j];
+            const float* wr = s_v1t + j * 256 + lane;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) hv[k] += xj * wr[32 * k];
+        }
         float part = 0.f;
-        for (int o = lane; o < 256; o += 32) {
-            float acc = s_v1b[o];
-#pragma unroll 1
-            for (int j = 0; j < 31; ++j) acc += in[61 + j] * s_v1t[j * 256 + o];
-            part += fmaxf(acc, 0.f) * s_v2[o];
-        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) part += fmaxf(hv[k], 0.f) * s_v2[lane + 32 * k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         if (lane == 0) values[board] = tanhf(part + s_cb[3]);
@@ -487,7 +577,8 @@ struct Network {
     HeadWeights heads{};
     CUtensorMap map_act[2], map_w;
     bool have_weights = false;
-    uint8_t order[NPOS];
+    uint32_t* sched = nullptr;         // [grid][MAX_ITEMS_PER_CTA]
+    int sched_tiles = -1, sched_grid = 0;
     // profiling (az_profile_network)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -496,7 +587,7 @@ struct Network {
 
 static int net_alloc_acts(az_engine* e, int boards) {
     Network* N = e->net;
-    int cap = ((boards + BLOCK_M - 1) / BLOCK_M) * BLOCK_M;
+    int cap = ((boards + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (2 * BLOCK_M);   // whole tile pairs
     if (cap <= N->capacity) return MCAZ_OK;
     for (int i = 0; i < 2; ++i) {
         if (N->act[i]) cudaFree(N->act[i]);
@@ -518,7 +609,7 @@ int network_create(az_engine* e) {
     e->net = N;
     MCAZ_CUDA(cudaMalloc(&N->w, (size_t)NLAYERS * 9 * C * C * sizeof(__nv_bfloat16)));
     MCAZ_CUDA(cudaMalloc(&N->bias, (size_t)NLAYERS * C * sizeof(float)));
-    MCAZ_CUDA(cudaMalloc(&N->stem_table, (size_t)9 * 14 * C * sizeof(float)));
+    MCAZ_CUDA(cudaMalloc(&N->stem_table, (size_t)9 * 13 * C * sizeof(float)));
     MCAZ_CUDA(cudaMalloc(&N->stem_bias, C * sizeof(float)));
     const size_t head_floats = 512 + 2 + 256 + 1 + 61 * 554 + 554 + 31 * 256 + 256 + 256 + 1 + 16;
     MCAZ_CUDA(cudaMalloc(&N->head_pool, head_floats * sizeof(float)));
@@ -533,18 +624,10 @@ int network_create(az_engine* e) {
     N->heads.v1b = p; p += 256;
     N->heads.v2 = p; p += 256;
     N->heads.v2b = p;
-    if (int rc = make_map_3d(&N->map_w, N->w, C, C, (uint64_t)NLAYERS * 9, BLOCK_K, C)) return rc;
-    // positions ordered by number of valid taps, heaviest first (static load balancing)
-    int idx = 0;
-    for (int want : {9, 6, 4})
-        for (int pos = 0; pos < NPOS; ++pos) {
-            int r = pos / 5, c = pos % 5;
-            int taps = ((r == 0 || r == 5) ? 2 : 3) * ((c == 0 || c == 4) ? 2 : 3);
-            if (taps == want) N->order[idx++] = (uint8_t)pos;
-        }
+    if (int rc = make_map_3d(&N->map_w, N->w, C, C, (uint64_t)NLAYERS * 9, BLOCK_K, C / 2)) return rc;
     MCAZ_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
     MCAZ_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_SMEM));
-    return net_alloc_acts(e, e->v.G);
+    return net_alloc_acts(e, std::min(e->v.G, MAX_CHUNK_BOARDS));
 }
 
 void network_destroy(az_engine* e) {
@@ -556,6 +639,7 @@ void network_destroy(az_engine* e) {
     if (N->stem_table) cudaFree(N->stem_table);
     if (N->stem_bias) cudaFree(N->stem_bias);
     if (N->head_pool) cudaFree(N->head_pool);
+    if (N->sched) cudaFree(N->sched);
     for (auto& ev : N->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     delete N;
     e->net = nullptr;
@@ -565,7 +649,7 @@ int network_set_weights(az_engine* e, const float* flat) {
     Network* N = e->net;
     prep_tower_kernel<<<dim3(C, NLAYERS), C, 0, e->stream>>>(flat, N->w, N->bias);
     MCAZ_CHECK_LAUNCH();
-    prep_stem_kernel<<<9 * 14, C, 0, e->stream>>>(flat, N->stem_table, N->stem_bias);
+    prep_stem_kernel<<<9 * 13, C, 0, e->stream>>>(flat, N->stem_table, N->stem_bias);
     MCAZ_CHECK_LAUNCH();
     prep_heads_kernel<<<64, 256, 0, e->stream>>>(flat, N->heads);
     MCAZ_CHECK_LAUNCH();
@@ -574,12 +658,58 @@ int network_set_weights(az_engine* e, const float* flat) {
     return MCAZ_OK;
 }
 
+// Longest-processing-time-first assignment of a layer's work items (position x tile pair, weighted
+// by the number of valid taps) to the CTA pairs.  Static, so every role in a CTA walks the same list.
+static int build_schedule(az_engine* e, int n_pairs) {
+    Network* N = e->net;
+    const int clusters = std::max(1, std::min(num_sms() / 2, n_pairs * NPOS));
+    if (N->sched_tiles == n_pairs && N->sched_grid == 2 * clusters) return MCAZ_OK;
+    struct Item { uint32_t code; int weight; };
+    std::vector<Item> items;
+    for (int pos = 0; pos < NPOS; ++pos) {
+        const int r = pos / 5, c = pos % 5;
+        const int taps = ((r == 0 || r == 5) ? 2 : 3) * ((c == 0 || c == 4) ? 2 : 3);
+        for (int tp = 0; tp < n_pairs; ++tp) items.push_back({(uint32_t)pos | ((uint32_t)tp << 8), taps});
+    }
+    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.weight > b.weight; });
+    std::vector<int> load(clusters, 0), count(clusters, 0);
+    std::vector<uint32_t> table((size_t)clusters * MAX_ITEMS_PER_CTA, SCHED_END);
+    for (const Item& it : items) {
+        int best = -1;
+        for (int c = 0; c < clusters; ++c)
+            if (count[c] < MAX_ITEMS_PER_CTA - 1 && (best < 0 || load[c] < load[best])) best = c;
+        if (best < 0) return fail(MCAZ_ECAPACITY, "conv schedule: too many items per CTA pair");
+        table[(size_t)best * MAX_ITEMS_PER_CTA + count[best]++] = it.code;
+        load[best] += it.weight;
+    }
+    if (N->sched) cudaFree(N->sched);
+    N->sched = nullptr;
+    MCAZ_CUDA(cudaMalloc(&N->sched, table.size() * sizeof(uint32_t)));
+    MCAZ_CUDA(cudaMemcpyAsync(N->sched, table.data(), table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    MCAZ_CUDA(cudaStreamSynchronize(e->stream));
+    N->sched_tiles = n_pairs;
+    N->sched_grid = 2 * clusters;
+    return MCAZ_OK;
+}
+
+static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clocks, int n, float* logits, float* values);
+
 int network_forward(az_engine* e, const uint8_t* tokens, const float* clocks, const uint8_t* /*active*/, int n, float* logits,
                     float* values) {
     Network* N = e->net;
     if (!N->have_weights) return fail(MCAZ_ESTATE, "network weights have not been set (az_set_weights)");
+    for (int off = 0; off < n; off += MAX_CHUNK_BOARDS) {
+        const int m = std::min(MAX_CHUNK_BOARDS, n - off);
+        if (int rc = forward_chunk(e, tokens + (size_t)off * MC_TOKENS, clocks + off, m, logits + (size_t)off * MC_NUM_ACTIONS, values + off))
+            return rc;
+    }
+    return MCAZ_OK;
+}
+
+static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clocks, int n, float* logits, float* values) {
+    Network* N = e->net;
     if (int rc = net_alloc_acts(e, n)) return rc;
-    const int n_tiles = (n + BLOCK_M - 1) / BLOCK_M, bpad = N->capacity;
+    const int n_pairs = (n + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = 2 * n_pairs, bpad = N->capacity;
     cudaStream_t st = e->stream;
     {
         long long warps = (long long)n_tiles * BLOCK_M * NPOS;
@@ -598,10 +728,10 @@ int network_forward(az_engine* e, const uint8_t* tokens, const float* clocks, co
         N->events_used++;
         cudaEventRecord(ev0, st);
     }
+    if (int rc = build_schedule(e, n_pairs)) return rc;
     ConvParams P;
-    P.n_tiles = n_tiles; P.bpad = bpad; P.relu = 1;
-    std::memcpy(P.order, N->order, NPOS);
-    const int grid = std::min(num_sms(), n_tiles * NPOS);
+    P.bpad = bpad; P.relu = 1; P.sched = N->sched;
+    const int grid = N->sched_grid;
     for (int L = 0; L < NLAYERS; ++L) {
         const int src = L & 1, dst = src ^ 1;          // conv1: act0 -> act1, conv2: act1 -> act0 (+ residual act0)
         P.layer = L;

@@ -125,14 +125,16 @@ int mc_legal_moves(const mc_state* states, int n, const mc_rules* rules, uint16_
     if (int rc = require_device()) return rc;
     if (n == 0) return MCAZ_OK;
     cudaStream_t st = 0;
+    Scratch& sc = thread_scratch();
+    sc.begin();
     In<mc_state> in;
     Out<uint16_t> oc;
     Out<int32_t> on;
     Out<int8_t> orr;
-    if (int rc = in.init(states, n, st)) return rc;
-    if (int rc = oc.init(codes, (size_t)n * MC_MAX_MOVES, st, true)) return rc;
-    if (int rc = on.init(counts, n, st)) return rc;
-    if (int rc = orr.init(results, n, st)) return rc;
+    if (int rc = in.init(states, n, st, sc)) return rc;
+    if (int rc = oc.init(codes, (size_t)n * MC_MAX_MOVES, st, sc, true)) return rc;
+    if (int rc = on.init(counts, n, st, sc)) return rc;
+    if (int rc = orr.init(results, n, st, sc)) return rc;
     legal_moves_kernel<<<grid_for(n, 128, 8), 128, 0, st>>>(in.ptr, n, rules_or_default(rules), oc.ptr, on.ptr, orr.ptr);
     MCAZ_CHECK_LAUNCH();
     if (int rc = oc.finish(st)) return rc;
@@ -148,14 +150,16 @@ int mc_apply(const mc_state* states, const uint16_t* codes, int n, const mc_rule
     if (int rc = require_device()) return rc;
     if (n == 0) return MCAZ_OK;
     cudaStream_t st = 0;
+    Scratch& sc = thread_scratch();
+    sc.begin();
     In<mc_state> in;
     In<uint16_t> ic;
     Out<mc_state> oo;
     Out<int8_t> os;
-    if (int rc = in.init(states, n, st)) return rc;
-    if (int rc = ic.init(codes, n, st)) return rc;
-    if (int rc = oo.init(out, n, st)) return rc;
-    if (int rc = os.init(status, n, st)) return rc;
+    if (int rc = in.init(states, n, st, sc)) return rc;
+    if (int rc = ic.init(codes, n, st, sc)) return rc;
+    if (int rc = oo.init(out, n, st, sc)) return rc;
+    if (int rc = os.init(status, n, st, sc)) return rc;
     apply_kernel<<<grid_for(n, 128, 8), 128, 0, st>>>(in.ptr, ic.ptr, n, rules_or_default(rules), oo.ptr, os.ptr);
     MCAZ_CHECK_LAUNCH();
     if (int rc = oo.finish(st)) return rc;
@@ -169,12 +173,14 @@ int mc_tokenize(const mc_state* states, int n, uint8_t* tokens, float* clocks) {
     if (int rc = require_device()) return rc;
     if (n == 0) return MCAZ_OK;
     cudaStream_t st = 0;
+    Scratch& sc = thread_scratch();
+    sc.begin();
     In<mc_state> in;
     Out<uint8_t> ot;
     Out<float> ok;
-    if (int rc = in.init(states, n, st)) return rc;
-    if (int rc = ot.init(tokens, (size_t)n * MC_TOKENS, st)) return rc;
-    if (int rc = ok.init(clocks, n, st)) return rc;
+    if (int rc = in.init(states, n, st, sc)) return rc;
+    if (int rc = ot.init(tokens, (size_t)n * MC_TOKENS, st, sc)) return rc;
+    if (int rc = ok.init(clocks, n, st, sc)) return rc;
     if (reinterpret_cast<uintptr_t>(ot.ptr) & 3u) return fail(MCAZ_EINVAL, "mc_tokenize: tokens must be 4-byte aligned");
     tokenize_kernel<<<grid_for(n, 128, 8), 128, 0, st>>>(in.ptr, n, ot.ptr, ok.ptr);
     MCAZ_CHECK_LAUNCH();
@@ -196,10 +202,12 @@ int mc_perft(const mc_state* roots, int n, int depth, const mc_rules* rules, uin
         else std::memcpy(nodes, ones.data(), n * sizeof(uint64_t));
         return MCAZ_OK;
     }
+    Scratch& sc = thread_scratch();
+    sc.begin();
     In<mc_state> in;
     Out<uint64_t> on;
-    if (int rc = in.init(roots, n, st)) return rc;
-    if (int rc = on.init(nodes, n, st, true)) return rc;
+    if (int rc = in.init(roots, n, st, sc)) return rc;
+    if (int rc = on.init(nodes, n, st, sc, true)) return rc;
     // ping-pong frontiers, grown on demand
     mc_state* fr[2] = {nullptr, nullptr};
     uint32_t* rt[2] = {nullptr, nullptr};

@@ -76,3 +76,26 @@ class BatchedSelfPlay:
 
     def drain(self):
         return self.engine.drain_replay()
+
+    # ---- measurement hooks used by bench.py ---------------------------------------------------
+    CONV_FLOP_PER_EVAL = 2 * 17694720          # one 3x3 256->256 convolution on one 6x5 board
+
+    def reset_kernel_timer(self):
+        """Start bracketing the tower-convolution launches with CUDA events on the engine's stream."""
+        if self.mode != 'builtin':
+            return None
+        self.engine.profile_network(True, read=True)
+        return True
+
+    def kernel_profile(self):
+        """Roofline record of the dominant kernel (conv3x3_tc_kernel) from the events recorded since
+        reset_kernel_timer(): algorithmic FLOP per launch / average launch duration."""
+        if self.mode != 'builtin':
+            return None
+        ms, n = self.engine.profile_network(False, read=True)
+        if n == 0 or ms <= 0:
+            return None
+        flop = self.n_games * self.CONV_FLOP_PER_EVAL
+        return {'bound': 'tensor', 'kernel': 'conv3x3_tc_kernel (tcgen05 3x3 conv 256->256, one launch per layer)',
+                'achieved': flop / (ms / 1e3) / 1e12, 'unit': 'TFLOP/s', 'traffic': None, 'ms_per_launch': ms,
+                'launches_timed': n * 18, 'flop_per_launch': flop}
