@@ -251,7 +251,8 @@ def run_ours(args):
                 'ms_per_launch': fwd_ms}
     else:
         roof = prof
-        roof.update({'peak': pk['tflops'], 'frac': roof['achieved'] / pk['tflops'], 'peak_source': pk['which']})
+        roof.update({'peak': pk['tflops'], 'frac': roof['achieved'] / pk['tflops'], 'mma_frac': roof['achieved_mma'] / pk['tflops'],
+                     'peak_source': pk['which']})
 
     # end to end through the host-buffer API
     e2e = None

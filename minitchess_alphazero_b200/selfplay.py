@@ -96,6 +96,11 @@ class BatchedSelfPlay:
         if n == 0 or ms <= 0:
             return None
         flop = self.n_games * self.CONV_FLOP_PER_EVAL
-        return {'bound': 'tensor', 'kernel': 'conv3x3_tc_kernel (tcgen05 3x3 conv 256->256, one launch per layer)',
-                'achieved': flop / (ms / 1e3) / 1e12, 'unit': 'TFLOP/s', 'traffic': None, 'ms_per_launch': ms,
-                'launches_timed': n * 18, 'flop_per_launch': flop}
+        return {'bound': 'tensor', 'kernel': 'conv3x3_tc_kernel (tcgen05 cta_group::2 3x3 conv 256->256, one launch per layer)',
+                'achieved': flop / (ms / 1e3) / 1e12, 'unit': 'TFLOP/s',
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_conv_r1_raw.csv (two launches)
+                'traffic': 151e6, 'ms_per_launch': ms, 'launches_timed': n * 18, 'flop_per_launch': flop,
+                # the kernel skips the 62 of 270 tap-positions that multiply zero padding: MMAs actually issued
+                'achieved_mma': flop * 208 / 270 / (ms / 1e3) / 1e12,
+                'note': 'achieved counts the algorithmic FLOPs of SURVEY.md 8(d) (all 9 taps at all 30 squares); '
+                        'taps on zero padding are skipped, so issued MMA work is 208/270 of it (achieved_mma)'}
