@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.cuh"
@@ -341,6 +342,259 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_cons
     }
 }
 
+// ---------------------------------------------------------------------------------- whole tower, one launch
+// The 18 convolutions as ONE persistent kernel: the same CTA-pair pipeline as above, but a work item is
+// (layer, position, tile pair) and layers are ordered by data flow instead of by kernel boundaries.
+// Item (L, p, tp) may start once the items (L-1, p', tp) for the valid taps p' of p have published their
+// outputs (per-item flags in global memory, release/acquire at gpu scope); that one rule also covers the
+// write-after-read hazards of the two ping-pong activation buffers.  CTA pairs that finish a layer early
+// move on instead of idling at a grid-wide barrier, which removes the per-layer tail and 17 launch gaps.
+constexpr int TOWER_MAX_ITEMS = 256;
+constexpr int TOWER_SMEM = STAGES * STAGE_BYTES + 1024 + 256 + NLAYERS * C * 4;
+
+struct TowerParams {
+    const float* bias;            // [18][256]
+    __nv_bfloat16* act0;          // layer input of even layers / residual + output of odd layers
+    __nv_bfloat16* act1;
+    const uint32_t* sched;        // [clusters][TOWER_MAX_ITEMS]: layer << 24 | tile pair << 8 | position
+    uint32_t* flags;              // [18][n_pairs][30][2] epoch stamps
+    int bpad;
+    int n_pairs;
+    uint32_t epoch;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta_shared(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cta_shared(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_cg_v4(const uint4* p) {   // L2-coherent: never a stale L1 line across layers
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
+tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_constant__ CUtensorMap map_act1,
+                const __grid_constant__ CUtensorMap map_w, const TowerParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* acc_full = bars + 2 * STAGES;
+    uint64_t* acc_empty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float* s_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // [18][256]
+    __shared__ uint32_t s_deps_ok;            // items [0, s_deps_ok) have all their inputs published (written by warp 3)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const uint32_t* sched = P.sched + (size_t)(blockIdx.x >> 1) * TOWER_MAX_ITEMS;
+
+    for (int i = threadIdx.x; i < NLAYERS * C; i += CONV_THREADS) s_bias[i] = P.bias[i];
+    if (threadIdx.x == 0) s_deps_ok = 0;
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------------------------------------------------------- TMA producer (both CTAs)
+        uint32_t it = 0;
+        for (int k = 0; k < TOWER_MAX_ITEMS; ++k) {
+            const uint32_t item = __ldg(&sched[k]);
+            if (item == SCHED_END) break;
+            const int pos = item & 0xff, tp = (item >> 8) & 0xffff, L = item >> 24;
+            const int tile = 2 * tp + (int)rank;
+            if (L > 0) {
+                // inputs published? (warp 3 polls the global flags ahead of us)
+                while (ld_acquire_cta_shared(&s_deps_ok) <= (uint32_t)k) {}
+                asm volatile("fence.proxy.async;" ::: "memory");   // order the acquired writes before our TMA reads
+            }
+            const CUtensorMap* map_in = (L & 1) ? &map_act1 : &map_act0;
+            for (int tap = 0; tap < 9; ++tap) {
+                int src;
+                if (!tap_valid(pos, tap, src)) continue;
+                for (int kc = 0; kc < C / BLOCK_K; ++kc, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    if (leader) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
+                    else mbar_arrive_remote(&full[s], 0);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    tma_load_3d_2sm(st, map_in, &full[s], kc * BLOCK_K, tile * BLOCK_M, src);
+                    tma_load_3d_2sm(st + A_BYTES, &map_w, &full[s], kc * BLOCK_K, (int)rank * (C / 2), L * 9 + tap);
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && leader) {
+        // ---------------------------------------------------------------- MMA issuer (leader CTA)
+        uint32_t it = 0;
+        for (int k = 0; k < TOWER_MAX_ITEMS; ++k) {
+            const uint32_t item = __ldg(&sched[k]);
+            if (item == SCHED_END) break;
+            const int pos = item & 0xff;
+            const uint32_t acc = k & 1;
+            mbar_wait(&acc_empty[acc], ((k >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * C;
+            uint32_t accumulate = 0;
+            for (int tap = 0; tap < 9; ++tap) {
+                int src;
+                if (!tap_valid(pos, tap, src)) continue;
+                for (int kc = 0; kc < C / BLOCK_K; ++kc, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full[s], (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t da = umma_desc(a_addr), db = umma_desc(a_addr + A_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
+                        umma_bf16_2sm(d_tmem, da + 2 * kk, db + 2 * kk, IDESC, accumulate);
+                        accumulate = 1;
+                    }
+                    umma_commit_2sm(&empty[s]);
+                }
+            }
+            umma_commit_2sm(&acc_full[acc]);
+        }
+    } else if (warp == 3) {
+        // ---------------------------------------------------------------- dependency watcher
+        // Item (L, p, tp) reads the previous layer's output at the valid taps of p (rows of this CTA's
+        // tile): lanes 0-8 each poll one of those flags, so a check costs one L2 round trip and runs
+        // ahead of the TMA producer instead of stalling it.
+        for (int k = 0; k < TOWER_MAX_ITEMS; ++k) {
+            const uint32_t item = __ldg(&sched[k]);
+            if (item == SCHED_END) break;
+            const int pos = item & 0xff, tp = (item >> 8) & 0xffff, L = item >> 24;
+            if (L > 0 && lane < 9) {
+                int src;
+                if (tap_valid(pos, lane, src)) {
+                    const uint32_t* fl = P.flags + (((size_t)(L - 1) * P.n_pairs + tp) * NPOS + src) * 2 + rank;
+                    while (ld_acquire_gpu(fl) != P.epoch) __nanosleep(32);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) st_release_cta_shared(&s_deps_ok, (uint32_t)k + 1);
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------------------- epilogue (TMEM -> HBM) + publish
+        const int q = warp & 3;
+        for (int k = 0; k < TOWER_MAX_ITEMS; ++k) {
+            const uint32_t item = __ldg(&sched[k]);
+            if (item == SCHED_END) break;
+            const int pos = item & 0xff, tp = (item >> 8) & 0xffff, L = item >> 24;
+            const int tile = 2 * tp + (int)rank;
+            const uint32_t acc = k & 1;
+            const bool odd = (L & 1) != 0;                     // second conv of a residual block
+            __nv_bfloat16* out = odd ? P.act0 : P.act1;
+            const float* bias = s_bias + L * C;
+            const size_t row_off = ((size_t)pos * P.bpad + (size_t)tile * BLOCK_M + q * 32 + lane) * C;
+            // residual rows (this block's input, written two layers back) are published once the item's
+            // dependencies are: fetch them while the MMAs still run
+            uint4 res[4][4];
+            if (odd) {
+                while (ld_acquire_cta_shared(&s_deps_ok) <= (uint32_t)k) {}
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(out + row_off + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) res[c][j] = ld_cg_v4(rp + j);
+                }
+            }
+            mbar_wait(&acc_full[acc], (k >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C;
+#pragma unroll
+            for (int c = 0; c < C / 32; ++c) {
+                uint32_t v[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr + c * 32)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c == C / 32 - 1) {
+                    // all TMEM reads of this accumulator are done: hand it back before the stores
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (leader) mbar_arrive(&acc_empty[acc]);
+                        else mbar_arrive_remote(&acc_empty[acc], 0);
+                    }
+                }
+                uint4 outv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t packed[4];
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const int e = j * 8 + h * 2;
+                        float x0 = __uint_as_float(v[e]) + bias[c * 32 + e];
+                        float x1 = __uint_as_float(v[e + 1]) + bias[c * 32 + e + 1];
+                        if (odd) {
+                            const uint32_t r = (&res[c & 3][j].x)[h];
+                            x0 += __uint_as_float(r << 16);
+                            x1 += __uint_as_float(r & 0xffff0000u);
+                        }
+                        x0 = fmaxf(x0, 0.f);
+                        x1 = fmaxf(x1, 0.f);
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(x0, x1);
+                        packed[h] = *reinterpret_cast<uint32_t*>(&b2);
+                    }
+                    outv[j] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                }
+                if (odd && c + 4 < C / 32) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(out + row_off + (c + 4) * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) res[c & 3][j] = ld_cg_v4(rp + j);
+                }
+                uint4* op = reinterpret_cast<uint4*>(out + row_off + c * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) op[j] = outv[j];
+            }
+            // publish: the barrier orders all 128 threads' stores before the (cumulative) gpu-scope release
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 4 && lane == 0)
+                st_release_gpu(P.flags + (((size_t)L * P.n_pairs + tp) * NPOS + pos) * 2 + rank, P.epoch);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------- weight preparation
 __global__ void prep_tower_kernel(const float* __restrict__ flat, __nv_bfloat16* __restrict__ w, float* __restrict__ bias) {
     // grid: (256 cout, 18 layers), block 256 (cin)
@@ -579,6 +833,12 @@ struct Network {
     bool have_weights = false;
     uint32_t* sched = nullptr;         // [grid][MAX_ITEMS_PER_CTA]
     int sched_tiles = -1, sched_grid = 0;
+    uint32_t* tower_sched = nullptr;   // [clusters][TOWER_MAX_ITEMS]
+    uint32_t* tower_flags = nullptr;   // [18][n_pairs][30][2]
+    int tower_pairs = -1, tower_grid = 0;
+    uint32_t epoch = 0;
+    bool per_layer = true;             // default: one launch per layer; MCAZ_TOWER=fused selects tower_tc_kernel (one launch,
+                                       // data-flow ordered; measured +1% under the power cap)
     // profiling (az_profile_network)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -626,6 +886,8 @@ int network_create(az_engine* e) {
     N->heads.v2b = p;
     if (int rc = make_map_3d(&N->map_w, N->w, C, C, (uint64_t)NLAYERS * 9, BLOCK_K, C / 2)) return rc;
     MCAZ_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
+    MCAZ_CUDA(cudaFuncSetAttribute(tower_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_SMEM));
+    { const char* m = getenv("MCAZ_TOWER"); N->per_layer = !(m && std::strcmp(m, "fused") == 0); }
     MCAZ_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_SMEM));
     return net_alloc_acts(e, std::min(e->v.G, MAX_CHUNK_BOARDS));
 }
@@ -640,6 +902,8 @@ void network_destroy(az_engine* e) {
     if (N->stem_bias) cudaFree(N->stem_bias);
     if (N->head_pool) cudaFree(N->head_pool);
     if (N->sched) cudaFree(N->sched);
+    if (N->tower_sched) cudaFree(N->tower_sched);
+    if (N->tower_flags) cudaFree(N->tower_flags);
     for (auto& ev : N->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     delete N;
     e->net = nullptr;
@@ -692,6 +956,50 @@ static int build_schedule(az_engine* e, int n_pairs) {
     return MCAZ_OK;
 }
 
+// Data-flow schedule of the whole tower: items in (layer, tile pair, position) order, each given to the
+// CTA pair with the least accumulated work (list scheduling).  Every pair therefore walks the layers in
+// order and the tile pairs in ascending order within a layer, so an item's inputs -- produced one layer
+// earlier at the same place of that order -- are normally long finished when it starts.
+static int build_tower_schedule(az_engine* e, int n_pairs) {
+    Network* N = e->net;
+    const int clusters = std::max(1, std::min(num_sms() / 2, n_pairs * NPOS));
+    if (N->tower_pairs == n_pairs && N->tower_grid == 2 * clusters) return MCAZ_OK;
+    int taps_of[NPOS];
+    std::vector<int> order;
+    for (int pos = 0; pos < NPOS; ++pos) {
+        const int r = pos / 5, c = pos % 5;
+        taps_of[pos] = ((r == 0 || r == 5) ? 2 : 3) * ((c == 0 || c == 4) ? 2 : 3);
+        order.push_back(pos);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return taps_of[a] > taps_of[b]; });
+    std::vector<long long> load(clusters, 0);
+    std::vector<int> count(clusters, 0);
+    std::vector<uint32_t> table((size_t)clusters * TOWER_MAX_ITEMS, SCHED_END);
+    for (int L = 0; L < NLAYERS; ++L)
+        for (int tp = 0; tp < n_pairs; ++tp)
+            for (int pos : order) {
+                int best = 0;
+                for (int c = 1; c < clusters; ++c)
+                    if (load[c] < load[best]) best = c;
+                if (count[best] >= TOWER_MAX_ITEMS - 1) return fail(MCAZ_ECAPACITY, "tower schedule: too many items per CTA pair");
+                table[(size_t)best * TOWER_MAX_ITEMS + count[best]++] = (uint32_t)pos | ((uint32_t)tp << 8) | ((uint32_t)L << 24);
+                load[best] += taps_of[pos];
+            }
+    if (N->tower_sched) cudaFree(N->tower_sched);
+    if (N->tower_flags) cudaFree(N->tower_flags);
+    N->tower_sched = nullptr; N->tower_flags = nullptr;
+    MCAZ_CUDA(cudaMalloc(&N->tower_sched, table.size() * sizeof(uint32_t)));
+    const size_t n_flags = (size_t)NLAYERS * n_pairs * NPOS * 2;
+    MCAZ_CUDA(cudaMalloc(&N->tower_flags, n_flags * sizeof(uint32_t)));
+    MCAZ_CUDA(cudaMemsetAsync(N->tower_flags, 0, n_flags * sizeof(uint32_t), e->stream));
+    MCAZ_CUDA(cudaMemcpyAsync(N->tower_sched, table.data(), table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    MCAZ_CUDA(cudaStreamSynchronize(e->stream));
+    N->tower_pairs = n_pairs;
+    N->tower_grid = 2 * clusters;
+    N->epoch = 0;
+    return MCAZ_OK;
+}
+
 static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clocks, int n, float* logits, float* values);
 
 int network_forward(az_engine* e, const uint8_t* tokens, const float* clocks, const uint8_t* /*active*/, int n, float* logits,
@@ -728,23 +1036,33 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
         N->events_used++;
         cudaEventRecord(ev0, st);
     }
-    if (int rc = build_schedule(e, n_pairs)) return rc;
-    ConvParams P;
-    P.bpad = bpad; P.relu = 1; P.sched = N->sched;
-    const int grid = N->sched_grid;
-    for (int L = 0; L < NLAYERS; ++L) {
-        const int src = L & 1, dst = src ^ 1;          // conv1: act0 -> act1, conv2: act1 -> act0 (+ residual act0)
-        P.layer = L;
-        P.bias = N->bias + L * C;
-        P.residual = (L & 1) ? N->act[dst] : nullptr;
-        P.out = N->act[dst];
-        conv3x3_tc_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(N->map_act[src], N->map_w, P);
+    if (N->per_layer) {
+        if (int rc = build_schedule(e, n_pairs)) return rc;
+        ConvParams P;
+        P.bpad = bpad; P.relu = 1; P.sched = N->sched;
+        const int grid = N->sched_grid;
+        for (int L = 0; L < NLAYERS; ++L) {
+            const int src = L & 1, dst = src ^ 1;          // conv1: act0 -> act1, conv2: act1 -> act0 (+ residual act0)
+            P.layer = L;
+            P.bias = N->bias + L * C;
+            P.residual = (L & 1) ? N->act[dst] : nullptr;
+            P.out = N->act[dst];
+            conv3x3_tc_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(N->map_act[src], N->map_w, P);
+            MCAZ_CHECK_LAUNCH();
+        }
+        e->launches += NLAYERS - 1;
+    } else {
+        if (int rc = build_tower_schedule(e, n_pairs)) return rc;
+        TowerParams T;
+        T.bias = N->bias; T.act0 = N->act[0]; T.act1 = N->act[1]; T.sched = N->tower_sched; T.flags = N->tower_flags;
+        T.bpad = bpad; T.n_pairs = n_pairs; T.epoch = ++N->epoch;
+        tower_tc_kernel<<<N->tower_grid, CONV_THREADS, TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, T);
         MCAZ_CHECK_LAUNCH();
     }
     if (ev1) cudaEventRecord(ev1, st);
     heads_kernel<<<num_sms(), HEADS_THREADS, HEADS_SMEM, st>>>(N->act[0], clocks, n, bpad, N->heads, logits, values);
     MCAZ_CHECK_LAUNCH();
-    e->launches += NLAYERS + 2;
+    e->launches += 3;
     return MCAZ_OK;
 }
 

@@ -32,6 +32,25 @@ def bn_perturbed_net():
     return net.eval()
 
 
+def test_fused_tower_kernel_matches_per_layer(mcaz_lib, monkeypatch):
+    """MCAZ_TOWER=fused runs the 18 convolutions as one data-flow-ordered persistent kernel; results must be
+    bit-identical to the one-launch-per-layer path (same MMAs, same order of accumulation)."""
+    from minitchess_alphazero_b200.policy import Network
+    torch.manual_seed(0)
+    net = Network().eval()
+    pos = np.ascontiguousarray(rc.random_positions(5, 3000)[:1000])
+    tokens, clocks = rc.tokenize(pos)
+    a = make_engine(net, n_games=1000)
+    la, va = a.network_forward(tokens, clocks)
+    monkeypatch.setenv('MCAZ_TOWER', 'fused')
+    b = make_engine(net, n_games=1000)
+    for _ in range(3):                      # repeated launches: epoch-stamped dependency flags
+        lb, vb = b.network_forward(tokens, clocks)
+        assert np.array_equal(la, lb) and np.array_equal(va, vb)
+    lb, vb = b.network_forward(tokens[:300], clocks[:300])
+    assert np.array_equal(la[:300], lb) and np.array_equal(va[:300], vb)
+
+
 def test_golden_forward_seed0(mcaz_lib):
     from minitchess_alphazero_b200.policy import Network
     g = load_golden('network_seed0.npz')
