@@ -19,80 +19,23 @@ using az::View;
 namespace mcaz {
 int num_sms();
 
-// ---- device RNG (throughput mode): Philox4x32-10 ------------------------------------------------
-struct Philox {
-    uint32_t key[2];
-    uint32_t ctr[4];
-    uint32_t out[4];
-    int have;
-    __device__ Philox(unsigned long long seed, uint32_t a, uint32_t b, uint32_t c) : have(0) {
-        key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
-        ctr[0] = 0; ctr[1] = a; ctr[2] = b; ctr[3] = c;
-    }
-    __device__ void round(uint32_t* c, const uint32_t* k) {
-        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-        uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
-        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-    }
-    __device__ void refill() {
-        uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]}, k[2] = {key[0], key[1]};
-#pragma unroll
-        for (int r = 0; r < 10; ++r) { round(c, k); k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u; }
-        out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
-        ctr[0] += 1;
-        have = 4;
-    }
-    __device__ uint32_t next() { if (!have) refill(); return out[--have]; }
-    __device__ double uniform() {  // (0,1)
-        uint32_t a = next() >> 5, b = next() >> 6;
-        return ((double)a * 67108864.0 + (double)b + 0.5) * (1.0 / 9007199254740992.0);
-    }
-    __device__ double normal() {
-        double u1 = uniform(), u2 = uniform();
-        return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
-    }
-    // Marsaglia-Tsang; shape < 1 via gamma(shape+1) * U^(1/shape)
-    __device__ double gamma(double shape) {
-        double boost = 1.0;
-        if (shape < 1.0) { boost = pow(uniform(), 1.0 / shape); shape += 1.0; }
-        double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
-        for (int it = 0; it < 64; ++it) {
-            double x = normal(), v = 1.0 + c * x;
-            if (v <= 0.0) continue;
-            v = v * v * v;
-            double u = uniform();
-            if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return boost * d * v;
-        }
-        return boost * d;
-    }
-};
-
-__global__ void __launch_bounds__(128) dirichlet_kernel(View V, unsigned long long sim_counter, double* noise) {
-    const int lane = threadIdx.x & 31;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < V.G; g += warps) {
-        if (V.game_result[g] != MC_ONGOING) continue;
-        const int t = 2 * g + (V.game_ply[g] & 1);
-        const uint32_t root = V.tree_root[t];
-        if (root == az::NONE) continue;
-        const int E = (int)(V.node_info[(size_t)t * V.NC + root] & 0xffffu);
-        double gam[3] = {0, 0, 0}, sum = 0;
-        for (int i = lane, k = 0; i < E; i += 32, ++k) {
-            Philox rng(V.seed, (uint32_t)g, (uint32_t)sim_counter, (uint32_t)(sim_counter >> 32) ^ ((uint32_t)i << 16));
-            gam[k] = rng.gamma((double)V.alpha);
-            sum += gam[k];
-        }
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        for (int i = lane, k = 0; i < E; i += 32, ++k) noise[(size_t)g * MC_MAX_MOVES + i] = gam[k] / sum;
-    }
-}
-
 __global__ void __launch_bounds__(128) select_expand_kernel(View V, const double* noise, uint8_t* noise_used) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < V.G; g += warps)
         az::select_expand_one(V, g, lane, noise, noise_used);
+}
+
+// az_search inner step: back up the previous simulation (if one is pending) and run the next descent in
+// the same launch -- both touch only this game's tree, so no grid-wide ordering is needed.
+__global__ void __launch_bounds__(128) search_step_kernel(View V, const float* logits, const float* values, int do_select) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < V.G; g += warps) {
+        az::backup_one(V, g, lane, logits, values, nullptr);
+        __syncwarp();
+        if (do_select) az::select_expand_one(V, g, lane, nullptr, nullptr);
+    }
 }
 
 __global__ void __launch_bounds__(128) backup_kernel(View V, const float* logits, const float* values, const float* priors) {
@@ -375,6 +318,7 @@ int az_create(const az_config* cfg, az_engine** out) {
     V.HC = hc;
     V.cpuct = cfg->cpuct; V.eps = cfg->dirichlet_epsilon; V.alpha = cfg->dirichlet_alpha;
     V.numpy1 = cfg->numpy1_dtype_flow; V.tau_change = cfg->tau_change; V.rules = cfg->rules; V.seed = cfg->seed;
+    V.device_rng = 0; V.sim_counter = 0;   // set per launch by az_search
     const size_t G = V.G, T = 2 * G, N = T * V.NC, E = T * V.EC;
     int rc = MCAZ_OK;
 #define A(ptr, n) if (!rc) rc = dev_alloc(e, &ptr, (n))
@@ -455,7 +399,7 @@ int az_set_positions(az_engine* e, const int32_t* game_ids, int n, const mc_stat
 int az_select_expand(az_engine* e, const double* root_noise, uint8_t* noise_used) {
     if (!e) return fail(MCAZ_EINVAL, "az_select_expand: null engine");
     if (e->leaf_pending) return fail(MCAZ_ESTATE, "az_select_expand: previous simulation not backed up");
-    const View& V = e->v;
+    View V = e->v;
     const double* noise = nullptr;
     if (root_noise) {
         if (is_device_pointer(root_noise)) noise = root_noise;
@@ -464,10 +408,8 @@ int az_select_expand(az_engine* e, const double* root_noise, uint8_t* noise_used
             noise = e->d_noise;
         }
     } else if (e->cfg.device_rng && V.eps > 0.0f) {
-        dirichlet_kernel<<<warp_grid(V.G, 128), 128, 0, e->stream>>>(V, e->sim_counter, e->d_noise);
-        MCAZ_CHECK_LAUNCH();
-        e->launches++;
-        noise = e->d_noise;
+        V.device_rng = 1;                     // Dirichlet noise drawn inside the kernel (Philox)
+        V.sim_counter = e->sim_counter;
     }
     e->sim_counter++;
     select_expand_kernel<<<warp_grid(V.G, 128), 128, 0, e->stream>>>(V, noise, e->d_noise_used);
@@ -520,11 +462,20 @@ int az_backup(az_engine* e, const float* logits, const float* values, const floa
 int az_search(az_engine* e, int n_sims) {
     if (!e || n_sims < 0) return fail(MCAZ_EINVAL, "az_search: bad argument");
     if (!e->net) return fail(MCAZ_ESTATE, "az_search: engine was created with network = 0 (use az_select_expand / az_backup)");
-    const View& V = e->v;
-    for (int s = 0; s < n_sims; ++s) {
-        if (int rc = az_select_expand(e, nullptr, nullptr)) return rc;
+    if (e->leaf_pending) return fail(MCAZ_ESTATE, "az_search: a simulation is pending (call az_backup first)");
+    View V = e->v;
+    V.device_rng = e->cfg.device_rng;
+    const int grid = warp_grid(V.G, 128);
+    for (int s = 0; s <= n_sims; ++s) {
+        // launch s: backup of simulation s-1 (none for s = 0) fused with the descent of simulation s
+        V.sim_counter = e->sim_counter;
+        const int do_select = s < n_sims;
+        if (do_select) e->sim_counter++;
+        search_step_kernel<<<grid, 128, 0, e->stream>>>(V, e->d_logits, e->d_values, do_select);
+        MCAZ_CHECK_LAUNCH();
+        e->launches++;
+        if (!do_select) break;
         if (int rc = network_forward(e, V.tokens, V.clocks, V.needs_eval, V.G, e->d_logits, e->d_values)) return rc;
-        if (int rc = az_backup(e, e->d_logits, e->d_values, nullptr)) return rc;
     }
     return engine_check_errors(e);
 }

@@ -20,6 +20,9 @@
 #include <stdint.h>
 
 #include "minitchess.cuh"
+#if defined(__CUDACC__)
+#include "philox.cuh"
+#endif
 
 namespace az {
 
@@ -54,6 +57,8 @@ struct View {
     // parameters
     float cpuct; float eps; float alpha; int numpy1; int tau_change; mc_rules rules;
     unsigned long long seed;
+    int device_rng;                 // throughput mode: root Dirichlet noise drawn in the select kernel
+    unsigned long long sim_counter; // RNG counter of the simulation being run
 };
 
 #if defined(__CUDA_ARCH__)
@@ -222,6 +227,118 @@ MC_HD uint32_t expand(const View& V, int g, int t, int lane, const mc_state& s, 
     return node;
 }
 
+#if defined(__CUDA_ARCH__)
+// Warp-cooperative expansion (device): lane = square in the mover's view.  Every lane generates the
+// legal targets of its own piece (bitboard attack sets), the queen-block and knight-block code counts
+// are prefix-summed across the warp, and each lane writes its codes -- already in ascending code order,
+// because codes are numbered by view square then (direction, distance) -- and zeroed statistics straight
+// into the tree's edge arrays.  Same results as the single-thread mc::generate used on the host.
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    *total = __shfl_sync(0xffffffffu, x, 31);
+    return x - v;
+}
+
+__device__ __forceinline__ uint32_t expand_warp(const View& V, int g, int t, int lane, const mc_state& s, uint8_t* kind,
+                                                double* value) {
+    const bool white = mc::white_to_move(s);
+    const mc::Sets st = mc::sets_of(s);
+    const int fv = lane;                                   // view square of this lane (30, 31: none)
+    const int sq = white ? fv : 29 - fv;
+    int type = 0;
+    uint32_t tg = 0;
+    if (fv < 30 && ((st.own >> sq) & 1u)) {
+        type = mc::piece_at(s, sq);
+        tg = mc::legal_targets(st, white, type, sq, V.rules);
+    }
+    const int r = fv < 30 ? fv / 5 : 0, f = fv < 30 ? fv % 5 : 0;
+    // width of this square's slice of the queen / knight code blocks (for the base code) and codes emitted
+    int qwidth = 0, nwidth = 0;
+    if (fv < 30) {
+        qwidth = mc::qcount(r, f);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) nwidth += mc::n_on(r, f, d) ? 1 : 0;
+    }
+    const bool knight = type == mc::KNIGHT;
+    int emit_n = mc::popc(tg);
+    if (type == mc::PAWN && V.rules.promo_multiplicity > 1)
+        emit_n += (V.rules.promo_multiplicity - 1) * mc::popc(tg & (white ? mc::RANK_6 : mc::RANK_1));
+    int tot_q, tot_n, tot_qw, tot_nw, tot_moves;
+    const int off_q = warp_excl_scan(knight ? 0 : emit_n, lane, &tot_q);
+    const int off_n = warp_excl_scan(knight ? emit_n : 0, lane, &tot_n);
+    const int qb = warp_excl_scan(qwidth, lane, &tot_qw);
+    const int nb = 430 + warp_excl_scan(nwidth, lane, &tot_nw);
+    warp_excl_scan(mc::popc(tg), lane, &tot_moves);
+    int E = tot_q + tot_n;
+    int res = mc::result_of(s, st, tot_moves, V.rules);
+    // lane 0 reserves the node and its edges
+    uint32_t node = NONE, off = 0;
+    int ok = 1;
+    if (lane == 0) {
+        const uint32_t n = V.tree_nodes[t];
+        off = V.tree_edges[t];
+        if (n >= (uint32_t)V.NC) { raise(V, ERR_NODE_CAP); ok = 0; }
+        else {
+            if (res == MC_ONGOING && off + (uint32_t)E > (uint32_t)V.EC) { raise(V, ERR_EDGE_CAP); ok = 2; }
+            node = n;
+        }
+    }
+    node = __shfl_sync(0xffffffffu, node, 0);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (ok == 0) { *kind = LEAF_TERMINAL; *value = 0.0; return NONE; }
+    const bool terminal = (res != MC_ONGOING) || ok == 2;
+    const bool decisive = (res == MC_WHITE_WINS || res == MC_BLACK_WINS);
+    if (terminal) E = 0;
+    const size_t gi = (size_t)t * V.NC + node;
+    if (!terminal && emit_n > 0) {
+        size_t w = (size_t)t * V.EC + off + (knight ? tot_q + off_n : off_q);
+        mc::emit_square_codes(fv, white, knight, tg, knight ? nb : qb, type == mc::PAWN, V.rules.promo_multiplicity,
+                              [&](uint16_t c) {
+                                  V.edge_Q[w] = 0.0; V.edge_N[w] = 0u; V.edge_P[w] = 0.0f; V.edge_child[w] = NONE; V.edge_code[w] = c;
+                                  ++w;
+                              });
+    }
+    if (!terminal && fv < 30) {
+        // tokens of FEN-order cell i = lane: Network.process_observation
+        int cell = 5 * (5 - lane / 5) + lane % 5;
+        if (!white) cell = 29 - cell;
+        const int ty = mc::piece_at(s, cell);
+        const bool mine = (st.own >> cell) & 1u;
+        V.tokens[(size_t)g * MC_TOKENS + lane] = (uint8_t)(mine ? ty : 0);
+        V.tokens[(size_t)g * MC_TOKENS + 30 + lane] = (uint8_t)(mine ? 0 : ty);
+    }
+    if (lane == 0) {
+        V.node_board[gi] = board_of(s);
+        V.node_meta[gi] = s.meta;
+        V.node_edge_off[gi] = off;
+        V.node_info[gi] = (uint32_t)E | (terminal ? INFO_TERMINAL : 0u) | ((terminal && decisive) ? INFO_DECISIVE : 0u);
+        V.tree_nodes[t] = node + 1;
+        V.tree_edges[t] = off + (uint32_t)E;
+        ht_insert(V, t, s, node);
+        if (!terminal) {
+            const double c = (double)mc::fullmove(s) + (white ? 0.0 : 0.5);
+            V.clocks[g] = (float)(c / 30.0);
+            V.leaf_states[g] = s;
+        }
+        count(V, C_NODES, 1);
+        count(V, C_EDGES, (unsigned long long)E);
+    }
+    __syncwarp();
+    if (terminal) { *kind = LEAF_TERMINAL; *value = decisive ? -1.0 : -0.0; }
+    else { *kind = LEAF_EVAL; *value = 0.0; }
+    return node;
+}
+#define AZ_EXPAND expand_warp
+#else
+#define AZ_EXPAND expand
+#endif
+
 // One simulation of game g down to its leaf (exp/agent.py:54-88 without the backup).
 // `noise`: per-game Dirichlet sample [MC_MAX_MOVES] or nullptr.
 MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise, uint8_t* noise_used) {
@@ -244,7 +361,7 @@ MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise
     if (node == NONE) {
         mc_state s = V.game_state[g];
         node = ht_find(V, t, s);
-        if (node == NONE) node = expand(V, g, t, lane, s, &kind, &value);
+        if (node == NONE) node = AZ_EXPAND(V, g, t, lane, s, &kind, &value);
         if (lane == 0 && node != NONE) V.tree_root[t] = node;
         AZ_SYNCWARP();
     }
@@ -264,7 +381,23 @@ MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise
         for (int o = 16; o > 0; o >>= 1) nsum_u += __shfl_xor_sync(0xffffffffu, nsum_u, o);
 #endif
         const double root_n = dsqrt((double)nsum_u);
-        const bool mix = (depth == 0) && (noise != nullptr) && (V.eps > 0.0f);
+        bool mix = (depth == 0) && (noise != nullptr) && (V.eps > 0.0f);
+#if defined(__CUDA_ARCH__)
+        // throughput mode: Dirichlet(alpha) over the root's edges drawn here, a fresh sample every simulation
+        double gam[3] = {0.0, 0.0, 0.0}, gsum = 1.0;
+        const bool dev_noise = (depth == 0) && (noise == nullptr) && V.device_rng && (V.eps > 0.0f);
+        if (dev_noise) {
+            double part = 0.0;
+            for (int i = lane, kk = 0; i < E && kk < 3; i += AZ_LANES, ++kk) {
+                mcaz::Philox rng(V.seed, (uint32_t)g, (uint32_t)V.sim_counter, (uint32_t)(V.sim_counter >> 32) ^ ((uint32_t)i << 16));
+                gam[kk] = rng.gamma((double)V.alpha);
+                part += gam[kk];
+            }
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            gsum = part;
+            mix = true;
+        }
+#endif
         double best_u = 0.0;
         int best_i = 0x7fffffff;
         for (int i = lane; i < E; i += AZ_LANES) {
@@ -272,8 +405,12 @@ MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise
             double x;
             if (mix) {
                 // P = (1-eps)*P + eps*dirichlet: float32 product, float64 sum (exp/agent.py:82 under NEP 50)
-                double pn = dadd((double)fmul((float)(1.0 - (double)V.eps), p),
-                                 dmul((double)V.eps, noise[(size_t)g * MC_MAX_MOVES + i]));
+#if defined(__CUDA_ARCH__)
+                const double nz = dev_noise ? gam[(i - lane) / AZ_LANES] / gsum : noise[(size_t)g * MC_MAX_MOVES + i];
+#else
+                const double nz = noise[(size_t)g * MC_MAX_MOVES + i];
+#endif
+                double pn = dadd((double)fmul((float)(1.0 - (double)V.eps), p), dmul((double)V.eps, nz));
                 x = dmul(dmul((double)V.cpuct, pn), root_n);
             } else if (V.numpy1) {
                 // numpy 1.x value-based casting: float32 array * float64 scalar stays float32 (Q6)
@@ -311,7 +448,7 @@ MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise
             const bool white = mc::white_to_move(ps);
             mc_state cs = mc::apply_move(ps, white ? fv : 29 - fv, white ? tv : 29 - tv);
             child = ht_find(V, t, cs);
-            if (child == NONE) child = expand(V, g, t, lane, cs, &kind, &value);
+            if (child == NONE) child = AZ_EXPAND(V, g, t, lane, cs, &kind, &value);
             if (lane == 0 && child != NONE) V.edge_child[e] = child;
             AZ_SYNCWARP();
             if (child == NONE) break;

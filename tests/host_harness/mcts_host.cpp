@@ -46,7 +46,7 @@ extern "C" {
 
 const char* mcaz_last_error(void) { return g_err.c_str(); }
 int mcaz_abi_version(void) { return MCAZ_ABI_VERSION; }
-unsigned long long mcaz_kernel_launches(void) { return 0; }
+uint64_t mcaz_kernel_launches(void) { return 0; }
 
 void mc_default_rules(mc_rules* r) { r->pawn_double_step = 0; r->promo_multiplicity = 1; r->max_fullmoves = 30; r->insufficient_material = 1; r->fivefold_repetition = 1; }
 
@@ -70,6 +70,7 @@ int az_create(const az_config* cfg, az_engine** out) {
     int hc = 64; while (hc < 2 * V.NC) hc <<= 1; V.HC = hc;
     V.cpuct = cfg->cpuct; V.eps = cfg->dirichlet_epsilon; V.alpha = cfg->dirichlet_alpha;
     V.numpy1 = cfg->numpy1_dtype_flow; V.tau_change = cfg->tau_change; V.rules = cfg->rules; V.seed = cfg->seed;
+    V.device_rng = 0; V.sim_counter = 0;
     size_t G = V.G, T = 2 * G, N = T * V.NC, E = T * V.EC;
     alloc(e, &V.game_state, G); alloc(e, &V.game_result, G); alloc(e, &V.game_ply, G); alloc(e, &V.game_start_ply, G);
     alloc(e, &V.game_hist, G * az::HIST); alloc(e, &V.game_hist_len, G);
