@@ -206,6 +206,10 @@ typedef struct az_replay_tuple {
 /* Moves up to `max` finished-game tuples into out (host or device); *n_out = count.         */
 int az_drain_replay(az_engine* e, az_replay_tuple* out, int max, int* n_out);
 
+/* Learner-side collate on the device (exp/learner.py:23-41 collate_fn): n packed tuples -> dense pi
+ * [n x 554] float32, tokens [n x 60] int64 (= channels [n,2,6,5]), clock [n] and reward [n] float32.    */
+int az_collate(const az_replay_tuple* tuples, int n, float* pi, int64_t* tokens, float* clock, float* reward);
+
 /* Counters since creation: [0] simulations, [1] network evaluations, [2] terminal leaves,
  * [3] moves played, [4] games finished, [5] nodes allocated, [6] edges allocated,
  * [7] kernels launched by this library.                                                     */

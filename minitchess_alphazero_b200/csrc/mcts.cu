@@ -633,3 +633,64 @@ int az_network_forward(az_engine* e, const uint8_t* tokens, const float* clocks,
 }
 
 }  // extern "C"
+
+// ---- learner-side collate (exp/learner.py:23-41) on the device -----------------------------------------
+// Packed replay tuples -> the four training tensors collate_fn builds: dense pi [n,554] (float32, pi
+// scattered to the legal codes), tokens [n,2,6,5] (int64, Network.process_observation), clock [n,1],
+// reward [n,1].  One warp per tuple.
+namespace mcaz {
+__global__ void __launch_bounds__(128) collate_kernel(const az_replay_tuple* __restrict__ tuples, int n, float* __restrict__ pi,
+                                                      long long* __restrict__ tokens, float* __restrict__ clock,
+                                                      float* __restrict__ reward) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        const az_replay_tuple* t = tuples + i;
+        float* row = pi + (size_t)i * MC_NUM_ACTIONS;
+        for (int k = lane; k < MC_NUM_ACTIONS; k += 32) row[k] = 0.f;
+        __syncwarp();
+        const int E = t->n_legal;
+        for (int k = lane; k < E; k += 32) row[t->codes[k]] = t->pi[k];
+        const mc_state s = t->observation;
+        if (lane < 30) {
+            const bool white = mc::white_to_move(s);
+            const uint32_t occ = s.pl0 | s.pl1 | s.pl2;
+            const uint32_t mine = white ? (s.white & occ) : (occ & ~s.white);
+            int cell = 5 * (5 - lane / 5) + lane % 5;
+            if (!white) cell = 29 - cell;
+            const int ty = mc::piece_at(s, cell);
+            const bool m = (mine >> cell) & 1u;
+            tokens[(size_t)i * MC_TOKENS + lane] = m ? ty : 0;
+            tokens[(size_t)i * MC_TOKENS + 30 + lane] = m ? 0 : ty;
+        }
+        if (lane == 0) {
+            const double c = (double)mc::fullmove(s) + (mc::white_to_move(s) ? 0.0 : 0.5);
+            clock[i] = (float)(c / 30.0);
+            reward[i] = (float)t->reward;
+        }
+    }
+}
+}  // namespace mcaz
+
+extern "C" int az_collate(const az_replay_tuple* tuples, int n, float* pi, int64_t* tokens, float* clock, float* reward) {
+    if (n < 0 || (n > 0 && (!tuples || !pi || !tokens || !clock || !reward))) return fail(MCAZ_EINVAL, "az_collate: bad argument");
+    if (int rc = require_device()) return rc;
+    if (n == 0) return MCAZ_OK;
+    cudaStream_t st = 0;
+    Scratch& sc = thread_scratch();
+    sc.begin();
+    In<az_replay_tuple> in; Out<float> op; Out<int64_t> ot; Out<float> oc; Out<float> orw;
+    if (int rc = in.init(tuples, n, st, sc)) return rc;
+    if (int rc = op.init(pi, (size_t)n * MC_NUM_ACTIONS, st, sc)) return rc;
+    if (int rc = ot.init(tokens, (size_t)n * MC_TOKENS, st, sc)) return rc;
+    if (int rc = oc.init(clock, n, st, sc)) return rc;
+    if (int rc = orw.init(reward, n, st, sc)) return rc;
+    collate_kernel<<<warp_grid(n, 128), 128, 0, st>>>(in.ptr, n, op.ptr, reinterpret_cast<long long*>(ot.ptr), oc.ptr, orw.ptr);
+    MCAZ_CHECK_LAUNCH();
+    if (int rc = op.finish(st)) return rc;
+    if (int rc = ot.finish(st)) return rc;
+    if (int rc = oc.finish(st)) return rc;
+    if (int rc = orw.finish(st)) return rc;
+    MCAZ_CUDA(cudaStreamSynchronize(st));
+    return MCAZ_OK;
+}

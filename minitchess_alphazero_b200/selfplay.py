@@ -24,6 +24,27 @@ def replay_to_episode_dicts(tuples):
     return out
 
 
+def collate_device(tuples, device='cuda'):
+    """exp/learner.py:23-41 `collate_fn` for packed replay tuples, on the GPU (az_collate): returns
+    [pi float32 (n,554), channels int64 (n,2,6,5), clock float32 (n,1), reward float32 (n,1)] as CUDA tensors.
+    `tuples` is a REPLAY_DTYPE numpy array or a uint8 CUDA tensor [n, 604]."""
+    import ctypes
+    from . import _lib
+    from .engine import REPLAY_DTYPE
+    if isinstance(tuples, np.ndarray):
+        n = len(tuples)
+        src = np.ascontiguousarray(tuples, dtype=REPLAY_DTYPE)
+    else:
+        n = tuples.shape[0]
+        src = tuples.contiguous()
+    pi = torch.empty(n, 554, dtype=torch.float32, device=device)
+    channels = torch.empty(n, 2, 6, 5, dtype=torch.int64, device=device)
+    clock = torch.empty(n, 1, dtype=torch.float32, device=device)
+    reward = torch.empty(n, 1, dtype=torch.float32, device=device)
+    _lib.check(_lib.lib().az_collate(_lib.ptr(src), n, _lib.ptr(pi), _lib.ptr(channels), _lib.ptr(clock), _lib.ptr(reward)))
+    return [pi, channels, clock, reward]
+
+
 class BatchedSelfPlay:
     """`n_games` concurrent games x `num_simulations` per move in throughput mode: Philox Dirichlet
     noise, move sampling, replay recording and game restarts all on the device.
