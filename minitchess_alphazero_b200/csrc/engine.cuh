@@ -41,6 +41,7 @@ int engine_check_errors(az_engine* e);   // reads the device error flag (synchro
 int network_create(az_engine* e);
 void network_destroy(az_engine* e);
 int network_set_weights(az_engine* e, const float* flat_device);
+int network_forward_search(az_engine* e, const az::View& V, float* values);
 int network_forward(az_engine* e, const uint8_t* tokens, const float* clocks, const uint8_t* active, int n,
                     float* logits, float* values);
 }  // namespace mcaz

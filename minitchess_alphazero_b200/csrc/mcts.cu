@@ -471,11 +471,11 @@ int az_search(az_engine* e, int n_sims) {
         V.sim_counter = e->sim_counter;
         const int do_select = s < n_sims;
         if (do_select) e->sim_counter++;
-        search_step_kernel<<<grid, 128, 0, e->stream>>>(V, e->d_logits, e->d_values, do_select);
+        search_step_kernel<<<grid, 128, 0, e->stream>>>(V, nullptr, e->d_values, do_select);   // priors: written by the policy head
         MCAZ_CHECK_LAUNCH();
         e->launches++;
         if (!do_select) break;
-        if (int rc = network_forward(e, V.tokens, V.clocks, V.needs_eval, V.G, e->d_logits, e->d_values)) return rc;
+        if (int rc = network_forward_search(e, V, e->d_values)) return rc;
     }
     return engine_check_errors(e);
 }

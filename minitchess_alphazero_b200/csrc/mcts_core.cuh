@@ -478,7 +478,7 @@ MC_HD void backup_one(const View& V, int g, int lane, const float* logits, const
         const size_t e0 = ebase + V.node_edge_off[nbase + node];
         if (priors) {
             for (int i = lane; i < E; i += AZ_LANES) V.edge_P[e0 + i] = priors[(size_t)g * MC_MAX_MOVES + i];
-        } else {
+        } else if (logits) {
             const float* lg = logits + (size_t)g * MC_NUM_ACTIONS;
             float m = -INFINITY;
             for (int i = lane; i < E; i += AZ_LANES) m = fmaxf(m, lg[V.edge_code[e0 + i]]);
@@ -491,7 +491,7 @@ MC_HD void backup_one(const View& V, int g, int lane, const float* logits, const
             for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
 #endif
             for (int i = lane; i < E; i += AZ_LANES) V.edge_P[e0 + i] = expf(lg[V.edge_code[e0 + i]] - m) / sum;
-        }
+        }   // else: the policy head already wrote the priors into edge_P (heads_legal_kernel)
         value = (double)values[g];
     }
     if (lane == 0) {

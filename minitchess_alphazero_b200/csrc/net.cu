@@ -610,7 +610,7 @@ __global__ void prep_tower_kernel(const float* __restrict__ flat, __nv_bfloat16*
 // stem table: T[tap][combo][c]; a square holds at most one piece, so the two token channels collapse into
 // 13 combinations: 0 = empty, 1..6 = mover's piece of that type, 7..12 = opponent's piece.  The entry is the
 // BatchNorm-folded contribution of that square through tap `t` to output channel c.
-__global__ void prep_stem_kernel(const float* __restrict__ flat, float* __restrict__ table, float* __restrict__ bias) {
+__global__ void prep_stem_kernel(const float* __restrict__ flat, __nv_bfloat16* __restrict__ table, float* __restrict__ bias) {
     const int c = threadIdx.x, combo = blockIdx.x % 13, t = blockIdx.x / 13;
     const float* sw = flat + OFF_STEM;
     const float *sb = sw + 18432, *gamma = sb + 256, *beta = gamma + 256, *mean = beta + 256, *var = mean + 256;
@@ -620,7 +620,7 @@ __global__ void prep_stem_kernel(const float* __restrict__ flat, float* __restri
     float acc = 0.f;
     for (int e = 0; e < 4; ++e)
         acc += sw[((size_t)c * 8 + e) * 9 + t] * emb[tok0 * 4 + e] + sw[((size_t)c * 8 + 4 + e) * 9 + t] * emb[tok1 * 4 + e];
-    table[((size_t)t * 13 + combo) * C + c] = acc * scale;
+    table[((size_t)t * 13 + combo) * C + c] = __float2bfloat16(acc * scale);
     if (blockIdx.x == 0) bias[c] = (sb[c] - mean[c]) * scale + beta[c];
 }
 
@@ -662,9 +662,10 @@ __global__ void prep_heads_kernel(const float* __restrict__ flat, HeadWeights H)
 }
 
 // ---------------------------------------------------------------------------------- stem
-// One warp per (board, position): 32 lanes x 8 channels; one 1 KB table row per valid tap.
+// One warp per (board, position): 32 lanes x 8 channels; one 512-byte bf16 table row per valid tap,
+// accumulated in fp32.  The table (60 KB) is L1-resident; L1 wavefronts bound this kernel.
 __global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ tokens, int n, int bpad,
-                                                   const float* __restrict__ table, const float* __restrict__ bias,
+                                                   const __nv_bfloat16* __restrict__ table, const float* __restrict__ bias,
                                                    __nv_bfloat16* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -681,10 +682,13 @@ __global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ t
                 if (!tap_valid(pos, t, src)) continue;
                 const int mine = tk[src], theirs = tk[30 + src];
                 const int combo = mine ? mine : (theirs ? 6 + theirs : 0);
-                const float* r = table + ((size_t)t * 13 + combo) * C + lane * 8;
-                const float4 a0 = *reinterpret_cast<const float4*>(r), a1 = *reinterpret_cast<const float4*>(r + 4);
-                acc[0] += a0.x; acc[1] += a0.y; acc[2] += a0.z; acc[3] += a0.w;
-                acc[4] += a1.x; acc[5] += a1.y; acc[6] += a1.z; acc[7] += a1.w;
+                const uint4 r = __ldg(reinterpret_cast<const uint4*>(table + ((size_t)t * 13 + combo) * C + lane * 8));
+                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    acc[2 * h] += __uint_as_float(rw[h] << 16);
+                    acc[2 * h + 1] += __uint_as_float(rw[h] & 0xffff0000u);
+                }
             }
         }
         uint32_t pk[4];
@@ -698,40 +702,30 @@ __global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ t
 }
 
 // ---------------------------------------------------------------------------------- heads
-// Persistent CTAs of 16 warps; plinear^T (135 KB) and vlinear.0^T (31 KB) staged in shared memory once
-// per CTA; one warp per board.  1x1 convolutions: lane = board position (30 of 32 lanes), each lane
-// walks its own 512-byte channel row; the dense layers keep 18 (policy) / 8 (value) independent
-// accumulators per lane so shared-memory latency is pipelined.
-constexpr int HEADS_THREADS = 512;
+// One warp per board.  1x1 convolutions: lane = board position (30 of 32 lanes), each lane walks its own
+// 512-byte channel row.  Dense layers: lane owns outputs lane + 32k and keeps 18 (policy) / 8 (value)
+// independent accumulators; the transposed weight matrices (135 KB + 31 KB) are read through the
+// read-only L1 path -- they stay L1/L2 resident, which costs no staging phase and leaves room for
+// several CTAs per SM.
+constexpr int HEADS_THREADS = 256;
 constexpr int HEADS_WARPS = HEADS_THREADS / 32;
-constexpr int HEADS_SMEM = (61 * 554 + 554 + 31 * 256 + 256 + 256 + 3 * 256 + 8 + HEADS_WARPS * 96) * 4;
 
-__global__ void __launch_bounds__(HEADS_THREADS, 1)
+__global__ void __launch_bounds__(HEADS_THREADS, 4)
 heads_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ clocks, int n, int bpad, HeadWeights H,
              float* __restrict__ logits, float* __restrict__ values) {
-    extern __shared__ float hs[];
-    float* s_plt = hs;                       // [61][554]
-    float* s_plb = s_plt + 61 * 554;         // [554]
-    float* s_v1t = s_plb + 554;              // [31][256]
-    float* s_v1b = s_v1t + 31 * 256;         // [256]
-    float* s_v2 = s_v1b + 256;               // [256]
-    float* s_cw = s_v2 + 256;                // [3][256]: policy conv rows 0,1 and value conv
-    float* s_cb = s_cw + 3 * 256;            // [8]: pb0, pb1, vb, v2b
-    float* s_in = s_cb + 8;                  // per warp [96]: px[60], clock, vx[30], clock
-    for (int i = threadIdx.x; i < 61 * 554; i += HEADS_THREADS) s_plt[i] = H.plt[i];
-    for (int i = threadIdx.x; i < 554; i += HEADS_THREADS) s_plb[i] = H.plb[i];
-    for (int i = threadIdx.x; i < 31 * 256; i += HEADS_THREADS) s_v1t[i] = H.v1t[i];
-    for (int i = threadIdx.x; i < 256; i += HEADS_THREADS) { s_v1b[i] = H.v1b[i]; s_v2[i] = H.v2[i]; s_cw[i] = H.pw[i]; s_cw[256 + i] = H.pw[256 + i]; s_cw[512 + i] = H.vw[i]; }
-    if (threadIdx.x == 0) { s_cb[0] = H.pb[0]; s_cb[1] = H.pb[1]; s_cb[2] = H.vb[0]; s_cb[3] = H.v2b[0]; }
+    __shared__ float s_cw[3 * C];             // policy conv rows 0,1 and value conv
+    __shared__ float s_in[HEADS_WARPS][96];   // per warp: px[60], clock, vx[30], clock
+    for (int i = threadIdx.x; i < C; i += HEADS_THREADS) { s_cw[i] = H.pw[i]; s_cw[C + i] = H.pw[C + i]; s_cw[2 * C + i] = H.vw[i]; }
     __syncthreads();
+    const float pb0 = __ldg(H.pb), pb1 = __ldg(H.pb + 1), vb = __ldg(H.vb), v2b = __ldg(H.v2b);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* in = s_in + warp * 96;
+    float* in = s_in[warp];
     const int pos = lane < NPOS ? lane : NPOS - 1;
     for (int board = blockIdx.x * HEADS_WARPS + warp; board < n; board += gridDim.x * HEADS_WARPS) {
         // ---- 1x1 convolutions 256 -> {2, 1} for this lane's position
         const uint4* row = reinterpret_cast<const uint4*>(act + ((size_t)pos * bpad + board) * C);
         float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-#pragma unroll 1
+#pragma unroll 2
         for (int c4 = 0; c4 < C / 8; c4 += 4) {
             uint4 raw[4];
 #pragma unroll
@@ -744,15 +738,15 @@ heads_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ cl
                 for (int h = 0; h < 4; ++h) {
                     const float x0 = __uint_as_float(rw[h] << 16), x1 = __uint_as_float(rw[h] & 0xffff0000u);
                     d0 += x0 * w0[2 * h] + x1 * w0[2 * h + 1];
-                    d1 += x0 * w0[256 + 2 * h] + x1 * w0[256 + 2 * h + 1];
-                    d2 += x0 * w0[512 + 2 * h] + x1 * w0[512 + 2 * h + 1];
+                    d1 += x0 * w0[C + 2 * h] + x1 * w0[C + 2 * h + 1];
+                    d2 += x0 * w0[2 * C + 2 * h] + x1 * w0[2 * C + 2 * h + 1];
                 }
             }
         }
         if (lane < NPOS) {
-            in[lane] = fmaxf(d0 + s_cb[0], 0.f);
-            in[30 + lane] = fmaxf(d1 + s_cb[1], 0.f);
-            in[61 + lane] = fmaxf(d2 + s_cb[2], 0.f);
+            in[lane] = fmaxf(d0 + pb0, 0.f);
+            in[30 + lane] = fmaxf(d1 + pb1, 0.f);
+            in[61 + lane] = fmaxf(d2 + vb, 0.f);
         } else if (lane == 30) {
             const float ck = clocks[board];
             in[60] = ck;
@@ -762,36 +756,128 @@ heads_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ cl
         // ---- policy: 554 logits = plinear([px, clock]); lane owns outputs lane + 32 k
         float acc[18];
 #pragma unroll
-        for (int k = 0; k < 18; ++k) acc[k] = (lane + 32 * k < MC_NUM_ACTIONS) ? s_plb[lane + 32 * k] : 0.f;
-#pragma unroll 1
+        for (int k = 0; k < 18; ++k) acc[k] = (lane + 32 * k < MC_NUM_ACTIONS) ? __ldg(H.plb + lane + 32 * k) : 0.f;
+        const bool tail = lane < MC_NUM_ACTIONS - 17 * 32;
+#pragma unroll 2
         for (int j = 0; j < 61; ++j) {
             const float xj = in[j];
-            const float* wr = s_plt + j * 554 + lane;
+            const float* wr = H.plt + j * 554 + lane;
 #pragma unroll
-            for (int k = 0; k < 17; ++k) acc[k] += xj * wr[32 * k];
-            if (lane < MC_NUM_ACTIONS - 17 * 32) acc[17] += xj * wr[32 * 17];
+            for (int k = 0; k < 17; ++k) acc[k] += xj * __ldg(wr + 32 * k);
+            if (tail) acc[17] += xj * __ldg(wr + 32 * 17);
         }
         float* lg = logits + (size_t)board * MC_NUM_ACTIONS + lane;
 #pragma unroll
         for (int k = 0; k < 17; ++k) lg[32 * k] = acc[k];
-        if (lane < MC_NUM_ACTIONS - 17 * 32) lg[32 * 17] = acc[17];
+        if (tail) lg[32 * 17] = acc[17];
         // ---- value: tanh(v2 . relu(v1 [vx, clock] + b1) + b2)
         float hv[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) hv[k] = s_v1b[lane + 32 * k];
-#pragma unroll 1
+        for (int k = 0; k < 8; ++k) hv[k] = __ldg(H.v1b + lane + 32 * k);
+#pragma unroll 2
         for (int j = 0; j < 31; ++j) {
             const float xj = in[61 + j];
-            const float* wr = s_v1t + j * 256 + lane;
+            const float* wr = H.v1t + j * 256 + lane;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) hv[k] += xj * wr[32 * k];
+            for (int k = 0; k < 8; ++k) hv[k] += xj * __ldg(wr + 32 * k);
         }
         float part = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) part += fmaxf(hv[k], 0.f) * s_v2[lane + 32 * k];
+        for (int k = 0; k < 8; ++k) part += fmaxf(hv[k], 0.f) * __ldg(H.v2 + lane + 32 * k);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0) values[board] = tanhf(part + s_cb[3]);
+        if (lane == 0) values[board] = tanhf(part + v2b);
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------- heads, search form
+// Inside az_search only the logits of the leaf's legal moves are ever read (exp/agent.py:68 takes
+// p[0][legal_moves].softmax(0)), ~9 of 554.  This variant computes just those, applies the legal-move
+// softmax and writes the priors straight into the new node's edges; the value goes to values[g].
+// One warp per game slot.
+__global__ void __launch_bounds__(HEADS_THREADS, 4)
+heads_legal_kernel(const __nv_bfloat16* __restrict__ act, int bpad, HeadWeights H, az::View V, float* __restrict__ values) {
+    __shared__ float s_cw[3 * C];
+    __shared__ float s_in[HEADS_WARPS][96];
+    for (int i = threadIdx.x; i < C; i += HEADS_THREADS) { s_cw[i] = H.pw[i]; s_cw[C + i] = H.pw[C + i]; s_cw[2 * C + i] = H.vw[i]; }
+    __syncthreads();
+    const float pb0 = __ldg(H.pb), pb1 = __ldg(H.pb + 1), vb = __ldg(H.vb), v2b = __ldg(H.v2b);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* in = s_in[warp];
+    const int pos = lane < NPOS ? lane : NPOS - 1;
+    for (int g = blockIdx.x * HEADS_WARPS + warp; g < V.G; g += gridDim.x * HEADS_WARPS) {
+        if (!V.needs_eval[g]) continue;
+        const uint4* row = reinterpret_cast<const uint4*>(act + ((size_t)pos * bpad + g) * C);
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll 2
+        for (int c4 = 0; c4 < C / 8; c4 += 4) {
+            uint4 raw[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) raw[u] = row[c4 + u];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t rw[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+                const float* w0 = s_cw + (c4 + u) * 8;
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const float x0 = __uint_as_float(rw[h] << 16), x1 = __uint_as_float(rw[h] & 0xffff0000u);
+                    d0 += x0 * w0[2 * h] + x1 * w0[2 * h + 1];
+                    d1 += x0 * w0[C + 2 * h] + x1 * w0[C + 2 * h + 1];
+                    d2 += x0 * w0[2 * C + 2 * h] + x1 * w0[2 * C + 2 * h + 1];
+                }
+            }
+        }
+        if (lane < NPOS) {
+            in[lane] = fmaxf(d0 + pb0, 0.f);
+            in[30 + lane] = fmaxf(d1 + pb1, 0.f);
+            in[61 + lane] = fmaxf(d2 + vb, 0.f);
+        } else if (lane == 30) {
+            const float ck = V.clocks[g];
+            in[60] = ck;
+            in[91] = ck;
+        }
+        __syncwarp();
+        // ---- legal logits -> softmax -> edge_P of the leaf
+        const int t = 2 * g + (V.game_ply[g] & 1);
+        const uint32_t node = V.leaf_node[g];
+        const size_t gi = (size_t)t * V.NC + node;
+        const int E = (int)(V.node_info[gi] & 0xffffu);
+        const size_t e0 = (size_t)t * V.EC + V.node_edge_off[gi];
+        float lg[3] = {-INFINITY, -INFINITY, -INFINITY};
+        float m = -INFINITY;
+        for (int i = lane, kk = 0; i < E && kk < 3; i += 32, ++kk) {
+            const int code = V.edge_code[e0 + i];
+            float acc = __ldg(H.plb + code);
+#pragma unroll 4
+            for (int j = 0; j < 61; ++j) acc += in[j] * __ldg(H.plt + j * 554 + code);
+            lg[kk] = acc;
+            m = fmaxf(m, acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float sum = 0.f;
+        for (int i = lane, kk = 0; i < E && kk < 3; i += 32, ++kk) sum += expf(lg[kk] - m);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        for (int i = lane, kk = 0; i < E && kk < 3; i += 32, ++kk) V.edge_P[e0 + i] = expf(lg[kk] - m) / sum;
+        // ---- value
+        float hv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hv[k] = __ldg(H.v1b + lane + 32 * k);
+#pragma unroll 2
+        for (int j = 0; j < 31; ++j) {
+            const float xj = in[61 + j];
+            const float* wr = H.v1t + j * 256 + lane;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) hv[k] += xj * __ldg(wr + 32 * k);
+        }
+        float part = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) part += fmaxf(hv[k], 0.f) * __ldg(H.v2 + lane + 32 * k);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) values[g] = tanhf(part + v2b);
         __syncwarp();
     }
 }
@@ -826,7 +912,8 @@ struct Network {
     __nv_bfloat16 *act[2] = {nullptr, nullptr};
     __nv_bfloat16* w = nullptr;        // [18][9][256][256]
     float* bias = nullptr;             // [18][256]
-    float *stem_table = nullptr, *stem_bias = nullptr;
+    __nv_bfloat16* stem_table = nullptr;   // [9 taps][13 square states][256] bf16
+    float* stem_bias = nullptr;
     float* head_pool = nullptr;
     HeadWeights heads{};
     CUtensorMap map_act[2], map_w;
@@ -869,7 +956,7 @@ int network_create(az_engine* e) {
     e->net = N;
     MCAZ_CUDA(cudaMalloc(&N->w, (size_t)NLAYERS * 9 * C * C * sizeof(__nv_bfloat16)));
     MCAZ_CUDA(cudaMalloc(&N->bias, (size_t)NLAYERS * C * sizeof(float)));
-    MCAZ_CUDA(cudaMalloc(&N->stem_table, (size_t)9 * 13 * C * sizeof(float)));
+    MCAZ_CUDA(cudaMalloc(&N->stem_table, (size_t)9 * 13 * C * sizeof(__nv_bfloat16)));
     MCAZ_CUDA(cudaMalloc(&N->stem_bias, C * sizeof(float)));
     const size_t head_floats = 512 + 2 + 256 + 1 + 61 * 554 + 554 + 31 * 256 + 256 + 256 + 1 + 16;
     MCAZ_CUDA(cudaMalloc(&N->head_pool, head_floats * sizeof(float)));
@@ -888,7 +975,6 @@ int network_create(az_engine* e) {
     MCAZ_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
     MCAZ_CUDA(cudaFuncSetAttribute(tower_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_SMEM));
     { const char* m = getenv("MCAZ_TOWER"); N->per_layer = !(m && std::strcmp(m, "fused") == 0); }
-    MCAZ_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_SMEM));
     return net_alloc_acts(e, std::min(e->v.G, MAX_CHUNK_BOARDS));
 }
 
@@ -1000,7 +1086,8 @@ static int build_tower_schedule(az_engine* e, int n_pairs) {
     return MCAZ_OK;
 }
 
-static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clocks, int n, float* logits, float* values);
+static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clocks, int n, float* logits, float* values,
+                         const az::View* search_view);
 
 int network_forward(az_engine* e, const uint8_t* tokens, const float* clocks, const uint8_t* /*active*/, int n, float* logits,
                     float* values) {
@@ -1008,13 +1095,15 @@ int network_forward(az_engine* e, const uint8_t* tokens, const float* clocks, co
     if (!N->have_weights) return fail(MCAZ_ESTATE, "network weights have not been set (az_set_weights)");
     for (int off = 0; off < n; off += MAX_CHUNK_BOARDS) {
         const int m = std::min(MAX_CHUNK_BOARDS, n - off);
-        if (int rc = forward_chunk(e, tokens + (size_t)off * MC_TOKENS, clocks + off, m, logits + (size_t)off * MC_NUM_ACTIONS, values + off))
+        if (int rc = forward_chunk(e, tokens + (size_t)off * MC_TOKENS, clocks + off, m, logits + (size_t)off * MC_NUM_ACTIONS, values + off,
+                                   nullptr))
             return rc;
     }
     return MCAZ_OK;
 }
 
-static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clocks, int n, float* logits, float* values) {
+static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clocks, int n, float* logits, float* values,
+                         const az::View* search_view) {
     Network* N = e->net;
     if (int rc = net_alloc_acts(e, n)) return rc;
     const int n_pairs = (n + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = 2 * n_pairs, bpad = N->capacity;
@@ -1060,10 +1149,21 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
         MCAZ_CHECK_LAUNCH();
     }
     if (ev1) cudaEventRecord(ev1, st);
-    heads_kernel<<<num_sms(), HEADS_THREADS, HEADS_SMEM, st>>>(N->act[0], clocks, n, bpad, N->heads, logits, values);
+    if (search_view)
+        heads_legal_kernel<<<std::min(num_sms() * 4, (n + HEADS_WARPS - 1) / HEADS_WARPS), HEADS_THREADS, 0, st>>>(N->act[0], bpad, N->heads, *search_view, values);
+    else
+        heads_kernel<<<std::min(num_sms() * 4, (n + HEADS_WARPS - 1) / HEADS_WARPS), HEADS_THREADS, 0, st>>>(N->act[0], clocks, n, bpad, N->heads, logits, values);
     MCAZ_CHECK_LAUNCH();
     e->launches += 3;
     return MCAZ_OK;
+}
+
+// Leaf evaluation inside az_search: the engine's own leaf batch (slot = game), priors written into the tree.
+int network_forward_search(az_engine* e, const az::View& V, float* values) {
+    Network* N = e->net;
+    if (!N->have_weights) return fail(MCAZ_ESTATE, "network weights have not been set (az_set_weights)");
+    if (V.G > MAX_CHUNK_BOARDS) return fail(MCAZ_EINVAL, "az_search: more than 8192 games per engine are not supported yet");
+    return forward_chunk(e, V.tokens, V.clocks, V.G, nullptr, values, &V);
 }
 
 int network_profile(az_engine* e, int on, double* avg_ms_per_conv_launch, int* n_forwards) {
