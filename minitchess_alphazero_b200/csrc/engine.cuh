@@ -31,6 +31,7 @@ struct az_engine {
     unsigned long long* d_replay_count = nullptr;
     size_t replay_capacity = 0;
     unsigned long long sim_counter = 0;    // feeds the device RNG
+    unsigned long long move_counter = 0;   // feeds the device RNG of the move choice
     mcaz::Network* net = nullptr;
     uint64_t launches = 0;
 };

@@ -562,9 +562,8 @@ int az_play_device(az_engine* e) {
     if (!e) return fail(MCAZ_EINVAL, "az_play_device: null engine");
     if (e->leaf_pending) return fail(MCAZ_ESTATE, "az_play_device: a simulation is pending");
     const View& V = e->v;
-    static unsigned long long move_counter = 0;
     play_device_kernel<<<warp_grid(V.G, 128), 128, 0, e->stream>>>(V, e->d_record, e->d_replay, e->d_replay_count,
-                                                                   (unsigned long long)e->replay_capacity, ++move_counter, start_state());
+                                                                   (unsigned long long)e->replay_capacity, ++e->move_counter, start_state());
     MCAZ_CHECK_LAUNCH();
     restart_finished_kernel<<<std::min(V.G, num_sms() * 8), 256, 0, e->stream>>>(V, start_state());
     MCAZ_CHECK_LAUNCH();
