@@ -130,6 +130,9 @@ typedef struct az_config {
     uint64_t seed;
     mc_rules rules;
     int32_t network;           /* 0 = external evaluator only; 1 = built-in bf16 tcgen05 net */
+    int32_t leaves_per_step;   /* 1 = the reference's sequential search (bit-exact); K > 1 = K descents per
+                                  tree and step kept apart by virtual loss (throughput option for few games;
+                                  changes visit counts); leaf batch rows = n_games * K, row = game * K + j   */
 } az_config;
 
 void az_default_config(az_config* out);
@@ -212,8 +215,8 @@ int az_collate(const az_replay_tuple* tuples, int n, float* pi, int64_t* tokens,
 
 /* Counters since creation: [0] simulations, [1] network evaluations, [2] terminal leaves,
  * [3] moves played, [4] games finished, [5] nodes allocated, [6] edges allocated,
- * [7] kernels launched by this library.                                                     */
-#define AZ_NUM_COUNTERS 8
+ * [7] kernels launched by this library, [8] descents dropped on a pending node (leaves_per_step > 1).   */
+#define AZ_NUM_COUNTERS 10
 int az_counters(az_engine* e, uint64_t* out);
 
 /* Stand-alone network forward (exp/policy.py:71-80) on n positions with the engine's weights:

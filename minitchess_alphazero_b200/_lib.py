@@ -14,7 +14,7 @@ MC_TOKENS = 60
 AZ_NUM_PARAMS = 10693458
 AZ_NUM_BN_STATS = 9734
 AZ_NUM_WEIGHT_FLOATS = AZ_NUM_PARAMS + AZ_NUM_BN_STATS
-AZ_NUM_COUNTERS = 8
+AZ_NUM_COUNTERS = 10
 
 STATE_DTYPE = np.dtype([('pl0', '<u4'), ('pl1', '<u4'), ('pl2', '<u4'), ('white', '<u4'), ('meta', '<u4')])
 RESULT_STRINGS = {0: '*', 1: '1-0', 2: '0-1', 3: '1/2-1/2'}
@@ -38,7 +38,8 @@ class Config(ctypes.Structure):
                 ('cpuct', ctypes.c_float), ('tau_change', ctypes.c_int32),
                 ('dirichlet_alpha', ctypes.c_float), ('dirichlet_epsilon', ctypes.c_float),
                 ('numpy1_dtype_flow', ctypes.c_int32), ('device_rng', ctypes.c_int32),
-                ('seed', ctypes.c_uint64), ('rules', Rules), ('network', ctypes.c_int32)]
+                ('seed', ctypes.c_uint64), ('rules', Rules), ('network', ctypes.c_int32),
+                ('leaves_per_step', ctypes.c_int32)]
 
 
 _lib = None

@@ -23,7 +23,10 @@ __global__ void __launch_bounds__(128) select_expand_kernel(View V, const double
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < V.G; g += warps)
-        az::select_expand_one(V, g, lane, noise, noise_used);
+        for (int j = 0; j < V.K; ++j) {
+            az::select_expand_one(V, g, lane, noise, noise_used, j);
+            __syncwarp();
+        }
 }
 
 // az_search inner step: back up the previous simulation (if one is pending) and run the next descent in
@@ -32,9 +35,17 @@ __global__ void __launch_bounds__(128) search_step_kernel(View V, const float* l
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < V.G; g += warps) {
-        az::backup_one(V, g, lane, logits, values, nullptr);
-        __syncwarp();
-        if (do_select) az::select_expand_one(V, g, lane, nullptr, nullptr);
+        for (int j = 0; j < V.K; ++j) {
+            az::backup_one(V, g, lane, logits, values, nullptr, j);
+            __syncwarp();
+        }
+        if (do_select)
+            for (int j = 0; j < V.K; ++j) {
+                View W = V;
+                W.sim_counter = V.sim_counter * (unsigned long long)V.K + j;   // a fresh noise draw per descent
+                az::select_expand_one(W, g, lane, nullptr, nullptr, j);
+                __syncwarp();
+            }
     }
 }
 
@@ -42,7 +53,10 @@ __global__ void __launch_bounds__(128) backup_kernel(View V, const float* logits
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < V.G; g += warps)
-        az::backup_one(V, g, lane, logits, values, priors);
+        for (int j = 0; j < V.K; ++j) {
+            az::backup_one(V, g, lane, logits, values, priors, j);
+            __syncwarp();
+        }
 }
 
 // (re)start games: position, history, both trees emptied (block per listed game)
@@ -61,9 +75,7 @@ __global__ void __launch_bounds__(256) reset_games_kernel(View V, const int32_t*
             az::hist_reset(V, g, s);
             V.game_result[g] = (int8_t)az::game_result_of(V, g, s);
             for (int t = 2 * g; t < 2 * g + 2; ++t) { V.tree_nodes[t] = 0; V.tree_edges[t] = 0; V.tree_root[t] = az::NONE; }
-            V.leaf_kind[g] = az::LEAF_NONE;
-            V.needs_eval[g] = 0;
-            V.path_len[g] = 0;
+            for (int j = 0; j < V.K; ++j) { V.leaf_kind[g * V.K + j] = az::LEAF_NONE; V.needs_eval[g * V.K + j] = 0; V.path_len[g * V.K + j] = 0; }
         }
     }
 }
@@ -80,7 +92,7 @@ __global__ void set_positions_kernel(View V, const int32_t* game_ids, int n, con
         V.game_result[g] = (int8_t)az::game_result_of(V, g, s);
         V.tree_root[2 * g] = az::NONE;
         V.tree_root[2 * g + 1] = az::NONE;
-        V.leaf_kind[g] = az::LEAF_NONE;
+        for (int j = 0; j < V.K; ++j) V.leaf_kind[g * V.K + j] = az::LEAF_NONE;
     }
 }
 
@@ -233,7 +245,7 @@ __global__ void __launch_bounds__(256) restart_finished_kernel(View V, mc_state 
             V.game_start_ply[g] = V.game_ply[g];
             az::hist_reset(V, g, start);
             for (int t = 2 * g; t < 2 * g + 2; ++t) { V.tree_nodes[t] = 0; V.tree_edges[t] = 0; V.tree_root[t] = az::NONE; }
-            V.leaf_kind[g] = az::LEAF_NONE;
+            for (int j = 0; j < V.K; ++j) V.leaf_kind[g * V.K + j] = az::LEAF_NONE;
             V.game_result[g] = MC_ONGOING;
         }
         __syncthreads();
@@ -296,6 +308,7 @@ void az_default_config(az_config* c) {
     c->seed = 0;
     mc_default_rules(&c->rules);
     c->network = 0;
+    c->leaves_per_step = 1;
 }
 
 int az_create(const az_config* cfg, az_engine** out) {
@@ -307,6 +320,8 @@ int az_create(const az_config* cfg, az_engine** out) {
     cudaGetDevice(&e->device);
     View& V = e->v;
     V.G = cfg->n_games;
+    V.K = cfg->leaves_per_step > 0 ? cfg->leaves_per_step : 1;
+    if (V.K > az::MAX_LEAVES) { delete e; return fail(MCAZ_EINVAL, "az_create: leaves_per_step > 16"); }
     // <= 1 new node per simulation, <= 31 searches per tree under the 30-move cap (+ roots)
     long long nc = cfg->node_capacity > 0 ? cfg->node_capacity : (long long)cfg->max_sims_per_move * 31 + 64;
     long long ec = cfg->edge_capacity > 0 ? cfg->edge_capacity : nc * 14;
@@ -319,7 +334,7 @@ int az_create(const az_config* cfg, az_engine** out) {
     V.cpuct = cfg->cpuct; V.eps = cfg->dirichlet_epsilon; V.alpha = cfg->dirichlet_alpha;
     V.numpy1 = cfg->numpy1_dtype_flow; V.tau_change = cfg->tau_change; V.rules = cfg->rules; V.seed = cfg->seed;
     V.device_rng = 0; V.sim_counter = 0;   // set per launch by az_search
-    const size_t G = V.G, T = 2 * G, N = T * V.NC, E = T * V.EC;
+    const size_t G = V.G, T = 2 * G, N = T * V.NC, E = T * V.EC, S = G * V.K;   // S: leaf slots
     int rc = MCAZ_OK;
 #define A(ptr, n) if (!rc) rc = dev_alloc(e, &ptr, (n))
     A(V.game_state, G); A(V.game_result, G); A(V.game_ply, G); A(V.game_hist, G * az::HIST); A(V.game_hist_len, G); A(V.game_start_ply, G);
@@ -327,12 +342,14 @@ int az_create(const az_config* cfg, az_engine** out) {
     A(V.node_board, N); A(V.node_meta, N); A(V.node_edge_off, N); A(V.node_info, N);
     A(V.edge_Q, E); A(V.edge_N, E); A(V.edge_P, E); A(V.edge_child, E); A(V.edge_code, E);
     A(V.ht, T * V.HC);
-    A(V.path_len, G); A(V.path_edge, G * az::MAX_DEPTH); A(V.path_node, G * az::MAX_DEPTH);
-    A(V.leaf_node, G); A(V.leaf_kind, G); A(V.leaf_value, G);
-    A(V.tokens, G * MC_TOKENS); A(V.clocks, G); A(V.needs_eval, G); A(V.leaf_states, G);
+    A(V.path_len, S); A(V.path_edge, S * az::MAX_DEPTH); A(V.path_node, S * az::MAX_DEPTH);
+    A(V.leaf_node, S); A(V.leaf_kind, S); A(V.leaf_value, S);
+    A(V.tokens, S * MC_TOKENS); A(V.clocks, S); A(V.needs_eval, S); A(V.leaf_states, S);
+    V.edge_vl = nullptr;
+    if (V.K > 1) { A(V.edge_vl, E); }
     A(V.counters, AZ_NUM_COUNTERS); A(V.error_flag, 1);
     A(e->d_noise, G * MC_MAX_MOVES); A(e->d_noise_used, G);
-    A(e->d_logits, G * MC_NUM_ACTIONS); A(e->d_values, G); A(e->d_priors, G * MC_MAX_MOVES);
+    A(e->d_logits, S * MC_NUM_ACTIONS); A(e->d_values, S); A(e->d_priors, S * MC_MAX_MOVES);
     A(e->d_record, G * az::MAX_DEPTH);
     e->replay_capacity = G * az::MAX_DEPTH;
     A(e->d_replay, e->replay_capacity); A(e->d_replay_count, 1);
@@ -430,7 +447,7 @@ int az_leaf_batch(az_engine* e, const uint8_t** tokens, const float** clocks, co
     if (clocks) *clocks = e->v.clocks;
     if (needs_eval) *needs_eval = e->v.needs_eval;
     if (leaf_states) *leaf_states = e->v.leaf_states;
-    if (n_slots) *n_slots = e->v.G;
+    if (n_slots) *n_slots = e->v.G * e->v.K;
     return MCAZ_OK;
 }
 
@@ -441,15 +458,15 @@ int az_backup(az_engine* e, const float* logits, const float* values, const floa
     const View& V = e->v;
     const float *lg = logits, *vl = values, *pr = priors;
     if (logits && !is_device_pointer(logits)) {
-        MCAZ_CUDA(cudaMemcpyAsync(e->d_logits, logits, (size_t)V.G * MC_NUM_ACTIONS * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        MCAZ_CUDA(cudaMemcpyAsync(e->d_logits, logits, (size_t)V.G * V.K * MC_NUM_ACTIONS * sizeof(float), cudaMemcpyHostToDevice, e->stream));
         lg = e->d_logits;
     }
     if (!is_device_pointer(values)) {
-        MCAZ_CUDA(cudaMemcpyAsync(e->d_values, values, (size_t)V.G * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        MCAZ_CUDA(cudaMemcpyAsync(e->d_values, values, (size_t)V.G * V.K * sizeof(float), cudaMemcpyHostToDevice, e->stream));
         vl = e->d_values;
     }
     if (priors && !is_device_pointer(priors)) {
-        MCAZ_CUDA(cudaMemcpyAsync(e->d_priors, priors, (size_t)V.G * MC_MAX_MOVES * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        MCAZ_CUDA(cudaMemcpyAsync(e->d_priors, priors, (size_t)V.G * V.K * MC_MAX_MOVES * sizeof(float), cudaMemcpyHostToDevice, e->stream));
         pr = e->d_priors;
     }
     backup_kernel<<<warp_grid(V.G, 128), 128, 0, e->stream>>>(V, lg, vl, pr);

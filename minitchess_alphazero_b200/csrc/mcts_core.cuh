@@ -31,15 +31,18 @@ constexpr int MAX_DEPTH = 64;        // a path cannot be longer than the plies l
 constexpr int HIST = 64;             // reversible-position history per game (fivefold repetition)
 constexpr uint32_t INFO_TERMINAL = 1u << 16;
 constexpr uint32_t INFO_DECISIVE = 1u << 17;  // terminal with reward 1.0 (else draw, reward 0.0)
+constexpr uint32_t INFO_PENDING = 1u << 18;   // expanded in this step, priors not written yet (leaves_per_step > 1)
+constexpr int MAX_LEAVES = 16;                // leaves_per_step limit
 
-enum LeafKind : uint8_t { LEAF_NONE = 0, LEAF_EVAL = 1, LEAF_TERMINAL = 2 };
-enum Counter : int { C_SIMS = 0, C_EVALS, C_TERMINAL, C_MOVES, C_GAMES, C_NODES, C_EDGES, C_LAUNCHES };
+enum LeafKind : uint8_t { LEAF_NONE = 0, LEAF_EVAL = 1, LEAF_TERMINAL = 2, LEAF_COLLISION = 3 };
+enum Counter : int { C_SIMS = 0, C_EVALS, C_TERMINAL, C_MOVES, C_GAMES, C_NODES, C_EDGES, C_LAUNCHES, C_COLLISIONS, C_SPARE };
 enum ErrorBit : int { ERR_NODE_CAP = 1, ERR_EDGE_CAP = 2, ERR_HASH_CAP = 4, ERR_DEPTH = 8, ERR_ILLEGAL = 16 };
 
 struct alignas(16) Board4 { uint32_t x, y, z, w; };
 
 struct View {
     int G, NC, EC, HC;
+    int K;                          // leaves per game per step (1 = the reference's sequential search)
     // real games
     mc_state* game_state; int8_t* game_result; int32_t* game_ply; int32_t* game_start_ply;
     Board4* game_hist; int32_t* game_hist_len;     // [G*HIST] positions since the last irreversible move
@@ -47,11 +50,12 @@ struct View {
     uint32_t* tree_nodes; uint32_t* tree_edges; uint32_t* tree_root;
     Board4* node_board; uint32_t* node_meta; uint32_t* node_edge_off; uint32_t* node_info;
     double* edge_Q; uint32_t* edge_N; float* edge_P; uint32_t* edge_child; uint16_t* edge_code;
+    uint16_t* edge_vl;              // virtual-loss counts of descents in flight (K > 1 only, else nullptr)
     uint32_t* ht;
-    // per-game simulation scratch
+    // per-slot simulation scratch (slot = game * K + leaf index)
     int32_t* path_len; uint32_t* path_edge; uint32_t* path_node;   // [G*MAX_DEPTH]
     uint32_t* leaf_node; uint8_t* leaf_kind; double* leaf_value;
-    // leaf batch (slot = game)
+    // leaf batch, one row per slot
     uint8_t* tokens; float* clocks; uint8_t* needs_eval; mc_state* leaf_states;
     unsigned long long* counters; int* error_flag;
     // parameters
@@ -161,7 +165,7 @@ MC_HD void ht_insert(const View& V, int t, const mc_state& s, uint32_t node) {
 
 // Create the node for an unvisited position (exp/agent.py:57-66).  Lane 0 writes; every lane
 // gets the node index, its kind and, for a finished position, the value to back up.
-MC_HD uint32_t expand(const View& V, int g, int t, int lane, const mc_state& s, uint8_t* kind, double* value) {
+MC_HD uint32_t expand(const View& V, int slot, int t, int lane, const mc_state& s, uint8_t* kind, double* value) {
     uint32_t node = NONE;
     int is_terminal = 0, decisive = 0;
 #if defined(__CUDA_ARCH__)
@@ -189,7 +193,8 @@ MC_HD uint32_t expand(const View& V, int g, int t, int lane, const mc_state& s, 
             V.node_board[gi] = board_of(s);
             V.node_meta[gi] = s.meta;
             V.node_edge_off[gi] = off;
-            V.node_info[gi] = (uint32_t)E | (is_terminal ? INFO_TERMINAL : 0u) | (decisive ? INFO_DECISIVE : 0u);
+            V.node_info[gi] = (uint32_t)E | (is_terminal ? INFO_TERMINAL : 0u) | (decisive ? INFO_DECISIVE : 0u) |
+                              ((!is_terminal && V.K > 1) ? INFO_PENDING : 0u);
             size_t ge = (size_t)t * V.EC + off;
             for (int k = 0; k < E; ++k) {
                 V.edge_Q[ge + k] = 0.0;
@@ -197,14 +202,15 @@ MC_HD uint32_t expand(const View& V, int g, int t, int lane, const mc_state& s, 
                 V.edge_P[ge + k] = 0.0f;
                 V.edge_child[ge + k] = NONE;
                 V.edge_code[ge + k] = codes[k];
+                if (V.edge_vl) V.edge_vl[ge + k] = 0;
             }
             V.tree_nodes[t] = n + 1;
             V.tree_edges[t] = off + (uint32_t)E;
             ht_insert(V, t, s, n);
             node = n;
             if (!is_terminal) {
-                mc::tokenize(s, V.tokens + (size_t)g * MC_TOKENS, &V.clocks[g]);
-                V.leaf_states[g] = s;
+                mc::tokenize(s, V.tokens + (size_t)slot * MC_TOKENS, &V.clocks[slot]);
+                V.leaf_states[slot] = s;
             }
             count(V, C_NODES, 1);
             count(V, C_EDGES, (unsigned long long)E);
@@ -244,7 +250,7 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
     return x - v;
 }
 
-__device__ __forceinline__ uint32_t expand_warp(const View& V, int g, int t, int lane, const mc_state& s, uint8_t* kind,
+__device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, int lane, const mc_state& s, uint8_t* kind,
                                                 double* value) {
     const bool white = mc::white_to_move(s);
     const mc::Sets st = mc::sets_of(s);
@@ -301,6 +307,7 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int g, int t, int
         mc::emit_square_codes(fv, white, knight, tg, knight ? nb : qb, type == mc::PAWN, V.rules.promo_multiplicity,
                               [&](uint16_t c) {
                                   V.edge_Q[w] = 0.0; V.edge_N[w] = 0u; V.edge_P[w] = 0.0f; V.edge_child[w] = NONE; V.edge_code[w] = c;
+                                  if (V.edge_vl) V.edge_vl[w] = 0;
                                   ++w;
                               });
     }
@@ -310,21 +317,22 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int g, int t, int
         if (!white) cell = 29 - cell;
         const int ty = mc::piece_at(s, cell);
         const bool mine = (st.own >> cell) & 1u;
-        V.tokens[(size_t)g * MC_TOKENS + lane] = (uint8_t)(mine ? ty : 0);
-        V.tokens[(size_t)g * MC_TOKENS + 30 + lane] = (uint8_t)(mine ? 0 : ty);
+        V.tokens[(size_t)slot * MC_TOKENS + lane] = (uint8_t)(mine ? ty : 0);
+        V.tokens[(size_t)slot * MC_TOKENS + 30 + lane] = (uint8_t)(mine ? 0 : ty);
     }
     if (lane == 0) {
         V.node_board[gi] = board_of(s);
         V.node_meta[gi] = s.meta;
         V.node_edge_off[gi] = off;
-        V.node_info[gi] = (uint32_t)E | (terminal ? INFO_TERMINAL : 0u) | ((terminal && decisive) ? INFO_DECISIVE : 0u);
+        V.node_info[gi] = (uint32_t)E | (terminal ? INFO_TERMINAL : 0u) | ((terminal && decisive) ? INFO_DECISIVE : 0u) |
+                          ((!terminal && V.K > 1) ? INFO_PENDING : 0u);
         V.tree_nodes[t] = node + 1;
         V.tree_edges[t] = off + (uint32_t)E;
         ht_insert(V, t, s, node);
         if (!terminal) {
             const double c = (double)mc::fullmove(s) + (white ? 0.0 : 0.5);
-            V.clocks[g] = (float)(c / 30.0);
-            V.leaf_states[g] = s;
+            V.clocks[slot] = (float)(c / 30.0);
+            V.leaf_states[slot] = s;
         }
         count(V, C_NODES, 1);
         count(V, C_EDGES, (unsigned long long)E);
@@ -341,18 +349,20 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int g, int t, int
 
 // One simulation of game g down to its leaf (exp/agent.py:54-88 without the backup).
 // `noise`: per-game Dirichlet sample [MC_MAX_MOVES] or nullptr.
-MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise, uint8_t* noise_used) {
+MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise, uint8_t* noise_used, int j = 0) {
+    const int slot = g * V.K + j;
     if (lane == 0) {
-        V.leaf_kind[g] = LEAF_NONE;
-        V.needs_eval[g] = 0;
-        V.path_len[g] = 0;
-        if (noise_used) noise_used[g] = 0;
+        V.leaf_kind[slot] = LEAF_NONE;
+        V.needs_eval[slot] = 0;
+        V.path_len[slot] = 0;
+        if (noise_used && j == 0) noise_used[g] = 0;
     }
     if (V.game_result[g] != MC_ONGOING) return;
     const int t = 2 * g + (V.game_ply[g] & 1);
     const size_t nbase = (size_t)t * V.NC, ebase = (size_t)t * V.EC;
-    uint32_t* pedge = V.path_edge + (size_t)g * MAX_DEPTH;
-    uint32_t* pnode = V.path_node + (size_t)g * MAX_DEPTH;
+    uint32_t* pedge = V.path_edge + (size_t)slot * MAX_DEPTH;
+    uint32_t* pnode = V.path_node + (size_t)slot * MAX_DEPTH;
+    const bool vloss = V.K > 1;
 
     uint8_t kind = LEAF_NONE;
     double value = 0.0;
@@ -361,7 +371,7 @@ MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise
     if (node == NONE) {
         mc_state s = V.game_state[g];
         node = ht_find(V, t, s);
-        if (node == NONE) node = AZ_EXPAND(V, g, t, lane, s, &kind, &value);
+        if (node == NONE) node = AZ_EXPAND(V, slot, t, lane, s, &kind, &value);
         if (lane == 0 && node != NONE) V.tree_root[t] = node;
         AZ_SYNCWARP();
     }
@@ -372,11 +382,16 @@ MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise
             value = (info & INFO_DECISIVE) ? 1.0 : 0.0;
             break;
         }
+        if (info & INFO_PENDING) {   // another descent of this step owns the node: drop this one (K > 1 only)
+            kind = LEAF_COLLISION;
+            value = 0.0;
+            break;
+        }
         const int E = (int)(info & 0xffffu);
         const size_t e0 = ebase + V.node_edge_off[nbase + node];
         // sum of visit counts (exact in float64: small integers)
         unsigned int nsum_u = 0;
-        for (int i = lane; i < E; i += AZ_LANES) nsum_u += V.edge_N[e0 + i];
+        for (int i = lane; i < E; i += AZ_LANES) nsum_u += V.edge_N[e0 + i] + (vloss ? (unsigned int)V.edge_vl[e0 + i] : 0u);
 #if defined(__CUDA_ARCH__)
         for (int o = 16; o > 0; o >>= 1) nsum_u += __shfl_xor_sync(0xffffffffu, nsum_u, o);
 #endif
@@ -418,7 +433,12 @@ MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise
             } else {
                 x = dmul((double)fmul(V.cpuct, p), root_n);
             }
-            const double u = dadd(V.edge_Q[e0 + i], ddiv(x, dadd(1.0, (double)V.edge_N[e0 + i])));
+            double q_i = V.edge_Q[e0 + i], n_i = (double)V.edge_N[e0 + i];
+            if (vloss) {   // descents in flight count as visits that lost (virtual loss)
+                const double vl = (double)V.edge_vl[e0 + i];
+                if (vl > 0.0) { q_i = (n_i * q_i - vl) / (n_i + vl); n_i += vl; }
+            }
+            const double u = dadd(q_i, ddiv(x, dadd(1.0, n_i)));
             if (best_i == 0x7fffffff || u > best_u) { best_u = u; best_i = i; }  // first max within the lane
         }
 #if defined(__CUDA_ARCH__)
@@ -437,6 +457,7 @@ MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise
         if (lane == 0) {
             pedge[depth] = (uint32_t)(e - ebase);
             pnode[depth] = node;
+            if (vloss) V.edge_vl[e] += 1;
         }
         ++depth;
         uint32_t child = V.edge_child[e];
@@ -448,7 +469,7 @@ MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise
             const bool white = mc::white_to_move(ps);
             mc_state cs = mc::apply_move(ps, white ? fv : 29 - fv, white ? tv : 29 - tv);
             child = ht_find(V, t, cs);
-            if (child == NONE) child = AZ_EXPAND(V, g, t, lane, cs, &kind, &value);
+            if (child == NONE) child = AZ_EXPAND(V, slot, t, lane, cs, &kind, &value);
             if (lane == 0 && child != NONE) V.edge_child[e] = child;
             AZ_SYNCWARP();
             if (child == NONE) break;
@@ -456,30 +477,31 @@ MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise
         node = child;
     }
     if (lane == 0) {
-        V.path_len[g] = depth;
-        V.leaf_node[g] = node;
-        V.leaf_kind[g] = kind;
-        V.leaf_value[g] = value;
-        V.needs_eval[g] = (kind == LEAF_EVAL) ? 1 : 0;
+        V.path_len[slot] = depth;
+        V.leaf_node[slot] = node;
+        V.leaf_kind[slot] = kind;
+        V.leaf_value[slot] = value;
+        V.needs_eval[slot] = (kind == LEAF_EVAL) ? 1 : 0;
     }
 }
 
 // Evaluate + backup for game g (exp/agent.py:67-72 and :47-52).
 // logits: [G x 554] float32 (softmax over the legal entries, float32) or priors: [G x MC_MAX_MOVES].
-MC_HD void backup_one(const View& V, int g, int lane, const float* logits, const float* values, const float* priors) {
-    const uint8_t kind = V.leaf_kind[g];
+MC_HD void backup_one(const View& V, int g, int lane, const float* logits, const float* values, const float* priors, int j = 0) {
+    const int slot = g * V.K + j;
+    const uint8_t kind = V.leaf_kind[slot];
     if (kind == LEAF_NONE) return;
     const int t = 2 * g + (V.game_ply[g] & 1);
     const size_t nbase = (size_t)t * V.NC, ebase = (size_t)t * V.EC;
-    double value = V.leaf_value[g];
+    double value = V.leaf_value[slot];
     if (kind == LEAF_EVAL) {
-        const uint32_t node = V.leaf_node[g];
+        const uint32_t node = V.leaf_node[slot];
         const int E = (int)(V.node_info[nbase + node] & 0xffffu);
         const size_t e0 = ebase + V.node_edge_off[nbase + node];
         if (priors) {
-            for (int i = lane; i < E; i += AZ_LANES) V.edge_P[e0 + i] = priors[(size_t)g * MC_MAX_MOVES + i];
+            for (int i = lane; i < E; i += AZ_LANES) V.edge_P[e0 + i] = priors[(size_t)slot * MC_MAX_MOVES + i];
         } else if (logits) {
-            const float* lg = logits + (size_t)g * MC_NUM_ACTIONS;
+            const float* lg = logits + (size_t)slot * MC_NUM_ACTIONS;
             float m = -INFINITY;
             for (int i = lane; i < E; i += AZ_LANES) m = fmaxf(m, lg[V.edge_code[e0 + i]]);
 #if defined(__CUDA_ARCH__)
@@ -492,20 +514,27 @@ MC_HD void backup_one(const View& V, int g, int lane, const float* logits, const
 #endif
             for (int i = lane; i < E; i += AZ_LANES) V.edge_P[e0 + i] = expf(lg[V.edge_code[e0 + i]] - m) / sum;
         }   // else: the policy head already wrote the priors into edge_P (heads_legal_kernel)
-        value = (double)values[g];
+        value = (double)values[slot];
+        if (V.K > 1 && lane == 0) V.node_info[nbase + node] &= ~INFO_PENDING;
     }
     if (lane == 0) {
-        const uint32_t* pedge = V.path_edge + (size_t)g * MAX_DEPTH;
-        for (int d = V.path_len[g] - 1; d >= 0; --d) {
-            value = -value;
+        const uint32_t* pedge = V.path_edge + (size_t)slot * MAX_DEPTH;
+        const bool vloss = V.K > 1;
+        for (int d = V.path_len[slot] - 1; d >= 0; --d) {
             const size_t e = ebase + pedge[d];
+            if (vloss) V.edge_vl[e] -= 1;
+            if (kind == LEAF_COLLISION) continue;      // dropped descent: only its virtual loss is undone
+            value = -value;
             const double n = (double)V.edge_N[e];
             V.edge_Q[e] = ddiv(dadd(dmul(n, V.edge_Q[e]), value), dadd(n, 1.0));
             V.edge_N[e] += 1u;
         }
-        count(V, C_SIMS, 1);
-        count(V, kind == LEAF_EVAL ? C_EVALS : C_TERMINAL, 1);
-        V.leaf_kind[g] = LEAF_NONE;
+        if (kind == LEAF_COLLISION) count(V, C_COLLISIONS, 1);
+        else {
+            count(V, C_SIMS, 1);
+            count(V, kind == LEAF_EVAL ? C_EVALS : C_TERMINAL, 1);
+        }
+        V.leaf_kind[slot] = LEAF_NONE;
     }
 }
 

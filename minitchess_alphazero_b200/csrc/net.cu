@@ -806,9 +806,10 @@ heads_legal_kernel(const __nv_bfloat16* __restrict__ act, int bpad, HeadWeights 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* in = s_in[warp];
     const int pos = lane < NPOS ? lane : NPOS - 1;
-    for (int g = blockIdx.x * HEADS_WARPS + warp; g < V.G; g += gridDim.x * HEADS_WARPS) {
-        if (!V.needs_eval[g]) continue;
-        const uint4* row = reinterpret_cast<const uint4*>(act + ((size_t)pos * bpad + g) * C);
+    for (int slot = blockIdx.x * HEADS_WARPS + warp; slot < V.G * V.K; slot += gridDim.x * HEADS_WARPS) {
+        if (!V.needs_eval[slot]) continue;
+        const int g = slot / V.K;
+        const uint4* row = reinterpret_cast<const uint4*>(act + ((size_t)pos * bpad + slot) * C);
         float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll 2
         for (int c4 = 0; c4 < C / 8; c4 += 4) {
@@ -833,14 +834,14 @@ heads_legal_kernel(const __nv_bfloat16* __restrict__ act, int bpad, HeadWeights 
             in[30 + lane] = fmaxf(d1 + pb1, 0.f);
             in[61 + lane] = fmaxf(d2 + vb, 0.f);
         } else if (lane == 30) {
-            const float ck = V.clocks[g];
+            const float ck = V.clocks[slot];
             in[60] = ck;
             in[91] = ck;
         }
         __syncwarp();
         // ---- legal logits -> softmax -> edge_P of the leaf
         const int t = 2 * g + (V.game_ply[g] & 1);
-        const uint32_t node = V.leaf_node[g];
+        const uint32_t node = V.leaf_node[slot];
         const size_t gi = (size_t)t * V.NC + node;
         const int E = (int)(V.node_info[gi] & 0xffffu);
         const size_t e0 = (size_t)t * V.EC + V.node_edge_off[gi];
@@ -877,7 +878,7 @@ heads_legal_kernel(const __nv_bfloat16* __restrict__ act, int bpad, HeadWeights 
         for (int k = 0; k < 8; ++k) part += fmaxf(hv[k], 0.f) * __ldg(H.v2 + lane + 32 * k);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0) values[g] = tanhf(part + v2b);
+        if (lane == 0) values[slot] = tanhf(part + v2b);
         __syncwarp();
     }
 }
@@ -975,7 +976,7 @@ int network_create(az_engine* e) {
     MCAZ_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
     MCAZ_CUDA(cudaFuncSetAttribute(tower_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_SMEM));
     { const char* m = getenv("MCAZ_TOWER"); N->per_layer = !(m && std::strcmp(m, "fused") == 0); }
-    return net_alloc_acts(e, std::min(e->v.G, MAX_CHUNK_BOARDS));
+    return net_alloc_acts(e, std::min(e->v.G * e->v.K, MAX_CHUNK_BOARDS));
 }
 
 void network_destroy(az_engine* e) {
@@ -1162,8 +1163,8 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
 int network_forward_search(az_engine* e, const az::View& V, float* values) {
     Network* N = e->net;
     if (!N->have_weights) return fail(MCAZ_ESTATE, "network weights have not been set (az_set_weights)");
-    if (V.G > MAX_CHUNK_BOARDS) return fail(MCAZ_EINVAL, "az_search: more than 8192 games per engine are not supported yet");
-    return forward_chunk(e, V.tokens, V.clocks, V.G, nullptr, values, &V);
+    if (V.G * V.K > MAX_CHUNK_BOARDS) return fail(MCAZ_EINVAL, "az_search: more than 8192 leaf slots (games x leaves_per_step) per engine are not supported yet");
+    return forward_chunk(e, V.tokens, V.clocks, V.G * V.K, nullptr, values, &V);
 }
 
 int network_profile(az_engine* e, int on, double* avg_ms_per_conv_launch, int* n_forwards) {

@@ -15,7 +15,7 @@ from ._lib import (AZ_NUM_COUNTERS, AZ_NUM_WEIGHT_FLOATS, MC_MAX_MOVES, MC_NUM_A
                    check, ptr)
 
 COUNTER_NAMES = ('simulations', 'evaluations', 'terminal_leaves', 'moves', 'games_finished', 'nodes', 'edges',
-                 'kernel_launches')
+                 'kernel_launches', 'collisions', 'spare')
 
 REPLAY_DTYPE = np.dtype([('observation', STATE_DTYPE), ('n_legal', '<u2'), ('action', '<u2'), ('reward', 'i1'),
                          ('pad', 'u1', 3), ('codes', '<u2', MC_MAX_MOVES), ('pi', '<f4', MC_MAX_MOVES)])
@@ -57,6 +57,7 @@ class Engine:
             setattr(cfg, k, v)
         self.config = cfg
         self.n_games = int(n_games)
+        self.n_slots = self.n_games * max(1, int(cfg.leaves_per_step))      # rows of the leaf batch
         self._h = ctypes.c_void_p()
         self._check(self._L.az_create(ctypes.byref(cfg), ctypes.byref(self._h)))
         self._noise_used = np.zeros(self.n_games, dtype=np.uint8)
@@ -167,9 +168,9 @@ class Engine:
                 x = np.ascontiguousarray(x, dtype=np.float32)
                 assert x.shape == shape, (x.shape, shape)
             return x
-        self._check(self._L.az_backup(self._h, ptr(prep(logits, (self.n_games, MC_NUM_ACTIONS))),
-                                      ptr(prep(values, (self.n_games,))),
-                                      ptr(prep(priors, (self.n_games, MC_MAX_MOVES)))))
+        self._check(self._L.az_backup(self._h, ptr(prep(logits, (self.n_slots, MC_NUM_ACTIONS))),
+                                      ptr(prep(values, (self.n_slots,))),
+                                      ptr(prep(priors, (self.n_slots, MC_MAX_MOVES)))))
 
     def search(self, n_sims):
         """n_sims simulations for every active game with the built-in network."""

@@ -54,6 +54,7 @@ void az_default_config(az_config* c) {
     memset(c, 0, sizeof(*c));
     c->n_games = 1; c->max_sims_per_move = 36; c->cpuct = 1.0f; c->tau_change = 6;
     c->dirichlet_alpha = 0.6f; c->dirichlet_epsilon = 0.25f;
+    c->leaves_per_step = 1;
     mc_default_rules(&c->rules);
 }
 
@@ -64,6 +65,7 @@ int az_create(const az_config* cfg, az_engine** out) {
     e->cfg = *cfg;
     az::View& V = e->v;
     V.G = cfg->n_games;
+    V.K = cfg->leaves_per_step > 0 ? cfg->leaves_per_step : 1;
     long long nc = cfg->node_capacity > 0 ? cfg->node_capacity : (long long)cfg->max_sims_per_move * 31 + 64;
     long long ec = cfg->edge_capacity > 0 ? cfg->edge_capacity : nc * 14;
     V.NC = (int)nc; V.EC = (int)ec;
@@ -71,16 +73,18 @@ int az_create(const az_config* cfg, az_engine** out) {
     V.cpuct = cfg->cpuct; V.eps = cfg->dirichlet_epsilon; V.alpha = cfg->dirichlet_alpha;
     V.numpy1 = cfg->numpy1_dtype_flow; V.tau_change = cfg->tau_change; V.rules = cfg->rules; V.seed = cfg->seed;
     V.device_rng = 0; V.sim_counter = 0;
-    size_t G = V.G, T = 2 * G, N = T * V.NC, E = T * V.EC;
+    size_t G = V.G, T = 2 * G, N = T * V.NC, E = T * V.EC, S = G * V.K;
     alloc(e, &V.game_state, G); alloc(e, &V.game_result, G); alloc(e, &V.game_ply, G); alloc(e, &V.game_start_ply, G);
     alloc(e, &V.game_hist, G * az::HIST); alloc(e, &V.game_hist_len, G);
     alloc(e, &V.tree_nodes, T); alloc(e, &V.tree_edges, T); alloc(e, &V.tree_root, T);
     alloc(e, &V.node_board, N); alloc(e, &V.node_meta, N); alloc(e, &V.node_edge_off, N); alloc(e, &V.node_info, N);
     alloc(e, &V.edge_Q, E); alloc(e, &V.edge_N, E); alloc(e, &V.edge_P, E); alloc(e, &V.edge_child, E); alloc(e, &V.edge_code, E);
     alloc(e, &V.ht, T * V.HC);
-    alloc(e, &V.path_len, G); alloc(e, &V.path_edge, G * az::MAX_DEPTH); alloc(e, &V.path_node, G * az::MAX_DEPTH);
-    alloc(e, &V.leaf_node, G); alloc(e, &V.leaf_kind, G); alloc(e, &V.leaf_value, G);
-    alloc(e, &V.tokens, G * MC_TOKENS); alloc(e, &V.clocks, G); alloc(e, &V.needs_eval, G); alloc(e, &V.leaf_states, G);
+    alloc(e, &V.path_len, S); alloc(e, &V.path_edge, S * az::MAX_DEPTH); alloc(e, &V.path_node, S * az::MAX_DEPTH);
+    alloc(e, &V.leaf_node, S); alloc(e, &V.leaf_kind, S); alloc(e, &V.leaf_value, S);
+    alloc(e, &V.tokens, S * MC_TOKENS); alloc(e, &V.clocks, S); alloc(e, &V.needs_eval, S); alloc(e, &V.leaf_states, S);
+    V.edge_vl = nullptr;
+    if (V.K > 1) alloc(e, &V.edge_vl, E);
     alloc(e, &V.counters, AZ_NUM_COUNTERS); alloc(e, &V.error_flag, 1);
     e->noise_used.assign(G, 0);
     *out = e;
@@ -113,7 +117,7 @@ int az_reset_games(az_engine* e, const int32_t* ids, int n, const mc_state* stat
         az::hist_reset(V, g, s);
         V.game_result[g] = (int8_t)az::game_result_of(V, g, s);
         for (int t = 2 * g; t < 2 * g + 2; ++t) { V.tree_nodes[t] = 0; V.tree_edges[t] = 0; V.tree_root[t] = az::NONE; }
-        V.leaf_kind[g] = az::LEAF_NONE; V.needs_eval[g] = 0; V.path_len[g] = 0;
+        for (int j = 0; j < V.K; ++j) { V.leaf_kind[g * V.K + j] = az::LEAF_NONE; V.needs_eval[g * V.K + j] = 0; V.path_len[g * V.K + j] = 0; }
     }
     e->leaf_pending = false;
     return 0;
@@ -130,7 +134,7 @@ int az_set_positions(az_engine* e, const int32_t* ids, int n, const mc_state* st
         az::hist_reset(V, g, s);
         V.game_result[g] = (int8_t)az::game_result_of(V, g, s);
         V.tree_root[2 * g] = az::NONE; V.tree_root[2 * g + 1] = az::NONE;
-        V.leaf_kind[g] = az::LEAF_NONE;
+        for (int j = 0; j < V.K; ++j) V.leaf_kind[g * V.K + j] = az::LEAF_NONE;
     }
     e->leaf_pending = false;
     return 0;
@@ -138,7 +142,8 @@ int az_set_positions(az_engine* e, const int32_t* ids, int n, const mc_state* st
 
 int az_select_expand(az_engine* e, const double* noise, uint8_t* noise_used) {
     if (e->leaf_pending) return fail(MCAZ_ESTATE, "previous simulation not backed up");
-    for (int g = 0; g < e->v.G; ++g) az::select_expand_one(e->v, g, 0, noise, e->noise_used.data());
+    for (int g = 0; g < e->v.G; ++g)
+        for (int j = 0; j < e->v.K; ++j) az::select_expand_one(e->v, g, 0, noise, e->noise_used.data(), j);
     if (noise_used) memcpy(noise_used, e->noise_used.data(), e->v.G);
     e->leaf_pending = true;
     return 0;
@@ -150,13 +155,14 @@ int az_leaf_batch(az_engine* e, const uint8_t** tokens, const float** clocks, co
     if (clocks) *clocks = e->v.clocks;
     if (needs_eval) *needs_eval = e->v.needs_eval;
     if (leaf_states) *leaf_states = e->v.leaf_states;
-    if (n_slots) *n_slots = e->v.G;
+    if (n_slots) *n_slots = e->v.G * e->v.K;
     return 0;
 }
 
 int az_backup(az_engine* e, const float* logits, const float* values, const float* priors) {
     if (!e->leaf_pending) return fail(MCAZ_ESTATE, "no simulation pending");
-    for (int g = 0; g < e->v.G; ++g) az::backup_one(e->v, g, 0, logits, values, priors);
+    for (int g = 0; g < e->v.G; ++g)
+        for (int j = 0; j < e->v.K; ++j) az::backup_one(e->v, g, 0, logits, values, priors, j);
     e->leaf_pending = false;
     return 0;
 }
