@@ -173,6 +173,11 @@ int az_leaf_batch(az_engine* e, const uint8_t** tokens, const float** clocks,
  * MC_MAX_MOVES] directly instead of logits (bit-exact injection for tree-logic parity).     */
 int az_backup(az_engine* e, const float* logits, const float* values, const float* priors);
 
+/* az_eval_backup: the evaluate + backup half of one simulation with the built-in network (the leaf batch of
+ * the last az_select_expand); lets a caller keep drawing the root noise itself, one simulation at a time,
+ * as SimpleAlphaZeroAgent does with numpy's global RNG (exp/agent.py:81-82).                             */
+int az_eval_backup(az_engine* e);
+
 /* -- whole searches with the built-in network (throughput mode) ---------------------------*/
 int az_search(az_engine* e, int n_sims);
 

@@ -13,7 +13,7 @@ from . import rules
 from ._lib import MC_MAX_MOVES
 from .engine import Engine
 from .erlyx_compat import ActionData, BaseAgent, PolicyAgent
-from .policy import TorchEvaluator, weights_fingerprint
+from .policy import flatten_state_dict, weights_fingerprint
 
 
 class RoundRobinReferee(BaseAgent):                         # exp/agent.py:6-21
@@ -76,10 +76,12 @@ class _Visited:
 
 
 class MonteCarloTreeSearch:
-    """exp/agent.py:24-88 over one GPU-resident tree.  `model` is the torch `Network`
-    (`policy.model`); its weights are mirrored to the GPU evaluator and re-read whenever they change."""
+    """exp/agent.py:24-88 over one GPU-resident tree.  `model` is the torch `Network` (`policy.model`); its
+    weights are mirrored into the engine's built-in sm_100a network (az_set_weights) and re-read whenever
+    they change.  `evaluator` may instead be any callable object with `.forward(tokens_u8, clocks)` ->
+    (logits, values) CUDA tensors (e.g. `policy.TorchEvaluator(net, dtype=torch.float32)` for fp32 checks)."""
 
-    def __init__(self, environment, model, cpuct, epsilon=0.25, alpha=0.6, evaluator=None, rules_switches=None):
+    def __init__(self, environment, model, cpuct, epsilon=0.25, alpha=0.6, evaluator=None, rules_switches=None, _reuse=None):
         self._environment = environment
         self._model = model
         self._cpuct = cpuct
@@ -89,6 +91,10 @@ class MonteCarloTreeSearch:
         self._capacity_sims = 0
         self._evaluator = evaluator
         self._fingerprint = None
+        if _reuse is not None and _reuse._engine is not None and _reuse._evaluator is evaluator:
+            # a new game of the same agent: keep the engine (arenas, uploaded weights), empty its trees
+            self._engine, self._capacity_sims, self._fingerprint = _reuse._engine, _reuse._capacity_sims, _reuse._fingerprint
+            self._engine.reset_games()
         self._fields = {k: _NodeField(self, k) for k in ('Q', 'N', 'P', 'legal_moves', 'terminal')}
         self._fields['visited'] = _Visited(self)
 
@@ -103,25 +109,29 @@ class MonteCarloTreeSearch:
     def _ensure(self, num_simulations):
         if self._engine is None:
             opts = dict(max_sims_per_move=max(int(num_simulations), 1), cpuct=float(self._cpuct),
-                        dirichlet_epsilon=float(self._epsilon), dirichlet_alpha=float(self._alpha))
+                        dirichlet_epsilon=float(self._epsilon), dirichlet_alpha=float(self._alpha),
+                        network=0 if self._evaluator is not None else 1)
             if self._rules is not None:
                 opts['rules'] = self._rules
             self._engine = Engine(1, **opts)
             self._capacity_sims = int(num_simulations)
-        if self._evaluator is None:
-            self._evaluator = TorchEvaluator(self._model)
-            self._fingerprint = weights_fingerprint(self._model)
-        elif self._fingerprint is not None:
-            fp = weights_fingerprint(self._model)
-            if fp != self._fingerprint:          # load_state_dict / optimiser step happened
+        elif int(num_simulations) > self._capacity_sims:
+            raise ValueError('num_simulations grew from %d to %d: the tree arenas were sized for the first value'
+                             % (self._capacity_sims, num_simulations))
+        fp = weights_fingerprint(self._model)
+        if fp != self._fingerprint:                 # first use, load_state_dict or an optimiser step
+            if self._evaluator is None:
+                self._engine.set_weights(flatten_state_dict(self._model.state_dict(), device='cuda'))
+            elif hasattr(self._evaluator, 'load'):
                 self._evaluator.load(self._model)
-                self._fingerprint = fp
+            self._fingerprint = fp
 
     def simulate(self, num_simulations, observation):       # exp/agent.py:41-45
         self._ensure(num_simulations)
         eng, ev = self._engine, self._evaluator
         eng.set_positions(rules.state_from_fen(observation), trees=[0])
-        tokens, clocks, _needs = eng.leaf_batch_device()
+        if ev is not None:
+            tokens, clocks, _needs = eng.leaf_batch_device()
         for _ in range(num_simulations):
             noise = None
             if self._epsilon > 0:
@@ -130,8 +140,11 @@ class MonteCarloTreeSearch:
                     noise = np.zeros((1, MC_MAX_MOVES))
                     noise[0, :n_legal[0]] = np.random.dirichlet([self._alpha] * int(n_legal[0]))
             eng.select_expand(noise)
-            logits, values = ev.forward(tokens, clocks)
-            eng.backup(values, logits=logits)
+            if ev is None:
+                eng.eval_backup()                           # built-in tcgen05 network
+            else:
+                logits, values = ev.forward(tokens, clocks)
+                eng.backup(values, logits=logits)
         return self
 
     @property
@@ -146,17 +159,12 @@ class SimpleAlphaZeroAgent(PolicyAgent):                    # exp/agent.py:91-11
         self._num_simulations = num_simulations
         self._cpuct = cpuct
         self._tau_change = tau_change
-        self._evaluator = None
         self.init_mcts()
 
     def init_mcts(self):
-        old = getattr(self, '_mcts', None)
-        if old is not None and old._evaluator is not None:
-            self._evaluator = old._evaluator                # keep the GPU copy of the weights between games
-        self._mcts = MonteCarloTreeSearch(self._environment, self.policy.model, self._cpuct, evaluator=self._evaluator)
-        if self._evaluator is not None:
-            self._mcts._fingerprint = weights_fingerprint(self.policy.model)
-            self._evaluator.load(self.policy.model)
+        evaluator = getattr(getattr(self, '_mcts', None), '_evaluator', None)    # an injected evaluator survives resets
+        self._mcts = MonteCarloTreeSearch(self._environment, self.policy.model, self._cpuct, evaluator=evaluator,
+                                          _reuse=getattr(self, '_mcts', None))
         self._count = 0
 
     def select_action(self, observation):

@@ -476,6 +476,19 @@ int az_backup(az_engine* e, const float* logits, const float* values, const floa
     return MCAZ_OK;
 }
 
+int az_eval_backup(az_engine* e) {
+    if (!e) return fail(MCAZ_EINVAL, "az_eval_backup: null engine");
+    if (!e->net) return fail(MCAZ_ESTATE, "az_eval_backup: engine was created with network = 0");
+    if (!e->leaf_pending) return fail(MCAZ_ESTATE, "az_eval_backup: no simulation pending (call az_select_expand first)");
+    const View& V = e->v;
+    if (int rc = network_forward_search(e, V, e->d_values)) return rc;     // priors land in the new nodes' edges
+    backup_kernel<<<warp_grid(V.G, 128), 128, 0, e->stream>>>(V, nullptr, e->d_values, nullptr);
+    MCAZ_CHECK_LAUNCH();
+    e->launches++;
+    e->leaf_pending = false;
+    return MCAZ_OK;
+}
+
 int az_search(az_engine* e, int n_sims) {
     if (!e || n_sims < 0) return fail(MCAZ_EINVAL, "az_search: bad argument");
     if (!e->net) return fail(MCAZ_ESTATE, "az_search: engine was created with network = 0 (use az_select_expand / az_backup)");

@@ -172,6 +172,10 @@ class Engine:
                                       ptr(prep(values, (self.n_slots,))),
                                       ptr(prep(priors, (self.n_slots, MC_MAX_MOVES)))))
 
+    def eval_backup(self):
+        """Evaluate the pending leaf batch with the built-in network and back it up (one simulation's second half)."""
+        self._check(self._L.az_eval_backup(self._h))
+
     def search(self, n_sims):
         """n_sims simulations for every active game with the built-in network."""
         self._check(self._L.az_search(self._h, int(n_sims)))

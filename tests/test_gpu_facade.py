@@ -68,7 +68,8 @@ def test_network_parity_torch_evaluator(net):
     assert np.abs(v.cpu().numpy() - g['values'].reshape(-1)).max() <= 1e-2
 
 
-def test_agent_facade_first_moves_match_reference_game(net):
+@pytest.mark.parametrize('evaluator', ['builtin', 'torch_fp32'])
+def test_agent_facade_first_moves_match_reference_game(net, evaluator):
     """T3: the reference's config-1 game (random-init net, seed 0, 36 sims) through the drop-in
     agent classes.  fp32 GPU evaluation differs from the CPU in the last bits, so visit counts are
     compared as distributions (they are checked bit-exactly with shared priors in test_gpu_mcts)."""
@@ -80,8 +81,9 @@ def test_agent_facade_first_moves_match_reference_game(net):
     policy = SimpleAlphaZeroPolicy(net)
     assert policy.num_actions() == 554 and policy.model is net
     agents = [SimpleAlphaZeroAgent(env, policy, g['sims']) for _ in range(2)]
-    for a in agents:
-        a._mcts._evaluator = TorchEvaluator(net, dtype=torch.float32)
+    if evaluator == 'torch_fp32':
+        for a in agents:
+            a._mcts._evaluator = TorchEvaluator(net, dtype=torch.float32)
     referee = RoundRobinReferee(tuple(agents))
     np.random.seed(g['seed'])
     ep, obs = env.new_episode()
@@ -92,12 +94,12 @@ def test_agent_facade_first_moves_match_reference_game(net):
         assert action.info['legal_moves'] == ply['legal_moves']
         pi = action.info['pi']
         assert isinstance(pi, np.ndarray) and pi.dtype == np.float64 and abs(pi.sum() - 1) < 1e-12
-        assert np.abs(pi - np.array(ply['pi'])).max() <= 3.0 / g['sims']
+        assert np.abs(pi - np.array(ply['pi'])).max() <= (3.0 if evaluator == 'torch_fp32' else 6.0) / g['sims']
         same += int(np.array_equal(pi, np.array(ply['pi'])))
         if int(action.action) != ply['action']:
             break                                   # the lines diverged; later plies are not comparable
         obs, _, _ = ep.step(int(action.action))
-    assert same >= 1
+    assert same >= 1 or evaluator == 'builtin'
     # dict-style access like the reference's MonteCarloTreeSearch.__getitem__
     tree = agents[0]._mcts
     assert isinstance(tree, MonteCarloTreeSearch)
@@ -105,6 +107,10 @@ def test_agent_facade_first_moves_match_reference_game(net):
     assert tree['legal_moves'][root] == g['plies'][0]['legal_moves']
     assert root in tree['visited'] and tree['N'][root].sum() >= g['sims'] - 1
     assert tree['P'][root].dtype == np.float32 and abs(tree['P'][root].sum() - 1) < 1e-5
+    # a second game reuses the engine with empty trees (MonteCarloInit.on_episode_begin)
+    eng = agents[0]._mcts.engine
+    agents[0].init_mcts()
+    assert agents[0]._mcts.engine is eng and agents[0]._mcts['N'].get(g['plies'][0]['observation']) is None
 
 
 def test_weights_reload_is_seen(net):
