@@ -60,3 +60,24 @@ def test_one_loop_iteration_updates_engine_weights(mcaz_lib):
     assert np.abs(torch.from_numpy(after).softmax(-1).numpy() - p_ref.softmax(-1).numpy()).max() < 1e-2
     assert np.abs(v_after - v_ref.numpy().reshape(-1)).max() < 2e-2
     sp.run(2)                                                    # self-play continues on the updated network
+
+
+def test_arena_bookkeeping(mcaz_lib):
+    """Row (f)-4: new-vs-old arena on one engine; each side's tree is evaluated with its own network."""
+    from minitchess_alphazero_b200.arena import Arena
+    from minitchess_alphazero_b200.policy import Network
+    torch.manual_seed(0)
+    net_a = Network().eval()
+    torch.manual_seed(1)
+    net_b = Network().eval()
+    arena = Arena(net_a, net_b, games_per_side=16, num_simulations=6, seed=3)
+    out = arena.play()
+    assert out['a'] + out['b'] + out['draws'] == 32 and 0.0 <= out['a_score'] <= 1.0 and out['plies'] <= 61
+    c = arena.engine.counters()
+    assert c['games_finished'] == 32 and c['simulations'] > 0
+    # both networks were really used: their evaluations of the start position differ
+    from oracle import rules_c as rc
+    tok, clk = rc.tokenize(rc.start_state())
+    l0, _ = arena._nets[0].network_forward(tok, clk)
+    l1, _ = arena._nets[1].network_forward(tok, clk)
+    assert not np.allclose(l0, l1)
