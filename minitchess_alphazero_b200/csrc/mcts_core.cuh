@@ -163,9 +163,25 @@ MC_HD void ht_insert(const View& V, int t, const mc_state& s, uint32_t node) {
     raise(V, ERR_HASH_CAP);
 }
 
+// Fivefold repetition inside one simulation: the reference builds a fresh Board(fen) per simulation and
+// pushes the selected moves, so board.result() at a new leaf sees the positions of this path only
+// (python-chess is_fivefold_repetition over the move stack).  A path needs >= 16 plies for that.
+MC_HD bool same_position(const Board4& b, uint32_t meta, const mc_state& s) {
+    return b.x == s.pl0 && b.y == s.pl1 && b.z == s.pl2 && b.w == s.white && ((meta ^ s.meta) & 1u) == 0;
+}
+MC_HD int path_repetitions(const View& V, int t, const uint32_t* pnode, int depth, const mc_state& s) {
+    int same = 0;
+    for (int d = 0; d < depth; ++d) {
+        const size_t gi = (size_t)t * V.NC + pnode[d];
+        same += same_position(V.node_board[gi], V.node_meta[gi], s) ? 1 : 0;
+    }
+    return same;
+}
+
 // Create the node for an unvisited position (exp/agent.py:57-66).  Lane 0 writes; every lane
 // gets the node index, its kind and, for a finished position, the value to back up.
-MC_HD uint32_t expand(const View& V, int slot, int t, int lane, const mc_state& s, uint8_t* kind, double* value) {
+MC_HD uint32_t expand(const View& V, int slot, int t, int lane, const mc_state& s, uint8_t* kind, double* value,
+                      const uint32_t* pnode, int depth) {
     uint32_t node = NONE;
     int is_terminal = 0, decisive = 0;
 #if defined(__CUDA_ARCH__)
@@ -179,6 +195,8 @@ MC_HD uint32_t expand(const View& V, int slot, int t, int lane, const mc_state& 
             uint16_t codes[MC_MAX_MOVES];
             int res;
             int E = mc::generate(s, V.rules, codes, &res);
+            if (res == MC_ONGOING && V.rules.fivefold_repetition && depth >= 16 && path_repetitions(V, t, pnode, depth, s) >= 4)
+                res = MC_DRAW;
             uint32_t off = V.tree_edges[t];
             size_t gi = (size_t)t * V.NC + n;
             if (res != MC_ONGOING) {
@@ -251,7 +269,7 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
 }
 
 __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, int lane, const mc_state& s, uint8_t* kind,
-                                                double* value) {
+                                                double* value, const uint32_t* pnode, int depth) {
     const bool white = mc::white_to_move(s);
     const mc::Sets st = mc::sets_of(s);
     const int fv = lane;                                   // view square of this lane (30, 31: none)
@@ -282,6 +300,15 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, 
     warp_excl_scan(mc::popc(tg), lane, &tot_moves);
     int E = tot_q + tot_n;
     int res = mc::result_of(s, st, tot_moves, V.rules);
+    if (res == MC_ONGOING && V.rules.fivefold_repetition && depth >= 16) {
+        int same = 0;
+        for (int d = lane; d < depth; d += 32) {
+            const size_t pi = (size_t)t * V.NC + pnode[d];
+            same += same_position(V.node_board[pi], V.node_meta[pi], s) ? 1 : 0;
+        }
+        for (int o = 16; o > 0; o >>= 1) same += __shfl_xor_sync(0xffffffffu, same, o);
+        if (same >= 4) res = MC_DRAW;
+    }
     // lane 0 reserves the node and its edges
     uint32_t node = NONE, off = 0;
     int ok = 1;
@@ -371,7 +398,7 @@ MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise
     if (node == NONE) {
         mc_state s = V.game_state[g];
         node = ht_find(V, t, s);
-        if (node == NONE) node = AZ_EXPAND(V, slot, t, lane, s, &kind, &value);
+        if (node == NONE) node = AZ_EXPAND(V, slot, t, lane, s, &kind, &value, pnode, 0);
         if (lane == 0 && node != NONE) V.tree_root[t] = node;
         AZ_SYNCWARP();
     }
@@ -469,7 +496,7 @@ MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise
             const bool white = mc::white_to_move(ps);
             mc_state cs = mc::apply_move(ps, white ? fv : 29 - fv, white ? tv : 29 - tv);
             child = ht_find(V, t, cs);
-            if (child == NONE) child = AZ_EXPAND(V, slot, t, lane, cs, &kind, &value);
+            if (child == NONE) { AZ_SYNCWARP(); child = AZ_EXPAND(V, slot, t, lane, cs, &kind, &value, pnode, depth); }
             if (lane == 0 && child != NONE) V.edge_child[e] = child;
             AZ_SYNCWARP();
             if (child == NONE) break;

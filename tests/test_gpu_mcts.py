@@ -9,7 +9,8 @@ from oracle import rules_c as rc
 from oracle.hash_eval import hash_evaluate
 from test_mcts_host import (test_golden_game_visit_counts_bit_exact, test_batched_games_match_restatement,  # noqa: F401
                             test_no_noise_and_numpy1_flow_switch, test_terminal_revisit_sign_flip,
-                            test_capacity_overflow_fails_loudly, test_phase_errors, make_engine)
+                            test_capacity_overflow_fails_loudly, test_phase_errors, test_fivefold_repetition_inside_a_simulation,
+                            make_engine)
 
 pytestmark = pytest.mark.gpu
 

@@ -96,6 +96,26 @@ def test_terminal_revisit_sign_flip(backend):
     pc.compare_with_tree(eng, 0, 0, tree)
 
 
+def test_fivefold_repetition_inside_a_simulation(backend):
+    """Both kings can only shuffle (a1-b1, e6-d6), every pawn is blocked: the search path is forced, so the
+    17th simulation reaches the start position for the fifth time along its own path and the reference's
+    board.result() calls it a draw there.  The engine must stop at the same depth."""
+    fen = '2p1k/2p1p/2P1P/p1p2/P1P2/K1P2 w 0 1'
+    from oracle.ref_selfplay import RefEpisode
+    ep = RefEpisode(fen)
+    assert len(ep.legal) == 1 and not ep.done
+    sims = 30
+    tree = rs.RefTree(hash_evaluate, 1, epsilon=0.0)
+    tree.simulate(sims, fen)
+    assert any(v == 0 for v in tree.terminal.values()) and tree.n_evals == 16
+    eng = make_engine(backend, 1, sims, dirichlet_epsilon=0.0)
+    records, _, _ = pc.play_games(eng, hash_evaluate, sims, [np.random.RandomState(0)], max_plies=1,
+                                  start_states=rc.fens_to_states([fen]), epsilon=0.0)
+    assert records[0][0]['N'] == tree.N[fen].tolist() and records[0][0]['Q'] == tree.Q[fen].tolist()
+    pc.compare_with_tree(eng, 0, 0, tree)
+    assert eng.counters()['evaluations'] == 16
+
+
 def test_capacity_overflow_fails_loudly(backend):
     from minitchess_alphazero_b200._lib import McazError
     eng = make_engine(backend, 1, 8, node_capacity=5, edge_capacity=64)
