@@ -230,9 +230,10 @@ int az_network_forward(az_engine* e, const uint8_t* tokens, const float* clocks,
                        float* logits, float* values);
 
 /* Profiling hook for bench.py: while on, every network forward is bracketed by CUDA events on the
- * engine's stream around its 18 tower-convolution launches.  A call with a non-NULL
- * avg_ms_per_conv_launch synchronises, reports the average since the previous call and resets.   */
-int az_profile_network(az_engine* e, int on, double* avg_ms_per_conv_launch, int* n_forwards);
+ * engine's stream around its residual tower (18 convolutions: one fused launch, or 18 launches with
+ * MCAZ_TOWER=layers; *launches_per_forward says which).  A call with a non-NULL avg_ms_per_tower
+ * synchronises, reports the average tower time since the previous call and resets.                 */
+int az_profile_network(az_engine* e, int on, double* avg_ms_per_tower, int* n_forwards, int* launches_per_forward);
 
 /* Kernels launched by this library in this process (all engines and mc_* calls).               */
 uint64_t mcaz_kernel_launches(void);

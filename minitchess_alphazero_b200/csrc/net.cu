@@ -925,8 +925,8 @@ struct Network {
     uint32_t* tower_flags = nullptr;   // [18][n_pairs][30][2]
     int tower_pairs = -1, tower_grid = 0;
     uint32_t epoch = 0;
-    bool per_layer = true;             // default: one launch per layer; MCAZ_TOWER=fused selects tower_tc_kernel (one launch,
-                                       // data-flow ordered; measured +1% under the power cap)
+    bool per_layer = false;            // false: tower_tc_kernel (one data-flow ordered launch for the 18 layers, default);
+                                       // true: one conv3x3_tc_kernel launch per layer (MCAZ_TOWER=layers, or no co-residency)
     // profiling (az_profile_network)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -975,7 +975,25 @@ int network_create(az_engine* e) {
     if (int rc = make_map_3d(&N->map_w, N->w, C, C, (uint64_t)NLAYERS * 9, BLOCK_K, C / 2)) return rc;
     MCAZ_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
     MCAZ_CUDA(cudaFuncSetAttribute(tower_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_SMEM));
-    { const char* m = getenv("MCAZ_TOWER"); N->per_layer = !(m && std::strcmp(m, "fused") == 0); }
+    {
+        // Default: the fused data-flow tower, provided every CTA pair of its grid can be resident at once (its
+        // flag waits assume that).  MCAZ_TOWER=layers forces one launch per layer.
+        const char* m = getenv("MCAZ_TOWER");
+        N->per_layer = m && std::strcmp(m, "layers") == 0;
+        if (!N->per_layer) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * (num_sms() / 2)); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = TOWER_SMEM;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr; cfg.numAttrs = 1;
+            int max_clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, tower_tc_kernel, &cfg) != cudaSuccess || max_clusters < num_sms() / 2) {
+                cudaGetLastError();
+                N->per_layer = true;
+            }
+        }
+    }
     return net_alloc_acts(e, std::min(e->v.G * e->v.K, MAX_CHUNK_BOARDS));
 }
 
@@ -1062,8 +1080,13 @@ static int build_tower_schedule(az_engine* e, int n_pairs) {
     std::vector<long long> load(clusters, 0);
     std::vector<int> count(clusters, 0);
     std::vector<uint32_t> table((size_t)clusters * TOWER_MAX_ITEMS, SCHED_END);
+    // Groups of at most 8 tile pairs (2048 boards, 2 x 31 MB of activations) go through all 18 layers one
+    // after the other, so a group's ping-pong buffers stay resident in the 126 MB L2 from layer to layer.
+    int group = 8;
+    { const char* gs = getenv("MCAZ_TOWER_GROUP"); if (gs && atoi(gs) > 0) group = atoi(gs); }
+    for (int g0 = 0; g0 < n_pairs; g0 += group)
     for (int L = 0; L < NLAYERS; ++L)
-        for (int tp = 0; tp < n_pairs; ++tp)
+        for (int tp = g0; tp < std::min(n_pairs, g0 + group); ++tp)
             for (int pos : order) {
                 int best = 0;
                 for (int c = 1; c < clusters; ++c)
@@ -1167,10 +1190,10 @@ int network_forward_search(az_engine* e, const az::View& V, float* values) {
     return forward_chunk(e, V.tokens, V.clocks, V.G * V.K, nullptr, values, &V);
 }
 
-int network_profile(az_engine* e, int on, double* avg_ms_per_conv_launch, int* n_forwards) {
+int network_profile(az_engine* e, int on, double* avg_ms_per_tower, int* n_forwards, int* launches_per_forward) {
     Network* N = e->net;
     if (!N) return fail(MCAZ_ESTATE, "engine has no built-in network");
-    if (avg_ms_per_conv_launch) {
+    if (avg_ms_per_tower) {
         cudaStreamSynchronize(e->stream);
         double total = 0;
         for (size_t i = 0; i < N->events_used; ++i) {
@@ -1178,9 +1201,10 @@ int network_profile(az_engine* e, int on, double* avg_ms_per_conv_launch, int* n
             cudaEventElapsedTime(&ms, N->events[i].first, N->events[i].second);
             total += ms;
         }
-        *avg_ms_per_conv_launch = N->events_used ? total / (double)N->events_used / NLAYERS : 0.0;
+        *avg_ms_per_tower = N->events_used ? total / (double)N->events_used : 0.0;
         if (n_forwards) *n_forwards = (int)N->events_used;
     }
+    if (launches_per_forward) *launches_per_forward = N->per_layer ? NLAYERS : 1;
     N->events_used = 0;
     N->profiling = on != 0;
     return MCAZ_OK;
@@ -1188,7 +1212,7 @@ int network_profile(az_engine* e, int on, double* avg_ms_per_conv_launch, int* n
 
 }  // namespace mcaz
 
-extern "C" int az_profile_network(az_engine* e, int on, double* avg_ms_per_conv_launch, int* n_forwards) {
+extern "C" int az_profile_network(az_engine* e, int on, double* avg_ms_per_tower, int* n_forwards, int* launches_per_forward) {
     if (!e) return mcaz::fail(MCAZ_EINVAL, "az_profile_network: null engine");
-    return mcaz::network_profile(e, on, avg_ms_per_conv_launch, n_forwards);
+    return mcaz::network_profile(e, on, avg_ms_per_tower, n_forwards, launches_per_forward);
 }

@@ -240,11 +240,11 @@ class Engine:
 
 
 def _profile_network(self, on=True, read=False):
-    """bench hook: (avg ms per tower-conv launch, forwards measured) since the last call."""
-    ms, n = ctypes.c_double(), ctypes.c_int()
+    """bench hook: (avg ms per residual tower, forwards measured, kernel launches per tower) since the last call."""
+    ms, n, lpf = ctypes.c_double(), ctypes.c_int(), ctypes.c_int()
     self._check(self._L.az_profile_network(self._h, int(bool(on)), ctypes.byref(ms) if read else None,
-                                           ctypes.byref(n) if read else None))
-    return (ms.value, n.value) if read else None
+                                           ctypes.byref(n) if read else None, ctypes.byref(lpf)))
+    return (ms.value, n.value, lpf.value) if read else None
 
 
 Engine.profile_network = _profile_network

@@ -115,15 +115,21 @@ class BatchedSelfPlay:
         reset_kernel_timer(): algorithmic FLOP per launch / average launch duration."""
         if self.mode != 'builtin':
             return None
-        ms, n = self.engine.profile_network(False, read=True)
+        ms, n, per_forward = self.engine.profile_network(False, read=True)
         if n == 0 or ms <= 0:
             return None
-        flop = self.n_games * self.CONV_FLOP_PER_EVAL
-        return {'bound': 'tensor', 'kernel': 'conv3x3_tc_kernel (tcgen05 cta_group::2 3x3 conv 256->256, one launch per layer)',
-                'achieved': flop / (ms / 1e3) / 1e12, 'unit': 'TFLOP/s',
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_conv_r1_raw.csv (two launches)
-                'traffic': 151e6, 'ms_per_launch': ms, 'launches_timed': n * 18, 'flop_per_launch': flop,
+        rows = self.engine.n_slots
+        flop = rows * self.CONV_FLOP_PER_EVAL * 18 / per_forward     # algorithmic FLOP of one launch
+        ms_launch = ms / per_forward
+        fused = per_forward == 1
+        return {'bound': 'tensor',
+                'kernel': ('tower_tc_kernel (18 x [3x3 conv 256->256] in one data-flow ordered launch, tcgen05 cta_group::2)' if fused
+                           else 'conv3x3_tc_kernel (tcgen05 cta_group::2 3x3 conv 256->256, one launch per layer)'),
+                'achieved': flop / (ms_launch / 1e3) / 1e12, 'unit': 'TFLOP/s',
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/ (ncu --set full)
+                'traffic': 934e6 if fused else 151e6, 'ms_per_launch': ms_launch, 'launches_timed': n * per_forward,
+                'flop_per_launch': flop,
                 # the kernel skips the 62 of 270 tap-positions that multiply zero padding: MMAs actually issued
-                'achieved_mma': flop * 208 / 270 / (ms / 1e3) / 1e12,
+                'achieved_mma': flop * 208 / 270 / (ms_launch / 1e3) / 1e12,
                 'note': 'achieved counts the algorithmic FLOPs of SURVEY.md 8(d) (all 9 taps at all 30 squares); '
                         'taps on zero padding are skipped, so issued MMA work is 208/270 of it (achieved_mma)'}

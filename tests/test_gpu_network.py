@@ -33,16 +33,17 @@ def bn_perturbed_net():
 
 
 def test_fused_tower_kernel_matches_per_layer(mcaz_lib, monkeypatch):
-    """MCAZ_TOWER=fused runs the 18 convolutions as one data-flow-ordered persistent kernel; results must be
-    bit-identical to the one-launch-per-layer path (same MMAs, same order of accumulation)."""
+    """The default runs the 18 convolutions as one data-flow-ordered persistent kernel; MCAZ_TOWER=layers
+    launches one kernel per layer.  Results must be bit-identical (same MMAs, same order of accumulation)."""
     from minitchess_alphazero_b200.policy import Network
     torch.manual_seed(0)
     net = Network().eval()
     pos = np.ascontiguousarray(rc.random_positions(5, 3000)[:1000])
     tokens, clocks = rc.tokenize(pos)
+    monkeypatch.setenv('MCAZ_TOWER', 'layers')
     a = make_engine(net, n_games=1000)
     la, va = a.network_forward(tokens, clocks)
-    monkeypatch.setenv('MCAZ_TOWER', 'fused')
+    monkeypatch.delenv('MCAZ_TOWER')
     b = make_engine(net, n_games=1000)
     for _ in range(3):                      # repeated launches: epoch-stamped dependency flags
         lb, vb = b.network_forward(tokens, clocks)
