@@ -132,13 +132,15 @@ class MonteCarloTreeSearch:
         eng.set_positions(rules.state_from_fen(observation), trees=[0])
         if ev is not None:
             tokens, clocks, _needs = eng.leaf_batch_device()
+        root_edges = -1                                     # unknown until the root is seen expanded
         for _ in range(num_simulations):
             noise = None
             if self._epsilon > 0:
-                _, _, _, n_legal = eng.root_stats(want_q=False)
-                if n_legal[0] > 0:                          # root already expanded: exp/agent.py:81-82
+                if root_edges < 0:
+                    root_edges = int(eng.root_stats(want_q=False)[3][0])
+                if root_edges > 0:                          # root already expanded: exp/agent.py:81-82
                     noise = np.zeros((1, MC_MAX_MOVES))
-                    noise[0, :n_legal[0]] = np.random.dirichlet([self._alpha] * int(n_legal[0]))
+                    noise[0, :root_edges] = np.random.dirichlet([self._alpha] * root_edges)
             eng.select_expand(noise)
             if ev is None:
                 eng.eval_backup()                           # built-in tcgen05 network
