@@ -133,6 +133,9 @@ typedef struct az_config {
     int32_t leaves_per_step;   /* 1 = the reference's sequential search (bit-exact); K > 1 = K descents per
                                   tree and step kept apart by virtual loss (throughput option for few games;
                                   changes visit counts); leaf batch rows = n_games * K, row = game * K + j   */
+    int32_t own_stream;        /* 1 = the engine works on its own non-blocking CUDA stream (several engines in one
+                                  process then overlap); 0 = the legacy default stream, ordered with the caller's
+                                  torch work (needed when device tensors are exchanged every simulation)            */
 } az_config;
 
 void az_default_config(az_config* out);

@@ -39,7 +39,7 @@ class Config(ctypes.Structure):
                 ('dirichlet_alpha', ctypes.c_float), ('dirichlet_epsilon', ctypes.c_float),
                 ('numpy1_dtype_flow', ctypes.c_int32), ('device_rng', ctypes.c_int32),
                 ('seed', ctypes.c_uint64), ('rules', Rules), ('network', ctypes.c_int32),
-                ('leaves_per_step', ctypes.c_int32)]
+                ('leaves_per_step', ctypes.c_int32), ('own_stream', ctypes.c_int32)]
 
 
 _lib = None

@@ -309,6 +309,7 @@ void az_default_config(az_config* c) {
     mc_default_rules(&c->rules);
     c->network = 0;
     c->leaves_per_step = 1;
+    c->own_stream = 0;
 }
 
 int az_create(const az_config* cfg, az_engine** out) {
@@ -318,6 +319,10 @@ int az_create(const az_config* cfg, az_engine** out) {
     az_engine* e = new az_engine();
     e->cfg = *cfg;
     cudaGetDevice(&e->device);
+    if (cfg->own_stream && cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete e;
+        return fail(MCAZ_ECUDA, "az_create: cudaStreamCreateWithFlags failed");
+    }
     View& V = e->v;
     V.G = cfg->n_games;
     V.K = cfg->leaves_per_step > 0 ? cfg->leaves_per_step : 1;
@@ -366,6 +371,7 @@ int az_destroy(az_engine* e) {
     if (e->net) network_destroy(e);
     for (void* p : e->allocs) cudaFree(p);
     e->scratch.release();
+    if (e->cfg.own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return MCAZ_OK;
 }

@@ -220,6 +220,9 @@ class Engine:
         """flat: float32 [AZ_NUM_WEIGHT_FLOATS] numpy array or CUDA tensor (policy.flatten_state_dict)."""
         n = flat.numel() if hasattr(flat, 'numel') else flat.size
         assert n == AZ_NUM_WEIGHT_FLOATS, n
+        if hasattr(flat, 'is_cuda') and flat.is_cuda:      # produced on torch's stream, consumed on the engine's
+            import torch
+            torch.cuda.current_stream().synchronize()
         self._check(self._L.az_set_weights(self._h, ptr(flat), ctypes.c_size_t(n)))
 
     def network_forward(self, tokens, clocks):
