@@ -1,10 +1,10 @@
 // net.cu -- the policy/value network of exp/policy.py:53-80 as hand-written sm_100a kernels.
 //
 //   stem_kernel        Embedding(7,4) + Conv3x3(8->256) + BN + ReLU as a table sum (no MACs)
-//   conv3x3_tc_kernel  the 18 tower convolutions 256->256: tcgen05.mma (UMMA 128x256x16, bf16 in,
-//                      fp32 accumulate in TMEM), operands staged by TMA (SWIZZLE_128B, K-major),
-//                      4-stage mbarrier pipeline, double-buffered TMEM accumulators, fused
-//                      bias(+BN) / residual / ReLU / bf16 epilogue
+//   tower_tc_kernel    the 18 tower convolutions 256->256: tcgen05.mma.cta_group::2 (UMMA 256x256x16 over a
+//                      CTA pair, bf16 in, fp32 accumulate in TMEM), operands staged by TMA (SWIZZLE_128B,
+//                      K-major), 6-stage mbarrier pipeline, double-buffered TMEM accumulators, fused
+//                      bias(+BN) / residual / ReLU / bf16 epilogue; one data-flow ordered launch
 //   heads_kernel       policy head (conv1x1 -> 61->554 linear) and value head (conv1x1 -> 31->256
 //                      -> 1, tanh), fp32
 //
@@ -38,11 +38,9 @@ constexpr int STAGES = 6;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB: this CTA's 128 boards x 64 input channels
 constexpr int B_BYTES = (C / 2) * BLOCK_K * 2;   // 16 KB: this CTA's half of the 256 output channels
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int CONV_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int CONV_THREADS = 256;                // TMA, MMA, TMEM-alloc, spare + 4 epilogue warps
-constexpr int MAX_ITEMS_PER_CTA = 16;
 constexpr uint32_t SCHED_END = 0xffffffffu;
-constexpr int MAX_CHUNK_BOARDS = 8192;           // keeps the per-CTA schedule within MAX_ITEMS_PER_CTA
+constexpr int MAX_CHUNK_BOARDS = 8192;           // boards per forward pass (keeps the per-pair schedule within TOWER_MAX_ITEMS)
 
 // flat state_dict offsets (floats), exp/policy.py:56-69 order without num_batches_tracked
 constexpr size_t OFF_EMB = 0;
@@ -156,208 +154,37 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 // cta_group::2: one instruction spans the CTA pair, M = 256 boards (128 per CTA), N = 256.
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
 
-struct ConvParams {
-    const float* bias;              // [256] folded conv bias + BatchNorm
-    const __nv_bfloat16* residual;  // same layout as out, or nullptr
-    __nv_bfloat16* out;
-    const uint32_t* sched;          // [grid][MAX_ITEMS_PER_CTA] work items: pos | tile << 8 | n_tiles << 24
-    int bpad;                       // boards per position plane (multiple of 128)
-    int layer;
-    int relu;
-};
-
 __device__ __forceinline__ bool tap_valid(int pos, int tap, int& src) {
     int row = pos / 5 + tap / 3 - 1, col = pos % 5 + tap % 3 - 1;
     src = row * 5 + col;
     return row >= 0 && row < 6 && col >= 0 && col < 5;
 }
 
-// One work item = one output position x a pair of 128-board tiles, computed by a CTA pair with
-// tcgen05.mma.cta_group::2: each CTA stages its own boards (A) and half of the output channels (B),
-// so every SM reads and writes half the weight bytes of the single-CTA form -- the shared-memory
-// port, not the tensor pipe, is what limits a 1-CTA 128x256 SS-mode MMA.  Roles per CTA: warp 0
-// lane 0 TMA producer, warp 1 lane 0 MMA issuer (leader CTA only), warp 2 TMEM allocator,
-// warps 4-7 epilogue of this CTA's 128 accumulator rows.  TMEM accumulators are double buffered.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_w, const ConvParams P) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* full = bars;                           // [STAGES]  TMA (both CTAs) -> MMA, lives in the leader
-    uint64_t* empty = bars + STAGES;                 // [STAGES]  MMA -> TMA, one copy per CTA
-    uint64_t* acc_full = bars + 2 * STAGES;          // [2]  MMA -> epilogue, one copy per CTA
-    uint64_t* acc_empty = bars + 2 * STAGES + 2;     // [2]  epilogue (both CTAs) -> MMA, lives in the leader
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-    __shared__ float s_bias[C];
-    __shared__ uint32_t s_sched[MAX_ITEMS_PER_CTA];
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
-
-    for (int i = threadIdx.x; i < C; i += CONV_THREADS) s_bias[i] = P.bias[i];
-    if (threadIdx.x < MAX_ITEMS_PER_CTA) s_sched[threadIdx.x] = P.sched[(blockIdx.x >> 1) * MAX_ITEMS_PER_CTA + threadIdx.x];
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();                              // the peer's barriers are initialised before any remote arrive
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0 && lane == 0) {
-        // ---------------------------------------------------------------- TMA producer (both CTAs)
-        uint32_t it = 0;
-        for (int k = 0; k < MAX_ITEMS_PER_CTA && s_sched[k] != SCHED_END; ++k) {
-            const uint32_t item = s_sched[k];
-            const int pos = item & 0xff, tile = 2 * (int)(item >> 8) + (int)rank;
-            for (int tap = 0; tap < 9; ++tap) {
-                int src;
-                if (!tap_valid(pos, tap, src)) continue;
-                for (int kc = 0; kc < C / BLOCK_K; ++kc, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
-                    if (leader) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
-                    else mbar_arrive_remote(&full[s], 0);
-                    uint8_t* st = smem + s * STAGE_BYTES;
-                    tma_load_3d_2sm(st, &map_act, &full[s], kc * BLOCK_K, tile * BLOCK_M, src);
-                    tma_load_3d_2sm(st + A_BYTES, &map_w, &full[s], kc * BLOCK_K, (int)rank * (C / 2), P.layer * 9 + tap);
-                }
-            }
-        }
-    } else if (warp == 1 && lane == 0 && leader) {
-        // ---------------------------------------------------------------- MMA issuer (leader CTA)
-        uint32_t it = 0;
-        for (int k = 0; k < MAX_ITEMS_PER_CTA && s_sched[k] != SCHED_END; ++k) {
-            const int pos = s_sched[k] & 0xff;
-            const uint32_t acc = k & 1;
-            mbar_wait(&acc_empty[acc], ((k >> 1) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * C;
-            uint32_t accumulate = 0;
-            for (int tap = 0; tap < 9; ++tap) {
-                int src;
-                if (!tap_valid(pos, tap, src)) continue;
-                for (int kc = 0; kc < C / BLOCK_K; ++kc, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&full[s], (it / STAGES) & 1);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-                    const uint64_t da = umma_desc(a_addr), db = umma_desc(a_addr + A_BYTES);
-#pragma unroll
-                    for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
-                        umma_bf16_2sm(d_tmem, da + 2 * kk, db + 2 * kk, IDESC, accumulate);
-                        accumulate = 1;
-                    }
-                    umma_commit_2sm(&empty[s]);      // frees this stage in both CTAs when the MMAs retire
-                }
-            }
-            umma_commit_2sm(&acc_full[acc]);         // accumulators complete -> both epilogues
-        }
-    } else if (warp >= 4) {
-        // ---------------------------------------------------------------- epilogue (TMEM -> HBM)
-        const int q = warp & 3;                      // TMEM lane quadrant this warp may read
-        for (int k = 0; k < MAX_ITEMS_PER_CTA && s_sched[k] != SCHED_END; ++k) {
-            const uint32_t item = s_sched[k];
-            const int pos = item & 0xff, tile = 2 * (int)(item >> 8) + (int)rank;
-            const uint32_t acc = k & 1;
-            const size_t row_off = ((size_t)pos * P.bpad + (size_t)tile * BLOCK_M + q * 32 + lane) * C;
-            // residual rows are outputs of the previous layer: fetch them while the MMAs still run
-            uint4 res[4][4];
-            if (P.residual) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(P.residual + row_off + c * 32);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) res[c][j] = rp[j];
-                }
-            }
-            mbar_wait(&acc_full[acc], (k >> 1) & 1);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C;
-#pragma unroll
-            for (int c = 0; c < C / 32; ++c) {
-                uint32_t v[32];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr + c * 32)
-                    : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                uint4 outv[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t packed[4];
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        const int e = j * 8 + h * 2;
-                        float x0 = __uint_as_float(v[e]) + s_bias[c * 32 + e];
-                        float x1 = __uint_as_float(v[e + 1]) + s_bias[c * 32 + e + 1];
-                        if (P.residual) {
-                            const uint32_t r = (&res[c & 3][j].x)[h];
-                            x0 += __uint_as_float(r << 16);
-                            x1 += __uint_as_float(r & 0xffff0000u);
-                        }
-                        if (P.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(x0, x1);
-                        packed[h] = *reinterpret_cast<uint32_t*>(&b2);
-                    }
-                    outv[j] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                }
-                if (P.residual && c + 4 < C / 32) {      // refill the ring slot just consumed
-                    const uint4* rp = reinterpret_cast<const uint4*>(P.residual + row_off + (c + 4) * 32);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) res[c & 3][j] = rp[j];
-                }
-                uint4* op = reinterpret_cast<uint4*>(P.out + row_off + c * 32);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) op[j] = outv[j];
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (leader) mbar_arrive(&acc_empty[acc]);
-                else mbar_arrive_remote(&acc_empty[acc], 0);
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();                              // nobody tears down TMEM / exits while the peer still uses it
-    if (warp == 2) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
-}
-
-// ---------------------------------------------------------------------------------- whole tower, one launch
-// The 18 convolutions as ONE persistent kernel: the same CTA-pair pipeline as above, but a work item is
-// (layer, position, tile pair) and layers are ordered by data flow instead of by kernel boundaries.
-// Item (L, p, tp) may start once the items (L-1, p', tp) for the valid taps p' of p have published their
-// outputs (per-item flags in global memory, release/acquire at gpu scope); that one rule also covers the
-// write-after-read hazards of the two ping-pong activation buffers.  CTA pairs that finish a layer early
-// move on instead of idling at a grid-wide barrier, which removes the per-layer tail and 17 launch gaps.
+// ---------------------------------------------------------------------------------- residual tower
+// One work item = (layer, output position, pair of 128-board tiles), computed by a CTA pair with
+// tcgen05.mma.cta_group::2: each CTA stages its own boards (A) and half of the output channels (B), so every
+// SM reads and writes half the weight bytes of the single-CTA form -- the shared-memory port, not the tensor
+// pipe, is what limits a 1-CTA 128x256 SS-mode MMA.  Roles per CTA: warp 0 lane 0 TMA producer, warp 1 lane 0
+// MMA issuer (leader CTA only), warp 2 TMEM allocator, warp 3 dependency watcher, warps 4-7 epilogue of this
+// CTA's 128 accumulator rows.  6-stage smem ring, double-buffered TMEM accumulators.
+//
+// Default form: the 18 convolutions are ONE persistent launch.  Layers are ordered by data flow instead of
+// by kernel boundaries: item (L, p, tp) may start once the items (L-1, p', tp) for the valid taps p' of p
+// have published their outputs (per-item epoch flags in global memory, release/acquire at gpu scope); that
+// one rule also covers the write-after-read hazards of the two ping-pong activation buffers.  CTA pairs
+// that finish a layer early move on instead of idling at a grid-wide barrier.
+// Fallback form (MCAZ_TOWER=layers, or when the pairs cannot all be resident): the same kernel is launched
+// once per layer with that layer's items and flags == nullptr -- kernel boundaries order the layers.
 constexpr int TOWER_MAX_ITEMS = 256;
 constexpr int TOWER_SMEM = STAGES * STAGE_BYTES + 1024 + 256 + NLAYERS * C * 4;
+constexpr unsigned long long WATCHDOG_CYCLES = 20ull * 1000 * 1000 * 1000;   // ~10 s: a dependency that never arrives
 
 struct TowerParams {
     const float* bias;            // [18][256]
     __nv_bfloat16* act0;          // layer input of even layers / residual + output of odd layers
     __nv_bfloat16* act1;
     const uint32_t* sched;        // [clusters][TOWER_MAX_ITEMS]: layer << 24 | tile pair << 8 | position
-    uint32_t* flags;              // [18][n_pairs][30][2] epoch stamps
+    uint32_t* flags;              // [18][n_pairs][30][2] epoch stamps; nullptr = one layer per launch, no dependencies
     int bpad;
     int n_pairs;
     uint32_t epoch;
@@ -429,7 +256,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             if (item == SCHED_END) break;
             const int pos = item & 0xff, tp = (item >> 8) & 0xffff, L = item >> 24;
             const int tile = 2 * tp + (int)rank;
-            if (L > 0) {
+            if (L > 0 && P.flags) {
                 // inputs published? (warp 3 polls the global flags ahead of us)
                 while (ld_acquire_cta_shared(&s_deps_ok) <= (uint32_t)k) {}
                 asm volatile("fence.proxy.async;" ::: "memory");   // order the acquired writes before our TMA reads
@@ -489,11 +316,17 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             const uint32_t item = __ldg(&sched[k]);
             if (item == SCHED_END) break;
             const int pos = item & 0xff, tp = (item >> 8) & 0xffff, L = item >> 24;
-            if (L > 0 && lane < 9) {
+            if (L > 0 && P.flags && lane < 9) {
                 int src;
                 if (tap_valid(pos, lane, src)) {
                     const uint32_t* fl = P.flags + (((size_t)(L - 1) * P.n_pairs + tp) * NPOS + src) * 2 + rank;
-                    while (ld_acquire_gpu(fl) != P.epoch) __nanosleep(32);
+                    const long long t0 = clock64();
+                    while (ld_acquire_gpu(fl) != P.epoch) {
+                        __nanosleep(32);
+                        // the producer of this flag is not resident (co-residency assumption broken): fail the
+                        // launch instead of hanging the GPU
+                        if ((unsigned long long)(clock64() - t0) > WATCHDOG_CYCLES) __trap();
+                    }
                 }
             }
             __syncwarp();
@@ -516,7 +349,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             // dependencies are: fetch them while the MMAs still run
             uint4 res[4][4];
             if (odd) {
-                while (ld_acquire_cta_shared(&s_deps_ok) <= (uint32_t)k) {}
+                if (P.flags) while (ld_acquire_cta_shared(&s_deps_ok) <= (uint32_t)k) {}
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint4* rp = reinterpret_cast<const uint4*>(out + row_off + c * 32);
@@ -582,7 +415,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             }
             // publish: the barrier orders all 128 threads' stores before the (cumulative) gpu-scope release
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (warp == 4 && lane == 0)
+            if (warp == 4 && lane == 0 && P.flags)
                 st_release_gpu(P.flags + (((size_t)L * P.n_pairs + tp) * NPOS + pos) * 2 + rank, P.epoch);
         }
     }
@@ -919,14 +752,14 @@ struct Network {
     HeadWeights heads{};
     CUtensorMap map_act[2], map_w;
     bool have_weights = false;
-    uint32_t* sched = nullptr;         // [grid][MAX_ITEMS_PER_CTA]
+    uint32_t* sched = nullptr;         // per-layer form: [18][clusters][TOWER_MAX_ITEMS]
     int sched_tiles = -1, sched_grid = 0;
     uint32_t* tower_sched = nullptr;   // [clusters][TOWER_MAX_ITEMS]
     uint32_t* tower_flags = nullptr;   // [18][n_pairs][30][2]
     int tower_pairs = -1, tower_grid = 0;
     uint32_t epoch = 0;
     bool per_layer = false;            // false: tower_tc_kernel (one data-flow ordered launch for the 18 layers, default);
-                                       // true: one conv3x3_tc_kernel launch per layer (MCAZ_TOWER=layers, or no co-residency)
+                                       // true: the same kernel launched once per layer (MCAZ_TOWER=layers, or no co-residency)
     // profiling (az_profile_network)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -973,7 +806,6 @@ int network_create(az_engine* e) {
     N->heads.v2 = p; p += 256;
     N->heads.v2b = p;
     if (int rc = make_map_3d(&N->map_w, N->w, C, C, (uint64_t)NLAYERS * 9, BLOCK_K, C / 2)) return rc;
-    MCAZ_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
     MCAZ_CUDA(cudaFuncSetAttribute(tower_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_SMEM));
     {
         // Default: the fused data-flow tower, provided every CTA pair of its grid can be resident at once (its
@@ -1027,8 +859,8 @@ int network_set_weights(az_engine* e, const float* flat) {
     return MCAZ_OK;
 }
 
-// Longest-processing-time-first assignment of a layer's work items (position x tile pair, weighted
-// by the number of valid taps) to the CTA pairs.  Static, so every role in a CTA walks the same list.
+// Per-layer form: longest-processing-time-first assignment of each layer's work items (position x tile pair,
+// weighted by the number of valid taps) to the CTA pairs; one table per layer, same kernel.
 static int build_schedule(az_engine* e, int n_pairs) {
     Network* N = e->net;
     const int clusters = std::max(1, std::min(num_sms() / 2, n_pairs * NPOS));
@@ -1042,13 +874,16 @@ static int build_schedule(az_engine* e, int n_pairs) {
     }
     std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.weight > b.weight; });
     std::vector<int> load(clusters, 0), count(clusters, 0);
-    std::vector<uint32_t> table((size_t)clusters * MAX_ITEMS_PER_CTA, SCHED_END);
+    const size_t per_layer = (size_t)clusters * TOWER_MAX_ITEMS;
+    std::vector<uint32_t> table(per_layer * NLAYERS, SCHED_END);
     for (const Item& it : items) {
         int best = -1;
         for (int c = 0; c < clusters; ++c)
-            if (count[c] < MAX_ITEMS_PER_CTA - 1 && (best < 0 || load[c] < load[best])) best = c;
+            if (count[c] < TOWER_MAX_ITEMS - 1 && (best < 0 || load[c] < load[best])) best = c;
         if (best < 0) return fail(MCAZ_ECAPACITY, "conv schedule: too many items per CTA pair");
-        table[(size_t)best * MAX_ITEMS_PER_CTA + count[best]++] = it.code;
+        for (int L = 0; L < NLAYERS; ++L)
+            table[L * per_layer + (size_t)best * TOWER_MAX_ITEMS + count[best]] = it.code | ((uint32_t)L << 24);
+        count[best]++;
         load[best] += it.weight;
     }
     if (N->sched) cudaFree(N->sched);
@@ -1149,26 +984,22 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
         N->events_used++;
         cudaEventRecord(ev0, st);
     }
+    TowerParams T;
+    T.bias = N->bias; T.act0 = N->act[0]; T.act1 = N->act[1];
+    T.bpad = bpad; T.n_pairs = n_pairs;
     if (N->per_layer) {
         if (int rc = build_schedule(e, n_pairs)) return rc;
-        ConvParams P;
-        P.bpad = bpad; P.relu = 1; P.sched = N->sched;
-        const int grid = N->sched_grid;
+        T.flags = nullptr; T.epoch = 0;
+        const size_t per_layer = (size_t)(N->sched_grid / 2) * TOWER_MAX_ITEMS;
         for (int L = 0; L < NLAYERS; ++L) {
-            const int src = L & 1, dst = src ^ 1;          // conv1: act0 -> act1, conv2: act1 -> act0 (+ residual act0)
-            P.layer = L;
-            P.bias = N->bias + L * C;
-            P.residual = (L & 1) ? N->act[dst] : nullptr;
-            P.out = N->act[dst];
-            conv3x3_tc_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(N->map_act[src], N->map_w, P);
+            T.sched = N->sched + L * per_layer;
+            tower_tc_kernel<<<N->sched_grid, CONV_THREADS, TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, T);
             MCAZ_CHECK_LAUNCH();
         }
         e->launches += NLAYERS - 1;
     } else {
         if (int rc = build_tower_schedule(e, n_pairs)) return rc;
-        TowerParams T;
-        T.bias = N->bias; T.act0 = N->act[0]; T.act1 = N->act[1]; T.sched = N->tower_sched; T.flags = N->tower_flags;
-        T.bpad = bpad; T.n_pairs = n_pairs; T.epoch = ++N->epoch;
+        T.sched = N->tower_sched; T.flags = N->tower_flags; T.epoch = ++N->epoch;
         tower_tc_kernel<<<N->tower_grid, CONV_THREADS, TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, T);
         MCAZ_CHECK_LAUNCH();
     }

@@ -111,7 +111,7 @@ class BatchedSelfPlay:
         return True
 
     def kernel_profile(self):
-        """Roofline record of the dominant kernel (conv3x3_tc_kernel) from the events recorded since
+        """Roofline record of the dominant kernel (tower_tc_kernel) from the events recorded since
         reset_kernel_timer(): algorithmic FLOP per launch / average launch duration."""
         if self.mode != 'builtin':
             return None
@@ -124,7 +124,7 @@ class BatchedSelfPlay:
         fused = per_forward == 1
         return {'bound': 'tensor',
                 'kernel': ('tower_tc_kernel (18 x [3x3 conv 256->256] in one data-flow ordered launch, tcgen05 cta_group::2)' if fused
-                           else 'conv3x3_tc_kernel (tcgen05 cta_group::2 3x3 conv 256->256, one launch per layer)'),
+                           else 'tower_tc_kernel (tcgen05 cta_group::2 3x3 conv 256->256, launched once per layer: MCAZ_TOWER=layers)'),
                 'achieved': flop / (ms_launch / 1e3) / 1e12, 'unit': 'TFLOP/s',
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/ (ncu --set full)
                 'traffic': 934e6 if fused else 151e6, 'ms_per_launch': ms_launch, 'launches_timed': n * per_forward,
