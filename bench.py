@@ -39,6 +39,14 @@ def parse_args():
     ap.add_argument('--sims', type=int, default=200, help='simulations per move')
     ap.add_argument('--evaluator', default='builtin', choices=['builtin', 'torch'])
     ap.add_argument('--cpu-seconds', type=float, default=15.0, help='budget of the CPU baseline sample')
+    ap.add_argument('--mode', default='lockstep', choices=['continuous', 'lockstep'],
+                    help='continuous: az_selfplay, every game moves as soon as its own simulations are done (a step = '
+                         'sims-per-move network batches); lockstep: az_search + az_play_device, one move in every game per step')
+    ap.add_argument('--eval-cache', type=int, default=24, help='log2 entries of the exact evaluation cache (0 = off)')
+    ap.add_argument('--free-sims', type=int, default=0, help='descents per game and launch (0 = library default)')
+    ap.add_argument('--no-stagger', action='store_true', help='start all games from the start position instead of spreading '
+                    'them over the plies of a game (see BatchedSelfPlay.stagger)')
+    ap.add_argument('--no-plain', action='store_true', help='skip the comparison pass without cache / continuous mode')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     return ap.parse_args()
@@ -186,8 +194,11 @@ def run_ours(args):
     G, S = args.games, args.sims
     torch.manual_seed(0)
     net = Network().eval()
-    sp = BatchedSelfPlay(net, n_games=G, num_simulations=S, seed=1234 + rank, evaluator=args.evaluator)
+    builtin = args.evaluator == 'builtin'
+    opts = {'eval_cache_log2': args.eval_cache, 'free_sims': args.free_sims} if builtin else {}
+    sp = BatchedSelfPlay(net, n_games=G, num_simulations=S, seed=1234 + rank, evaluator=args.evaluator, **opts)
     eng = sp.engine
+    continuous = builtin and args.mode == 'continuous'
 
     def barrier():
         torch.cuda.synchronize()
@@ -196,10 +207,18 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def one_step():
-        sp.step()
+        if continuous:
+            sp.run_continuous(S)        # S network batches: one move's worth of simulations for a game that hits nothing
+        else:
+            sp.step()
         if world > 1:
             gather_replay(eng, world, max_tuples=2 * G)     # replay gather of config 4 (NCCL all_gather)
 
+    # population: games spread uniformly over plies 0..59 (what a long-running actor holds), not 4096 copies of the
+    # start position marching through the opening together -- with the evaluation cache the latter would measure
+    # mostly cache hits.  Low-simulation pre-roll, outside the timed region.
+    if builtin and not args.no_stagger:
+        sp.stagger()
     for _ in range(args.warmup):
         one_step()
     barrier()
@@ -226,15 +245,21 @@ def run_ours(args):
     sims = c1['simulations'] - c0['simulations']
     evals = c1['evaluations'] - c0['evaluations']
     moves = c1['moves'] - c0['moves']
-    tot = torch.tensor([sims, evals, moves], dtype=torch.float64, device='cuda')
+    cached = c1['cached_evaluations'] - c0['cached_evaluations']
+    terminal = c1['terminal_leaves'] - c0['terminal_leaves']
+    tot = torch.tensor([sims, evals, moves, cached, terminal], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(tot)
-    sims_all, evals_all, moves_all = (float(x) for x in tot.tolist())
+    sims_all, evals_all, moves_all, cached_all, terminal_all = (float(x) for x in tot.tolist())
     value = sims_all / (ms / 1000.0)
 
-    # roofline of the dominant kernel: the network tower (tensor-bound)
+    # roofline of the dominant kernel: the network tower (tensor-bound), from the rows it actually evaluated
     pk = peaks()
-    prof = sp.kernel_profile() if hasattr(sp, 'kernel_profile') else None
+    prof = sp.kernel_profile(evaluations=evals) if builtin else None
+    tree = sp.tree_profile(c0, c1) if builtin else None
+    if tree is not None:
+        tree.update({'peak': pk['hbm_gbs'], 'frac': tree['achieved'] / pk['hbm_gbs'],
+                     'note': 'latency-bound pointer chasing: one warp walks one tree; see profiles/ for warp efficiency'})
     if prof is None:
         # library evaluator: time the whole forward over the resident leaf batch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -259,6 +284,38 @@ def run_ours(args):
     if not args.no_e2e:
         e2e = measure_e2e(sp, args, world)
 
+    # the same workload without the evaluation cache, in lock-step (every simulation that is not terminal takes a
+    # network row): what the cache and the continuous schedule buy, reported beside the headline
+    plain = None
+    if builtin and not args.no_plain and (args.eval_cache > 0 or continuous):
+        eng.close()                     # frees the first engine's arenas
+        sp2 = BatchedSelfPlay(net, n_games=G, num_simulations=S, seed=1234 + rank, evaluator='builtin')
+        if not args.no_stagger:
+            sp2.stagger()
+        for _ in range(min(args.warmup, 3)):
+            sp2.step()
+        barrier()
+        p0 = sp2.engine.counters()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        n_plain = max(1, min(args.steps, 2))
+        for _ in range(n_plain):
+            sp2.step()
+        t1.record()
+        barrier()
+        p1 = sp2.engine.counters()
+        pms = t0.elapsed_time(t1)
+        pt = torch.tensor([pms, float(p1['simulations'] - p0['simulations']), float(p1['evaluations'] - p0['evaluations'])],
+                          dtype=torch.float64, device='cuda')
+        if world > 1:
+            pmax = pt.clone()
+            dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(pt)
+            pt[0] = pmax[0]
+        plain = {'value': float(pt[1]) / (float(pt[0]) / 1000.0), 'unit': 'sims/s', 'evals_per_second': float(pt[2]) / (float(pt[0]) / 1000.0),
+                 'steps': n_plain, 'mode': 'lockstep, eval_cache off'}
+        sp2.engine.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = torch.get_num_threads()
@@ -273,11 +330,19 @@ def run_ours(args):
             'dtype': 'bf16 network / f64 tree statistics', 'data': 'synthetic',
             'config': {'workload': 'BASELINE.json configs[2]: batched self-play, %d concurrent games x %d sims/move per GPU, random-init '
                                    'reference-size net' % (G, S), 'games_per_gpu': G, 'sims_per_move': S, 'evaluator': args.evaluator,
+                       'mode': ('continuous (az_selfplay): a step = %d network batches; games move on their own' % S) if continuous
+                               else 'lockstep (az_search + az_play_device): a step = one move in every game',
+                       'eval_cache': ('exact, 2^%d entries' % args.eval_cache) if builtin and args.eval_cache > 0 else 'off',
+                       'population': 'all games from the start position' if (args.no_stagger or not builtin) else
+                                     'games spread uniformly over plies 0..59 by an 8-simulation pre-roll before the warm-up',
                        'parallelism': 'games sharded over %d GPU(s), no data-path collective except replay all_gather' % world,
                        'l2': 'inputs larger than L2 (tree arenas ~%d MB, activations %d MB per layer)' % (
                            int(c1['edges'] * 22 / 1e6), int(G * 30 * 256 * 2 * 2 / 1e6))},
             'positions_per_second': moves_all / (ms / 1000.0), 'evals_per_second': evals_all / (ms / 1000.0),
-            'roofline': roof, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+            'sims_breakdown': {'network_rows': evals_all / max(sims_all, 1), 'cache_hits': cached_all / max(sims_all, 1),
+                               'terminal': terminal_all / max(sims_all, 1)},
+            'roofline': roof, 'tree_roofline': tree, 'without_cache_lockstep': plain,
+            'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
         }
         print(json.dumps(out))
     if world > 1:
@@ -295,10 +360,12 @@ def measure_e2e(sp, args, world):
     rng = np.random.RandomState(7)
     pinned = torch.empty(G * 5, dtype=torch.int32).pin_memory()
     host_states = pinned.numpy().view(np.uint32).view(STATE_DTYPE)
-    start = eng.game_states()[0]
-    eng.reset_games()
+    # carry on with the games of the timed run where they stand (mid-game, trees kept): restarting all of them from
+    # the start position would replay an opening the evaluation cache has just seen
+    from minitchess_alphazero_b200 import rules
+    start = np.full(G, rules.state_from_fen(rules.STARTING_FEN), dtype=STATE_DTYPE)
     host_states[:] = eng.game_states()[0]
-    plies = np.zeros(G, dtype=np.int32)
+    plies = np.where(host_states['meta'] & 1, 0, 1).astype(np.int32)       # white to move -> white's tree (tree 0)
 
     def step():
         eng.set_positions(host_states, trees=plies & 1)                    # H2D: positions

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MCAZ_ABI_VERSION 1
+#define MCAZ_ABI_VERSION 2
 
 /* ---- geometry and action indexing (exp/generate_moves_list.py:5-57, exp/moves_dict.json) */
 #define MC_FILES 5
@@ -136,6 +136,16 @@ typedef struct az_config {
     int32_t own_stream;        /* 1 = the engine works on its own non-blocking CUDA stream (several engines in one
                                   process then overlap); 0 = the legacy default stream, ordered with the caller's
                                   torch work (needed when device tensors are exchanged every simulation)            */
+    int32_t eval_cache_log2;   /* > 0: exact evaluation cache of 2^k entries (192 B each) shared by all trees of the
+                                  engine, used by az_search / az_selfplay: a new position whose (board, side to move,
+                                  fullmove number) -- all the network sees, exp/policy.py:96-105 -- was evaluated before
+                                  with the current weights takes the stored priors and value instead of a network row.
+                                  Results are bit-identical with the cache on or off; az_set_weights invalidates it.
+                                  0 = off (default)                                                                      */
+    int32_t free_sims;         /* descents a game may start per launch of az_search / az_selfplay: simulations that end
+                                  on a terminal or cached position need no network row, complete on the spot and the
+                                  game goes on to its next simulation in the same launch.  0 = default (1: measured
+                                  best on B200 -- longer chains stretch the launch by more than the fuller batch saves)  */
 } az_config;
 
 void az_default_config(az_config* out);
@@ -184,6 +194,14 @@ int az_eval_backup(az_engine* e);
 /* -- whole searches with the built-in network (throughput mode) ---------------------------*/
 int az_search(az_engine* e, int n_sims);
 
+/* Continuous self-play (throughput mode, device_rng = 1, leaves_per_step = 1): n_steps network batches.  Every
+ * game runs its own loop inside the search kernel -- sims_per_move simulations, then the move choice, replay
+ * recording, the move and, when the game is over, a restart (what az_search + az_play_device do for all games
+ * in lock-step) -- so a game that needs fewer network rows for a move (terminal or cached leaves) simply moves
+ * earlier and the batch stays full.  On return no simulation is pending; a later call carries on where this
+ * one stopped.  With the same seed a game slot plays the same games as under az_search + az_play_device.        */
+int az_selfplay(az_engine* e, int n_steps, int sims_per_move);
+
 /* Root statistics of the tree of the side to move (exp/policy.py:118-121): sorted legal
  * codes, visit counts N and Q per edge; pi = N / sum(N) is left to the caller.              */
 int az_root_stats(az_engine* e, const int32_t* game_ids, int n, uint16_t* codes,
@@ -223,8 +241,10 @@ int az_collate(const az_replay_tuple* tuples, int n, float* pi, int64_t* tokens,
 
 /* Counters since creation: [0] simulations, [1] network evaluations, [2] terminal leaves,
  * [3] moves played, [4] games finished, [5] nodes allocated, [6] edges allocated,
- * [7] kernels launched by this library, [8] descents dropped on a pending node (leaves_per_step > 1).   */
-#define AZ_NUM_COUNTERS 10
+ * [7] kernels launched by this library, [8] descents dropped on a pending node (leaves_per_step > 1),
+ * [9] simulations whose leaf evaluation came from the evaluation cache ([0] = [1] + [2] + [9]),
+ * [10] tree levels descended and [11] edges read on the way (bytes-per-simulation accounting).          */
+#define AZ_NUM_COUNTERS 12
 int az_counters(az_engine* e, uint64_t* out);
 
 /* Stand-alone network forward (exp/policy.py:71-80) on n positions with the engine's weights:
@@ -237,6 +257,10 @@ int az_network_forward(az_engine* e, const uint8_t* tokens, const float* clocks,
  * MCAZ_TOWER=layers; *launches_per_forward says which).  A call with a non-NULL avg_ms_per_tower
  * synchronises, reports the average tower time since the previous call and resets.                 */
 int az_profile_network(az_engine* e, int on, double* avg_ms_per_tower, int* n_forwards, int* launches_per_forward);
+
+/* Same for the tree kernel (search_step_kernel: backup + select + expand): total milliseconds and launches since
+ * the previous read.                                                                                            */
+int az_profile_tree(az_engine* e, int on, double* total_ms, int* n_launches);
 
 /* Kernels launched by this library in this process (all engines and mc_* calls).               */
 uint64_t mcaz_kernel_launches(void);

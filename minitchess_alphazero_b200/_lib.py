@@ -14,7 +14,7 @@ MC_TOKENS = 60
 AZ_NUM_PARAMS = 10693458
 AZ_NUM_BN_STATS = 9734
 AZ_NUM_WEIGHT_FLOATS = AZ_NUM_PARAMS + AZ_NUM_BN_STATS
-AZ_NUM_COUNTERS = 10
+AZ_NUM_COUNTERS = 12
 
 STATE_DTYPE = np.dtype([('pl0', '<u4'), ('pl1', '<u4'), ('pl2', '<u4'), ('white', '<u4'), ('meta', '<u4')])
 RESULT_STRINGS = {0: '*', 1: '1-0', 2: '0-1', 3: '1/2-1/2'}
@@ -24,6 +24,9 @@ class McazError(RuntimeError):
     def __init__(self, code, message):
         super().__init__('libmcaz error %d: %s' % (code, message))
         self.code = code
+
+
+ABI_VERSION = 2      # MCAZ_ABI_VERSION of include/mcaz.h
 
 
 class Rules(ctypes.Structure):
@@ -39,7 +42,8 @@ class Config(ctypes.Structure):
                 ('dirichlet_alpha', ctypes.c_float), ('dirichlet_epsilon', ctypes.c_float),
                 ('numpy1_dtype_flow', ctypes.c_int32), ('device_rng', ctypes.c_int32),
                 ('seed', ctypes.c_uint64), ('rules', Rules), ('network', ctypes.c_int32),
-                ('leaves_per_step', ctypes.c_int32), ('own_stream', ctypes.c_int32)]
+                ('leaves_per_step', ctypes.c_int32), ('own_stream', ctypes.c_int32),
+                ('eval_cache_log2', ctypes.c_int32), ('free_sims', ctypes.c_int32)]
 
 
 _lib = None
@@ -55,7 +59,7 @@ def lib():
         L = ctypes.CDLL(SO_PATH)
         L.mcaz_last_error.restype = ctypes.c_char_p
         L.mcaz_kernel_launches.restype = ctypes.c_uint64
-        if L.mcaz_abi_version() != 1:
+        if L.mcaz_abi_version() != ABI_VERSION:
             raise ImportError('libmcaz.so ABI mismatch')
         _lib = L
     return _lib

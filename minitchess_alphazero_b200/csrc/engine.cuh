@@ -30,8 +30,15 @@ struct az_engine {
     az_replay_tuple* d_replay = nullptr;   // ring of finished-game tuples
     unsigned long long* d_replay_count = nullptr;
     size_t replay_capacity = 0;
-    unsigned long long sim_counter = 0;    // feeds the device RNG
-    unsigned long long move_counter = 0;   // feeds the device RNG of the move choice
+    unsigned long long sim_counter = 0;    // launches of the search (device RNG key only where no per-game serial exists)
+    az::CacheEntry* d_cache = nullptr;     // exact evaluation cache (eval_cache_log2 > 0)
+    uint32_t cache_mask = 0;
+    uint32_t cache_epoch = 1;              // bumped by az_set_weights
+    int parity = 0;                        // row counter of the last search launch
+    // az_profile_tree: CUDA events around every search_step_kernel launch
+    bool tree_profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tree_events;
+    size_t tree_events_used = 0;
     mcaz::Network* net = nullptr;
     uint64_t launches = 0;
 };

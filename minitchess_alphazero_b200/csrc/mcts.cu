@@ -29,21 +29,130 @@ __global__ void __launch_bounds__(128) select_expand_kernel(View V, const double
         }
 }
 
-// az_search inner step: back up the previous simulation (if one is pending) and run the next descent in
-// the same launch -- both touch only this game's tree, so no grid-wide ordering is needed.
-__global__ void __launch_bounds__(128) search_step_kernel(View V, const float* logits, const float* values, int do_select) {
+// ---- device move choice (throughput mode) -------------------------------------------------------------
+// Empties both trees of game g and puts it back on the start position (warp-cooperative).
+__device__ __forceinline__ void restart_one(const View& V, int g, int lane, const mc_state& start) {
+    uint4* tab = reinterpret_cast<uint4*>(V.ht + (size_t)(2 * g) * V.HC);     // HC is a power of two >= 64
+    for (int i = lane; i < 2 * V.HC / 4; i += 32) tab[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    if (lane == 0) {
+        V.game_state[g] = start;
+        V.game_ply[g] = mc::white_to_move(start) ? 0 : 1;
+        V.game_start_ply[g] = V.game_ply[g];
+        az::hist_reset(V, g, start);
+        for (int t = 2 * g; t < 2 * g + 2; ++t) { V.tree_nodes[t] = 0; V.tree_edges[t] = 0; V.tree_root[t] = az::NONE; }
+        for (int j = 0; j < V.K; ++j) V.leaf_kind[g * V.K + j] = az::LEAF_NONE;
+        V.game_result[g] = MC_ONGOING;
+    }
+    __syncwarp();
+}
+
+// Pick a move from the root visit counts, record the replay tuple, play it and back-fill the rewards of a
+// finished game (exp/agent.py:110-119, exp/callbacks.py:31-54).  Warp-cooperative; returns false when the
+// root has no visits yet (nothing to choose from).
+__device__ __forceinline__ bool play_device_one(const View& V, int g, int lane) {
+    if (V.game_result[g] != MC_ONGOING) return false;
+    const int ply = V.game_ply[g];
+    const int t = 2 * g + (ply & 1);
+    uint32_t root = V.tree_root[t];
+    if (root == az::NONE) root = az::ht_find(V, t, V.game_state[g]);
+    if (root == az::NONE) return false;
+    const size_t gi = (size_t)t * V.NC + root;
+    const int E = (int)(V.node_info[gi] & 0xffffu);
+    const size_t e0 = (size_t)t * V.EC + V.node_edge_off[gi];
+    const mc_state s = V.game_state[g];
+    unsigned int nsum = 0, nmax = 0;
+    for (int i = lane; i < E; i += 32) { unsigned int c = V.edge_N[e0 + i]; nsum += c; nmax = max(nmax, c); }
+    for (int o = 16; o > 0; o >>= 1) { nsum += __shfl_xor_sync(0xffffffffu, nsum, o); nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o)); }
+    if (nsum == 0) return false;
+    const uint32_t serial = V.move_serial[g];          // the game slot's own move counter keys the RNG
+    __syncwarp();
+    if (lane == 0) V.move_serial[g] = serial + 1;
+    Philox rng(V.seed ^ 0xA5A5A5A5DEADBEEFull, (uint32_t)g, serial, 0u);
+    const double u = rng.uniform();     // same on every lane
+    int choice = -1;
+    if (mc::fullmove(s) < V.tau_change) {
+        // sample proportionally to N (np.random.choice(legal, p=pi))
+        const double target = u * (double)nsum;
+        double acc = 0;
+        for (int i = 0; i < E && choice < 0; ++i) { acc += (double)V.edge_N[e0 + i]; if (target < acc) choice = i; }
+        if (choice < 0) choice = E - 1;
+    } else {
+        int n_best = 0;
+        for (int i = 0; i < E; ++i) n_best += (V.edge_N[e0 + i] == nmax);
+        int pick = min((int)(u * n_best), n_best - 1);
+        for (int i = 0; i < E; ++i) if (V.edge_N[e0 + i] == nmax) { if (pick == 0) { choice = i; break; } --pick; }
+    }
+    const int code = V.edge_code[e0 + choice];
+    // replay tuple of this ply
+    az_replay_tuple* rec = V.record + (size_t)g * az::MAX_DEPTH + min(ply - V.game_start_ply[g], az::MAX_DEPTH - 1);
+    for (int i = lane; i < E; i += 32) { rec->codes[i] = V.edge_code[e0 + i]; rec->pi[i] = (float)((double)V.edge_N[e0 + i] / (double)nsum); }
+    if (lane == 0) { rec->observation = s; rec->n_legal = (uint16_t)E; rec->action = (uint16_t)code; rec->reward = 0; }
+    __syncwarp();
+    if (lane == 0) {
+        az::play_one(V, g, code);
+        const int res = V.game_result[g];
+        if (res != MC_ONGOING) {
+            // exp/callbacks.py:49-53: the side that moved last gets +reward, alternating backwards
+            const int n_rec = min(V.game_ply[g] - V.game_start_ply[g], az::MAX_DEPTH);
+            unsigned long long base = atomicAdd(V.replay_count, (unsigned long long)n_rec);
+            int reward = (res == MC_DRAW) ? 0 : 1;
+            for (int p = n_rec - 1; p >= 0; --p) {
+                az_replay_tuple* r = V.record + (size_t)g * az::MAX_DEPTH + p;
+                r->reward = (int8_t)reward;
+                reward = -reward;
+                unsigned long long dst = base + (unsigned long long)p;
+                if (dst < V.replay_cap) V.replay[dst] = *r;
+            }
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
+// One launch of the search for game g (leaves_per_step = 1): finish the simulation whose leaf the network just
+// evaluated, then start descents while the game's budget lasts.  A descent that ends on a terminal position
+// or on one found in the evaluation cache needs no network row: it is backed up on the spot and the game goes
+// straight on (at most free_max descents per launch); the first leaf that needs the network takes a row of the
+// batch V.batch and ends the game's turn.  The order of a game's simulations -- all that the reference's
+// sequential search depends on -- is unchanged (exp/agent.py:41-45).
+__device__ __forceinline__ void search_one(const View& V, int g, int lane, const float* values, const mc_state& start) {
+    az::backup_one(V, g, lane, nullptr, values, nullptr, 0);
+    __syncwarp();
+    int left = V.new_budget >= 0 ? V.new_budget : V.sims_left[g];
+    for (int it = 0; it < V.free_max; ++it) {
+        if (left <= 0) {
+            if (!V.async_play) break;
+            // az_selfplay: all simulations of this move are backed up -> choose, record, play, maybe restart
+            if (play_device_one(V, g, lane) && V.game_result[g] != MC_ONGOING) restart_one(V, g, lane, start);
+            left = V.sims_per_move;
+        }
+        if (V.game_result[g] != MC_ONGOING) break;
+        --left;
+        const uint8_t kind = az::select_expand_one(V, g, lane, nullptr, nullptr, 0);
+        __syncwarp();
+        if (kind != az::LEAF_TERMINAL && kind != az::LEAF_CACHED) break;
+        az::backup_one(V, g, lane, nullptr, values, nullptr, 0);
+        __syncwarp();
+    }
+    if (lane == 0) V.sims_left[g] = left;
+}
+
+// az_search / az_selfplay inner step.  leaves_per_step = K > 1 keeps the fixed form: back up the K descents of
+// the previous launch, start K new ones (virtual loss keeps them apart), one row per slot.
+__global__ void __launch_bounds__(128, 8) search_step_kernel(View V, const float* values, mc_state start) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
+    if (V.compact && blockIdx.x == 0 && threadIdx.x == 0) V.row_count[V.parity ^ 1] = 0u;   // the next launch's counter
     for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < V.G; g += warps) {
+        if (V.K == 1) { search_one(V, g, lane, values, start); continue; }
         for (int j = 0; j < V.K; ++j) {
-            az::backup_one(V, g, lane, logits, values, nullptr, j);
+            az::backup_one(V, g, lane, nullptr, values, nullptr, j);
             __syncwarp();
         }
-        if (do_select)
+        if (V.free_max > 0)
             for (int j = 0; j < V.K; ++j) {
-                View W = V;
-                W.sim_counter = V.sim_counter * (unsigned long long)V.K + j;   // a fresh noise draw per descent
-                az::select_expand_one(W, g, lane, nullptr, nullptr, j);
+                az::select_expand_one(V, g, lane, nullptr, nullptr, j);
                 __syncwarp();
             }
     }
@@ -76,6 +185,7 @@ __global__ void __launch_bounds__(256) reset_games_kernel(View V, const int32_t*
             V.game_result[g] = (int8_t)az::game_result_of(V, g, s);
             for (int t = 2 * g; t < 2 * g + 2; ++t) { V.tree_nodes[t] = 0; V.tree_edges[t] = 0; V.tree_root[t] = az::NONE; }
             for (int j = 0; j < V.K; ++j) { V.leaf_kind[g * V.K + j] = az::LEAF_NONE; V.needs_eval[g * V.K + j] = 0; V.path_len[g * V.K + j] = 0; }
+            V.sims_left[g] = 0;
         }
     }
 }
@@ -93,6 +203,7 @@ __global__ void set_positions_kernel(View V, const int32_t* game_ids, int n, con
         V.tree_root[2 * g] = az::NONE;
         V.tree_root[2 * g + 1] = az::NONE;
         for (int j = 0; j < V.K; ++j) V.leaf_kind[g * V.K + j] = az::LEAF_NONE;
+        V.sims_left[g] = 0;
     }
 }
 
@@ -168,68 +279,11 @@ __global__ void node_stats_kernel(View V, int g, int tree, mc_state s, NodeStats
     }
 }
 
-// Throughput mode: pick a move from the root visit counts, record the replay tuple, play it,
-// back-fill rewards and restart finished games (exp/agent.py:110-119, exp/callbacks.py:31-54).
-__global__ void __launch_bounds__(128) play_device_kernel(View V, az_replay_tuple* record, az_replay_tuple* replay,
-                                                          unsigned long long* replay_count, unsigned long long replay_cap,
-                                                          unsigned long long move_counter, mc_state start) {
+// Throughput mode, one move in every game (az_play_device): choose, record, play; then restart finished games.
+__global__ void __launch_bounds__(128) play_device_kernel(View V) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < V.G; g += warps) {
-        if (V.game_result[g] != MC_ONGOING) continue;
-        const int ply = V.game_ply[g];
-        const int t = 2 * g + (ply & 1);
-        uint32_t root = V.tree_root[t];
-        if (root == az::NONE) root = az::ht_find(V, t, V.game_state[g]);
-        if (root == az::NONE) continue;
-        const size_t gi = (size_t)t * V.NC + root;
-        const int E = (int)(V.node_info[gi] & 0xffffu);
-        const size_t e0 = (size_t)t * V.EC + V.node_edge_off[gi];
-        const mc_state s = V.game_state[g];
-        unsigned int nsum = 0, nmax = 0;
-        for (int i = lane; i < E; i += 32) { unsigned int c = V.edge_N[e0 + i]; nsum += c; nmax = max(nmax, c); }
-        for (int o = 16; o > 0; o >>= 1) { nsum += __shfl_xor_sync(0xffffffffu, nsum, o); nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o)); }
-        if (nsum == 0) continue;
-        Philox rng(V.seed ^ 0xA5A5A5A5DEADBEEFull, (uint32_t)g, (uint32_t)move_counter, (uint32_t)(move_counter >> 32));
-        const double u = rng.uniform();     // same on every lane
-        int choice = -1;
-        if (mc::fullmove(s) < V.tau_change) {
-            // sample proportionally to N (np.random.choice(legal, p=pi))
-            const double target = u * (double)nsum;
-            double acc = 0;
-            for (int i = 0; i < E && choice < 0; ++i) { acc += (double)V.edge_N[e0 + i]; if (target < acc) choice = i; }
-            if (choice < 0) choice = E - 1;
-        } else {
-            int n_best = 0;
-            for (int i = 0; i < E; ++i) n_best += (V.edge_N[e0 + i] == nmax);
-            int pick = min((int)(u * n_best), n_best - 1);
-            for (int i = 0; i < E; ++i) if (V.edge_N[e0 + i] == nmax) { if (pick == 0) { choice = i; break; } --pick; }
-        }
-        const int code = V.edge_code[e0 + choice];
-        // replay tuple of this ply
-        az_replay_tuple* rec = record + (size_t)g * az::MAX_DEPTH + min(ply - V.game_start_ply[g], az::MAX_DEPTH - 1);
-        for (int i = lane; i < E; i += 32) { rec->codes[i] = V.edge_code[e0 + i]; rec->pi[i] = (float)((double)V.edge_N[e0 + i] / (double)nsum); }
-        if (lane == 0) { rec->observation = s; rec->n_legal = (uint16_t)E; rec->action = (uint16_t)code; rec->reward = 0; }
-        __syncwarp();
-        if (lane == 0) {
-            az::play_one(V, g, code);
-            const int res = V.game_result[g];
-            if (res != MC_ONGOING) {
-                // exp/callbacks.py:49-53: the side that moved last gets +reward, alternating backwards
-                const int n_rec = min(V.game_ply[g] - V.game_start_ply[g], az::MAX_DEPTH);
-                unsigned long long base = atomicAdd(replay_count, (unsigned long long)n_rec);
-                int reward = (res == MC_DRAW) ? 0 : 1;
-                for (int p = n_rec - 1; p >= 0; --p) {
-                    az_replay_tuple* r = record + (size_t)g * az::MAX_DEPTH + p;
-                    r->reward = (int8_t)reward;
-                    reward = -reward;
-                    unsigned long long dst = base + (unsigned long long)p;
-                    if (dst < replay_cap) replay[dst] = *r;
-                }
-            }
-        }
-        __syncwarp();
-    }
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < V.G; g += warps) play_device_one(V, g, lane);
 }
 
 // restart every finished game from the start position (block per game; clears both hash tables)
@@ -310,6 +364,8 @@ void az_default_config(az_config* c) {
     c->network = 0;
     c->leaves_per_step = 1;
     c->own_stream = 0;
+    c->eval_cache_log2 = 0;
+    c->free_sims = 0;
 }
 
 int az_create(const az_config* cfg, az_engine** out) {
@@ -353,12 +409,22 @@ int az_create(const az_config* cfg, az_engine** out) {
     V.edge_vl = nullptr;
     if (V.K > 1) { A(V.edge_vl, E); }
     A(V.counters, AZ_NUM_COUNTERS); A(V.error_flag, 1);
+    A(V.sim_serial, G); A(V.move_serial, G); A(V.sims_left, G); A(V.row_count, 2); A(V.row_slot, S);
+    V.sims_per_move = cfg->max_sims_per_move; V.new_budget = -1; V.free_max = 1; V.async_play = 0; V.compact = 0; V.parity = 0;
+    V.cache = nullptr; V.cache_mask = 0; V.cache_epoch = 1;
+    if (cfg->eval_cache_log2 < 0 || cfg->eval_cache_log2 > 28) rc = fail(MCAZ_EINVAL, "az_create: eval_cache_log2 must be in [0, 28]");
+    if (!rc && cfg->eval_cache_log2 > 0 && cfg->network && V.K == 1) {
+        A(e->d_cache, (size_t)1 << cfg->eval_cache_log2);
+        e->cache_mask = (1u << cfg->eval_cache_log2) - 1u;
+    }
     A(e->d_noise, G * MC_MAX_MOVES); A(e->d_noise_used, G);
     A(e->d_logits, S * MC_NUM_ACTIONS); A(e->d_values, S); A(e->d_priors, S * MC_MAX_MOVES);
     A(e->d_record, G * az::MAX_DEPTH);
     e->replay_capacity = G * az::MAX_DEPTH;
     A(e->d_replay, e->replay_capacity); A(e->d_replay_count, 1);
 #undef A
+    V.record = e->d_record; V.replay = e->d_replay; V.replay_count = e->d_replay_count;
+    V.replay_cap = (unsigned long long)e->replay_capacity;
     if (!rc && cfg->network) rc = network_create(e);
     if (rc) { az_destroy(e); return rc; }
     *out = e;
@@ -369,6 +435,7 @@ int az_destroy(az_engine* e) {
     if (!e) return MCAZ_OK;
     cudaDeviceSynchronize();
     if (e->net) network_destroy(e);
+    for (auto& ev : e->tree_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (void* p : e->allocs) cudaFree(p);
     e->scratch.release();
     if (e->cfg.own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -385,6 +452,7 @@ int az_set_weights(az_engine* e, const float* flat, size_t n) {
     if (int rc = in.init(flat, n, e->stream, e->scratch)) return rc;
     int rc = network_set_weights(e, in.ptr);
     if (!rc) MCAZ_CUDA(cudaStreamSynchronize(e->stream));
+    if (++e->cache_epoch == 0) e->cache_epoch = 1;   // cached evaluations belong to the old weights (0 = never written)
     return rc;
 }
 
@@ -495,25 +563,91 @@ int az_eval_backup(az_engine* e) {
     return MCAZ_OK;
 }
 
+// View of one az_search / az_selfplay launch: dense rows, the launch's row counter, the evaluation cache.
+static View search_view(az_engine* e) {
+    View V = e->v;
+    V.device_rng = e->cfg.device_rng;
+    V.compact = V.K == 1;
+    V.parity = V.compact ? (e->parity ^= 1) : 0;
+    V.cache = e->d_cache; V.cache_mask = e->cache_mask; V.cache_epoch = e->cache_epoch;
+    V.free_max = V.K == 1 ? (e->cfg.free_sims > 0 ? e->cfg.free_sims : 1) : 1;
+    return V;
+}
+
+static int search_launch(az_engine* e, const View& V) {
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (e->tree_profiling) {
+        if (e->tree_events_used == e->tree_events.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            e->tree_events.emplace_back(a, b);
+        }
+        ev0 = e->tree_events[e->tree_events_used].first; ev1 = e->tree_events[e->tree_events_used].second;
+        e->tree_events_used++;
+        cudaEventRecord(ev0, e->stream);
+    }
+    search_step_kernel<<<warp_grid(V.G, 128), 128, 0, e->stream>>>(V, e->d_values, start_state());   // priors: written by the policy head
+    MCAZ_CHECK_LAUNCH();
+    if (ev1) cudaEventRecord(ev1, e->stream);
+    e->launches++;
+    return MCAZ_OK;
+}
+
+// n_batches network batches of the search: step launch -> network forward -> ... -> a closing step launch that
+// only backs up.  new_budget >= 0: every game gets that many simulations (az_search); async: games choose and
+// play their own moves (az_selfplay).
+// (An overlap variant -- the chains of free simulations running on a side stream while the tower evaluates the
+// batch -- was measured and dropped: the B200 runs this workload at its power cap, the tree work costs the same
+// energy wherever it runs, and the tower slowed down by more than the hidden time; tools/sweep_modes.py.)
+static int run_search(az_engine* e, int n_batches, int new_budget, bool async, int sims_per_move) {
+    for (int s = 0; s <= n_batches; ++s) {
+        View V = search_view(e);
+        V.new_budget = s == 0 ? new_budget : -1;
+        V.async_play = async ? 1 : 0;
+        V.sims_per_move = sims_per_move;
+        if (s == n_batches) V.free_max = 0;       // closing launch: back up what the last batch evaluated, start nothing
+        if (int rc = search_launch(e, V)) return rc;
+        if (s == n_batches) break;
+        if (int rc = network_forward_search(e, V, e->d_values)) return rc;
+    }
+    return engine_check_errors(e);
+}
+
 int az_search(az_engine* e, int n_sims) {
     if (!e || n_sims < 0) return fail(MCAZ_EINVAL, "az_search: bad argument");
     if (!e->net) return fail(MCAZ_ESTATE, "az_search: engine was created with network = 0 (use az_select_expand / az_backup)");
     if (e->leaf_pending) return fail(MCAZ_ESTATE, "az_search: a simulation is pending (call az_backup first)");
-    View V = e->v;
-    V.device_rng = e->cfg.device_rng;
-    const int grid = warp_grid(V.G, 128);
-    for (int s = 0; s <= n_sims; ++s) {
-        // launch s: backup of simulation s-1 (none for s = 0) fused with the descent of simulation s
-        V.sim_counter = e->sim_counter;
-        const int do_select = s < n_sims;
-        if (do_select) e->sim_counter++;
-        search_step_kernel<<<grid, 128, 0, e->stream>>>(V, nullptr, e->d_values, do_select);   // priors: written by the policy head
-        MCAZ_CHECK_LAUNCH();
-        e->launches++;
-        if (!do_select) break;
-        if (int rc = network_forward_search(e, V, e->d_values)) return rc;
+    // Every game starts at least one simulation per batch, so n_sims batches start them all and the closing
+    // launch backs up the rest.
+    return run_search(e, n_sims, n_sims, false, e->cfg.max_sims_per_move);
+}
+
+int az_selfplay(az_engine* e, int n_steps, int sims_per_move) {
+    if (!e || n_steps < 0 || sims_per_move <= 0) return fail(MCAZ_EINVAL, "az_selfplay: bad argument");
+    if (!e->net) return fail(MCAZ_ESTATE, "az_selfplay: engine was created with network = 0");
+    if (!e->cfg.device_rng) return fail(MCAZ_ESTATE, "az_selfplay: needs device_rng = 1 (moves are chosen on the device)");
+    if (e->v.K != 1) return fail(MCAZ_ESTATE, "az_selfplay: leaves_per_step must be 1");
+    if (sims_per_move > e->cfg.max_sims_per_move) return fail(MCAZ_EINVAL, "az_selfplay: sims_per_move exceeds max_sims_per_move (arena size)");
+    if (e->leaf_pending) return fail(MCAZ_ESTATE, "az_selfplay: a simulation is pending (call az_backup first)");
+    return run_search(e, n_steps, -1, true, sims_per_move);
+}
+
+int az_profile_tree(az_engine* e, int on, double* total_ms, int* n_launches) {
+    if (!e) return fail(MCAZ_EINVAL, "az_profile_tree: null engine");
+    if (total_ms) {
+        cudaStreamSynchronize(e->stream);
+        double total = 0;
+        for (size_t i = 0; i < e->tree_events_used; ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e->tree_events[i].first, e->tree_events[i].second);
+            total += ms;
+        }
+        *total_ms = total;
+        if (n_launches) *n_launches = (int)e->tree_events_used;
     }
-    return engine_check_errors(e);
+    e->tree_events_used = 0;
+    e->tree_profiling = on != 0;
+    return MCAZ_OK;
 }
 
 int az_root_stats(az_engine* e, const int32_t* game_ids, int n, uint16_t* codes, uint32_t* visits, double* q, int32_t* n_legal) {
@@ -598,8 +732,8 @@ int az_play_device(az_engine* e) {
     if (!e) return fail(MCAZ_EINVAL, "az_play_device: null engine");
     if (e->leaf_pending) return fail(MCAZ_ESTATE, "az_play_device: a simulation is pending");
     const View& V = e->v;
-    play_device_kernel<<<warp_grid(V.G, 128), 128, 0, e->stream>>>(V, e->d_record, e->d_replay, e->d_replay_count,
-                                                                   (unsigned long long)e->replay_capacity, ++e->move_counter, start_state());
+    if (!e->cfg.device_rng) return fail(MCAZ_ESTATE, "az_play_device: needs device_rng = 1");
+    play_device_kernel<<<warp_grid(V.G, 128), 128, 0, e->stream>>>(V);
     MCAZ_CHECK_LAUNCH();
     restart_finished_kernel<<<std::min(V.G, num_sms() * 8), 256, 0, e->stream>>>(V, start_state());
     MCAZ_CHECK_LAUNCH();

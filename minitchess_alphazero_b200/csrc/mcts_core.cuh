@@ -34,11 +34,27 @@ constexpr uint32_t INFO_DECISIVE = 1u << 17;  // terminal with reward 1.0 (else 
 constexpr uint32_t INFO_PENDING = 1u << 18;   // expanded in this step, priors not written yet (leaves_per_step > 1)
 constexpr int MAX_LEAVES = 16;                // leaves_per_step limit
 
-enum LeafKind : uint8_t { LEAF_NONE = 0, LEAF_EVAL = 1, LEAF_TERMINAL = 2, LEAF_COLLISION = 3 };
-enum Counter : int { C_SIMS = 0, C_EVALS, C_TERMINAL, C_MOVES, C_GAMES, C_NODES, C_EDGES, C_LAUNCHES, C_COLLISIONS, C_SPARE };
+// LEAF_CACHED: a new position whose priors and value were found in the exact evaluation cache -- the
+// simulation is complete without a network row, like a terminal one.
+enum LeafKind : uint8_t { LEAF_NONE = 0, LEAF_EVAL = 1, LEAF_TERMINAL = 2, LEAF_COLLISION = 3, LEAF_CACHED = 4 };
+enum Counter : int { C_SIMS = 0, C_EVALS, C_TERMINAL, C_MOVES, C_GAMES, C_NODES, C_EDGES, C_LAUNCHES, C_COLLISIONS, C_CACHED, C_DEPTH, C_PATH_EDGES };
 enum ErrorBit : int { ERR_NODE_CAP = 1, ERR_EDGE_CAP = 2, ERR_HASH_CAP = 4, ERR_DEPTH = 8, ERR_ILLEGAL = 16 };
 
 struct alignas(16) Board4 { uint32_t x, y, z, w; };
+
+// Exact evaluation cache (SURVEY.md 7.3 point 6): the network sees (tokens, clock) = board, side to move and
+// fullmove number -- not the halfmove clock -- so two nodes with that key get bit-identical priors and value,
+// whichever tree or game they belong to.  Direct-mapped, newest entry wins; entries carry the weight epoch.
+// Every entry is a seqlock (seq odd = being written; a reader accepts only what it read between two equal even
+// seq), so readers (tree kernels) and writers (the policy head) need not be ordered by the stream.
+constexpr int CACHE_MAX_E = 40;                    // positions with more legal moves are not cached
+constexpr uint32_t CACHE_KEY_META = 0x00ff0001u;   // side to move + fullmove number; bits 8-15 of the key word hold n
+struct alignas(64) CacheEntry {
+    uint32_t seq, pl0, pl1, pl2, white, meta_n, epoch;
+    float value;
+    float priors[CACHE_MAX_E];
+};
+static_assert(sizeof(CacheEntry) == 192, "CacheEntry layout");
 
 struct View {
     int G, NC, EC, HC;
@@ -62,7 +78,26 @@ struct View {
     float cpuct; float eps; float alpha; int numpy1; int tau_change; mc_rules rules;
     unsigned long long seed;
     int device_rng;                 // throughput mode: root Dirichlet noise drawn in the select kernel
-    unsigned long long sim_counter; // RNG counter of the simulation being run
+    unsigned long long sim_counter; // RNG counter of the simulation being run (when sim_serial == nullptr)
+    // ---- az_search / az_selfplay bookkeeping (nullptr / 0 elsewhere, e.g. in the host test build)
+    unsigned long long* sim_serial; // [G] descents started in this game slot: device RNG key, independent of batching
+    uint32_t* move_serial;          // [G] moves chosen on the device: RNG key of the move choice
+    int32_t* sims_left;             // [G] descents the game may still start in the running search
+    int sims_per_move;              // budget a game gets after each device move (az_selfplay)
+    int new_budget;                 // >= 0: the launch first sets sims_left of every game to this (az_search start)
+    int free_max;                   // descents a game may start per launch: those that end on a terminal or cached
+                                    // position complete on the spot and the game goes straight on to the next
+    int async_play;                 // 1: a game whose budget is spent chooses and plays its move inside the search
+                                    // kernel and carries on (az_selfplay); 0: it waits for az_play / az_play_device
+    // dense leaf rows: the network batch holds only the leaves that need it
+    int compact;                    // 1: row = atomic counter (az_search); 0: row = slot (external evaluator API)
+    int parity;                     // which of the two row counters this launch fills
+    uint32_t* row_count;            // [2]
+    int32_t* row_slot;              // [S] row -> slot
+    // exact evaluation cache (nullptr = off)
+    CacheEntry* cache; uint32_t cache_mask; uint32_t cache_epoch;
+    // replay recording of the device move choice
+    az_replay_tuple* record; az_replay_tuple* replay; unsigned long long* replay_count; unsigned long long replay_cap;
 };
 
 #if defined(__CUDA_ARCH__)
@@ -135,6 +170,13 @@ MC_HD uint32_t hash_state(const mc_state& s) {
     h = (h ^ (h >> 15)) + s.meta * 0x165667B1u;
     h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
     return h;
+}
+
+MC_HD uint32_t cache_hash(const mc_state& s) {
+    mc_state k = s;
+    k.meta = s.meta & CACHE_KEY_META;
+    const uint32_t h = hash_state(k);
+    return h ^ (h >> 11) ^ (s.pl0 * 0x2545F491u);   // decorrelated from the per-tree tables
 }
 
 // Position -> node of tree t, or NONE.  Scalar: every lane computes the same answer.
@@ -257,6 +299,12 @@ MC_HD uint32_t expand(const View& V, int slot, int t, int lane, const mc_state& 
 // are prefix-summed across the warp, and each lane writes its codes -- already in ascending code order,
 // because codes are numbered by view square then (direction, distance) -- and zeroed statistics straight
 // into the tree's edge arrays.  Same results as the single-thread mc::generate used on the host.
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {      // L2-coherent load (never a stale L1 line)
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
     int x = v;
 #pragma unroll
@@ -329,6 +377,27 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, 
     const bool decisive = (res == MC_WHITE_WINS || res == MC_BLACK_WINS);
     if (terminal) E = 0;
     const size_t gi = (size_t)t * V.NC + node;
+    // exact evaluation cache: same (board, side, fullmove) evaluated before with these weights?
+    bool hit = false;
+    float hit_value = 0.f, hit_p0 = 0.f, hit_p1 = 0.f;      // priors of edges lane and lane + 32
+    if (!terminal && V.cache && E <= CACHE_MAX_E) {
+        const CacheEntry* c = V.cache + (cache_hash(s) & V.cache_mask);
+        const uint32_t s1 = ld_cg_u32(&c->seq);
+        if (!(s1 & 1u)) {
+            __threadfence();
+            const bool key_ok = ld_cg_u32(&c->epoch) == V.cache_epoch && ld_cg_u32(&c->pl0) == s.pl0 && ld_cg_u32(&c->pl1) == s.pl1 &&
+                                ld_cg_u32(&c->pl2) == s.pl2 && ld_cg_u32(&c->white) == s.white &&
+                                ld_cg_u32(&c->meta_n) == ((s.meta & CACHE_KEY_META) | ((uint32_t)E << 8));
+            if (key_ok) {        // the same on every lane unless a writer is at work, which the seq check below catches
+                hit_value = __uint_as_float(ld_cg_u32(reinterpret_cast<const uint32_t*>(&c->value)));
+                if (lane < E) hit_p0 = __uint_as_float(ld_cg_u32(reinterpret_cast<const uint32_t*>(&c->priors[lane])));
+                if (lane + 32 < E) hit_p1 = __uint_as_float(ld_cg_u32(reinterpret_cast<const uint32_t*>(&c->priors[lane + 32])));
+                __threadfence();
+                hit = ld_cg_u32(&c->seq) == s1;
+            }
+        }
+        hit = __all_sync(0xffffffffu, hit);
+    }
     if (!terminal && emit_n > 0) {
         size_t w = (size_t)t * V.EC + off + (knight ? tot_q + off_n : off_q);
         mc::emit_square_codes(fv, white, knight, tg, knight ? nb : qb, type == mc::PAWN, V.rules.promo_multiplicity,
@@ -338,27 +407,40 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, 
                                   ++w;
                               });
     }
-    if (!terminal && fv < 30) {
+    if (hit) {
+        __syncwarp();            // the zeroed priors above are overwritten by the cached ones
+        const size_t w0 = (size_t)t * V.EC + off;
+        if (lane < E) V.edge_P[w0 + lane] = hit_p0;
+        if (lane + 32 < E) V.edge_P[w0 + lane + 32] = hit_p1;
+    }
+    // network row of this leaf: dense (az_search) or the slot itself
+    int row = slot;
+    const bool needs_net = !terminal && !hit;
+    if (needs_net && V.compact) {
+        if (lane == 0) { row = (int)atomicAdd(&V.row_count[V.parity], 1u); V.row_slot[row] = slot; }
+        row = __shfl_sync(0xffffffffu, row, 0);
+    }
+    if (needs_net && fv < 30) {
         // tokens of FEN-order cell i = lane: Network.process_observation
         int cell = 5 * (5 - lane / 5) + lane % 5;
         if (!white) cell = 29 - cell;
         const int ty = mc::piece_at(s, cell);
         const bool mine = (st.own >> cell) & 1u;
-        V.tokens[(size_t)slot * MC_TOKENS + lane] = (uint8_t)(mine ? ty : 0);
-        V.tokens[(size_t)slot * MC_TOKENS + 30 + lane] = (uint8_t)(mine ? 0 : ty);
+        V.tokens[(size_t)row * MC_TOKENS + lane] = (uint8_t)(mine ? ty : 0);
+        V.tokens[(size_t)row * MC_TOKENS + 30 + lane] = (uint8_t)(mine ? 0 : ty);
     }
     if (lane == 0) {
         V.node_board[gi] = board_of(s);
         V.node_meta[gi] = s.meta;
         V.node_edge_off[gi] = off;
         V.node_info[gi] = (uint32_t)E | (terminal ? INFO_TERMINAL : 0u) | ((terminal && decisive) ? INFO_DECISIVE : 0u) |
-                          ((!terminal && V.K > 1) ? INFO_PENDING : 0u);
+                          ((needs_net && V.K > 1) ? INFO_PENDING : 0u);
         V.tree_nodes[t] = node + 1;
         V.tree_edges[t] = off + (uint32_t)E;
         ht_insert(V, t, s, node);
-        if (!terminal) {
+        if (needs_net) {
             const double c = (double)mc::fullmove(s) + (white ? 0.0 : 0.5);
-            V.clocks[slot] = (float)(c / 30.0);
+            V.clocks[row] = (float)(c / 30.0);
             V.leaf_states[slot] = s;
         }
         count(V, C_NODES, 1);
@@ -366,6 +448,7 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, 
     }
     __syncwarp();
     if (terminal) { *kind = LEAF_TERMINAL; *value = decisive ? -1.0 : -0.0; }
+    else if (hit) { *kind = LEAF_CACHED; *value = (double)hit_value; }
     else { *kind = LEAF_EVAL; *value = 0.0; }
     return node;
 }
@@ -376,7 +459,8 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, 
 
 // One simulation of game g down to its leaf (exp/agent.py:54-88 without the backup).
 // `noise`: per-game Dirichlet sample [MC_MAX_MOVES] or nullptr.
-MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise, uint8_t* noise_used, int j = 0) {
+// Returns the leaf kind (the same on every lane).
+MC_HD uint8_t select_expand_one(const View& V, int g, int lane, const double* noise, uint8_t* noise_used, int j = 0) {
     const int slot = g * V.K + j;
     if (lane == 0) {
         V.leaf_kind[slot] = LEAF_NONE;
@@ -384,7 +468,15 @@ MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise
         V.path_len[slot] = 0;
         if (noise_used && j == 0) noise_used[g] = 0;
     }
-    if (V.game_result[g] != MC_ONGOING) return;
+    if (V.game_result[g] != MC_ONGOING) return LEAF_NONE;
+    // device RNG counter of this descent: the game's own serial number when the engine keeps one (results then do
+    // not depend on how descents are batched into launches), else the caller's global counter
+    unsigned long long rng_counter = V.sim_counter;
+    if (V.sim_serial) {
+        rng_counter = V.sim_serial[g];
+        AZ_SYNCWARP();
+        if (lane == 0) V.sim_serial[g] = rng_counter + 1;
+    }
     const int t = 2 * g + (V.game_ply[g] & 1);
     const size_t nbase = (size_t)t * V.NC, ebase = (size_t)t * V.EC;
     uint32_t* pedge = V.path_edge + (size_t)slot * MAX_DEPTH;
@@ -395,6 +487,7 @@ MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise
     double value = 0.0;
     uint32_t node = V.tree_root[t];
     int depth = 0;
+    unsigned int path_edges = 0;       // edges read on the way down (bytes-per-simulation accounting)
     if (node == NONE) {
         mc_state s = V.game_state[g];
         node = ht_find(V, t, s);
@@ -415,6 +508,7 @@ MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise
             break;
         }
         const int E = (int)(info & 0xffffu);
+        path_edges += (unsigned int)E;
         const size_t e0 = ebase + V.node_edge_off[nbase + node];
         // sum of visit counts (exact in float64: small integers)
         unsigned int nsum_u = 0;
@@ -431,7 +525,7 @@ MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise
         if (dev_noise) {
             double part = 0.0;
             for (int i = lane, kk = 0; i < E && kk < 3; i += AZ_LANES, ++kk) {
-                mcaz::Philox rng(V.seed, (uint32_t)g, (uint32_t)V.sim_counter, (uint32_t)(V.sim_counter >> 32) ^ ((uint32_t)i << 16));
+                mcaz::Philox rng(V.seed, (uint32_t)g, (uint32_t)rng_counter, (uint32_t)(rng_counter >> 32) ^ ((uint32_t)i << 16));
                 gam[kk] = rng.gamma((double)V.alpha);
                 part += gam[kk];
             }
@@ -509,7 +603,9 @@ MC_HD void select_expand_one(const View& V, int g, int lane, const double* noise
         V.leaf_kind[slot] = kind;
         V.leaf_value[slot] = value;
         V.needs_eval[slot] = (kind == LEAF_EVAL) ? 1 : 0;
+        if (kind != LEAF_COLLISION) { count(V, C_DEPTH, (unsigned long long)depth); count(V, C_PATH_EDGES, path_edges); }
     }
+    return kind;
 }
 
 // Evaluate + backup for game g (exp/agent.py:67-72 and :47-52).
@@ -559,7 +655,7 @@ MC_HD void backup_one(const View& V, int g, int lane, const float* logits, const
         if (kind == LEAF_COLLISION) count(V, C_COLLISIONS, 1);
         else {
             count(V, C_SIMS, 1);
-            count(V, kind == LEAF_EVAL ? C_EVALS : C_TERMINAL, 1);
+            count(V, kind == LEAF_EVAL ? C_EVALS : (kind == LEAF_CACHED ? C_CACHED : C_TERMINAL), 1);
         }
         V.leaf_kind[slot] = LEAF_NONE;
     }

@@ -185,6 +185,7 @@ struct TowerParams {
     __nv_bfloat16* act1;
     const uint32_t* sched;        // [clusters][TOWER_MAX_ITEMS]: layer << 24 | tile pair << 8 | position
     uint32_t* flags;              // [18][n_pairs][30][2] epoch stamps; nullptr = one layer per launch, no dependencies
+    const uint32_t* count;        // device row count of this forward (dense leaf batch) or nullptr: all n_pairs are live
     int bpad;
     int n_pairs;
     uint32_t epoch;
@@ -230,6 +231,8 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const uint32_t* sched = P.sched + (size_t)(blockIdx.x >> 1) * TOWER_MAX_ITEMS;
+    // dense leaf batch: only the tile pairs that hold rows are computed; every role skips the same items
+    const int live_pairs = P.count ? min(P.n_pairs, (int)((__ldg(P.count) + 2 * BLOCK_M - 1) / (2 * BLOCK_M))) : P.n_pairs;
 
     for (int i = threadIdx.x; i < NLAYERS * C; i += CONV_THREADS) s_bias[i] = P.bias[i];
     if (threadIdx.x == 0) s_deps_ok = 0;
@@ -255,6 +258,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             const uint32_t item = __ldg(&sched[k]);
             if (item == SCHED_END) break;
             const int pos = item & 0xff, tp = (item >> 8) & 0xffff, L = item >> 24;
+            if (tp >= live_pairs) continue;
             const int tile = 2 * tp + (int)rank;
             if (L > 0 && P.flags) {
                 // inputs published? (warp 3 polls the global flags ahead of us)
@@ -278,13 +282,15 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
         }
     } else if (warp == 1 && lane == 0 && leader) {
         // ---------------------------------------------------------------- MMA issuer (leader CTA)
-        uint32_t it = 0;
+        uint32_t it = 0, j = 0;                       // j: items actually computed (accumulator ring position)
         for (int k = 0; k < TOWER_MAX_ITEMS; ++k) {
             const uint32_t item = __ldg(&sched[k]);
             if (item == SCHED_END) break;
             const int pos = item & 0xff;
-            const uint32_t acc = k & 1;
-            mbar_wait(&acc_empty[acc], ((k >> 1) & 1) ^ 1);
+            if ((int)((item >> 8) & 0xffff) >= live_pairs) continue;
+            const uint32_t acc = j & 1;
+            mbar_wait(&acc_empty[acc], ((j >> 1) & 1) ^ 1);
+            ++j;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * C;
             uint32_t accumulate = 0;
@@ -316,7 +322,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             const uint32_t item = __ldg(&sched[k]);
             if (item == SCHED_END) break;
             const int pos = item & 0xff, tp = (item >> 8) & 0xffff, L = item >> 24;
-            if (L > 0 && P.flags && lane < 9) {
+            if (tp < live_pairs && L > 0 && P.flags && lane < 9) {
                 int src;
                 if (tap_valid(pos, lane, src)) {
                     const uint32_t* fl = P.flags + (((size_t)(L - 1) * P.n_pairs + tp) * NPOS + src) * 2 + rank;
@@ -335,12 +341,15 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- epilogue (TMEM -> HBM) + publish
         const int q = warp & 3;
+        uint32_t j = 0;
         for (int k = 0; k < TOWER_MAX_ITEMS; ++k) {
             const uint32_t item = __ldg(&sched[k]);
             if (item == SCHED_END) break;
             const int pos = item & 0xff, tp = (item >> 8) & 0xffff, L = item >> 24;
+            if (tp >= live_pairs) continue;
             const int tile = 2 * tp + (int)rank;
-            const uint32_t acc = k & 1;
+            const uint32_t acc = j & 1, acc_phase = (j >> 1) & 1;
+            ++j;
             const bool odd = (L & 1) != 0;                     // second conv of a residual block
             __nv_bfloat16* out = odd ? P.act0 : P.act1;
             const float* bias = s_bias + L * C;
@@ -357,7 +366,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                     for (int j = 0; j < 4; ++j) res[c][j] = ld_cg_v4(rp + j);
                 }
             }
-            mbar_wait(&acc_full[acc], (k >> 1) & 1);
+            mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C;
 #pragma unroll
@@ -499,10 +508,16 @@ __global__ void prep_heads_kernel(const float* __restrict__ flat, HeadWeights H)
 // accumulated in fp32.  The table (60 KB) is L1-resident; L1 wavefronts bound this kernel.
 __global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ tokens, int n, int bpad,
                                                    const __nv_bfloat16* __restrict__ table, const float* __restrict__ bias,
-                                                   __nv_bfloat16* __restrict__ out) {
+                                                   __nv_bfloat16* __restrict__ out, const uint32_t* __restrict__ count) {
     const int lane = threadIdx.x & 31;
     const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long total = (long long)bpad * NPOS;
+    // dense leaf batch: `count` rows are live; the rest of their last tile pair gets the bias-only filler
+    int rows = bpad;
+    if (count) {
+        n = min(n, (int)__ldg(count));
+        rows = min(bpad, ((n + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (2 * BLOCK_M));
+    }
+    const long long total = (long long)rows * NPOS;
     const float4 b0 = *reinterpret_cast<const float4*>(bias + lane * 8), b1 = *reinterpret_cast<const float4*>(bias + lane * 8 + 4);
     for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
         const int board = (int)(w / NPOS), pos = (int)(w % NPOS);
@@ -631,6 +646,8 @@ heads_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ cl
 // One warp per game slot.
 __global__ void __launch_bounds__(HEADS_THREADS, 4)
 heads_legal_kernel(const __nv_bfloat16* __restrict__ act, int bpad, HeadWeights H, az::View V, float* __restrict__ values) {
+    // rows of the batch: dense (row -> slot through row_slot, az_search) or one row per slot with a needs_eval mask
+    const int n_rows = V.compact ? min((int)__ldg(V.row_count + V.parity), V.G * V.K) : V.G * V.K;
     __shared__ float s_cw[3 * C];
     __shared__ float s_in[HEADS_WARPS][96];
     for (int i = threadIdx.x; i < C; i += HEADS_THREADS) { s_cw[i] = H.pw[i]; s_cw[C + i] = H.pw[C + i]; s_cw[2 * C + i] = H.vw[i]; }
@@ -639,10 +656,11 @@ heads_legal_kernel(const __nv_bfloat16* __restrict__ act, int bpad, HeadWeights 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* in = s_in[warp];
     const int pos = lane < NPOS ? lane : NPOS - 1;
-    for (int slot = blockIdx.x * HEADS_WARPS + warp; slot < V.G * V.K; slot += gridDim.x * HEADS_WARPS) {
-        if (!V.needs_eval[slot]) continue;
+    for (int r = blockIdx.x * HEADS_WARPS + warp; r < n_rows; r += gridDim.x * HEADS_WARPS) {
+        const int slot = V.compact ? V.row_slot[r] : r;
+        if (!V.compact && !V.needs_eval[slot]) continue;
         const int g = slot / V.K;
-        const uint4* row = reinterpret_cast<const uint4*>(act + ((size_t)pos * bpad + slot) * C);
+        const uint4* row = reinterpret_cast<const uint4*>(act + ((size_t)pos * bpad + r) * C);
         float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll 2
         for (int c4 = 0; c4 < C / 8; c4 += 4) {
@@ -667,7 +685,7 @@ heads_legal_kernel(const __nv_bfloat16* __restrict__ act, int bpad, HeadWeights 
             in[30 + lane] = fmaxf(d1 + pb1, 0.f);
             in[61 + lane] = fmaxf(d2 + vb, 0.f);
         } else if (lane == 30) {
-            const float ck = V.clocks[slot];
+            const float ck = V.clocks[r];
             in[60] = ck;
             in[91] = ck;
         }
@@ -694,7 +712,7 @@ heads_legal_kernel(const __nv_bfloat16* __restrict__ act, int bpad, HeadWeights 
         for (int i = lane, kk = 0; i < E && kk < 3; i += 32, ++kk) sum += expf(lg[kk] - m);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        for (int i = lane, kk = 0; i < E && kk < 3; i += 32, ++kk) V.edge_P[e0 + i] = expf(lg[kk] - m) / sum;
+        for (int i = lane, kk = 0; i < E && kk < 3; i += 32, ++kk) { lg[kk] = expf(lg[kk] - m) / sum; V.edge_P[e0 + i] = lg[kk]; }
         // ---- value
         float hv[8];
 #pragma unroll
@@ -711,7 +729,29 @@ heads_legal_kernel(const __nv_bfloat16* __restrict__ act, int bpad, HeadWeights 
         for (int k = 0; k < 8; ++k) part += fmaxf(hv[k], 0.f) * __ldg(H.v2 + lane + 32 * k);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0) values[slot] = tanhf(part + v2b);
+        const float value = tanhf(part + v2b);
+        if (lane == 0) values[slot] = value;
+        // ---- remember the evaluation (exact cache: key = everything the network saw).  Tree kernels of the other
+        // stream may be reading the entry: seqlock (odd seq = being written)
+        if (V.cache && E <= az::CACHE_MAX_E) {
+            const mc_state s = V.leaf_states[slot];
+            az::CacheEntry* c = V.cache + (az::cache_hash(s) & V.cache_mask);
+            uint32_t old = 1;
+            if (lane == 0) old = atomicOr(&c->seq, 1u);
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (!(old & 1u)) {                   // else another warp is filling this entry right now: skip
+                __threadfence();
+                for (int i = lane, kk = 0; i < E && kk < 3; i += 32, ++kk) c->priors[i] = lg[kk];
+                if (lane == 0) {
+                    c->pl0 = s.pl0; c->pl1 = s.pl1; c->pl2 = s.pl2; c->white = s.white;
+                    c->meta_n = (s.meta & az::CACHE_KEY_META) | ((uint32_t)E << 8);
+                    c->epoch = V.cache_epoch; c->value = value;
+                }
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicExch(&c->seq, old + 2u);
+            }
+        }
         __syncwarp();
     }
 }
@@ -967,10 +1007,12 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
     if (int rc = net_alloc_acts(e, n)) return rc;
     const int n_pairs = (n + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = 2 * n_pairs, bpad = N->capacity;
     cudaStream_t st = e->stream;
+    // dense leaf batch of az_search: the number of live rows is only known on the device
+    const uint32_t* count = (search_view && search_view->compact) ? search_view->row_count + search_view->parity : nullptr;
     {
         long long warps = (long long)n_tiles * BLOCK_M * NPOS;
         int grid = (int)std::min<long long>((warps * 32 + 255) / 256, (long long)num_sms() * 16);
-        stem_kernel<<<grid, 256, 0, st>>>(tokens, n, bpad, N->stem_table, N->stem_bias, N->act[0]);
+        stem_kernel<<<grid, 256, 0, st>>>(tokens, n, bpad, N->stem_table, N->stem_bias, N->act[0], count);
         MCAZ_CHECK_LAUNCH();
     }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -986,7 +1028,7 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
     }
     TowerParams T;
     T.bias = N->bias; T.act0 = N->act[0]; T.act1 = N->act[1];
-    T.bpad = bpad; T.n_pairs = n_pairs;
+    T.bpad = bpad; T.n_pairs = n_pairs; T.count = count;
     if (N->per_layer) {
         if (int rc = build_schedule(e, n_pairs)) return rc;
         T.flags = nullptr; T.epoch = 0;

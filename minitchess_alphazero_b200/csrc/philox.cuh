@@ -34,23 +34,30 @@ struct Philox {
         uint32_t a = next() >> 5, b = next() >> 6;
         return ((double)a * 67108864.0 + (double)b + 0.5) * (1.0 / 9007199254740992.0);
     }
-    __device__ double normal() {
-        double u1 = uniform(), u2 = uniform();
-        return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    __device__ float uniformf() { return ((float)(next() >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0,1)
+    __device__ float normalf() {
+        const float u1 = uniformf(), u2 = uniformf();
+        return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
     }
-    // Marsaglia-Tsang; shape < 1 via gamma(shape+1) * U^(1/shape)
-    __device__ double gamma(double shape) {
-        double boost = 1.0;
-        if (shape < 1.0) { boost = pow(uniform(), 1.0 / shape); shape += 1.0; }
-        double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    // Marsaglia-Tsang in single precision (the noise only has to be a Dirichlet sample; nothing is compared
+    // against numpy's stream here); shape < 1 via gamma(shape+1) * U^(1/shape).  The squeeze test accepts most
+    // candidates without a logarithm.
+    __device__ double gamma(double shape_d) {
+        float shape = (float)shape_d, boost = 1.0f;
+        if (shape < 1.0f) { boost = powf(uniformf(), 1.0f / shape); shape += 1.0f; }
+        const float d = shape - 1.0f / 3.0f, c = rsqrtf(9.0f * d);
         for (int it = 0; it < 64; ++it) {
-            double x = normal(), v = 1.0 + c * x;
-            if (v <= 0.0) continue;
+            const float x = normalf();
+            float v = 1.0f + c * x;
+            if (v <= 0.0f) continue;
             v = v * v * v;
-            double u = uniform();
-            if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return boost * d * v;
+            const float u = uniformf(), x2 = x * x;
+            if (u < 1.0f - 0.0331f * x2 * x2 || logf(u) < 0.5f * x2 + d - d * v + d * logf(v)) {
+                const float g = boost * d * v;
+                return (double)(g > 1e-30f ? g : 1e-30f);     // never exactly zero: the draws are normalised by their sum
+            }
         }
-        return boost * d;
+        return (double)(boost * d);
     }
 };
 

@@ -15,7 +15,7 @@ from ._lib import (AZ_NUM_COUNTERS, AZ_NUM_WEIGHT_FLOATS, MC_MAX_MOVES, MC_NUM_A
                    check, ptr)
 
 COUNTER_NAMES = ('simulations', 'evaluations', 'terminal_leaves', 'moves', 'games_finished', 'nodes', 'edges',
-                 'kernel_launches', 'collisions', 'spare')
+                 'kernel_launches', 'collisions', 'cached_evaluations', 'path_depth', 'path_edges')
 
 REPLAY_DTYPE = np.dtype([('observation', STATE_DTYPE), ('n_legal', '<u2'), ('action', '<u2'), ('reward', 'i1'),
                          ('pad', 'u1', 3), ('codes', '<u2', MC_MAX_MOVES), ('pi', '<f4', MC_MAX_MOVES)])
@@ -180,6 +180,11 @@ class Engine:
         """n_sims simulations for every active game with the built-in network."""
         self._check(self._L.az_search(self._h, int(n_sims)))
 
+    def selfplay(self, n_steps, sims_per_move):
+        """Continuous self-play (az_selfplay): n_steps network batches; every game searches, moves, records and
+        restarts on its own inside the search kernel, so the batch stays full whatever each move costs."""
+        self._check(self._L.az_selfplay(self._h, int(n_steps), int(sims_per_move)))
+
     # ------------------------------------------------------------------ read-back
     def root_stats(self, game_ids=None, want_q=True):
         """-> codes uint16[n,M], visits uint32[n,M], q float64[n,M] or None, n_legal int32[n] (-1: not visited)."""
@@ -250,4 +255,13 @@ def _profile_network(self, on=True, read=False):
     return (ms.value, n.value, lpf.value) if read else None
 
 
+def _profile_tree(self, on=True, read=False):
+    """bench hook: (total ms in search_step_kernel, launches) since the last call."""
+    ms, n = ctypes.c_double(), ctypes.c_int()
+    self._check(self._L.az_profile_tree(self._h, int(bool(on)), ctypes.byref(ms) if read else None,
+                                        ctypes.byref(n) if read else None))
+    return (ms.value, n.value) if read else None
+
+
 Engine.profile_network = _profile_network
+Engine.profile_tree = _profile_tree

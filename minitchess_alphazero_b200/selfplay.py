@@ -97,6 +97,33 @@ class BatchedSelfPlay:
         for _ in range(int(n_moves)):
             self.step()
 
+    def stagger(self, max_ply=60, sims=8):
+        """Spread the games uniformly over the plies 0..max_ply-1 of a game (game g ends up at ply g*max_ply//n_games)
+        with a cheap pre-roll of `sims` simulations per move: the stationary population of a long-running actor,
+        instead of n_games copies of the start position marching through the opening together.  `sims` must be
+        large enough for the visit counts to spread over the root's moves (with 2 simulations every game would play
+        edge 0, exp/agent.py:84-85 on an all-zero u), or all games of one ply would share one position."""
+        import numpy as np
+        assert self.mode == 'builtin'
+        target = (np.arange(self.n_games, dtype=np.int64) * max_ply) // self.n_games
+        for step in range(max_ply):
+            ids = np.nonzero(target == max_ply - step)[0].astype(np.int32)
+            if len(ids):
+                self.engine.reset_games(game_ids=ids)
+            self.engine.search(min(sims, self.num_simulations))
+            self.engine.play_device()
+        ids = np.nonzero(target == 0)[0].astype(np.int32)
+        if len(ids):
+            self.engine.reset_games(game_ids=ids)
+        self.engine.drain_replay()          # the pre-roll's games are not training data
+
+    def run_continuous(self, n_batches):
+        """Continuous self-play (az_selfplay): `n_batches` network batches; every game searches, chooses, records,
+        plays and restarts on its own inside the search kernel, so a game whose move needed fewer network rows
+        (terminal or cached leaves) simply moves earlier and the batch stays full."""
+        assert self.mode == 'builtin', 'continuous self-play runs on the built-in network'
+        self.engine.selfplay(int(n_batches), self.num_simulations)
+
     def drain(self):
         return self.engine.drain_replay()
 
@@ -108,17 +135,19 @@ class BatchedSelfPlay:
         if self.mode != 'builtin':
             return None
         self.engine.profile_network(True, read=True)
+        self.engine.profile_tree(True, read=True)
         return True
 
-    def kernel_profile(self):
+    def kernel_profile(self, evaluations=None):
         """Roofline record of the dominant kernel (tower_tc_kernel) from the events recorded since
-        reset_kernel_timer(): algorithmic FLOP per launch / average launch duration."""
+        reset_kernel_timer(): algorithmic FLOP of the rows it evaluated / the time it ran.  `evaluations` = rows
+        evaluated in that window (the engine's evaluation counter); default: every launch had a full batch."""
         if self.mode != 'builtin':
             return None
         ms, n, per_forward = self.engine.profile_network(False, read=True)
         if n == 0 or ms <= 0:
             return None
-        rows = self.engine.n_slots
+        rows = self.engine.n_slots if evaluations is None else evaluations / n     # mean rows per forward
         flop = rows * self.CONV_FLOP_PER_EVAL * 18 / per_forward     # algorithmic FLOP of one launch
         ms_launch = ms / per_forward
         fused = per_forward == 1
@@ -128,8 +157,26 @@ class BatchedSelfPlay:
                 'achieved': flop / (ms_launch / 1e3) / 1e12, 'unit': 'TFLOP/s',
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/ (ncu --set full)
                 'traffic': 934e6 if fused else 151e6, 'ms_per_launch': ms_launch, 'launches_timed': n * per_forward,
-                'flop_per_launch': flop,
+                'rows_per_launch': rows, 'flop_per_launch': flop,
                 # the kernel skips the 62 of 270 tap-positions that multiply zero padding: MMAs actually issued
                 'achieved_mma': flop * 208 / 270 / (ms_launch / 1e3) / 1e12,
-                'note': 'achieved counts the algorithmic FLOPs of SURVEY.md 8(d) (all 9 taps at all 30 squares); '
-                        'taps on zero padding are skipped, so issued MMA work is 208/270 of it (achieved_mma)'}
+                'note': 'achieved counts the algorithmic FLOPs of SURVEY.md 8(d) (all 9 taps at all 30 squares) of the rows '
+                        'actually evaluated; taps on zero padding are skipped, so issued MMA work is 208/270 of it (achieved_mma)'}
+
+    def tree_profile(self, counters0, counters1):
+        """HBM-side record of search_step_kernel (backup + select + expand) between two counter snapshots:
+        algorithmic bytes per simulation after SURVEY.md 8(d) -- select d x (32 B node header + E x 20 B of Q, N, P),
+        expand 32 B + E' x 22 B written, backup d x 32 B read-modify-write -- over the kernel's measured time."""
+        ms, n = self.engine.profile_tree(False, read=True)
+        d = {k: counters1[k] - counters0[k] for k in counters1}
+        sims = d['simulations']
+        if n == 0 or ms <= 0 or sims == 0:
+            return None
+        select_b = d['path_depth'] * 32 + d['path_edges'] * 20
+        expand_b = d['nodes'] * 32 + d['edges'] * 22
+        backup_b = d['path_depth'] * 32
+        total = select_b + expand_b + backup_b
+        return {'bound': 'hbm', 'kernel': 'search_step_kernel (backup + PUCT select + expand, warp per game)',
+                'achieved': total / (ms / 1e3) / 1e9, 'unit': 'GB/s', 'bytes_per_sim': total / sims,
+                'mean_depth': d['path_depth'] / sims, 'mean_edges_per_level': d['path_edges'] / max(d['path_depth'], 1),
+                'ms_per_launch': ms / n, 'launches_timed': n, 'sims_per_launch': sims / n}

@@ -1,0 +1,147 @@
+"""GPU: the three levers of SURVEY.md 7.3 point 6 that raise simulations/s above evaluations/s without changing
+a single visit count -- simulations that end on terminal positions complete inside the search launch
+(`free_sims`), the exact evaluation cache (`eval_cache_log2`), and continuous self-play (`az_selfplay`, every
+game moves as soon as its own simulations are done).  Each is checked bit-for-bit against the plain lock-step
+search: the order of a game's simulations, which is all the reference's sequential MCTS depends on
+(exp/agent.py:41-45), must not change."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def net(mcaz_lib):
+    from minitchess_alphazero_b200.policy import Network
+    torch.manual_seed(0)
+    return Network().eval()
+
+
+def make(net, n_games, sims, **kw):
+    from minitchess_alphazero_b200.engine import Engine
+    from minitchess_alphazero_b200.policy import flatten_state_dict
+    eng = Engine(n_games, max_sims_per_move=sims, network=1, device_rng=1, **kw)
+    eng.set_weights(flatten_state_dict(net.state_dict(), device='cuda'))
+    return eng
+
+
+def snapshot(eng):
+    codes, visits, q, n_legal = eng.root_stats()
+    states, results = eng.game_states()
+    return codes, visits, q, n_legal, states, results
+
+
+def same(a, b):
+    return all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_cache_and_free_sims_leave_every_visit_count_unchanged(net):
+    G, sims = 300, 24
+    plain = make(net, G, sims, seed=5, free_sims=1)
+    free = make(net, G, sims, seed=5, free_sims=6)
+    cached = make(net, G, sims, seed=5, free_sims=4, eval_cache_log2=18)
+    tiny = make(net, G, sims, seed=5, eval_cache_log2=6)            # 64 entries: constant replacement
+    engines = (plain, free, cached, tiny)
+    for move in range(12):
+        for e in engines:
+            e.search(sims)
+        ref = snapshot(plain)
+        for e in engines[1:]:
+            assert same(ref, snapshot(e)), move                       # N, Q (float64 bits), codes, positions
+        for e in engines:
+            e.play_device()
+    counters = [e.counters() for e in engines]
+    for c in counters:
+        assert c['simulations'] == 12 * sims * G
+        assert c['simulations'] == c['evaluations'] + c['terminal_leaves'] + c['cached_evaluations']
+        assert c['nodes'] == counters[0]['nodes'] and c['edges'] == counters[0]['edges']
+    assert counters[0]['cached_evaluations'] == 0 and counters[1]['cached_evaluations'] == 0
+    assert counters[2]['cached_evaluations'] > 0.2 * counters[2]['simulations']   # 300 games share the opening
+    assert 0 < counters[3]['cached_evaluations'] < counters[2]['cached_evaluations']
+    assert counters[2]['evaluations'] < counters[0]['evaluations']
+
+
+def test_late_game_terminal_leaves_need_no_network_rows(net):
+    """Near the 30-move cap most leaves are finished positions: they are backed up inside the launch."""
+    from oracle import rules_c as rc
+    G, sims = 64, 40
+    pos = rc.random_positions(17, 60000)
+    late = np.ascontiguousarray(pos[((pos['meta'] >> 16) & 0xff) >= 30][:G])
+    assert len(late) == G
+    got = []
+    for free in (1, 8):
+        eng = make(net, G, sims, seed=3, free_sims=free)
+        eng.reset_games(states=late)
+        eng.search(sims)
+        got.append((snapshot(eng), eng.counters()))
+    assert same(got[0][0], got[1][0])
+    c = got[1][1]
+    assert c['terminal_leaves'] > c['evaluations']
+    assert c['simulations'] == c['evaluations'] + c['terminal_leaves'] == got[0][1]['simulations']
+
+
+def test_cache_is_dropped_when_the_weights_change(net):
+    from minitchess_alphazero_b200.policy import Network, flatten_state_dict
+    G, sims = 128, 16
+    eng = make(net, G, sims, seed=9, eval_cache_log2=16)
+    eng.search(sims)
+    assert eng.counters()['cached_evaluations'] > 0
+    torch.manual_seed(123)
+    other = Network().eval()
+    flat = flatten_state_dict(other.state_dict(), device='cuda')
+    eng.set_weights(flat)
+    eng.reset_games()
+    before = eng.counters()['cached_evaluations']
+    eng.search(1)                                                   # the root of every game: all must be evaluated afresh
+    assert eng.counters()['cached_evaluations'] == before
+    eng.search(sims - 1)
+    fresh = make(other, G, sims, seed=9)                            # no cache; same per-game RNG position as `eng`
+    fresh.search(sims)
+    fresh.reset_games()
+    fresh.search(sims)
+    assert same(snapshot(eng), snapshot(fresh))
+
+
+def finished_games(tuples):
+    """Replay stream -> list of games, each the raw bytes of its tuples (a game starts at the start position)."""
+    from minitchess_alphazero_b200 import rules
+    start = rules.state_from_fen(rules.STARTING_FEN)
+    is_start = np.array([t['observation'] == start for t in tuples])
+    cuts = list(np.nonzero(is_start)[0]) + [len(tuples)]
+    return [tuples[a:b].tobytes() for a, b in zip(cuts[:-1], cuts[1:])]
+
+
+def test_continuous_selfplay_plays_the_same_games_as_lockstep(net):
+    from collections import Counter
+    G, sims = 96, 6
+    lock = make(net, G, sims, seed=21, eval_cache_log2=14)
+    for _ in range(62):                                            # every slot finishes its first game (<= 60 plies)
+        lock.search(sims)
+        lock.play_device()
+    want = Counter(finished_games(lock.drain_replay()))
+    assert sum(want.values()) >= G
+
+    cont = make(net, G, sims, seed=21, eval_cache_log2=14, free_sims=3)
+    got = Counter()
+    for _ in range(40):
+        cont.selfplay(64, sims)
+        got.update(finished_games(cont.drain_replay()))
+        if all(got[k] >= n for k, n in want.items()):
+            break
+    missing = [k for k, n in want.items() if got[k] < n]
+    assert not missing, '%d of %d lock-step games were not reproduced by az_selfplay' % (len(missing), len(want))
+    c = cont.counters()
+    assert c['simulations'] == c['evaluations'] + c['terminal_leaves'] + c['cached_evaluations']
+    assert c['moves'] * sims <= c['simulations'] + G * sims           # every move was preceded by its simulations
+
+
+def test_selfplay_argument_checks(net):
+    from minitchess_alphazero_b200._lib import McazError
+    eng = make(net, 8, 8)
+    with pytest.raises(McazError):
+        eng.selfplay(4, 9)                                          # more simulations than the arenas were sized for
+    with pytest.raises(McazError):
+        eng.selfplay(-1, 4)
+    eng.selfplay(0, 4)                                              # nothing to do
+    assert eng.counters()['simulations'] == 0
