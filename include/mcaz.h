@@ -146,6 +146,13 @@ typedef struct az_config {
                                   on a terminal or cached position need no network row, complete on the spot and the
                                   game goes on to its next simulation in the same launch.  0 = default (1: measured
                                   best on B200 -- longer chains stretch the launch by more than the fuller batch saves)  */
+    int32_t recycle;           /* 1: before every az_search / az_selfplay call the trees that could not take the call's
+                                  new nodes are compacted: nodes whose ply is not greater than the game's current
+                                  position (other than that position) can never be reached again -- their ply is part
+                                  of the key -- so no result changes, and node_capacity = 0 then derives a 5x smaller
+                                  arena (6 x max_sims_per_move + 64).  For engines whose positions only move forward
+                                  (az_play / az_play_device / az_selfplay); leave 0 when az_set_positions may jump back
+                                  to an earlier position of a kept tree (the per-agent facade).  Default 0              */
 } az_config;
 
 void az_default_config(az_config* out);
@@ -243,8 +250,9 @@ int az_collate(const az_replay_tuple* tuples, int n, float* pi, int64_t* tokens,
  * [3] moves played, [4] games finished, [5] nodes allocated, [6] edges allocated,
  * [7] kernels launched by this library, [8] descents dropped on a pending node (leaves_per_step > 1),
  * [9] simulations whose leaf evaluation came from the evaluation cache ([0] = [1] + [2] + [9]),
- * [10] tree levels descended and [11] edges read on the way (bytes-per-simulation accounting).          */
-#define AZ_NUM_COUNTERS 12
+ * [10] tree levels descended and [11] edges read on the way (bytes-per-simulation accounting),
+ * [12] nodes dropped by the recycler (recycle = 1).                                                     */
+#define AZ_NUM_COUNTERS 13
 int az_counters(az_engine* e, uint64_t* out);
 
 /* Stand-alone network forward (exp/policy.py:71-80) on n positions with the engine's weights:

@@ -14,7 +14,7 @@ MC_TOKENS = 60
 AZ_NUM_PARAMS = 10693458
 AZ_NUM_BN_STATS = 9734
 AZ_NUM_WEIGHT_FLOATS = AZ_NUM_PARAMS + AZ_NUM_BN_STATS
-AZ_NUM_COUNTERS = 12
+AZ_NUM_COUNTERS = 13
 
 STATE_DTYPE = np.dtype([('pl0', '<u4'), ('pl1', '<u4'), ('pl2', '<u4'), ('white', '<u4'), ('meta', '<u4')])
 RESULT_STRINGS = {0: '*', 1: '1-0', 2: '0-1', 3: '1/2-1/2'}
@@ -43,7 +43,7 @@ class Config(ctypes.Structure):
                 ('numpy1_dtype_flow', ctypes.c_int32), ('device_rng', ctypes.c_int32),
                 ('seed', ctypes.c_uint64), ('rules', Rules), ('network', ctypes.c_int32),
                 ('leaves_per_step', ctypes.c_int32), ('own_stream', ctypes.c_int32),
-                ('eval_cache_log2', ctypes.c_int32), ('free_sims', ctypes.c_int32)]
+                ('eval_cache_log2', ctypes.c_int32), ('free_sims', ctypes.c_int32), ('recycle', ctypes.c_int32)]
 
 
 _lib = None

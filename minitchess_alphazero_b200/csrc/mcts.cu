@@ -306,6 +306,130 @@ __global__ void __launch_bounds__(256) restart_finished_kernel(View V, mc_state 
     }
 }
 
+// ---- recycling of unreachable plies (SURVEY.md 7.3 point 7) ------------------------------------------
+// The reference never prunes its dicts.  Here nodes are stratified by ply (side to move and fullmove number are
+// part of the key) and every future root of a game is a descendant of its current position, so a node whose ply is
+// not greater than the current position's -- other than that position itself -- can never be reached again, by an
+// edge or by transposition: dropping it changes no result.  Block per tree; a tree is compacted in place when it
+// could not take `need_nodes` / `need_edges` more.  Order-preserving, so every block of data only moves towards
+// the front; the hash-table region serves as the old -> new index map and is rebuilt afterwards.  Runs between
+// searches (no simulation pending).
+MC_HD int ply_of_meta(uint32_t meta) { return 2 * (int)((meta >> 16) & 0xffu) + ((meta & 1u) ? 0 : 1); }
+
+constexpr int RECYCLE_THREADS = 256;
+__global__ void __launch_bounds__(RECYCLE_THREADS) recycle_kernel(View V, int need_nodes, int need_edges) {
+    __shared__ uint32_t s_scan[RECYCLE_THREADS / 32][2];
+    __shared__ uint32_t s_tot[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int WARPS = RECYCLE_THREADS / 32;
+    for (int t = blockIdx.x; t < 2 * V.G; t += gridDim.x) {
+        const uint32_t n = V.tree_nodes[t], m = V.tree_edges[t];
+        __syncthreads();                                    // everyone has read the counters of this tree
+        if (n + (uint32_t)need_nodes <= (uint32_t)V.NC && m + (uint32_t)need_edges <= (uint32_t)V.EC) continue;
+        const int g = t >> 1;
+        const mc_state cur = V.game_state[g];
+        const int cur_ply = ply_of_meta(cur.meta);
+        const size_t nb = (size_t)t * V.NC, eb = (size_t)t * V.EC;
+        uint32_t* map = V.ht + (size_t)t * V.HC;            // old node -> new node (HC >= 2 NC)
+        if (tid == 0) { s_tot[0] = 0; s_tot[1] = 0; }
+        __syncthreads();
+        // ---- pass 1: node headers (chunks of 256 nodes: read, scan, barrier, write)
+        for (uint32_t base = 0; base < n; base += RECYCLE_THREADS) {
+            const uint32_t i = base + tid;
+            az::Board4 board{}; uint32_t meta = 0, off = 0, info = 0;
+            bool live = false;
+            if (i < n) {
+                board = V.node_board[nb + i]; meta = V.node_meta[nb + i]; off = V.node_edge_off[nb + i]; info = V.node_info[nb + i];
+                const int ply = ply_of_meta(meta);
+                live = ply > cur_ply || (meta == cur.meta && board.x == cur.pl0 && board.y == cur.pl1 && board.z == cur.pl2 && board.w == cur.white);
+            }
+            const uint32_t E = live && !(info & az::INFO_TERMINAL) ? (info & 0xffffu) : 0u;
+            // block-wide exclusive scan of (live, E)
+            uint32_t a = live ? 1u : 0u, b = E;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t ya = __shfl_up_sync(0xffffffffu, a, o), yb = __shfl_up_sync(0xffffffffu, b, o);
+                if (lane >= o) { a += ya; b += yb; }
+            }
+            if (lane == 31) { s_scan[warp][0] = a; s_scan[warp][1] = b; }
+            __syncthreads();
+            uint32_t pa = s_tot[0], pb = s_tot[1];
+            for (int w = 0; w < warp; ++w) { pa += s_scan[w][0]; pb += s_scan[w][1]; }
+            const uint32_t new_i = pa + a - (live ? 1u : 0u);
+            __syncthreads();
+            if (tid == RECYCLE_THREADS - 1) { s_tot[0] = pa + a; s_tot[1] = pb + b; }
+            if (i < n) map[i] = live ? new_i : az::NONE;
+            if (live) {                                     // new_i <= i and every older chunk is already moved
+                V.node_board[nb + new_i] = board; V.node_meta[nb + new_i] = meta; V.node_info[nb + new_i] = info;
+                V.node_edge_off[nb + new_i] = off;          // old offset for now: pass 2 moves the edges and fixes it
+            }
+            __syncthreads();
+        }
+        const uint32_t n_live = s_tot[0], m_live = s_tot[1];
+        __syncthreads();
+        if (tid == 0) s_tot[0] = 0;                          // edges placed so far
+        // ---- pass 2: edge blocks, one node per warp and round: all warps read, barrier, all write
+        for (uint32_t base = 0; base < n_live; base += WARPS) {
+            const uint32_t j = base + warp;
+            uint32_t old_off = 0, E = 0;
+            double q[3]; uint32_t nn[3], ch[3]; float pp[3]; uint16_t cd[3], vl[3];
+            if (j < n_live) {
+                old_off = V.node_edge_off[nb + j];
+                const uint32_t info = V.node_info[nb + j];
+                E = (info & az::INFO_TERMINAL) ? 0u : (info & 0xffffu);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t i = lane + 32 * k;
+                if (i < E) {
+                    const size_t e = eb + old_off + i;
+                    q[k] = V.edge_Q[e]; nn[k] = V.edge_N[e]; pp[k] = V.edge_P[e]; ch[k] = V.edge_child[e]; cd[k] = V.edge_code[e];
+                    vl[k] = V.edge_vl ? V.edge_vl[e] : (uint16_t)0;
+                }
+            }
+            if (lane == 0) s_scan[warp][0] = E;
+            __syncthreads();                                  // this round's reads are done, its sizes published
+            uint32_t new_off = s_tot[0], round_total = 0;
+            for (int w = 0; w < WARPS; ++w) {
+                if (w < warp) new_off += s_scan[w][0];
+                round_total += s_scan[w][0];
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t i = lane + 32 * k;
+                if (i < E) {
+                    const size_t e = eb + new_off + i;
+                    V.edge_Q[e] = q[k]; V.edge_N[e] = nn[k]; V.edge_P[e] = pp[k]; V.edge_code[e] = cd[k];
+                    V.edge_child[e] = ch[k] == az::NONE ? az::NONE : map[ch[k]];    // children are deeper: always live
+                    if (V.edge_vl) V.edge_vl[e] = vl[k];
+                }
+            }
+            if (j < n_live && lane == 0) V.node_edge_off[nb + j] = new_off;
+            __syncthreads();                                  // this round's writes are done, s_tot[0] has been read
+            if (tid == 0) s_tot[0] += round_total;
+        }
+        __syncthreads();
+        // ---- roots, then the hash table
+        if (tid == 0) {
+            const uint32_t r = V.tree_root[t];
+            V.tree_root[t] = (r != az::NONE && r < n) ? map[r] : az::NONE;
+            V.tree_nodes[t] = n_live;
+            V.tree_edges[t] = m_live;
+            atomicAdd(&V.counters[az::C_RECYCLED], (unsigned long long)(n - n_live));
+        }
+        __syncthreads();
+        uint32_t* tab = V.ht + (size_t)t * V.HC;
+        for (int i = tid; i < V.HC; i += RECYCLE_THREADS) tab[i] = 0u;
+        __syncthreads();
+        const uint32_t mask = (uint32_t)V.HC - 1u;
+        for (uint32_t i = tid; i < n_live; i += RECYCLE_THREADS) {
+            const mc_state s = az::state_of(V.node_board[nb + i], V.node_meta[nb + i]);
+            uint32_t h = az::hash_state(s) & mask;
+            while (atomicCAS(&tab[h], 0u, i + 1u) != 0u) h = (h + 1u) & mask;
+        }
+        __syncthreads();
+    }
+}
+
 int warp_grid(int n_warps, int block) {
     int per = block / 32;
     int want = (n_warps + per - 1) / per;
@@ -366,6 +490,7 @@ void az_default_config(az_config* c) {
     c->own_stream = 0;
     c->eval_cache_log2 = 0;
     c->free_sims = 0;
+    c->recycle = 0;
 }
 
 int az_create(const az_config* cfg, az_engine** out) {
@@ -384,7 +509,8 @@ int az_create(const az_config* cfg, az_engine** out) {
     V.K = cfg->leaves_per_step > 0 ? cfg->leaves_per_step : 1;
     if (V.K > az::MAX_LEAVES) { delete e; return fail(MCAZ_EINVAL, "az_create: leaves_per_step > 16"); }
     // <= 1 new node per simulation, <= 31 searches per tree under the 30-move cap (+ roots)
-    long long nc = cfg->node_capacity > 0 ? cfg->node_capacity : (long long)cfg->max_sims_per_move * 31 + 64;
+    // without recycling a tree keeps every node of the game; with it only the plies still ahead (measured ~1.5 x sims live)
+    long long nc = cfg->node_capacity > 0 ? cfg->node_capacity : (long long)cfg->max_sims_per_move * (cfg->recycle ? 6 : 31) + 64;
     long long ec = cfg->edge_capacity > 0 ? cfg->edge_capacity : nc * 14;
     if (nc > 0x3fffffff || ec > 0x7fffffff) { delete e; return fail(MCAZ_EINVAL, "az_create: arena too large"); }
     V.NC = (int)nc;
@@ -600,6 +726,15 @@ static int search_launch(az_engine* e, const View& V) {
 // batch -- was measured and dropped: the B200 runs this workload at its power cap, the tree work costs the same
 // energy wherever it runs, and the tower slowed down by more than the hidden time; tools/sweep_modes.py.)
 static int run_search(az_engine* e, int n_batches, int new_budget, bool async, int sims_per_move) {
+    if (e->cfg.recycle && n_batches > 0) {
+        // make room for what this call can add: at most one node per descent
+        const long long per_game = (long long)n_batches * (e->v.K == 1 ? std::max(1, e->cfg.free_sims) : e->v.K);
+        const int need_nodes = (int)std::min<long long>(new_budget >= 0 ? std::min<long long>(per_game, new_budget) : per_game, e->v.NC);
+        const int need_edges = (int)std::min<long long>((long long)need_nodes * 40, e->v.EC);
+        recycle_kernel<<<std::min(2 * e->v.G, num_sms() * 8), RECYCLE_THREADS, 0, e->stream>>>(e->v, need_nodes, need_edges);
+        MCAZ_CHECK_LAUNCH();
+        e->launches++;
+    }
     for (int s = 0; s <= n_batches; ++s) {
         View V = search_view(e);
         V.new_budget = s == 0 ? new_budget : -1;

@@ -59,6 +59,7 @@ class BatchedSelfPlay:
         self.mode = evaluator
         # with leaves_per_step = K every search step runs K descents per tree: size the arenas for all of them
         leaves = int(engine_options.get('leaves_per_step', 1) or 1)
+        engine_options.setdefault('recycle', 1)       # games only move forward here: plies behind them can be dropped
         self.engine = Engine(n_games, max_sims_per_move=num_simulations * leaves, cpuct=float(cpuct), tau_change=int(tau_change),
                              dirichlet_epsilon=float(epsilon), dirichlet_alpha=float(alpha), seed=int(seed),
                              device_rng=1, network=1 if evaluator == 'builtin' else 0, **engine_options)

@@ -145,3 +145,32 @@ def test_selfplay_argument_checks(net):
         eng.selfplay(-1, 4)
     eng.selfplay(0, 4)                                              # nothing to do
     assert eng.counters()['simulations'] == 0
+
+
+def test_recycling_unreachable_plies_changes_nothing(net):
+    """SURVEY.md 7.3 point 7: nodes are stratified by ply, so everything not ahead of the current position can be
+    dropped.  Same games, visit counts and Q with 5x (and, forced, 8x) smaller arenas; whole games incl. restarts."""
+    G, sims = 160, 20
+    keep = make(net, G, sims, seed=13)                                           # 31 x sims + 64 nodes per tree
+    small = make(net, G, sims, seed=13, recycle=1, eval_cache_log2=15)           # 6 x sims + 64
+    tight = make(net, G, sims, seed=13, recycle=1, node_capacity=4 * sims)       # compacts almost every move
+    for move in range(70):
+        for e in (keep, small, tight):
+            e.search(sims)
+        if move % 5 == 0 or move > 55:
+            ref = snapshot(keep)
+            assert same(ref, snapshot(small)) and same(ref, snapshot(tight)), move
+        for e in (keep, small, tight):
+            e.play_device()
+    ck, cs, ct = keep.counters(), small.counters(), tight.counters()
+    assert ck['recycled_nodes'] == 0 and cs['recycled_nodes'] > 0 and ct['recycled_nodes'] > cs['recycled_nodes']
+    assert ck['games_finished'] == cs['games_finished'] == ct['games_finished'] >= G
+    assert ck['nodes'] == cs['nodes'] == ct['nodes']
+    from collections import Counter                                            # same games (games that end in one launch
+    a, b = keep.drain_replay(), tight.drain_replay()                           # reach the replay ring in any order)
+    assert len(a) == len(b) and Counter(finished_games(a)) == Counter(finished_games(b))
+    # continuous self-play on recycled arenas: runs whole games without overflowing the small arenas
+    cont = make(net, G, sims, seed=13, recycle=1, eval_cache_log2=15)
+    for _ in range(8):
+        cont.selfplay(10 * sims, sims)
+    assert cont.counters()['games_finished'] >= G and cont.counters()['recycled_nodes'] > 0
