@@ -725,15 +725,22 @@ static int search_launch(az_engine* e, const View& V) {
 // (An overlap variant -- the chains of free simulations running on a side stream while the tower evaluates the
 // batch -- was measured and dropped: the B200 runs this workload at its power cap, the tree work costs the same
 // energy wherever it runs, and the tower slowed down by more than the hidden time; tools/sweep_modes.py.)
+// recycle = 1: compact the trees that could not take `need_nodes` more nodes (one per descent).  Called where no
+// simulation is pending: after the moves of az_play / az_play_device and at the start of az_search / az_selfplay.
+static int maybe_recycle(az_engine* e, long long need) {
+    if (!e->cfg.recycle || need <= 0) return MCAZ_OK;
+    const int need_nodes = (int)std::min<long long>(need, e->v.NC);
+    const int need_edges = (int)std::min<long long>((long long)need_nodes * 40, e->v.EC);
+    recycle_kernel<<<std::min(2 * e->v.G, num_sms() * 8), RECYCLE_THREADS, 0, e->stream>>>(e->v, need_nodes, need_edges);
+    MCAZ_CHECK_LAUNCH();
+    e->launches++;
+    return MCAZ_OK;
+}
+
 static int run_search(az_engine* e, int n_batches, int new_budget, bool async, int sims_per_move) {
-    if (e->cfg.recycle && n_batches > 0) {
-        // make room for what this call can add: at most one node per descent
+    {
         const long long per_game = (long long)n_batches * (e->v.K == 1 ? std::max(1, e->cfg.free_sims) : e->v.K);
-        const int need_nodes = (int)std::min<long long>(new_budget >= 0 ? std::min<long long>(per_game, new_budget) : per_game, e->v.NC);
-        const int need_edges = (int)std::min<long long>((long long)need_nodes * 40, e->v.EC);
-        recycle_kernel<<<std::min(2 * e->v.G, num_sms() * 8), RECYCLE_THREADS, 0, e->stream>>>(e->v, need_nodes, need_edges);
-        MCAZ_CHECK_LAUNCH();
-        e->launches++;
+        if (int rc = maybe_recycle(e, new_budget >= 0 ? std::min<long long>(per_game, new_budget) : per_game)) return rc;
     }
     for (int s = 0; s <= n_batches; ++s) {
         View V = search_view(e);
@@ -859,6 +866,7 @@ int az_play(az_engine* e, const int32_t* game_ids, const uint16_t* codes, int n,
     play_kernel<<<std::max(1, std::min((n + 127) / 128, num_sms() * 8)), 128, 0, e->stream>>>(e->v, ids.ptr, ic.ptr, n, orr.ptr);
     MCAZ_CHECK_LAUNCH();
     e->launches++;
+    if (int rc = maybe_recycle(e, e->cfg.max_sims_per_move)) return rc;     // room for the next move's search
     if (int rc = orr.finish(e->stream)) return rc;
     return engine_check_errors(e);
 }
@@ -873,7 +881,7 @@ int az_play_device(az_engine* e) {
     restart_finished_kernel<<<std::min(V.G, num_sms() * 8), 256, 0, e->stream>>>(V, start_state());
     MCAZ_CHECK_LAUNCH();
     e->launches += 2;
-    return MCAZ_OK;
+    return maybe_recycle(e, e->cfg.max_sims_per_move);                      // room for the next move's search
 }
 
 int az_game_states(az_engine* e, const int32_t* game_ids, int n, mc_state* states, int8_t* results) {

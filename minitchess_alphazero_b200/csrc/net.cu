@@ -186,6 +186,8 @@ struct TowerParams {
     const uint32_t* sched;        // [clusters][TOWER_MAX_ITEMS]: layer << 24 | tile pair << 8 | position
     uint32_t* flags;              // [18][n_pairs][30][2] epoch stamps; nullptr = one layer per launch, no dependencies
     const uint32_t* count;        // device row count of this forward (dense leaf batch) or nullptr: all n_pairs are live
+    size_t sched_stride;          // words between the schedules for k and k + 1 live pairs (0: one schedule, dead pairs skipped)
+    uint32_t row_base;            // first row of this chunk within the batch that `count` counts
     int bpad;
     int n_pairs;
     uint32_t epoch;
@@ -230,9 +232,14 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
-    const uint32_t* sched = P.sched + (size_t)(blockIdx.x >> 1) * TOWER_MAX_ITEMS;
-    // dense leaf batch: only the tile pairs that hold rows are computed; every role skips the same items
-    const int live_pairs = P.count ? min(P.n_pairs, (int)((__ldg(P.count) + 2 * BLOCK_M - 1) / (2 * BLOCK_M))) : P.n_pairs;
+    // dense leaf batch: only the tile pairs that hold rows are computed.  The fused form has one schedule per number
+    // of live pairs (sched_stride apart); in the per-layer form every role skips the items of the dead pairs.
+    int live_pairs = P.n_pairs;
+    if (P.count) {
+        const uint32_t total = __ldg(P.count), rows = total > P.row_base ? total - P.row_base : 0u;
+        live_pairs = (int)min((uint32_t)P.n_pairs, (rows + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
+    }
+    const uint32_t* sched = P.sched + (size_t)max(live_pairs - 1, 0) * P.sched_stride + (size_t)(blockIdx.x >> 1) * TOWER_MAX_ITEMS;
 
     for (int i = threadIdx.x; i < NLAYERS * C; i += CONV_THREADS) s_bias[i] = P.bias[i];
     if (threadIdx.x == 0) s_deps_ok = 0;
@@ -508,13 +515,14 @@ __global__ void prep_heads_kernel(const float* __restrict__ flat, HeadWeights H)
 // accumulated in fp32.  The table (60 KB) is L1-resident; L1 wavefronts bound this kernel.
 __global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ tokens, int n, int bpad,
                                                    const __nv_bfloat16* __restrict__ table, const float* __restrict__ bias,
-                                                   __nv_bfloat16* __restrict__ out, const uint32_t* __restrict__ count) {
+                                                   __nv_bfloat16* __restrict__ out, const uint32_t* __restrict__ count, uint32_t row_base) {
     const int lane = threadIdx.x & 31;
     const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
     // dense leaf batch: `count` rows are live; the rest of their last tile pair gets the bias-only filler
     int rows = bpad;
     if (count) {
-        n = min(n, (int)__ldg(count));
+        const uint32_t total = __ldg(count);
+        n = min(n, (int)(total > row_base ? total - row_base : 0u));
         rows = min(bpad, ((n + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (2 * BLOCK_M));
     }
     const long long total = (long long)rows * NPOS;
@@ -645,9 +653,12 @@ heads_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ cl
 // softmax and writes the priors straight into the new node's edges; the value goes to values[g].
 // One warp per game slot.
 __global__ void __launch_bounds__(HEADS_THREADS, 4)
-heads_legal_kernel(const __nv_bfloat16* __restrict__ act, int bpad, HeadWeights H, az::View V, float* __restrict__ values) {
-    // rows of the batch: dense (row -> slot through row_slot, az_search) or one row per slot with a needs_eval mask
-    const int n_rows = V.compact ? min((int)__ldg(V.row_count + V.parity), V.G * V.K) : V.G * V.K;
+heads_legal_kernel(const __nv_bfloat16* __restrict__ act, int bpad, HeadWeights H, az::View V, float* __restrict__ values,
+                   int row_base, int chunk_rows) {
+    // rows of the batch: dense (row -> slot through row_slot, az_search) or one row per slot with a needs_eval mask;
+    // this launch covers rows [row_base, row_base + chunk_rows) of it, which sit in act rows [0, chunk_rows)
+    const int total = V.compact ? min((int)__ldg(V.row_count + V.parity), V.G * V.K) : V.G * V.K;
+    const int n_rows = max(0, min(chunk_rows, total - row_base));
     __shared__ float s_cw[3 * C];
     __shared__ float s_in[HEADS_WARPS][96];
     for (int i = threadIdx.x; i < C; i += HEADS_THREADS) { s_cw[i] = H.pw[i]; s_cw[C + i] = H.pw[C + i]; s_cw[2 * C + i] = H.vw[i]; }
@@ -657,7 +668,7 @@ heads_legal_kernel(const __nv_bfloat16* __restrict__ act, int bpad, HeadWeights 
     float* in = s_in[warp];
     const int pos = lane < NPOS ? lane : NPOS - 1;
     for (int r = blockIdx.x * HEADS_WARPS + warp; r < n_rows; r += gridDim.x * HEADS_WARPS) {
-        const int slot = V.compact ? V.row_slot[r] : r;
+        const int slot = V.compact ? V.row_slot[row_base + r] : row_base + r;
         if (!V.compact && !V.needs_eval[slot]) continue;
         const int g = slot / V.K;
         const uint4* row = reinterpret_cast<const uint4*>(act + ((size_t)pos * bpad + r) * C);
@@ -685,7 +696,7 @@ heads_legal_kernel(const __nv_bfloat16* __restrict__ act, int bpad, HeadWeights 
             in[30 + lane] = fmaxf(d1 + pb1, 0.f);
             in[61 + lane] = fmaxf(d2 + vb, 0.f);
         } else if (lane == 30) {
-            const float ck = V.clocks[r];
+            const float ck = V.clocks[row_base + r];
             in[60] = ck;
             in[91] = ck;
         }
@@ -866,7 +877,7 @@ int network_create(az_engine* e) {
             }
         }
     }
-    return net_alloc_acts(e, std::min(e->v.G * e->v.K, MAX_CHUNK_BOARDS));
+    return net_alloc_acts(e, std::min(e->v.G * e->v.K, MAX_CHUNK_BOARDS));   // grows on demand (network_forward batches)
 }
 
 void network_destroy(az_engine* e) {
@@ -952,24 +963,34 @@ static int build_tower_schedule(az_engine* e, int n_pairs) {
         order.push_back(pos);
     }
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return taps_of[a] > taps_of[b]; });
-    std::vector<long long> load(clusters, 0);
-    std::vector<int> count(clusters, 0);
-    std::vector<uint32_t> table((size_t)clusters * TOWER_MAX_ITEMS, SCHED_END);
+    // One schedule per number of live tile pairs (the dense leaf batch of az_search shrinks and grows; the kernel reads
+    // the row count on the device and picks the table built for exactly that many pairs).
     // Groups of at most 8 tile pairs (2048 boards, 2 x 31 MB of activations) go through all 18 layers one
-    // after the other, so a group's ping-pong buffers stay resident in the 126 MB L2 from layer to layer.
-    int group = 8;
-    { const char* gs = getenv("MCAZ_TOWER_GROUP"); if (gs && atoi(gs) > 0) group = atoi(gs); }
-    for (int g0 = 0; g0 < n_pairs; g0 += group)
-    for (int L = 0; L < NLAYERS; ++L)
-        for (int tp = g0; tp < std::min(n_pairs, g0 + group); ++tp)
-            for (int pos : order) {
-                int best = 0;
-                for (int c = 1; c < clusters; ++c)
-                    if (load[c] < load[best]) best = c;
-                if (count[best] >= TOWER_MAX_ITEMS - 1) return fail(MCAZ_ECAPACITY, "tower schedule: too many items per CTA pair");
-                table[(size_t)best * TOWER_MAX_ITEMS + count[best]++] = (uint32_t)pos | ((uint32_t)tp << 8) | ((uint32_t)L << 24);
-                load[best] += taps_of[pos];
-            }
+    // after the other, so a group's ping-pong buffers stay resident in the 126 MB L2 from layer to layer;
+    // the pairs are split evenly over the groups (11 pairs -> 6 + 5, not 8 + 3).
+    int group_max = 8;
+    { const char* gs = getenv("MCAZ_TOWER_GROUP"); if (gs && atoi(gs) > 0) group_max = atoi(gs); }
+    const size_t per_table = (size_t)clusters * TOWER_MAX_ITEMS;
+    std::vector<uint32_t> table(per_table * n_pairs, SCHED_END);
+    for (int live = 1; live <= n_pairs; ++live) {
+        std::vector<long long> load(clusters, 0);
+        std::vector<int> count(clusters, 0);
+        uint32_t* tab = table.data() + (size_t)(live - 1) * per_table;
+        const int n_groups = (live + group_max - 1) / group_max;
+        for (int gi = 0; gi < n_groups; ++gi) {
+            const int g0 = (int)((long long)live * gi / n_groups), g1 = (int)((long long)live * (gi + 1) / n_groups);
+            for (int L = 0; L < NLAYERS; ++L)
+                for (int tp = g0; tp < g1; ++tp)
+                    for (int pos : order) {
+                        int best = 0;
+                        for (int c = 1; c < clusters; ++c)
+                            if (load[c] < load[best]) best = c;
+                        if (count[best] >= TOWER_MAX_ITEMS - 1) return fail(MCAZ_ECAPACITY, "tower schedule: too many items per CTA pair");
+                        tab[(size_t)best * TOWER_MAX_ITEMS + count[best]++] = (uint32_t)pos | ((uint32_t)tp << 8) | ((uint32_t)L << 24);
+                        load[best] += taps_of[pos];
+                    }
+        }
+    }
     if (N->tower_sched) cudaFree(N->tower_sched);
     if (N->tower_flags) cudaFree(N->tower_flags);
     N->tower_sched = nullptr; N->tower_flags = nullptr;
@@ -986,7 +1007,7 @@ static int build_tower_schedule(az_engine* e, int n_pairs) {
 }
 
 static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clocks, int n, float* logits, float* values,
-                         const az::View* search_view);
+                         const az::View* search_view, int row_base, int sched_rows = 0);
 
 int network_forward(az_engine* e, const uint8_t* tokens, const float* clocks, const uint8_t* /*active*/, int n, float* logits,
                     float* values) {
@@ -995,24 +1016,26 @@ int network_forward(az_engine* e, const uint8_t* tokens, const float* clocks, co
     for (int off = 0; off < n; off += MAX_CHUNK_BOARDS) {
         const int m = std::min(MAX_CHUNK_BOARDS, n - off);
         if (int rc = forward_chunk(e, tokens + (size_t)off * MC_TOKENS, clocks + off, m, logits + (size_t)off * MC_NUM_ACTIONS, values + off,
-                                   nullptr))
+                                   nullptr, 0))
             return rc;
     }
     return MCAZ_OK;
 }
 
 static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clocks, int n, float* logits, float* values,
-                         const az::View* search_view) {
+                         const az::View* search_view, int row_base, int sched_rows) {
     Network* N = e->net;
-    if (int rc = net_alloc_acts(e, n)) return rc;
-    const int n_pairs = (n + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = 2 * n_pairs, bpad = N->capacity;
+    // sched_rows >= n: size the schedule (and buffers) for that many rows, so equal chunks of one batch share a schedule
+    const int plan = std::max(n, sched_rows);
+    if (int rc = net_alloc_acts(e, plan)) return rc;
+    const int n_pairs = (plan + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = 2 * n_pairs, bpad = N->capacity;
     cudaStream_t st = e->stream;
     // dense leaf batch of az_search: the number of live rows is only known on the device
     const uint32_t* count = (search_view && search_view->compact) ? search_view->row_count + search_view->parity : nullptr;
     {
         long long warps = (long long)n_tiles * BLOCK_M * NPOS;
         int grid = (int)std::min<long long>((warps * 32 + 255) / 256, (long long)num_sms() * 16);
-        stem_kernel<<<grid, 256, 0, st>>>(tokens, n, bpad, N->stem_table, N->stem_bias, N->act[0], count);
+        stem_kernel<<<grid, 256, 0, st>>>(tokens, n, bpad, N->stem_table, N->stem_bias, N->act[0], count, (uint32_t)row_base);
         MCAZ_CHECK_LAUNCH();
     }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1028,10 +1051,10 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
     }
     TowerParams T;
     T.bias = N->bias; T.act0 = N->act[0]; T.act1 = N->act[1];
-    T.bpad = bpad; T.n_pairs = n_pairs; T.count = count;
+    T.bpad = bpad; T.n_pairs = n_pairs; T.count = count; T.row_base = (uint32_t)row_base;
     if (N->per_layer) {
         if (int rc = build_schedule(e, n_pairs)) return rc;
-        T.flags = nullptr; T.epoch = 0;
+        T.flags = nullptr; T.epoch = 0; T.sched_stride = 0;
         const size_t per_layer = (size_t)(N->sched_grid / 2) * TOWER_MAX_ITEMS;
         for (int L = 0; L < NLAYERS; ++L) {
             T.sched = N->sched + L * per_layer;
@@ -1042,12 +1065,14 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
     } else {
         if (int rc = build_tower_schedule(e, n_pairs)) return rc;
         T.sched = N->tower_sched; T.flags = N->tower_flags; T.epoch = ++N->epoch;
+        T.sched_stride = (size_t)(N->tower_grid / 2) * TOWER_MAX_ITEMS;
         tower_tc_kernel<<<N->tower_grid, CONV_THREADS, TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, T);
         MCAZ_CHECK_LAUNCH();
     }
     if (ev1) cudaEventRecord(ev1, st);
     if (search_view)
-        heads_legal_kernel<<<std::min(num_sms() * 4, (n + HEADS_WARPS - 1) / HEADS_WARPS), HEADS_THREADS, 0, st>>>(N->act[0], bpad, N->heads, *search_view, values);
+        heads_legal_kernel<<<std::min(num_sms() * 4, (n + HEADS_WARPS - 1) / HEADS_WARPS), HEADS_THREADS, 0, st>>>(N->act[0], bpad, N->heads, *search_view, values,
+                                                                                                                     row_base, n);
     else
         heads_kernel<<<std::min(num_sms() * 4, (n + HEADS_WARPS - 1) / HEADS_WARPS), HEADS_THREADS, 0, st>>>(N->act[0], clocks, n, bpad, N->heads, logits, values);
     MCAZ_CHECK_LAUNCH();
@@ -1059,8 +1084,15 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
 int network_forward_search(az_engine* e, const az::View& V, float* values) {
     Network* N = e->net;
     if (!N->have_weights) return fail(MCAZ_ESTATE, "network weights have not been set (az_set_weights)");
-    if (V.G * V.K > MAX_CHUNK_BOARDS) return fail(MCAZ_EINVAL, "az_search: more than 8192 leaf slots (games x leaves_per_step) per engine are not supported yet");
-    return forward_chunk(e, V.tokens, V.clocks, V.G * V.K, nullptr, values, &V);
+    // more rows than one pass holds: chunks of 8192 rows of the (dense) batch, one after the other
+    const int rows = V.G * V.K;
+    const int n_chunks = (rows + MAX_CHUNK_BOARDS - 1) / MAX_CHUNK_BOARDS;
+    const int chunk = (((rows + n_chunks - 1) / n_chunks + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (2 * BLOCK_M);
+    for (int base = 0; base < rows; base += chunk) {
+        const int m = std::min(chunk, rows - base);
+        if (int rc = forward_chunk(e, V.tokens + (size_t)base * MC_TOKENS, V.clocks + base, m, nullptr, values, &V, base, chunk)) return rc;
+    }
+    return MCAZ_OK;
 }
 
 int network_profile(az_engine* e, int on, double* avg_ms_per_tower, int* n_forwards, int* launches_per_forward) {

@@ -174,3 +174,19 @@ def test_recycling_unreachable_plies_changes_nothing(net):
     for _ in range(8):
         cont.selfplay(10 * sims, sims)
     assert cont.counters()['games_finished'] >= G and cont.counters()['recycled_nodes'] > 0
+
+
+def test_more_games_than_one_network_pass(net):
+    """More than 8192 leaf rows per batch are evaluated in equal chunks; results do not depend on the chunking:
+    the first 300 games of a 9000-game engine play exactly like a 300-game engine with the same seed."""
+    sims = 6
+    big = make(net, 9000, sims, seed=31, recycle=1, eval_cache_log2=16)
+    small = make(net, 300, sims, seed=31)
+    for move in range(5):
+        big.search(sims); small.search(sims)
+        ids = np.arange(300, dtype=np.int32)
+        a = big.root_stats(game_ids=ids) + big.game_states(game_ids=ids)
+        assert same(a, snapshot(small)), move
+        big.play_device(); small.play_device()
+    c = big.counters()
+    assert c['simulations'] == 5 * sims * 9000 and c['moves'] == 5 * 9000
