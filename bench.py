@@ -3,9 +3,15 @@
 
 Contract:  python bench.py --gpus N --steps K --warmup W
   * workload = BASELINE.json configs[2]: 4096 concurrent games x 200 simulations/move per GPU,
-    random-init reference-size network (seed 0), synthetic self-play from STARTING_FEN.
+    random-init reference-size network (seed 0), synthetic self-play.  The games are spread uniformly
+    over the plies of a game by a low-simulation pre-roll before the warm-up (the population a
+    long-running actor holds), not started together from STARTING_FEN.
   * one "step" = one move in every game: 200 simulations (select/expand -> network -> backup)
     for each of the 4096 active trees, then move choice, replay recording, play, restarts.
+    A simulation whose leaf is a finished position, or a position the exact evaluation cache has
+    seen (same board, side, fullmove number = everything the network reads), needs no network row;
+    `evals_per_second` and `sims_breakdown` say how many did, `without_cache_lockstep` is the same
+    workload with the cache off, and `roofline` is computed from the rows actually evaluated.
   * `value` = simulations/s of the whole job, everything resident in HBM (device RNG, device move
     choice).  `e2e` = the same metric through the host-buffer API: per step the positions go up
     from pinned host memory, root statistics come back, the host samples the moves.
@@ -328,8 +334,10 @@ def run_ours(args):
             'metric': METRIC, 'value': value, 'unit': 'sims/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms / max(args.steps, 1), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16 network / f64 tree statistics', 'data': 'synthetic',
-            'config': {'workload': 'BASELINE.json configs[2]: batched self-play, %d concurrent games x %d sims/move per GPU, random-init '
-                                   'reference-size net' % (G, S), 'games_per_gpu': G, 'sims_per_move': S, 'evaluator': args.evaluator,
+            'config': {'workload': '%s: batched self-play, %d concurrent games x %d sims/move per GPU, random-init reference-size net' % (
+                           'BASELINE.json configs[3] (32768 games x 800 sims/move sharded over the GPUs)' if (G * world == 32768 and S == 800)
+                           else 'BASELINE.json configs[2]' if (G == 4096 and S == 200) else 'custom size', G, S),
+                       'games_per_gpu': G, 'sims_per_move': S, 'evaluator': args.evaluator,
                        'mode': ('continuous (az_selfplay): a step = %d network batches; games move on their own' % S) if continuous
                                else 'lockstep (az_search + az_play_device): a step = one move in every game',
                        'eval_cache': ('exact, 2^%d entries' % args.eval_cache) if builtin and args.eval_cache > 0 else 'off',
