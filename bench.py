@@ -358,45 +358,35 @@ def run_ours(args):
 
 
 def measure_e2e(sp, args, world):
-    """Same metric through the host-buffer API: every step uploads the positions from pinned host
-    memory, searches, downloads the root statistics, samples moves on the host and plays them."""
+    """Same metric through the reference-facing call: BatchedAlphaZeroAgent.select_actions_packed, the batched
+    `SimpleAlphaZeroAgent.select_action`.  Every step uploads the positions from pinned host memory, searches,
+    downloads the root statistics, picks the moves on the host like exp/agent.py:113-118 and plays them through
+    the environment call (`az_play`), reading the results and the new positions back."""
     import numpy as np
     import torch
     import torch.distributed as dist
+    from minitchess_alphazero_b200 import rules
     from minitchess_alphazero_b200._lib import MC_MAX_MOVES, STATE_DTYPE
+    from minitchess_alphazero_b200.agent import BatchedAlphaZeroAgent
+    from minitchess_alphazero_b200.policy import SimpleAlphaZeroPolicy
     eng, G, S = sp.engine, sp.n_games, sp.num_simulations
-    rng = np.random.RandomState(7)
+    # the agent adopts the engine of the timed run: its games carry on mid-game with their trees
+    agent = BatchedAlphaZeroAgent(SimpleAlphaZeroPolicy(sp.network), G, S, rng=np.random.RandomState(7), engine=eng)
     pinned = torch.empty(G * 5, dtype=torch.int32).pin_memory()
     host_states = pinned.numpy().view(np.uint32).view(STATE_DTYPE)
-    # carry on with the games of the timed run where they stand (mid-game, trees kept): restarting all of them from
-    # the start position would replay an opening the evaluation cache has just seen
-    from minitchess_alphazero_b200 import rules
+    # restarting all games from the start position would replay an opening the evaluation cache has just seen
     start = np.full(G, rules.state_from_fen(rules.STARTING_FEN), dtype=STATE_DTYPE)
     host_states[:] = eng.game_states()[0]
-    plies = np.where(host_states['meta'] & 1, 0, 1).astype(np.int32)       # white to move -> white's tree (tree 0)
 
     def step():
-        eng.set_positions(host_states, trees=plies & 1)                    # H2D: positions
-        sp.search()
-        codes, visits, _, n_legal = eng.root_stats(want_q=False)           # D2H: root statistics
-        E = np.maximum(n_legal, 1)
-        w = visits.astype(np.float64)
-        cum = np.cumsum(w, axis=1)
-        u = rng.random_sample(G) * cum[np.arange(G), E - 1]
-        pick = np.minimum((cum <= u[:, None]).sum(1), E - 1)
-        greedy = w.argmax(1)
-        fullmove = (host_states['meta'] >> 16) & 0xff
-        pick = np.where(fullmove < 6, pick, greedy)
-        actions = codes[np.arange(G), pick]
+        actions, _codes, _pi, _n = agent.select_actions_packed(host_states)    # H2D: positions; D2H: root statistics
         results = eng.play(actions)                                         # H2D: moves, D2H: results
         new_states, _ = eng.game_states()                                   # D2H: positions
         host_states[:] = new_states
-        plies[:] += 1
         done = np.nonzero(results != 0)[0].astype(np.int32)
         if len(done):
-            eng.reset_games(game_ids=done)
+            agent.init_mcts(game_ids=done)                                  # new episodes
             host_states[done] = start[done]
-            plies[done] = 0
         return G * 20 + G * 4 + G * 2, G * MC_MAX_MOVES * 6 + G * 4 + G + G * 21
 
     for _ in range(2):
@@ -421,7 +411,8 @@ def measure_e2e(sp, args, world):
     else:
         sims = float(t[1])
     return {'value': sims / dt, 'unit': 'sims/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h), 'steps': steps,
-            'api': 'Engine.set_positions / search / root_stats / play with host (pinned) buffers'}
+            'api': 'BatchedAlphaZeroAgent.select_actions_packed (set_positions / search / root_stats, host move choice) + Engine.play, '
+                   'host (pinned) buffers'}
 
 
 if __name__ == '__main__':

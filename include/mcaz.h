@@ -80,6 +80,9 @@ void mc_default_rules(mc_rules* out);
 
 /* ---- library */
 int mcaz_abi_version(void);
+/* sizeof of the structs of this header as the library was compiled: 0 mc_state, 1 mc_rules, 2 az_config,
+ * 3 az_replay_tuple (0 for anything else).  A binding checks its own mirror against these at load time.   */
+size_t mcaz_struct_size(int which);
 const char* mcaz_last_error(void);
 int mcaz_device_count(void);         /* 0 when no CUDA device is usable                    */
 int mcaz_set_device(int device);
@@ -251,8 +254,9 @@ int az_collate(const az_replay_tuple* tuples, int n, float* pi, int64_t* tokens,
  * [7] kernels launched by this library, [8] descents dropped on a pending node (leaves_per_step > 1),
  * [9] simulations whose leaf evaluation came from the evaluation cache ([0] = [1] + [2] + [9]),
  * [10] tree levels descended and [11] edges read on the way (bytes-per-simulation accounting),
- * [12] nodes dropped by the recycler (recycle = 1).                                                     */
-#define AZ_NUM_COUNTERS 13
+ * [12] nodes dropped by the recycler (recycle = 1), [13] network rows whose position was already in the
+ * evaluation cache when they were stored (evaluated more than once within one batch).                  */
+#define AZ_NUM_COUNTERS 14
 int az_counters(az_engine* e, uint64_t* out);
 
 /* Stand-alone network forward (exp/policy.py:71-80) on n positions with the engine's weights:

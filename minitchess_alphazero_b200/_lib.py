@@ -14,7 +14,7 @@ MC_TOKENS = 60
 AZ_NUM_PARAMS = 10693458
 AZ_NUM_BN_STATS = 9734
 AZ_NUM_WEIGHT_FLOATS = AZ_NUM_PARAMS + AZ_NUM_BN_STATS
-AZ_NUM_COUNTERS = 13
+AZ_NUM_COUNTERS = 14
 
 STATE_DTYPE = np.dtype([('pl0', '<u4'), ('pl1', '<u4'), ('pl2', '<u4'), ('white', '<u4'), ('meta', '<u4')])
 RESULT_STRINGS = {0: '*', 1: '1-0', 2: '0-1', 3: '1/2-1/2'}
@@ -61,6 +61,11 @@ def lib():
         L.mcaz_kernel_launches.restype = ctypes.c_uint64
         if L.mcaz_abi_version() != ABI_VERSION:
             raise ImportError('libmcaz.so ABI mismatch')
+        L.mcaz_struct_size.restype = ctypes.c_size_t
+        for which, mirror in ((0, STATE_DTYPE.itemsize), (1, ctypes.sizeof(Rules)), (2, ctypes.sizeof(Config))):
+            if L.mcaz_struct_size(which) != mirror:
+                raise ImportError('libmcaz.so struct %d is %d bytes, the Python mirror %d: rebuild the library'
+                                  % (which, L.mcaz_struct_size(which), mirror))
         _lib = L
     return _lib
 

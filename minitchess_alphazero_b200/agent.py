@@ -178,3 +178,84 @@ class SimpleAlphaZeroAgent(PolicyAgent):                    # exp/agent.py:91-11
             maxima = np.where(info['pi'] == info['pi'].max())[0]
             action = info['legal_moves'][np.random.choice(maxima)]
         return ActionData(action=action, info=info)
+
+
+class BatchedAlphaZeroAgent:
+    """The batched superset of `SimpleAlphaZeroAgent`: `n_games` concurrent games, each with
+    the two per-colour trees the reference's two agents keep (app/base.py:113), searched together on one engine.
+
+        agent = BatchedAlphaZeroAgent(policy, n_games=4096, num_simulations=200)
+        actions = agent.select_actions(observations)          # list of FEN strings, one per game
+        # ... step the environments with [a.action for a in actions] ...
+
+    `select_actions` is `select_action` (exp/agent.py:110-119) for every game at once: the position of each game is
+    handed to the tree of its side to move (kept from that side's previous move), `num_simulations` simulations run
+    with the built-in network, and the move is chosen on the host exactly like the reference does -- sampled from
+    pi while fullmove < tau_change, else uniformly among the maxima.  Root Dirichlet noise comes from the engine's
+    Philox streams (one per game) instead of numpy's global RNG, which cannot serve thousands of games in a defined order.
+    """
+
+    def __init__(self, policy, n_games, num_simulations, cpuct=1, tau_change=6, seed=0, rng=None, engine=None, **engine_options):
+        self._policy = policy
+        self.n_games, self._num_simulations, self._tau_change = int(n_games), int(num_simulations), int(tau_change)
+        if engine is not None:                                  # adopt a running engine (its games, trees and weights)
+            assert engine.n_games == self.n_games and not engine_options
+            self._engine = engine
+        else:
+            engine_options.setdefault('recycle', 1)             # positions only move forward within a game
+            engine_options.setdefault('eval_cache_log2', 20)
+            self._engine = Engine(self.n_games, max_sims_per_move=self._num_simulations, cpuct=float(cpuct), tau_change=self._tau_change,
+                                  device_rng=1, network=1, seed=int(seed), **engine_options)
+        self._rng = rng if rng is not None else np.random
+        self._fingerprint = None
+        self._all = np.arange(self.n_games, dtype=np.int32)
+
+    @property
+    def policy(self):
+        return self._policy
+
+    @property
+    def engine(self):
+        return self._engine
+
+    def init_mcts(self, game_ids=None):
+        """MonteCarloInit.on_episode_begin (exp/callbacks.py:57-62) for the listed games (default: all)."""
+        self._engine.reset_games(game_ids=game_ids)
+
+    def _sync_weights(self):
+        fp = weights_fingerprint(self._policy.model)
+        if fp != self._fingerprint:                 # first use, load_state_dict or an optimiser step
+            self._engine.set_weights(flatten_state_dict(self._policy.model.state_dict(), device='cuda'))
+            self._fingerprint = fp
+
+    def select_actions_packed(self, states):
+        """`select_actions` on packed positions (STATE_DTYPE array, one per game).  Returns (actions uint16 [n],
+        codes uint16 [n, M], pi float64 [n, M], n_legal int32 [n]).  A game whose position is finished gets n_legal 0."""
+        eng = self._engine
+        states = np.ascontiguousarray(states)
+        assert len(states) == self.n_games, 'one position per game (the search advances every game of the engine)'
+        self._sync_weights()
+        eng.set_positions(states, trees=1 - (states['meta'] & 1).astype(np.int32))   # white to move -> tree 0
+        eng.search(self._num_simulations)
+        codes, visits, _, n_legal = eng.root_stats(want_q=False)
+        n_legal = np.maximum(n_legal, 0)
+        n = self.n_games
+        E = np.maximum(n_legal, 1)
+        w = visits.astype(np.float64)
+        total = w.sum(1, keepdims=True)
+        pi = w / np.maximum(total, 1.0)
+        # exp/agent.py:113-118, vectorised: sample from pi early in the game, else pick uniformly among the maxima
+        cum = np.cumsum(pi, axis=1)
+        pick = np.minimum((cum <= self._rng.random_sample(n)[:, None] * cum[np.arange(n), E - 1][:, None]).sum(1), E - 1)
+        is_max = (w == w.max(1, keepdims=True)) & (np.arange(w.shape[1])[None, :] < E[:, None])
+        order = np.where(is_max, self._rng.random_sample(w.shape), -1.0).argmax(1)                  # a random maximum
+        fullmove = (states['meta'] >> 16) & 0xff
+        choice = np.where(fullmove < self._tau_change, pick, order)
+        return codes[np.arange(n), choice], codes, pi, n_legal
+
+    def select_actions(self, observations):
+        """observations: one FEN string per game -> list of ActionData(action, info={'legal_moves', 'pi'})."""
+        actions, codes, pi, n_legal = self.select_actions_packed(rules.states_from_fens(list(observations)))
+        return [ActionData(action=int(actions[k]),
+                           info={'legal_moves': codes[k, :n_legal[k]].astype(int).tolist(), 'pi': pi[k, :n_legal[k]].copy()})
+                for k in range(len(actions))]

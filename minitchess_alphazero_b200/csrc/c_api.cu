@@ -48,6 +48,15 @@ void mc_default_rules(mc_rules* out) {
 }
 
 int mcaz_abi_version(void) { return MCAZ_ABI_VERSION; }
+size_t mcaz_struct_size(int which) {
+    switch (which) {
+        case 0: return sizeof(mc_state);
+        case 1: return sizeof(mc_rules);
+        case 2: return sizeof(az_config);
+        case 3: return sizeof(az_replay_tuple);
+        default: return 0;
+    }
+}
 const char* mcaz_last_error(void) { return t_last_error.c_str(); }
 
 int mcaz_device_count(void) {

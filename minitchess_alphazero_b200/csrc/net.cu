@@ -78,23 +78,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 // ---- CTA-pair (cta_group::2) variants
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the even CTA of the pair
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -747,6 +730,10 @@ heads_legal_kernel(const __nv_bfloat16* __restrict__ act, int bpad, HeadWeights 
         if (V.cache && E <= az::CACHE_MAX_E) {
             const mc_state s = V.leaf_states[slot];
             az::CacheEntry* c = V.cache + (az::cache_hash(s) & V.cache_mask);
+            // a row whose key is already stored was evaluated twice in this batch (or since its lookup): count them
+            if (lane == 0 && c->epoch == V.cache_epoch && c->pl0 == s.pl0 && c->pl1 == s.pl1 && c->pl2 == s.pl2 && c->white == s.white &&
+                c->meta_n == ((s.meta & az::CACHE_KEY_META) | ((uint32_t)E << 8)))
+                atomicAdd(&V.counters[az::C_DUP_ROWS], 1ull);
             uint32_t old = 1;
             if (lane == 0) old = atomicOr(&c->seq, 1u);
             old = __shfl_sync(0xffffffffu, old, 0);

@@ -15,10 +15,13 @@ from ._lib import (AZ_NUM_COUNTERS, AZ_NUM_WEIGHT_FLOATS, MC_MAX_MOVES, MC_NUM_A
                    check, ptr)
 
 COUNTER_NAMES = ('simulations', 'evaluations', 'terminal_leaves', 'moves', 'games_finished', 'nodes', 'edges',
-                 'kernel_launches', 'collisions', 'cached_evaluations', 'path_depth', 'path_edges', 'recycled_nodes')
+                 'kernel_launches', 'collisions', 'cached_evaluations', 'path_depth', 'path_edges', 'recycled_nodes', 'duplicate_rows')
 
 REPLAY_DTYPE = np.dtype([('observation', STATE_DTYPE), ('n_legal', '<u2'), ('action', '<u2'), ('reward', 'i1'),
                          ('pad', 'u1', 3), ('codes', '<u2', MC_MAX_MOVES), ('pi', '<f4', MC_MAX_MOVES)])
+
+
+assert REPLAY_DTYPE.itemsize == 604          # az_replay_tuple; checked against the library in Engine.__init__
 
 
 class _CudaView:
@@ -48,6 +51,8 @@ class Engine:
         # (tests/host_harness).  The product always uses libmcaz.so.
         self._L = _backend if _backend is not None else _lib.lib()
         self._host = _backend is not None
+        if not self._host and self._L.mcaz_struct_size(3) != REPLAY_DTYPE.itemsize:
+            raise ImportError('az_replay_tuple size mismatch between libmcaz.so and engine.REPLAY_DTYPE')
         cfg = Config()
         self._L.az_default_config(ctypes.byref(cfg))
         cfg.n_games = int(n_games)

@@ -151,3 +151,42 @@ def test_batched_selfplay_torch_evaluator(net):
     if len(first) >= 2:
         game = eps[first[0]:first[1]]
         assert all(game[k]['reward'] == -game[k + 1]['reward'] for k in range(len(game) - 1))
+
+
+def test_batched_agent_select_actions(mcaz_lib):
+    """BatchedAlphaZeroAgent.select_actions = select_action for many games at once: legal moves and pi of every game
+    equal the engine's root statistics, actions are legal, trees are kept per colour across moves."""
+    from minitchess_alphazero_b200.agent import BatchedAlphaZeroAgent
+    from minitchess_alphazero_b200.environment import MinitChessEnvironment
+    from minitchess_alphazero_b200.policy import Network, SimpleAlphaZeroPolicy
+    torch.manual_seed(0)
+    policy = SimpleAlphaZeroPolicy(Network().eval())
+    n, sims = 48, 12
+    agent = BatchedAlphaZeroAgent(policy, n_games=n, num_simulations=sims, seed=4, rng=np.random.RandomState(0))
+    env = MinitChessEnvironment()
+    episodes, obs = zip(*[env.new_episode() for _ in range(n)])
+    obs = list(obs)
+    agent.init_mcts()
+    for ply in range(6):
+        actions = agent.select_actions(obs)
+        assert len(actions) == n
+        for k, (ep, a) in enumerate(zip(episodes, actions)):
+            assert a.info['legal_moves'] == ep.get_legal_moves()
+            assert a.action in a.info['legal_moves']
+            assert abs(a.info['pi'].sum() - 1.0) < 1e-12
+            visits = a.info['pi'] * (sims - 1 if ply < 2 else 1)
+            if ply < 2:                                          # fresh trees: sims - 1 edge visits (exp/policy.py:118-121)
+                assert np.allclose(visits, np.round(visits))
+            obs[k] = ep.step(a.action).observation
+    assert len(set(obs)) > n // 2                                # per-game noise and sampling: the games diverge
+    c = agent.engine.counters()
+    assert c['simulations'] == 6 * n * sims
+    # new episodes for some games: MonteCarloInit empties their trees
+    agent.init_mcts(game_ids=np.array([3, 7], dtype=np.int32))
+    for i in (3, 7):
+        episodes = list(episodes)
+        episodes[i], obs[i] = env.new_episode()
+    again = agent.select_actions(obs)
+    for i in (3, 7):
+        v = again[i].info['pi'] * (sims - 1)
+        assert np.allclose(v, np.round(v)) and again[i].info['legal_moves'] == episodes[i].get_legal_moves()

@@ -35,8 +35,8 @@ for cont, cache, free in configs:
     tower_ms, n_fwd, _ = sp.engine.profile_network(False, read=True)
     tree_ms, n_tree = sp.engine.profile_tree(False, read=True)
     print('%s cache=%2d free=%2d: %.3f M sims/s, %.3f M evals/s, rows/fwd %.0f, hits %.3f, terminal %.4f, tower %.3f ms, tree %.3f ms/launch, '
-          'moves %d' % ('continuous' if cont else 'lockstep  ', cache, free, d['simulations'] / dt / 1e6, d['evaluations'] / dt / 1e6,
+          'moves %d, duplicate rows %.4f' % ('continuous' if cont else 'lockstep  ', cache, free, d['simulations'] / dt / 1e6, d['evaluations'] / dt / 1e6,
                         d['evaluations'] / max(n_fwd, 1), d['cached_evaluations'] / d['simulations'], d['terminal_leaves'] / d['simulations'],
-                        tower_ms, tree_ms / max(n_tree, 1), d['moves']), flush=True)
+                        tower_ms, tree_ms / max(n_tree, 1), d['moves'], d['duplicate_rows'] / max(d['evaluations'], 1)), flush=True)
     sp.engine.close()
     del sp
