@@ -241,16 +241,23 @@ class BatchedAlphaZeroAgent:
         n_legal = np.maximum(n_legal, 0)
         n = self.n_games
         E = np.maximum(n_legal, 1)
-        w = visits.astype(np.float64)
-        total = w.sum(1, keepdims=True)
-        pi = w / np.maximum(total, 1.0)
+        width = int(E.max())                                    # the arrays are MC_MAX_MOVES wide; few positions need that
+        w = visits[:, :width].astype(np.float64)
+        pi = np.zeros(visits.shape, dtype=np.float64)
+        pi[:, :width] = w / np.maximum(w.sum(1, keepdims=True), 1.0)
         # exp/agent.py:113-118, vectorised: sample from pi early in the game, else pick uniformly among the maxima
-        cum = np.cumsum(pi, axis=1)
-        pick = np.minimum((cum <= self._rng.random_sample(n)[:, None] * cum[np.arange(n), E - 1][:, None]).sum(1), E - 1)
-        is_max = (w == w.max(1, keepdims=True)) & (np.arange(w.shape[1])[None, :] < E[:, None])
-        order = np.where(is_max, self._rng.random_sample(w.shape), -1.0).argmax(1)                  # a random maximum
-        fullmove = (states['meta'] >> 16) & 0xff
-        choice = np.where(fullmove < self._tau_change, pick, order)
+        rows = np.arange(n)
+        choice = w.argmax(1)                                    # the only maximum in most positions
+        is_max = w == w[rows, choice][:, None]
+        is_max &= np.arange(width)[None, :] < E[:, None]
+        tied = np.nonzero(is_max.sum(1) > 1)[0]
+        if len(tied):
+            choice[tied] = np.where(is_max[tied], self._rng.random_sample((len(tied), width)), -1.0).argmax(1)
+        early = np.nonzero(((states['meta'] >> 16) & 0xff) < self._tau_change)[0]
+        if len(early):
+            cum = np.cumsum(w[early], axis=1)
+            u = self._rng.random_sample(len(early)) * cum[np.arange(len(early)), E[early] - 1]
+            choice[early] = np.minimum((cum <= u[:, None]).sum(1), E[early] - 1)
         return codes[np.arange(n), choice], codes, pi, n_legal
 
     def select_actions(self, observations):

@@ -952,10 +952,11 @@ static int build_tower_schedule(az_engine* e, int n_pairs) {
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return taps_of[a] > taps_of[b]; });
     // One schedule per number of live tile pairs (the dense leaf batch of az_search shrinks and grows; the kernel reads
     // the row count on the device and picks the table built for exactly that many pairs).
-    // Groups of at most 8 tile pairs (2048 boards, 2 x 31 MB of activations) go through all 18 layers one
-    // after the other, so a group's ping-pong buffers stay resident in the 126 MB L2 from layer to layer;
-    // the pairs are split evenly over the groups (11 pairs -> 6 + 5, not 8 + 3).
-    int group_max = 8;
+    // Groups of tile pairs go through all 18 layers one after the other, so a group's ping-pong buffers stay
+    // resident in the 126 MB L2 from layer to layer: at most 12 pairs per group (3072 boards, 2 x 47 MB), split
+    // evenly (16 pairs -> 8 + 8).  Small groups leave too few items per layer to hide the waits on the previous
+    // layer (measured on 2 800-row batches: groups of <= 4 pairs 1.40 ms, <= 6: 1.27, <= 8: 1.17, <= 12: 1.165, 16: 1.19).
+    int group_max = 12;
     { const char* gs = getenv("MCAZ_TOWER_GROUP"); if (gs && atoi(gs) > 0) group_max = atoi(gs); }
     const size_t per_table = (size_t)clusters * TOWER_MAX_ITEMS;
     std::vector<uint32_t> table(per_table * n_pairs, SCHED_END);
