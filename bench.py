@@ -295,7 +295,7 @@ def run_ours(args):
     plain = None
     if builtin and not args.no_plain and (args.eval_cache > 0 or continuous):
         eng.close()                     # frees the first engine's arenas
-        sp2 = BatchedSelfPlay(net, n_games=G, num_simulations=S, seed=1234 + rank, evaluator='builtin')
+        sp2 = BatchedSelfPlay(net, n_games=G, num_simulations=S, seed=1234 + rank, evaluator='builtin', eval_cache_log2=0)
         if not args.no_stagger:
             sp2.stagger()
         for _ in range(min(args.warmup, 3)):

@@ -159,6 +159,9 @@ __device__ __forceinline__ bool tap_valid(int pos, int tap, int& src) {
 // Fallback form (MCAZ_TOWER=layers, or when the pairs cannot all be resident): the same kernel is launched
 // once per layer with that layer's items and flags == nullptr -- kernel boundaries order the layers.
 constexpr int TOWER_MAX_ITEMS = 256;
+#ifndef SPIN_NS
+#define SPIN_NS 40     // back-off of the waits on the dependency watcher: a hot spin costs issue slots and power
+#endif
 constexpr int TOWER_SMEM = STAGES * STAGE_BYTES + 1024 + 256 + NLAYERS * C * 4;
 constexpr unsigned long long WATCHDOG_CYCLES = 20ull * 1000 * 1000 * 1000;   // ~10 s: a dependency that never arrives
 
@@ -252,7 +255,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             const int tile = 2 * tp + (int)rank;
             if (L > 0 && P.flags) {
                 // inputs published? (warp 3 polls the global flags ahead of us)
-                while (ld_acquire_cta_shared(&s_deps_ok) <= (uint32_t)k) {}
+                while (ld_acquire_cta_shared(&s_deps_ok) <= (uint32_t)k) __nanosleep(SPIN_NS);
                 asm volatile("fence.proxy.async;" ::: "memory");   // order the acquired writes before our TMA reads
             }
             const CUtensorMap* map_in = (L & 1) ? &map_act1 : &map_act0;
@@ -348,7 +351,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             // dependencies are: fetch them while the MMAs still run
             uint4 res[4][4];
             if (odd) {
-                if (P.flags) while (ld_acquire_cta_shared(&s_deps_ok) <= (uint32_t)k) {}
+                if (P.flags) while (ld_acquire_cta_shared(&s_deps_ok) <= (uint32_t)k) __nanosleep(SPIN_NS);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint4* rp = reinterpret_cast<const uint4*>(out + row_off + c * 32);

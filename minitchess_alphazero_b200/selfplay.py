@@ -60,6 +60,10 @@ class BatchedSelfPlay:
         # with leaves_per_step = K every search step runs K descents per tree: size the arenas for all of them
         leaves = int(engine_options.get('leaves_per_step', 1) or 1)
         engine_options.setdefault('recycle', 1)       # games only move forward here: plies behind them can be dropped
+        if evaluator == 'builtin' and leaves == 1:
+            # exact evaluation cache sized for a few moves' worth of evaluations (192 B per entry; 4096 x 200 -> 2^23 = 1.6 GB)
+            want = max(1, self.n_games * self.num_simulations * 8)
+            engine_options.setdefault('eval_cache_log2', min(24, max(12, (want - 1).bit_length())))
         self.engine = Engine(n_games, max_sims_per_move=num_simulations * leaves, cpuct=float(cpuct), tau_change=int(tau_change),
                              dirichlet_epsilon=float(epsilon), dirichlet_alpha=float(alpha), seed=int(seed),
                              device_rng=1, network=1 if evaluator == 'builtin' else 0, **engine_options)
