@@ -204,6 +204,13 @@ int az_eval_backup(az_engine* e);
 /* -- whole searches with the built-in network (throughput mode) ---------------------------*/
 int az_search(az_engine* e, int n_sims);
 
+/* n_sims simulations with the built-in network and caller-drawn root noise: simulation s of game g mixes
+ * root_noise[(s * n_games + g) * MC_MAX_MOVES ...] into the root priors if the root is expanded by then
+ * (exp/agent.py:81-82), exactly like n_sims rounds of az_select_expand(noise_s) + az_eval_backup.  The drop-in
+ * MonteCarloTreeSearch.simulate draws the whole block from numpy's global RNG in one call (the same stream as the
+ * reference's one dirichlet() per simulation) and makes this single call per move.                              */
+int az_search_noise(az_engine* e, int n_sims, const double* root_noise);
+
 /* Continuous self-play (throughput mode, device_rng = 1, leaves_per_step = 1): n_steps network batches.  Every
  * game runs its own loop inside the search kernel -- sims_per_move simulations, then the move choice, replay
  * recording, the move and, when the game is over, a restart (what az_search + az_play_device do for all games

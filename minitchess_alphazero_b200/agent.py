@@ -132,6 +132,8 @@ class MonteCarloTreeSearch:
         eng.set_positions(rules.state_from_fen(observation), trees=[0])
         if ev is not None:
             tokens, clocks, _needs = eng.leaf_batch_device()
+        if ev is None:
+            return self._simulate_builtin(num_simulations)
         root_edges = -1                                     # unknown until the root is seen expanded
         for _ in range(num_simulations):
             noise = None
@@ -147,6 +149,28 @@ class MonteCarloTreeSearch:
             else:
                 logits, values = ev.forward(tokens, clocks)
                 eng.backup(values, logits=logits)
+        return self
+
+    def _simulate_builtin(self, num_simulations):
+        """Built-in network: one library call per move.  The reference draws one Dirichlet sample per simulation
+        whose root is already expanded (exp/agent.py:81-82); `np.random.dirichlet(alpha, size=k)` consumes numpy's
+        global stream exactly like k successive calls, so the block is drawn up front and handed over whole."""
+        eng, left = self._engine, int(num_simulations)
+        if self._epsilon <= 0:
+            eng.search(left)                                # no noise (the engine was created with device_rng = 0)
+            return self
+        root_edges = int(eng.root_stats(want_q=False)[3][0])
+        if root_edges <= 0 and left > 0:                    # unseen root: the first simulation only expands it, no noise
+            eng.select_expand(None)
+            eng.eval_backup()
+            left -= 1
+            root_edges = int(eng.root_stats(want_q=False)[3][0])
+        if left > 0 and root_edges > 0:
+            noise = np.zeros((left, 1, MC_MAX_MOVES))
+            noise[:, 0, :root_edges] = np.random.dirichlet([self._alpha] * root_edges, size=left)
+            eng.search_noise(noise)
+        elif left > 0:                                      # finished position: nothing to mix, simulations still count
+            eng.search_noise(np.zeros((left, 1, MC_MAX_MOVES)))
         return self
 
     @property

@@ -764,6 +764,29 @@ int az_search(az_engine* e, int n_sims) {
     return run_search(e, n_sims, n_sims, false, e->cfg.max_sims_per_move);
 }
 
+int az_search_noise(az_engine* e, int n_sims, const double* root_noise) {
+    if (!e || n_sims < 0 || (n_sims > 0 && !root_noise)) return fail(MCAZ_EINVAL, "az_search_noise: bad argument");
+    if (!e->net) return fail(MCAZ_ESTATE, "az_search_noise: engine was created with network = 0");
+    if (e->leaf_pending) return fail(MCAZ_ESTATE, "az_search_noise: a simulation is pending (call az_backup first)");
+    if (n_sims == 0) return MCAZ_OK;
+    const View& V = e->v;
+    const size_t per_sim = (size_t)V.G * MC_MAX_MOVES;
+    e->scratch.begin();
+    In<double> noise;
+    if (int rc = noise.init(root_noise, per_sim * n_sims, e->stream, e->scratch)) return rc;
+    const int grid = warp_grid(V.G, 128);
+    for (int s = 0; s < n_sims; ++s) {
+        // exp/agent.py:54-88 once per game: descent with this simulation's noise, evaluation, backup
+        select_expand_kernel<<<grid, 128, 0, e->stream>>>(V, noise.ptr + per_sim * s, e->d_noise_used);
+        MCAZ_CHECK_LAUNCH();
+        if (int rc = network_forward_search(e, V, e->d_values)) return rc;
+        backup_kernel<<<grid, 128, 0, e->stream>>>(V, nullptr, e->d_values, nullptr);
+        MCAZ_CHECK_LAUNCH();
+        e->launches += 2;
+    }
+    return engine_check_errors(e);
+}
+
 int az_selfplay(az_engine* e, int n_steps, int sims_per_move) {
     if (!e || n_steps < 0 || sims_per_move <= 0) return fail(MCAZ_EINVAL, "az_selfplay: bad argument");
     if (!e->net) return fail(MCAZ_ESTATE, "az_selfplay: engine was created with network = 0");

@@ -185,6 +185,13 @@ class Engine:
         """n_sims simulations for every active game with the built-in network."""
         self._check(self._L.az_search(self._h, int(n_sims)))
 
+    def search_noise(self, noise):
+        """len(noise) simulations with the built-in network; noise: float64 [n_sims, n_games, MC_MAX_MOVES], row s is
+        the root Dirichlet sample of simulation s (used where the root is expanded by then, exp/agent.py:81-82)."""
+        noise = np.ascontiguousarray(noise, dtype=np.float64)
+        assert noise.ndim == 3 and noise.shape[1:] == (self.n_games, MC_MAX_MOVES), noise.shape
+        self._check(self._L.az_search_noise(self._h, int(noise.shape[0]), ptr(noise)))
+
     def selfplay(self, n_steps, sims_per_move):
         """Continuous self-play (az_selfplay): n_steps network batches; every game searches, moves, records and
         restarts on its own inside the search kernel, so the batch stays full whatever each move costs."""
