@@ -190,3 +190,35 @@ def test_more_games_than_one_network_pass(net):
         big.play_device(); small.play_device()
     c = big.counters()
     assert c['simulations'] == 5 * sims * 9000 and c['moves'] == 5 * 9000
+
+
+def test_full_size_config3_invariants(net):
+    """BASELINE.json configs[2] at full size (4096 games x 200 sims/move) through the public batched API, on a game
+    population spread over all plies: size-independent properties of the search."""
+    from minitchess_alphazero_b200.selfplay import BatchedSelfPlay
+    G, sims = 4096, 200
+    free0 = torch.cuda.mem_get_info()[0]
+    sp = BatchedSelfPlay(net, n_games=G, num_simulations=sims, seed=77)
+    sp.stagger()
+    states, _ = sp.engine.game_states()
+    plies = 2 * (((states['meta'] >> 16) & 0xff).astype(int) - 1) + (1 - (states['meta'] & 1).astype(int))
+    assert len(np.unique(states)) > 0.8 * G and plies.min() == 0 and plies.max() >= 55       # all phases, distinct games
+    c0 = sp.engine.counters()
+    for _ in range(2):
+        sp.search()
+        codes, visits, q, n_legal = sp.engine.root_stats()
+        assert (n_legal > 0).all()
+        total = visits.sum(1)
+        assert (total >= sims - 1).all()                  # sims - 1 edge visits on a fresh root, more on a reused one
+        assert (np.abs(q) <= 1.0).all() and np.isfinite(q).all()
+        live = np.arange(visits.shape[1])[None, :] < n_legal[:, None]
+        assert (visits[~live] == 0).all() and (np.diff(codes.astype(int), axis=1)[live[:, 1:]] > 0).all()   # sorted legal codes
+        sp.engine.play_device()
+    c1 = sp.engine.counters()
+    d = {k: c1[k] - c0[k] for k in c1}
+    assert d['simulations'] == 2 * G * sims and d['moves'] == 2 * G
+    assert d['simulations'] == d['evaluations'] + d['terminal_leaves'] + d['cached_evaluations']
+    assert d['nodes'] <= d['simulations'] and d['cached_evaluations'] > 0.1 * d['simulations']
+    assert d['path_depth'] >= d['simulations'] - G * 2    # every simulation but a root expansion descends at least one level
+    used = free0 - torch.cuda.mem_get_info()[0]
+    assert used < 12e9, used                              # recycled arenas (~4 GB) + cache + activations, not 18 GB of trees
