@@ -3,8 +3,12 @@
 // Kernels (one warp per game/tree, grid-stride over games, grid sized to the SM count):
 //   select_expand_kernel  PUCT descent + expansion of the leaf (exp/agent.py:54-66,75-88)
 //   backup_kernel         legal-logit softmax -> priors, value backup (exp/agent.py:47-52,67-72)
+//   search_step_kernel    az_search / az_selfplay inner step: backup of the evaluated leaf, next descents while the
+//                         game's budget lasts (finished / cached leaves complete on the spot), dense network rows;
+//                         in az_selfplay also the game's own move choice, replay record, move and restart
 //   play_kernel / play_device_kernel   the real game line (exp/environment.py:68-82,
 //                         exp/agent.py:110-119, exp/callbacks.py:31-54)
+//   recycle_kernel        in-place compaction of trees whose old plies can no longer be reached (block per tree)
 //   root_stats_kernel / node_stats_kernel   what exp/policy.py:118-121 reads back
 #include <algorithm>
 #include <chrono>

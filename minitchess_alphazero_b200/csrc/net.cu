@@ -1,12 +1,14 @@
 // net.cu -- the policy/value network of exp/policy.py:53-80 as hand-written sm_100a kernels.
 //
-//   stem_kernel        Embedding(7,4) + Conv3x3(8->256) + BN + ReLU as a table sum (no MACs)
+//   stem_kernel        Embedding(7,4) + Conv3x3(8->256) + BN + ReLU as a table sum (no MACs), warp per board
 //   tower_tc_kernel    the 18 tower convolutions 256->256: tcgen05.mma.cta_group::2 (UMMA 256x256x16 over a
 //                      CTA pair, bf16 in, fp32 accumulate in TMEM), operands staged by TMA (SWIZZLE_128B,
 //                      K-major), 6-stage mbarrier pipeline, double-buffered TMEM accumulators, fused
-//                      bias(+BN) / residual / ReLU / bf16 epilogue; one data-flow ordered launch
+//                      bias(+BN) / residual / ReLU / bf16 epilogue; one data-flow ordered launch; works on the
+//                      tile pairs that hold rows of the (dense) leaf batch, one list schedule per count
 //   heads_kernel       policy head (conv1x1 -> 61->554 linear) and value head (conv1x1 -> 31->256
-//                      -> 1, tanh), fp32
+//                      -> 1, tanh), fp32; heads_legal_kernel: only the leaf's legal logits, softmax into the
+//                      tree's priors, evaluation-cache insert (az_search)
 //
 // Tower data layout in HBM: act[pos 30][board Bpad][channel 256] bf16 (two ping-pong buffers).
 // With boards as the GEMM M dimension a 3x3 tap is a plain shift of the *position* index, so the
@@ -497,13 +499,15 @@ __global__ void prep_heads_kernel(const float* __restrict__ flat, HeadWeights H)
 }
 
 // ---------------------------------------------------------------------------------- stem
-// One warp per (board, position): 32 lanes x 8 channels; one 512-byte bf16 table row per valid tap,
-// accumulated in fp32.  The table (60 KB) is L1-resident; L1 wavefronts bound this kernel.
+// One warp per board.  Lane l < 30 first turns the two tokens of square l into the square's state (0 = empty,
+// 1..6 = mover's piece, 7..12 = opponent's); then, for each of the 30 output positions, the warp sums one 512-byte
+// bf16 table row per valid tap -- the state of the tapped square comes from its lane by shuffle, every lane adds its
+// 8 channels in fp32 -- and stores the 512-byte output row.  The table (60 KB) stays L1-resident.
 __global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ tokens, int n, int bpad,
                                                    const __nv_bfloat16* __restrict__ table, const float* __restrict__ bias,
                                                    __nv_bfloat16* __restrict__ out, const uint32_t* __restrict__ count, uint32_t row_base) {
     const int lane = threadIdx.x & 31;
-    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
     // dense leaf batch: `count` rows are live; the rest of their last tile pair gets the bias-only filler
     int rows = bpad;
     if (count) {
@@ -511,35 +515,45 @@ __global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ t
         n = min(n, (int)(total > row_base ? total - row_base : 0u));
         rows = min(bpad, ((n + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (2 * BLOCK_M));
     }
-    const long long total = (long long)rows * NPOS;
     const float4 b0 = *reinterpret_cast<const float4*>(bias + lane * 8), b1 = *reinterpret_cast<const float4*>(bias + lane * 8 + 4);
-    for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
-        const int board = (int)(w / NPOS), pos = (int)(w % NPOS);
-        float acc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        if (board < n) {
-            const uint8_t* tk = tokens + (size_t)board * MC_TOKENS;
+    const uint4* tab = reinterpret_cast<const uint4*>(table) + lane;          // this lane's 8 channels of every table row
+    for (int board = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; board < rows; board += warps) {
+        int combo = 0;
+        const bool live = board < n;
+        if (live && lane < NPOS) {
+            const int mine = tokens[(size_t)board * MC_TOKENS + lane], theirs = tokens[(size_t)board * MC_TOKENS + NPOS + lane];
+            combo = mine ? mine : (theirs ? 6 + theirs : 0);
+        }
+#pragma unroll 1
+        for (int r = 0; r < 6; ++r) {
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                int src;
-                if (!tap_valid(pos, t, src)) continue;
-                const int mine = tk[src], theirs = tk[30 + src];
-                const int combo = mine ? mine : (theirs ? 6 + theirs : 0);
-                const uint4 r = __ldg(reinterpret_cast<const uint4*>(table + ((size_t)t * 13 + combo) * C + lane * 8));
-                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+            for (int c = 0; c < 5; ++c) {
+                const int pos = r * 5 + c;
+                float acc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const int rr = r + t / 3 - 1, cc = c + t % 3 - 1;           // cc is a compile-time constant
+                    if (cc < 0 || cc > 4) continue;
+                    const int src = rr * 5 + cc;
+                    const int st = __shfl_sync(0xffffffffu, combo, src & 31);   // executed by the whole warp; used if on board
+                    if (rr < 0 || rr > 5 || !live) continue;
+                    const uint4 v = __ldg(tab + (size_t)(t * 13 + st) * (C / 8));
+                    const uint32_t rw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        acc[2 * h] += __uint_as_float(rw[h] << 16);
+                        acc[2 * h + 1] += __uint_as_float(rw[h] & 0xffff0000u);
+                    }
+                }
+                uint32_t pk[4];
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
-                    acc[2 * h] += __uint_as_float(rw[h] << 16);
-                    acc[2 * h + 1] += __uint_as_float(rw[h] & 0xffff0000u);
+                    __nv_bfloat162 b2 = __floats2bfloat162_rn(fmaxf(acc[2 * h], 0.f), fmaxf(acc[2 * h + 1], 0.f));
+                    pk[h] = *reinterpret_cast<uint32_t*>(&b2);
                 }
+                *reinterpret_cast<uint4*>(out + ((size_t)pos * bpad + board) * C + lane * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
         }
-        uint32_t pk[4];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(fmaxf(acc[2 * h], 0.f), fmaxf(acc[2 * h + 1], 0.f));
-            pk[h] = *reinterpret_cast<uint32_t*>(&b2);
-        }
-        *reinterpret_cast<uint4*>(out + ((size_t)pos * bpad + board) * C + lane * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
 }
 
@@ -549,42 +563,82 @@ __global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ t
 // independent accumulators; the transposed weight matrices (135 KB + 31 KB) are read through the
 // read-only L1 path -- they stay L1/L2 resident, which costs no staging phase and leaves room for
 // several CTAs per SM.
-constexpr int HEADS_THREADS = 256;
+// 1x1 convolutions 256 -> {policy 0, policy 1, value} of one board, shared by both head kernels.  The warp reads the
+// board's 30 activation rows of 512 bytes whole (lane = 8 channels: coalesced, 6 rows in flight), every lane keeps its
+// partial sums of the 3 outputs for the 30 positions in registers, and a transposed butterfly (31 shuffles per 32 values
+// instead of 5 per value) leaves the three sums of position p on lane p.
+__device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const float send = upper ? x[i] : x[i + o];
+            const float keep = upper ? x[i + o] : x[i];
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return x[0];     // lane L holds the total of index L
+}
+
+struct HeadConvWeights { float w[3][8]; };     // this lane's 8 input channels of the three 1x1 filters
+
+__device__ __forceinline__ HeadConvWeights load_head_conv_weights(const HeadWeights& H, int lane) {
+    HeadConvWeights W;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        W.w[0][k] = __ldg(H.pw + lane * 8 + k);
+        W.w[1][k] = __ldg(H.pw + C + lane * 8 + k);
+        W.w[2][k] = __ldg(H.vw + lane * 8 + k);
+    }
+    return W;
+}
+
+__device__ __forceinline__ void heads_conv1x1(const __nv_bfloat16* __restrict__ act, int bpad, int row, int lane, const HeadConvWeights& W,
+                                              float& d0, float& d1, float& d2) {
+    float x0[32], x1[32], x2[32];
+    x0[30] = x0[31] = x1[30] = x1[31] = x2[30] = x2[31] = 0.f;
+    const uint4* base = reinterpret_cast<const uint4*>(act + (size_t)row * C) + lane;
+    const size_t stride = (size_t)bpad * (C / 8);      // uint4 between the rows of consecutive positions
+#pragma unroll
+    for (int p0 = 0; p0 < NPOS; p0 += 6) {
+        uint4 raw[6];
+#pragma unroll
+        for (int u = 0; u < 6; ++u) raw[u] = base[(size_t)(p0 + u) * stride];
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+            const uint32_t rw[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const float lo = __uint_as_float(rw[h] << 16), hi = __uint_as_float(rw[h] & 0xffff0000u);
+                a0 += lo * W.w[0][2 * h] + hi * W.w[0][2 * h + 1];
+                a1 += lo * W.w[1][2 * h] + hi * W.w[1][2 * h + 1];
+                a2 += lo * W.w[2][2 * h] + hi * W.w[2][2 * h + 1];
+            }
+            x0[p0 + u] = a0; x1[p0 + u] = a1; x2[p0 + u] = a2;
+        }
+    }
+    d0 = warp_transpose_sum(x0, lane);
+    d1 = warp_transpose_sum(x1, lane);
+    d2 = warp_transpose_sum(x2, lane);
+}
+
+constexpr int HEADS_THREADS = 128;
 constexpr int HEADS_WARPS = HEADS_THREADS / 32;
 
-__global__ void __launch_bounds__(HEADS_THREADS, 4)
+__global__ void __launch_bounds__(HEADS_THREADS, 3)
 heads_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ clocks, int n, int bpad, HeadWeights H,
              float* __restrict__ logits, float* __restrict__ values) {
-    __shared__ float s_cw[3 * C];             // policy conv rows 0,1 and value conv
     __shared__ float s_in[HEADS_WARPS][96];   // per warp: px[60], clock, vx[30], clock
-    for (int i = threadIdx.x; i < C; i += HEADS_THREADS) { s_cw[i] = H.pw[i]; s_cw[C + i] = H.pw[C + i]; s_cw[2 * C + i] = H.vw[i]; }
-    __syncthreads();
     const float pb0 = __ldg(H.pb), pb1 = __ldg(H.pb + 1), vb = __ldg(H.vb), v2b = __ldg(H.v2b);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const HeadConvWeights W = load_head_conv_weights(H, lane);
     float* in = s_in[warp];
-    const int pos = lane < NPOS ? lane : NPOS - 1;
     for (int board = blockIdx.x * HEADS_WARPS + warp; board < n; board += gridDim.x * HEADS_WARPS) {
-        // ---- 1x1 convolutions 256 -> {2, 1} for this lane's position
-        const uint4* row = reinterpret_cast<const uint4*>(act + ((size_t)pos * bpad + board) * C);
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-#pragma unroll 2
-        for (int c4 = 0; c4 < C / 8; c4 += 4) {
-            uint4 raw[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) raw[u] = row[c4 + u];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t rw[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
-                const float* w0 = s_cw + (c4 + u) * 8;
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const float x0 = __uint_as_float(rw[h] << 16), x1 = __uint_as_float(rw[h] & 0xffff0000u);
-                    d0 += x0 * w0[2 * h] + x1 * w0[2 * h + 1];
-                    d1 += x0 * w0[C + 2 * h] + x1 * w0[C + 2 * h + 1];
-                    d2 += x0 * w0[2 * C + 2 * h] + x1 * w0[2 * C + 2 * h + 1];
-                }
-            }
-        }
+        // ---- 1x1 convolutions 256 -> {2, 1}: lane p ends up with the sums of position p
+        float d0, d1, d2;
+        heads_conv1x1(act, bpad, board, lane, W, d0, d1, d2);
         if (lane < NPOS) {
             in[lane] = fmaxf(d0 + pb0, 0.f);
             in[30 + lane] = fmaxf(d1 + pb1, 0.f);
@@ -638,45 +692,24 @@ heads_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ cl
 // p[0][legal_moves].softmax(0)), ~9 of 554.  This variant computes just those, applies the legal-move
 // softmax and writes the priors straight into the new node's edges; the value goes to values[g].
 // One warp per game slot.
-__global__ void __launch_bounds__(HEADS_THREADS, 4)
+__global__ void __launch_bounds__(HEADS_THREADS, 3)
 heads_legal_kernel(const __nv_bfloat16* __restrict__ act, int bpad, HeadWeights H, az::View V, float* __restrict__ values,
                    int row_base, int chunk_rows) {
     // rows of the batch: dense (row -> slot through row_slot, az_search) or one row per slot with a needs_eval mask;
     // this launch covers rows [row_base, row_base + chunk_rows) of it, which sit in act rows [0, chunk_rows)
     const int total = V.compact ? min((int)__ldg(V.row_count + V.parity), V.G * V.K) : V.G * V.K;
     const int n_rows = max(0, min(chunk_rows, total - row_base));
-    __shared__ float s_cw[3 * C];
     __shared__ float s_in[HEADS_WARPS][96];
-    for (int i = threadIdx.x; i < C; i += HEADS_THREADS) { s_cw[i] = H.pw[i]; s_cw[C + i] = H.pw[C + i]; s_cw[2 * C + i] = H.vw[i]; }
-    __syncthreads();
     const float pb0 = __ldg(H.pb), pb1 = __ldg(H.pb + 1), vb = __ldg(H.vb), v2b = __ldg(H.v2b);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const HeadConvWeights W = load_head_conv_weights(H, lane);
     float* in = s_in[warp];
-    const int pos = lane < NPOS ? lane : NPOS - 1;
     for (int r = blockIdx.x * HEADS_WARPS + warp; r < n_rows; r += gridDim.x * HEADS_WARPS) {
         const int slot = V.compact ? V.row_slot[row_base + r] : row_base + r;
         if (!V.compact && !V.needs_eval[slot]) continue;
         const int g = slot / V.K;
-        const uint4* row = reinterpret_cast<const uint4*>(act + ((size_t)pos * bpad + r) * C);
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-#pragma unroll 2
-        for (int c4 = 0; c4 < C / 8; c4 += 4) {
-            uint4 raw[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) raw[u] = row[c4 + u];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t rw[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
-                const float* w0 = s_cw + (c4 + u) * 8;
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const float x0 = __uint_as_float(rw[h] << 16), x1 = __uint_as_float(rw[h] & 0xffff0000u);
-                    d0 += x0 * w0[2 * h] + x1 * w0[2 * h + 1];
-                    d1 += x0 * w0[C + 2 * h] + x1 * w0[C + 2 * h + 1];
-                    d2 += x0 * w0[2 * C + 2 * h] + x1 * w0[2 * C + 2 * h + 1];
-                }
-            }
-        }
+        float d0, d1, d2;
+        heads_conv1x1(act, bpad, r, lane, W, d0, d1, d2);
         if (lane < NPOS) {
             in[lane] = fmaxf(d0 + pb0, 0.f);
             in[30 + lane] = fmaxf(d1 + pb1, 0.f);
@@ -698,8 +731,8 @@ heads_legal_kernel(const __nv_bfloat16* __restrict__ act, int bpad, HeadWeights 
         for (int i = lane, kk = 0; i < E && kk < 3; i += 32, ++kk) {
             const int code = V.edge_code[e0 + i];
             float acc = __ldg(H.plb + code);
-#pragma unroll 4
-            for (int j = 0; j < 61; ++j) acc += in[j] * __ldg(H.plt + j * 554 + code);
+#pragma unroll
+            for (int j = 0; j < 61; ++j) acc += in[j] * __ldg(H.plt + j * 554 + code);   // 61 independent gathers in flight
             lg[kk] = acc;
             m = fmaxf(m, acc);
         }
@@ -1024,8 +1057,8 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
     // dense leaf batch of az_search: the number of live rows is only known on the device
     const uint32_t* count = (search_view && search_view->compact) ? search_view->row_count + search_view->parity : nullptr;
     {
-        long long warps = (long long)n_tiles * BLOCK_M * NPOS;
-        int grid = (int)std::min<long long>((warps * 32 + 255) / 256, (long long)num_sms() * 16);
+        long long warps = (long long)n_tiles * BLOCK_M;                          // one warp per board
+        int grid = (int)std::max<long long>(1, std::min<long long>((warps * 32 + 255) / 256, (long long)num_sms() * 8));
         stem_kernel<<<grid, 256, 0, st>>>(tokens, n, bpad, N->stem_table, N->stem_bias, N->act[0], count, (uint32_t)row_base);
         MCAZ_CHECK_LAUNCH();
     }
@@ -1062,10 +1095,10 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
     }
     if (ev1) cudaEventRecord(ev1, st);
     if (search_view)
-        heads_legal_kernel<<<std::min(num_sms() * 4, (n + HEADS_WARPS - 1) / HEADS_WARPS), HEADS_THREADS, 0, st>>>(N->act[0], bpad, N->heads, *search_view, values,
+        heads_legal_kernel<<<std::min(num_sms() * 3, (n + HEADS_WARPS - 1) / HEADS_WARPS), HEADS_THREADS, 0, st>>>(N->act[0], bpad, N->heads, *search_view, values,
                                                                                                                      row_base, n);
     else
-        heads_kernel<<<std::min(num_sms() * 4, (n + HEADS_WARPS - 1) / HEADS_WARPS), HEADS_THREADS, 0, st>>>(N->act[0], clocks, n, bpad, N->heads, logits, values);
+        heads_kernel<<<std::min(num_sms() * 3, (n + HEADS_WARPS - 1) / HEADS_WARPS), HEADS_THREADS, 0, st>>>(N->act[0], clocks, n, bpad, N->heads, logits, values);
     MCAZ_CHECK_LAUNCH();
     e->launches += 3;
     return MCAZ_OK;
