@@ -51,6 +51,50 @@ __device__ __forceinline__ void restart_one(const View& V, int g, int lane, cons
     __syncwarp();
 }
 
+// Play a move taken from the tree's own edge list of the current position (legal by construction) -- what
+// az::play_one does on one thread, warp-cooperatively: the result of the new position needs its legal-move count
+// (lane = square, as in the expansion) and the fivefold-repetition count over the game line (lanes split the history).
+__device__ __forceinline__ void play_chosen_move(const View& V, int g, int lane, int code) {
+    const mc_state s = V.game_state[g];
+    int fv, tv;
+    mc::code_to_view(code, fv, tv);
+    const bool white = mc::white_to_move(s);
+    const mc_state o = mc::apply_move(s, white ? fv : 29 - fv, white ? tv : 29 - tv);
+    const mc::Sets st = mc::sets_of(o);
+    const bool mover_white = mc::white_to_move(o);
+    const int sq = mover_white ? lane : 29 - lane;
+    int n_moves = 0;
+    if (lane < 30 && ((st.own >> sq) & 1u)) n_moves = mc::popc(mc::legal_targets(st, mover_white, mc::piece_at(o, sq), sq, V.rules));
+    for (int k = 16; k > 0; k >>= 1) n_moves += __shfl_xor_sync(0xffffffffu, n_moves, k);
+    int res = mc::result_of(o, st, n_moves, V.rules);
+    // game line (exp/environment.py:39: board.result() sees the move stack): positions since the last irreversible move
+    int n = V.game_hist_len[g];
+    __syncwarp();
+    if (mc::halfmove(o) == 0) n = 0;
+    const az::Board4 key = az::rep_key(o);
+    az::Board4* h = V.game_hist + (size_t)g * az::HIST;
+    if (lane == 0 && n < az::HIST) h[n] = key;
+    if (n < az::HIST) ++n;
+    __syncwarp();
+    if (res == MC_ONGOING && V.rules.fivefold_repetition) {
+        int same = 0;
+        for (int i = lane; i < n; i += 32) same += (h[i].x == key.x && h[i].y == key.y && h[i].z == key.z && h[i].w == key.w) ? 1 : 0;
+        for (int k = 16; k > 0; k >>= 1) same += __shfl_xor_sync(0xffffffffu, same, k);
+        if (same >= 5) res = MC_DRAW;
+    }
+    if (lane == 0) {
+        V.game_hist_len[g] = n;
+        V.game_state[g] = o;
+        V.game_ply[g] += 1;
+        V.tree_root[2 * g] = az::NONE;
+        V.tree_root[2 * g + 1] = az::NONE;
+        V.game_result[g] = (int8_t)res;
+        az::count(V, az::C_MOVES, 1);
+        if (res != MC_ONGOING) az::count(V, az::C_GAMES, 1);
+    }
+    __syncwarp();
+}
+
 // Pick a move from the root visit counts, record the replay tuple, play it and back-fill the rewards of a
 // finished game (exp/agent.py:110-119, exp/callbacks.py:31-54).  Warp-cooperative; returns false when the
 // root has no visits yet (nothing to choose from).
@@ -93,20 +137,26 @@ __device__ __forceinline__ bool play_device_one(const View& V, int g, int lane) 
     for (int i = lane; i < E; i += 32) { rec->codes[i] = V.edge_code[e0 + i]; rec->pi[i] = (float)((double)V.edge_N[e0 + i] / (double)nsum); }
     if (lane == 0) { rec->observation = s; rec->n_legal = (uint16_t)E; rec->action = (uint16_t)code; rec->reward = 0; }
     __syncwarp();
-    if (lane == 0) {
-        az::play_one(V, g, code);
-        const int res = V.game_result[g];
-        if (res != MC_ONGOING) {
-            // exp/callbacks.py:49-53: the side that moved last gets +reward, alternating backwards
-            const int n_rec = min(V.game_ply[g] - V.game_start_ply[g], az::MAX_DEPTH);
-            unsigned long long base = atomicAdd(V.replay_count, (unsigned long long)n_rec);
-            int reward = (res == MC_DRAW) ? 0 : 1;
-            for (int p = n_rec - 1; p >= 0; --p) {
-                az_replay_tuple* r = V.record + (size_t)g * az::MAX_DEPTH + p;
-                r->reward = (int8_t)reward;
-                reward = -reward;
-                unsigned long long dst = base + (unsigned long long)p;
-                if (dst < V.replay_cap) V.replay[dst] = *r;
+    play_chosen_move(V, g, lane, code);
+    const int res = V.game_result[g];
+    if (res != MC_ONGOING) {
+        // exp/callbacks.py:49-53: the side that moved last gets +reward, alternating backwards; the finished game's
+        // tuples go to the replay ring (lanes copy the 604-byte tuples word by word)
+        static_assert(sizeof(az_replay_tuple) % 4 == 0, "az_replay_tuple is copied by words");
+        const int n_rec = min(V.game_ply[g] - V.game_start_ply[g], az::MAX_DEPTH);
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(V.replay_count, (unsigned long long)n_rec);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const int last_reward = (res == MC_DRAW) ? 0 : 1;
+        for (int p = n_rec - 1; p >= 0; --p) {
+            az_replay_tuple* r = V.record + (size_t)g * az::MAX_DEPTH + p;
+            if (lane == 0) r->reward = (int8_t)(((n_rec - 1 - p) & 1) ? -last_reward : last_reward);
+            __syncwarp();
+            const unsigned long long dst = base + (unsigned long long)p;
+            if (dst < V.replay_cap) {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(r);
+                uint32_t* out = reinterpret_cast<uint32_t*>(V.replay + dst);
+                for (int w = lane; w < (int)(sizeof(az_replay_tuple) / 4); w += 32) out[w] = src[w];
             }
         }
     }

@@ -95,4 +95,12 @@ def test_replay_rewards_and_restarts(net):
         states = rc.fens_to_states([g['observation'] for g in game])
         nxt, st = rc.apply(states[:-1], np.array([g['action'] for g in game[:-1]], dtype=np.uint16))
         assert (st == 0).all() and [rc.state_to_fen(s) for s in nxt] == [g['observation'] for g in game[1:]]
+        # ... and ends where the rules say it ends: the last move leads to a finished position whose result gives the
+        # last mover's reward (a game may also end by fivefold repetition, which a single position does not show)
+        last, st = rc.apply(states[-1:], np.array([game[-1]['action']], dtype=np.uint16))
+        assert st[0] == 0
+        result = int(rc.legal_moves(last)[2][0])
+        assert result != 0 or len(game) >= 9, rc.state_to_fen(last[0])
+        if result != 0:
+            assert game[-1]['reward'] == (0.0 if result == 3 else 1.0)
     assert len(sp.drain()) == 0                         # drained
