@@ -63,8 +63,8 @@ __device__ __forceinline__ void play_chosen_move(const View& V, int g, int lane,
     const mc::Sets st = mc::sets_of(o);
     const bool mover_white = mc::white_to_move(o);
     const int sq = mover_white ? lane : 29 - lane;
-    int n_moves = 0;
-    if (lane < 30 && ((st.own >> sq) & 1u)) n_moves = mc::popc(mc::legal_targets(st, mover_white, mc::piece_at(o, sq), sq, V.rules));
+    const int type = (lane < 30 && ((st.own >> sq) & 1u)) ? mc::piece_at(o, sq) : 0;
+    int n_moves = mc::popc(az::legal_targets_warp(st, mover_white, type, sq & 31, lane, V.rules));
     for (int k = 16; k > 0; k >>= 1) n_moves += __shfl_xor_sync(0xffffffffu, n_moves, k);
     int res = mc::result_of(o, st, n_moves, V.rules);
     // game line (exp/environment.py:39: board.result() sees the move stack): positions since the last irreversible move

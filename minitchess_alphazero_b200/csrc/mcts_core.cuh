@@ -293,6 +293,62 @@ MC_HD uint32_t expand(const View& V, int slot, int t, int lane, const mc_state& 
     return node;
 }
 
+#if defined(__CUDACC__)
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    *total = __shfl_sync(0xffffffffu, x, 31);
+    return x - v;
+}
+
+// Legal targets of the piece on this lane's square (lane = square in the mover's view), warp-cooperative: every lane
+// lists the pseudo-legal targets of its own piece, the (piece, target) pairs of the whole position are dealt out one per
+// lane, each lane runs the king-safety test of its pair (mc::leaves_king_safe, the same predicate mc::legal_targets
+// applies target by target), and a ballot carries the verdicts back.  A position has 15-30 pseudo-legal moves, so one
+// round of ~250 instructions replaces up to ten on the lane that holds the queen.
+__device__ __forceinline__ uint32_t legal_targets_warp(const mc::Sets& st, bool white, int type, int sq, int lane, const mc_rules& R) {
+    const uint32_t ps = type ? mc::pseudo_targets(st, white, type, sq, R) : 0u;
+    const int cnt = mc::popc(ps);
+    int tot;
+    const int off = warp_excl_scan(cnt, lane, &tot);
+    uint32_t tg = 0;
+    for (int base = 0; base < tot; base += 32) {
+        const int m = base + lane;                         // the pair this lane tests
+        int owner = 0;                                     // largest lane whose first pair index is <= m
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int cand = owner + step;
+            const int o = __shfl_sync(0xffffffffu, off, cand & 31);
+            if (cand < 32 && o <= m) owner = cand;
+        }
+        const uint32_t owner_ps = __shfl_sync(0xffffffffu, ps, owner);
+        const int owner_off = __shfl_sync(0xffffffffu, off, owner);
+        const int owner_type = __shfl_sync(0xffffffffu, type, owner);
+        const int owner_sq = __shfl_sync(0xffffffffu, sq, owner);
+        bool ok = false;
+        if (m < tot) {
+            const int to = (int)__fns(owner_ps, 0u, m - owner_off + 1);     // the (m - owner_off)-th set bit
+            ok = mc::leaves_king_safe(st, white, owner_type, owner_sq, to);
+        }
+        const uint32_t verdict = __ballot_sync(0xffffffffu, ok);
+        // collect the verdicts of this lane's own pairs that fell into this round
+        uint32_t rest = ps;
+        for (int q = 0; rest; ++q) {
+            const int to = mc::lsb(rest);
+            rest &= rest - 1;
+            const int idx = off + q - base;
+            if (idx >= 0 && idx < 32 && ((verdict >> idx) & 1u)) tg |= 1u << to;
+        }
+    }
+    return tg;
+}
+
+#endif
+
 #if defined(__CUDA_ARCH__)
 // Warp-cooperative expansion (device): lane = square in the mover's view.  Every lane generates the
 // legal targets of its own piece (bitboard attack sets), the queen-block and knight-block code counts
@@ -305,17 +361,6 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {      // L2-co
     return v;
 }
 
-__device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
-    int x = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
-    }
-    *total = __shfl_sync(0xffffffffu, x, 31);
-    return x - v;
-}
-
 __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, int lane, const mc_state& s, uint8_t* kind,
                                                 double* value, const uint32_t* pnode, int depth) {
     const bool white = mc::white_to_move(s);
@@ -323,11 +368,8 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, 
     const int fv = lane;                                   // view square of this lane (30, 31: none)
     const int sq = white ? fv : 29 - fv;
     int type = 0;
-    uint32_t tg = 0;
-    if (fv < 30 && ((st.own >> sq) & 1u)) {
-        type = mc::piece_at(s, sq);
-        tg = mc::legal_targets(st, white, type, sq, V.rules);
-    }
+    if (fv < 30 && ((st.own >> sq) & 1u)) type = mc::piece_at(s, sq);
+    const uint32_t tg = legal_targets_warp(st, white, type, sq & 31, lane, V.rules);
     const int r = fv < 30 ? fv / 5 : 0, f = fv < 30 ? fv % 5 : 0;
     // width of this square's slice of the queen / knight code blocks (for the base code) and codes emitted
     int qwidth = 0, nwidth = 0;
