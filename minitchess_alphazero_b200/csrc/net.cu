@@ -1,14 +1,17 @@
 // net.cu -- the policy/value network of exp/policy.py:53-80 as hand-written sm_100a kernels.
 //
-//   stem_kernel        Embedding(7,4) + Conv3x3(8->256) + BN + ReLU as a table sum (no MACs), warp per board
-//   tower_tc_kernel    the 18 tower convolutions 256->256: tcgen05.mma.cta_group::2 (UMMA 256x256x16 over a
+//   stem_onehot_kernel tokens -> one-hot rows (7 mover's + 7 opponent's token channels of 64) for the stem level
+//   tower_tc_kernel    level 0: Embedding(7,4) + Conv3x3(8->256) + BN + ReLU as a one-hot x folded-table MMA (K = 16 per
+//                      tap); levels 1-18: the tower convolutions 256->256: tcgen05.mma.cta_group::2 (UMMA 256x256x16 over a
 //                      CTA pair, bf16 in, fp32 accumulate in TMEM), operands staged by TMA (SWIZZLE_128B,
 //                      K-major), 6-stage mbarrier pipeline, double-buffered TMEM accumulators, fused
 //                      bias(+BN) / residual / ReLU / bf16 epilogue; one data-flow ordered launch; works on the
-//                      tile pairs that hold rows of the (dense) leaf batch, one list schedule per count
-//   heads_kernel       policy head (conv1x1 -> 61->554 linear) and value head (conv1x1 -> 31->256
-//                      -> 1, tanh), fp32; heads_legal_kernel: only the leaf's legal logits, softmax into the
-//                      tree's priors, evaluation-cache insert (az_search)
+//                      tile pairs that hold rows of the (dense) leaf batch, one list schedule per count; the epilogue
+//                      of the last level also takes the three 1x1 head convolutions (fp32 dot products of the row it
+//                      holds) and writes 90 floats per board instead of the 15 KB activation rows
+//   heads_kernel       policy head (61->554 linear) and value head (31->256 -> 1, tanh) on those sums, fp32;
+//                      heads_legal_kernel: only the leaf's legal logits, softmax into the tree's priors,
+//                      evaluation-cache insert (az_search)
 //
 // Tower data layout in HBM: act[pos 30][board Bpad][channel 256] bf16 (two ping-pong buffers).
 // With boards as the GEMM M dimension a 3x3 tap is a plain shift of the *position* index, so the
@@ -34,6 +37,8 @@ namespace {
 constexpr int C = 256;            // tower width
 constexpr int NPOS = 30;
 constexpr int NLAYERS = 18;       // 9 residual blocks x 2 convolutions
+constexpr int NLEVELS = NLAYERS + 1;   // work-item levels of the tower kernel: 0 = stem, 1..18 = the convolutions
+constexpr int HEAD_IN = 96;       // floats per board handed to the heads: p0[30], p1[30], -, v[30] at 0 / 30 / 61 (raw 1x1 sums)
 constexpr int BLOCK_M = 128;      // boards per tile
 constexpr int BLOCK_K = 64;       // bf16 elements = one 128-byte swizzle row
 constexpr int STAGES = 6;
@@ -160,19 +165,21 @@ __device__ __forceinline__ bool tap_valid(int pos, int tap, int& src) {
 // that finish a layer early move on instead of idling at a grid-wide barrier.
 // Fallback form (MCAZ_TOWER=layers, or when the pairs cannot all be resident): the same kernel is launched
 // once per layer with that layer's items and flags == nullptr -- kernel boundaries order the layers.
-constexpr int TOWER_MAX_ITEMS = 256;
+constexpr int TOWER_MAX_ITEMS = 320;
 #ifndef SPIN_NS
 #define SPIN_NS 40     // back-off of the waits on the dependency watcher: a hot spin costs issue slots and power
 #endif
-constexpr int TOWER_SMEM = STAGES * STAGE_BYTES + 1024 + 256 + NLAYERS * C * 4;
+constexpr int TOWER_SMEM = STAGES * STAGE_BYTES + 1024 + 256 + NLEVELS * C * 4 + C * 16;
 constexpr unsigned long long WATCHDOG_CYCLES = 20ull * 1000 * 1000 * 1000;   // ~10 s: a dependency that never arrives
 
 struct TowerParams {
-    const float* bias;            // [18][256]
+    const float* bias;            // [19][256]: stem, then the 18 convolutions
+    const float* head_w;          // [256][4]: folded 1x1 filters policy 0, policy 1, value, 0
+    float* head_in;               // [bpad][HEAD_IN]: written by the last level's epilogue
     __nv_bfloat16* act0;          // layer input of even layers / residual + output of odd layers
     __nv_bfloat16* act1;
-    const uint32_t* sched;        // [clusters][TOWER_MAX_ITEMS]: layer << 24 | tile pair << 8 | position
-    uint32_t* flags;              // [18][n_pairs][30][2] epoch stamps; nullptr = one layer per launch, no dependencies
+    const uint32_t* sched;        // [clusters][TOWER_MAX_ITEMS]: level << 24 | tile pair << 8 | position
+    uint32_t* flags;              // [19][n_pairs][30][2] epoch stamps; nullptr = one level per launch, no dependencies
     const uint32_t* count;        // device row count of this forward (dense leaf batch) or nullptr: all n_pairs are live
     size_t sched_stride;          // words between the schedules for k and k + 1 live pairs (0: one schedule, dead pairs skipped)
     uint32_t row_base;            // first row of this chunk within the batch that `count` counts
@@ -203,9 +210,49 @@ __device__ __forceinline__ uint4 ld_cg_v4(const uint4* p) {   // L2-coherent: ne
     return v;
 }
 
+// Epilogue of the last level for one accumulator row (this thread's board at one position): 8 chunks of 32 channels.
+// Kept out of line so that its registers do not weigh on the common epilogue.
+__device__ __noinline__ void epilogue_heads(uint32_t taddr, const float* bias, const float4* s_hw, const __nv_bfloat16* res_row, float* h) {
+    float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < C / 32; ++c) {
+        uint4 res[4];
+        const uint4* rp = reinterpret_cast<const uint4*>(res_row + c * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) res[j] = ld_cg_v4(rp + j);
+        uint32_t v[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr + c * 32)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int hh = 0; hh < 4; ++hh) {
+                const int e = j * 8 + hh * 2;
+                const uint32_t r = (&res[j].x)[hh];
+                const float x0 = fmaxf(__uint_as_float(v[e]) + bias[c * 32 + e] + __uint_as_float(r << 16), 0.f);
+                const float x1 = fmaxf(__uint_as_float(v[e + 1]) + bias[c * 32 + e + 1] + __uint_as_float(r & 0xffff0000u), 0.f);
+                const float4 w0 = s_hw[c * 32 + e], w1 = s_hw[c * 32 + e + 1];
+                h0 = fmaf(x0, w0.x, h0); h1 = fmaf(x0, w0.y, h1); h2 = fmaf(x0, w0.z, h2);
+                h0 = fmaf(x1, w1.x, h0); h1 = fmaf(x1, w1.y, h1); h2 = fmaf(x1, w1.z, h2);
+            }
+        }
+    }
+    h[0] = h0; h[1] = h1; h[2] = h2;
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
 tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_constant__ CUtensorMap map_act1,
-                const __grid_constant__ CUtensorMap map_w, const TowerParams P) {
+                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_stem_in,
+                const __grid_constant__ CUtensorMap map_stem_w, const TowerParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -214,7 +261,8 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
     uint64_t* acc_full = bars + 2 * STAGES;
     uint64_t* acc_empty = bars + 2 * STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-    float* s_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // [18][256]
+    float* s_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // [19][256]
+    float4* s_hw = reinterpret_cast<float4*>(s_bias + NLEVELS * C);                // [256] head filters per channel
     __shared__ uint32_t s_deps_ok;            // items [0, s_deps_ok) have all their inputs published (written by warp 3)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -229,7 +277,8 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
     }
     const uint32_t* sched = P.sched + (size_t)max(live_pairs - 1, 0) * P.sched_stride + (size_t)(blockIdx.x >> 1) * TOWER_MAX_ITEMS;
 
-    for (int i = threadIdx.x; i < NLAYERS * C; i += CONV_THREADS) s_bias[i] = P.bias[i];
+    for (int i = threadIdx.x; i < NLEVELS * C; i += CONV_THREADS) s_bias[i] = P.bias[i];
+    for (int i = threadIdx.x; i < C; i += CONV_THREADS) s_hw[i] = reinterpret_cast<const float4*>(P.head_w)[i];
     if (threadIdx.x == 0) s_deps_ok = 0;
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
@@ -260,18 +309,23 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                 while (ld_acquire_cta_shared(&s_deps_ok) <= (uint32_t)k) __nanosleep(SPIN_NS);
                 asm volatile("fence.proxy.async;" ::: "memory");   // order the acquired writes before our TMA reads
             }
-            const CUtensorMap* map_in = (L & 1) ? &map_act1 : &map_act0;
+            // level 0 (stem): one-hot rows x folded embedding/conv table, one 64-channel chunk per tap;
+            // level L >= 1: convolution L - 1 reads act0 (even) / act1 (odd), four chunks per tap
+            const int conv = L - 1, chunks = L == 0 ? 1 : C / BLOCK_K;
+            const CUtensorMap* map_in = L == 0 ? &map_stem_in : ((conv & 1) ? &map_act1 : &map_act0);
+            const CUtensorMap* map_wt = L == 0 ? &map_stem_w : &map_w;
+            const int w_base = L == 0 ? 0 : conv * 9;
             for (int tap = 0; tap < 9; ++tap) {
                 int src;
                 if (!tap_valid(pos, tap, src)) continue;
-                for (int kc = 0; kc < C / BLOCK_K; ++kc, ++it) {
+                for (int kc = 0; kc < chunks; ++kc, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
                     if (leader) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
                     else mbar_arrive_remote(&full[s], 0);
                     uint8_t* st = smem + s * STAGE_BYTES;
                     tma_load_3d_2sm(st, map_in, &full[s], kc * BLOCK_K, tile * BLOCK_M, src);
-                    tma_load_3d_2sm(st + A_BYTES, &map_w, &full[s], kc * BLOCK_K, (int)rank * (C / 2), L * 9 + tap);
+                    tma_load_3d_2sm(st + A_BYTES, map_wt, &full[s], kc * BLOCK_K, (int)rank * (C / 2), w_base + tap);
                 }
             }
         }
@@ -283,6 +337,8 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             if (item == SCHED_END) break;
             const int pos = item & 0xff;
             if ((int)((item >> 8) & 0xffff) >= live_pairs) continue;
+            const bool stem = (item >> 24) == 0;          // K = 16 per tap: the 14 one-hot channels
+            const int chunks = stem ? 1 : C / BLOCK_K, ksteps = stem ? 1 : BLOCK_K / 16;
             const uint32_t acc = j & 1;
             mbar_wait(&acc_empty[acc], ((j >> 1) & 1) ^ 1);
             ++j;
@@ -292,7 +348,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             for (int tap = 0; tap < 9; ++tap) {
                 int src;
                 if (!tap_valid(pos, tap, src)) continue;
-                for (int kc = 0; kc < C / BLOCK_K; ++kc, ++it) {
+                for (int kc = 0; kc < chunks; ++kc, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&full[s], (it / STAGES) & 1);
                     tc_fence_after();
@@ -300,8 +356,10 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                     const uint64_t da = umma_desc(a_addr), db = umma_desc(a_addr + A_BYTES);
 #pragma unroll
                     for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
-                        umma_bf16_2sm(d_tmem, da + 2 * kk, db + 2 * kk, IDESC, accumulate);
-                        accumulate = 1;
+                        if (kk < ksteps) {
+                            umma_bf16_2sm(d_tmem, da + 2 * kk, db + 2 * kk, IDESC, accumulate);
+                            accumulate = 1;
+                        }
                     }
                     umma_commit_2sm(&empty[s]);
                 }
@@ -345,10 +403,32 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             const int tile = 2 * tp + (int)rank;
             const uint32_t acc = j & 1, acc_phase = (j >> 1) & 1;
             ++j;
-            const bool odd = (L & 1) != 0;                     // second conv of a residual block
-            __nv_bfloat16* out = odd ? P.act0 : P.act1;
+            const bool odd = L >= 2 && (L & 1) == 0;           // second conv of a residual block
+            const bool last = L == NLAYERS;                    // its output only feeds the three 1x1 head convolutions
+            __nv_bfloat16* out = (odd || L == 0) ? P.act0 : P.act1;
             const float* bias = s_bias + L * C;
             const size_t row_off = ((size_t)pos * P.bpad + (size_t)tile * BLOCK_M + q * 32 + lane) * C;
+            if (last) {
+                // the tower's output row never leaves the SM: bias + residual + ReLU in fp32, then the three 1x1 head
+                // filters as dot products over the row this thread holds
+                if (P.flags) while (ld_acquire_cta_shared(&s_deps_ok) <= (uint32_t)k) __nanosleep(SPIN_NS);
+                mbar_wait(&acc_full[acc], acc_phase);
+                tc_fence_after();
+                float h[3];
+                epilogue_heads(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C, bias, s_hw, out + row_off, h);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (leader) mbar_arrive(&acc_empty[acc]);
+                    else mbar_arrive_remote(&acc_empty[acc], 0);
+                }
+                float* hin = P.head_in + ((size_t)tile * BLOCK_M + q * 32 + lane) * HEAD_IN;
+                hin[pos] = h[0]; hin[NPOS + pos] = h[1]; hin[2 * NPOS + 1 + pos] = h[2];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (warp == 4 && lane == 0 && P.flags)
+                    st_release_gpu(P.flags + (((size_t)L * P.n_pairs + tp) * NPOS + pos) * 2 + rank, P.epoch);
+                continue;
+            }
             // residual rows (this block's input, written two layers back) are published once the item's
             // dependencies are: fetch them while the MMAs still run
             uint4 res[4][4];
@@ -444,21 +524,24 @@ __global__ void prep_tower_kernel(const float* __restrict__ flat, __nv_bfloat16*
     if (k == 0) bias[L * C + n] = (cb[n] - mean[n]) * scale + beta[n];
 }
 
-// stem table: T[tap][combo][c]; a square holds at most one piece, so the two token channels collapse into
-// 13 combinations: 0 = empty, 1..6 = mover's piece of that type, 7..12 = opponent's piece.  The entry is the
-// BatchNorm-folded contribution of that square through tap `t` to output channel c.
-__global__ void prep_stem_kernel(const float* __restrict__ flat, __nv_bfloat16* __restrict__ table, float* __restrict__ bias) {
-    const int c = threadIdx.x, combo = blockIdx.x % 13, t = blockIdx.x / 13;
+// stem level weights: Ws[tap][cout][64] bf16.  The stem's input row of a square is one-hot: channel k < 7 = "the mover's
+// token is k", channel 7 + k = "the opponent's token is k" (token 0 = none there; Embedding(7,4) gives it a vector too),
+// so Embedding + Conv3x3(8->256) + BatchNorm collapse into one table per tap -- the MMA then just adds two of its rows.
+__global__ void prep_stem_kernel(const float* __restrict__ flat, __nv_bfloat16* __restrict__ ws, float* __restrict__ bias) {
+    const int c = threadIdx.x, t = blockIdx.x;
     const float* sw = flat + OFF_STEM;
     const float *sb = sw + 18432, *gamma = sb + 256, *beta = gamma + 256, *mean = beta + 256, *var = mean + 256;
     const float* emb = flat + OFF_EMB;
     const float scale = gamma[c] / sqrtf(var[c] + BN_EPS);
-    const int tok0 = combo <= 6 ? combo : 0, tok1 = combo > 6 ? combo - 6 : 0;
-    float acc = 0.f;
-    for (int e = 0; e < 4; ++e)
-        acc += sw[((size_t)c * 8 + e) * 9 + t] * emb[tok0 * 4 + e] + sw[((size_t)c * 8 + 4 + e) * 9 + t] * emb[tok1 * 4 + e];
-    table[((size_t)t * 13 + combo) * C + c] = __float2bfloat16(acc * scale);
-    if (blockIdx.x == 0) bias[c] = (sb[c] - mean[c]) * scale + beta[c];
+    for (int k = 0; k < BLOCK_K; ++k) {
+        float acc = 0.f;
+        if (k < 14) {
+            const int ch = k / 7, tok = k % 7;
+            for (int e = 0; e < 4; ++e) acc += sw[((size_t)c * 8 + ch * 4 + e) * 9 + t] * emb[tok * 4 + e];
+        }
+        ws[((size_t)t * C + c) * BLOCK_K + k] = __float2bfloat16(acc * scale);
+    }
+    if (t == 0) bias[c] = (sb[c] - mean[c]) * scale + beta[c];
 }
 
 struct HeadWeights {
@@ -472,6 +555,7 @@ struct HeadWeights {
     float* v1b;    // [256]
     float* v2;     // [256]
     float* v2b;    // [1]
+    float* hw4;    // [256][4]: pw[0][c], pw[1][c], vw[c], 0 -- the tower's last epilogue reads these
 };
 
 __global__ void prep_heads_kernel(const float* __restrict__ flat, HeadWeights H) {
@@ -496,64 +580,36 @@ __global__ void prep_heads_kernel(const float* __restrict__ flat, HeadWeights H)
     const float* v2 = flat + OFF_V2;
     for (int i = tid; i < 256; i += nthr) H.v2[i] = v2[i];
     if (tid == 0) H.v2b[0] = v2[256];
+    for (int i = tid; i < 256; i += nthr) {
+        H.hw4[4 * i] = pc[i] * (pg[0] / sqrtf(pv[0] + BN_EPS));
+        H.hw4[4 * i + 1] = pc[256 + i] * (pg[1] / sqrtf(pv[1] + BN_EPS));
+        H.hw4[4 * i + 2] = vc[i] * vscale;
+        H.hw4[4 * i + 3] = 0.f;
+    }
 }
 
-// ---------------------------------------------------------------------------------- stem
-// One warp per board.  Lane l < 30 first turns the two tokens of square l into the square's state (0 = empty,
-// 1..6 = mover's piece, 7..12 = opponent's); then, for each of the 30 output positions, the warp sums one 512-byte
-// bf16 table row per valid tap -- the state of the tapped square comes from its lane by shuffle, every lane adds its
-// 8 channels in fp32 -- and stores the 512-byte output row.  The table (60 KB) stays L1-resident.
-__global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ tokens, int n, int bpad,
-                                                   const __nv_bfloat16* __restrict__ table, const float* __restrict__ bias,
-                                                   __nv_bfloat16* __restrict__ out, const uint32_t* __restrict__ count, uint32_t row_base) {
-    const int lane = threadIdx.x & 31;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    // dense leaf batch: `count` rows are live; the rest of their last tile pair gets the bias-only filler
-    int rows = bpad;
+// ---------------------------------------------------------------------------------- stem input
+// One thread per (board, square): the square's two tokens become the 16 leading channels of its one-hot row
+// (32 bytes; channels 16..63 of the 128-byte row stay zero from the allocation).  Rows past the live ones keep
+// whatever an earlier batch left there: rows never mix, and nobody reads the results of dead rows.
+__global__ void __launch_bounds__(256) stem_onehot_kernel(const uint8_t* __restrict__ tokens, int n, int bpad,
+                                                          __nv_bfloat16* __restrict__ stem_in, const uint32_t* __restrict__ count,
+                                                          uint32_t row_base) {
     if (count) {
         const uint32_t total = __ldg(count);
         n = min(n, (int)(total > row_base ? total - row_base : 0u));
-        rows = min(bpad, ((n + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (2 * BLOCK_M));
     }
-    const float4 b0 = *reinterpret_cast<const float4*>(bias + lane * 8), b1 = *reinterpret_cast<const float4*>(bias + lane * 8 + 4);
-    const uint4* tab = reinterpret_cast<const uint4*>(table) + lane;          // this lane's 8 channels of every table row
-    for (int board = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; board < rows; board += warps) {
-        int combo = 0;
-        const bool live = board < n;
-        if (live && lane < NPOS) {
-            const int mine = tokens[(size_t)board * MC_TOKENS + lane], theirs = tokens[(size_t)board * MC_TOKENS + NPOS + lane];
-            combo = mine ? mine : (theirs ? 6 + theirs : 0);
-        }
-#pragma unroll 1
-        for (int r = 0; r < 6; ++r) {
+    const int total_sq = n * NPOS;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total_sq; idx += gridDim.x * blockDim.x) {
+        const int board = idx / NPOS, pos = idx - board * NPOS;
+        const int mine = tokens[(size_t)board * MC_TOKENS + pos], theirs = 7 + tokens[(size_t)board * MC_TOKENS + NPOS + pos];
+        uint32_t w[8];
 #pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                const int pos = r * 5 + c;
-                float acc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const int rr = r + t / 3 - 1, cc = c + t % 3 - 1;           // cc is a compile-time constant
-                    if (cc < 0 || cc > 4) continue;
-                    const int src = rr * 5 + cc;
-                    const int st = __shfl_sync(0xffffffffu, combo, src & 31);   // executed by the whole warp; used if on board
-                    if (rr < 0 || rr > 5 || !live) continue;
-                    const uint4 v = __ldg(tab + (size_t)(t * 13 + st) * (C / 8));
-                    const uint32_t rw[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        acc[2 * h] += __uint_as_float(rw[h] << 16);
-                        acc[2 * h + 1] += __uint_as_float(rw[h] & 0xffff0000u);
-                    }
-                }
-                uint32_t pk[4];
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    __nv_bfloat162 b2 = __floats2bfloat162_rn(fmaxf(acc[2 * h], 0.f), fmaxf(acc[2 * h + 1], 0.f));
-                    pk[h] = *reinterpret_cast<uint32_t*>(&b2);
-                }
-                *reinterpret_cast<uint4*>(out + ((size_t)pos * bpad + board) * C + lane * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
-        }
+        for (int k = 0; k < 8; ++k)
+            w[k] = ((mine == 2 * k || theirs == 2 * k) ? 0x3F80u : 0u) | ((mine == 2 * k + 1 || theirs == 2 * k + 1) ? 0x3F800000u : 0u);
+        uint4* dst = reinterpret_cast<uint4*>(stem_in + ((size_t)pos * bpad + board) * BLOCK_K);
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
 }
 
@@ -563,82 +619,28 @@ __global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ t
 // independent accumulators; the transposed weight matrices (135 KB + 31 KB) are read through the
 // read-only L1 path -- they stay L1/L2 resident, which costs no staging phase and leaves room for
 // several CTAs per SM.
-// 1x1 convolutions 256 -> {policy 0, policy 1, value} of one board, shared by both head kernels.  The warp reads the
-// board's 30 activation rows of 512 bytes whole (lane = 8 channels: coalesced, 6 rows in flight), every lane keeps its
-// partial sums of the 3 outputs for the 30 positions in registers, and a transposed butterfly (31 shuffles per 32 values
-// instead of 5 per value) leaves the three sums of position p on lane p.
-__device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        const bool upper = (lane & o) != 0;
-#pragma unroll
-        for (int i = 0; i < o; ++i) {
-            const float send = upper ? x[i] : x[i + o];
-            const float keep = upper ? x[i + o] : x[i];
-            x[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-        }
-    }
-    return x[0];     // lane L holds the total of index L
-}
-
-struct HeadConvWeights { float w[3][8]; };     // this lane's 8 input channels of the three 1x1 filters
-
-__device__ __forceinline__ HeadConvWeights load_head_conv_weights(const HeadWeights& H, int lane) {
-    HeadConvWeights W;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        W.w[0][k] = __ldg(H.pw + lane * 8 + k);
-        W.w[1][k] = __ldg(H.pw + C + lane * 8 + k);
-        W.w[2][k] = __ldg(H.vw + lane * 8 + k);
-    }
-    return W;
-}
-
-__device__ __forceinline__ void heads_conv1x1(const __nv_bfloat16* __restrict__ act, int bpad, int row, int lane, const HeadConvWeights& W,
-                                              float& d0, float& d1, float& d2) {
-    float x0[32], x1[32], x2[32];
-    x0[30] = x0[31] = x1[30] = x1[31] = x2[30] = x2[31] = 0.f;
-    const uint4* base = reinterpret_cast<const uint4*>(act + (size_t)row * C) + lane;
-    const size_t stride = (size_t)bpad * (C / 8);      // uint4 between the rows of consecutive positions
-#pragma unroll
-    for (int p0 = 0; p0 < NPOS; p0 += 6) {
-        uint4 raw[6];
-#pragma unroll
-        for (int u = 0; u < 6; ++u) raw[u] = base[(size_t)(p0 + u) * stride];
-#pragma unroll
-        for (int u = 0; u < 6; ++u) {
-            const uint32_t rw[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                const float lo = __uint_as_float(rw[h] << 16), hi = __uint_as_float(rw[h] & 0xffff0000u);
-                a0 += lo * W.w[0][2 * h] + hi * W.w[0][2 * h + 1];
-                a1 += lo * W.w[1][2 * h] + hi * W.w[1][2 * h + 1];
-                a2 += lo * W.w[2][2 * h] + hi * W.w[2][2 * h + 1];
-            }
-            x0[p0 + u] = a0; x1[p0 + u] = a1; x2[p0 + u] = a2;
-        }
-    }
-    d0 = warp_transpose_sum(x0, lane);
-    d1 = warp_transpose_sum(x1, lane);
-    d2 = warp_transpose_sum(x2, lane);
+// The three 1x1 convolutions 256 -> {policy 0, policy 1, value} were taken by the tower's last epilogue; lane p < 30
+// picks up the raw sums of position p from the board's head_in row (384 bytes, coalesced).
+__device__ __forceinline__ void heads_load_sums(const float* __restrict__ head_in, int row, int lane, float& d0, float& d1, float& d2) {
+    const float* hin = head_in + (size_t)row * HEAD_IN;
+    d0 = d1 = d2 = 0.f;
+    if (lane < NPOS) { d0 = hin[lane]; d1 = hin[NPOS + lane]; d2 = hin[2 * NPOS + 1 + lane]; }
 }
 
 constexpr int HEADS_THREADS = 128;
 constexpr int HEADS_WARPS = HEADS_THREADS / 32;
 
-__global__ void __launch_bounds__(HEADS_THREADS, 3)
-heads_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ clocks, int n, int bpad, HeadWeights H,
+__global__ void __launch_bounds__(HEADS_THREADS, 4)
+heads_kernel(const float* __restrict__ head_in, const float* __restrict__ clocks, int n, HeadWeights H,
              float* __restrict__ logits, float* __restrict__ values) {
     __shared__ float s_in[HEADS_WARPS][96];   // per warp: px[60], clock, vx[30], clock
     const float pb0 = __ldg(H.pb), pb1 = __ldg(H.pb + 1), vb = __ldg(H.vb), v2b = __ldg(H.v2b);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const HeadConvWeights W = load_head_conv_weights(H, lane);
     float* in = s_in[warp];
     for (int board = blockIdx.x * HEADS_WARPS + warp; board < n; board += gridDim.x * HEADS_WARPS) {
-        // ---- 1x1 convolutions 256 -> {2, 1}: lane p ends up with the sums of position p
+        // ---- 1x1 convolutions 256 -> {2, 1}: lane p gets the sums of position p
         float d0, d1, d2;
-        heads_conv1x1(act, bpad, board, lane, W, d0, d1, d2);
+        heads_load_sums(head_in, board, lane, d0, d1, d2);
         if (lane < NPOS) {
             in[lane] = fmaxf(d0 + pb0, 0.f);
             in[30 + lane] = fmaxf(d1 + pb1, 0.f);
@@ -692,8 +694,8 @@ heads_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ cl
 // p[0][legal_moves].softmax(0)), ~9 of 554.  This variant computes just those, applies the legal-move
 // softmax and writes the priors straight into the new node's edges; the value goes to values[g].
 // One warp per game slot.
-__global__ void __launch_bounds__(HEADS_THREADS, 3)
-heads_legal_kernel(const __nv_bfloat16* __restrict__ act, int bpad, HeadWeights H, az::View V, float* __restrict__ values,
+__global__ void __launch_bounds__(HEADS_THREADS, 4)
+heads_legal_kernel(const float* __restrict__ head_in, HeadWeights H, az::View V, float* __restrict__ values,
                    int row_base, int chunk_rows) {
     // rows of the batch: dense (row -> slot through row_slot, az_search) or one row per slot with a needs_eval mask;
     // this launch covers rows [row_base, row_base + chunk_rows) of it, which sit in act rows [0, chunk_rows)
@@ -702,14 +704,13 @@ heads_legal_kernel(const __nv_bfloat16* __restrict__ act, int bpad, HeadWeights 
     __shared__ float s_in[HEADS_WARPS][96];
     const float pb0 = __ldg(H.pb), pb1 = __ldg(H.pb + 1), vb = __ldg(H.vb), v2b = __ldg(H.v2b);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const HeadConvWeights W = load_head_conv_weights(H, lane);
     float* in = s_in[warp];
     for (int r = blockIdx.x * HEADS_WARPS + warp; r < n_rows; r += gridDim.x * HEADS_WARPS) {
         const int slot = V.compact ? V.row_slot[row_base + r] : row_base + r;
         if (!V.compact && !V.needs_eval[slot]) continue;
         const int g = slot / V.K;
         float d0, d1, d2;
-        heads_conv1x1(act, bpad, r, lane, W, d0, d1, d2);
+        heads_load_sums(head_in, r, lane, d0, d1, d2);
         if (lane < NPOS) {
             in[lane] = fmaxf(d0 + pb0, 0.f);
             in[30 + lane] = fmaxf(d1 + pb1, 0.f);
@@ -820,16 +821,17 @@ struct Network {
     __nv_bfloat16 *act[2] = {nullptr, nullptr};
     __nv_bfloat16* w = nullptr;        // [18][9][256][256]
     float* bias = nullptr;             // [18][256]
-    __nv_bfloat16* stem_table = nullptr;   // [9 taps][13 square states][256] bf16
-    float* stem_bias = nullptr;
+    __nv_bfloat16* stem_w = nullptr;       // [9 taps][256 cout][64] bf16: folded embedding x stem conv x BN table (14 live channels)
+    __nv_bfloat16* stem_in = nullptr;      // [30 pos][capacity][64] bf16 one-hot token rows
+    float* head_in = nullptr;              // [capacity][HEAD_IN]
     float* head_pool = nullptr;
     HeadWeights heads{};
-    CUtensorMap map_act[2], map_w;
+    CUtensorMap map_act[2], map_w, map_stem_in, map_stem_w;
     bool have_weights = false;
     uint32_t* sched = nullptr;         // per-layer form: [18][clusters][TOWER_MAX_ITEMS]
     int sched_tiles = -1, sched_grid = 0;
     uint32_t* tower_sched = nullptr;   // [clusters][TOWER_MAX_ITEMS]
-    uint32_t* tower_flags = nullptr;   // [18][n_pairs][30][2]
+    uint32_t* tower_flags = nullptr;   // [19][n_pairs][30][2]
     int tower_pairs = -1, tower_grid = 0;
     uint32_t epoch = 0;
     bool per_layer = false;            // false: tower_tc_kernel (one data-flow ordered launch for the 18 layers, default);
@@ -851,6 +853,14 @@ static int net_alloc_acts(az_engine* e, int boards) {
         MCAZ_CUDA(cudaMemset(N->act[i], 0, (size_t)NPOS * cap * C * sizeof(__nv_bfloat16)));
         if (int rc = make_map_3d(&N->map_act[i], N->act[i], C, cap, NPOS, BLOCK_K, BLOCK_M)) return rc;
     }
+    if (N->stem_in) cudaFree(N->stem_in);
+    if (N->head_in) cudaFree(N->head_in);
+    N->stem_in = nullptr; N->head_in = nullptr;
+    MCAZ_CUDA(cudaMalloc(&N->stem_in, (size_t)NPOS * cap * BLOCK_K * sizeof(__nv_bfloat16)));
+    MCAZ_CUDA(cudaMemset(N->stem_in, 0, (size_t)NPOS * cap * BLOCK_K * sizeof(__nv_bfloat16)));
+    MCAZ_CUDA(cudaMalloc(&N->head_in, (size_t)cap * HEAD_IN * sizeof(float)));
+    MCAZ_CUDA(cudaMemset(N->head_in, 0, (size_t)cap * HEAD_IN * sizeof(float)));
+    if (int rc = make_map_3d(&N->map_stem_in, N->stem_in, BLOCK_K, cap, NPOS, BLOCK_K, BLOCK_M)) return rc;
     N->capacity = cap;
     return MCAZ_OK;
 }
@@ -863,10 +873,9 @@ int network_create(az_engine* e) {
     Network* N = new Network();
     e->net = N;
     MCAZ_CUDA(cudaMalloc(&N->w, (size_t)NLAYERS * 9 * C * C * sizeof(__nv_bfloat16)));
-    MCAZ_CUDA(cudaMalloc(&N->bias, (size_t)NLAYERS * C * sizeof(float)));
-    MCAZ_CUDA(cudaMalloc(&N->stem_table, (size_t)9 * 13 * C * sizeof(__nv_bfloat16)));
-    MCAZ_CUDA(cudaMalloc(&N->stem_bias, C * sizeof(float)));
-    const size_t head_floats = 512 + 2 + 256 + 1 + 61 * 554 + 554 + 31 * 256 + 256 + 256 + 1 + 16;
+    MCAZ_CUDA(cudaMalloc(&N->bias, (size_t)NLEVELS * C * sizeof(float)));
+    MCAZ_CUDA(cudaMalloc(&N->stem_w, (size_t)9 * C * BLOCK_K * sizeof(__nv_bfloat16)));
+    const size_t head_floats = 512 + 4 + 256 + 4 + 61 * 554 + 554 + 31 * 256 + 256 + 256 + 4 + 4 * 256 + 16;
     MCAZ_CUDA(cudaMalloc(&N->head_pool, head_floats * sizeof(float)));
     float* p = N->head_pool;
     N->heads.pw = p; p += 512;
@@ -878,8 +887,11 @@ int network_create(az_engine* e) {
     N->heads.v1t = p; p += 31 * 256;
     N->heads.v1b = p; p += 256;
     N->heads.v2 = p; p += 256;
-    N->heads.v2b = p;
+    N->heads.v2b = p; p += 4;
+    p += (4 - ((p - N->head_pool) & 3)) & 3;                 // float4 reads
+    N->heads.hw4 = p;
     if (int rc = make_map_3d(&N->map_w, N->w, C, C, (uint64_t)NLAYERS * 9, BLOCK_K, C / 2)) return rc;
+    if (int rc = make_map_3d(&N->map_stem_w, N->stem_w, BLOCK_K, C, 9, BLOCK_K, C / 2)) return rc;
     MCAZ_CUDA(cudaFuncSetAttribute(tower_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_SMEM));
     {
         // Default: the fused data-flow tower, provided every CTA pair of its grid can be resident at once (its
@@ -909,8 +921,9 @@ void network_destroy(az_engine* e) {
     for (int i = 0; i < 2; ++i) if (N->act[i]) cudaFree(N->act[i]);
     if (N->w) cudaFree(N->w);
     if (N->bias) cudaFree(N->bias);
-    if (N->stem_table) cudaFree(N->stem_table);
-    if (N->stem_bias) cudaFree(N->stem_bias);
+    if (N->stem_w) cudaFree(N->stem_w);
+    if (N->stem_in) cudaFree(N->stem_in);
+    if (N->head_in) cudaFree(N->head_in);
     if (N->head_pool) cudaFree(N->head_pool);
     if (N->sched) cudaFree(N->sched);
     if (N->tower_sched) cudaFree(N->tower_sched);
@@ -922,9 +935,9 @@ void network_destroy(az_engine* e) {
 
 int network_set_weights(az_engine* e, const float* flat) {
     Network* N = e->net;
-    prep_tower_kernel<<<dim3(C, NLAYERS), C, 0, e->stream>>>(flat, N->w, N->bias);
+    prep_tower_kernel<<<dim3(C, NLAYERS), C, 0, e->stream>>>(flat, N->w, N->bias + C);     // bias row 0 is the stem's
     MCAZ_CHECK_LAUNCH();
-    prep_stem_kernel<<<9 * 13, C, 0, e->stream>>>(flat, N->stem_table, N->stem_bias);
+    prep_stem_kernel<<<9, C, 0, e->stream>>>(flat, N->stem_w, N->bias);
     MCAZ_CHECK_LAUNCH();
     prep_heads_kernel<<<64, 256, 0, e->stream>>>(flat, N->heads);
     MCAZ_CHECK_LAUNCH();
@@ -949,13 +962,13 @@ static int build_schedule(az_engine* e, int n_pairs) {
     std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.weight > b.weight; });
     std::vector<int> load(clusters, 0), count(clusters, 0);
     const size_t per_layer = (size_t)clusters * TOWER_MAX_ITEMS;
-    std::vector<uint32_t> table(per_layer * NLAYERS, SCHED_END);
+    std::vector<uint32_t> table(per_layer * NLEVELS, SCHED_END);
     for (const Item& it : items) {
         int best = -1;
         for (int c = 0; c < clusters; ++c)
             if (count[c] < TOWER_MAX_ITEMS - 1 && (best < 0 || load[c] < load[best])) best = c;
         if (best < 0) return fail(MCAZ_ECAPACITY, "conv schedule: too many items per CTA pair");
-        for (int L = 0; L < NLAYERS; ++L)
+        for (int L = 0; L < NLEVELS; ++L)
             table[L * per_layer + (size_t)best * TOWER_MAX_ITEMS + count[best]] = it.code | ((uint32_t)L << 24);
         count[best]++;
         load[best] += it.weight;
@@ -1003,7 +1016,7 @@ static int build_tower_schedule(az_engine* e, int n_pairs) {
         const int n_groups = (live + group_max - 1) / group_max;
         for (int gi = 0; gi < n_groups; ++gi) {
             const int g0 = (int)((long long)live * gi / n_groups), g1 = (int)((long long)live * (gi + 1) / n_groups);
-            for (int L = 0; L < NLAYERS; ++L)
+            for (int L = 0; L < NLEVELS; ++L)       // level 0 = stem: nine K = 16 MMAs at most, its cost is the epilogue
                 for (int tp = g0; tp < g1; ++tp)
                     for (int pos : order) {
                         int best = 0;
@@ -1011,7 +1024,7 @@ static int build_tower_schedule(az_engine* e, int n_pairs) {
                             if (load[c] < load[best]) best = c;
                         if (count[best] >= TOWER_MAX_ITEMS - 1) return fail(MCAZ_ECAPACITY, "tower schedule: too many items per CTA pair");
                         tab[(size_t)best * TOWER_MAX_ITEMS + count[best]++] = (uint32_t)pos | ((uint32_t)tp << 8) | ((uint32_t)L << 24);
-                        load[best] += taps_of[pos];
+                        load[best] += L == 0 ? 1 : taps_of[pos];
                     }
         }
     }
@@ -1019,7 +1032,7 @@ static int build_tower_schedule(az_engine* e, int n_pairs) {
     if (N->tower_flags) cudaFree(N->tower_flags);
     N->tower_sched = nullptr; N->tower_flags = nullptr;
     MCAZ_CUDA(cudaMalloc(&N->tower_sched, table.size() * sizeof(uint32_t)));
-    const size_t n_flags = (size_t)NLAYERS * n_pairs * NPOS * 2;
+    const size_t n_flags = (size_t)NLEVELS * n_pairs * NPOS * 2;
     MCAZ_CUDA(cudaMalloc(&N->tower_flags, n_flags * sizeof(uint32_t)));
     MCAZ_CUDA(cudaMemsetAsync(N->tower_flags, 0, n_flags * sizeof(uint32_t), e->stream));
     MCAZ_CUDA(cudaMemcpyAsync(N->tower_sched, table.data(), table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
@@ -1052,14 +1065,14 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
     // sched_rows >= n: size the schedule (and buffers) for that many rows, so equal chunks of one batch share a schedule
     const int plan = std::max(n, sched_rows);
     if (int rc = net_alloc_acts(e, plan)) return rc;
-    const int n_pairs = (plan + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = 2 * n_pairs, bpad = N->capacity;
+    const int n_pairs = (plan + 2 * BLOCK_M - 1) / (2 * BLOCK_M), bpad = N->capacity;
     cudaStream_t st = e->stream;
     // dense leaf batch of az_search: the number of live rows is only known on the device
     const uint32_t* count = (search_view && search_view->compact) ? search_view->row_count + search_view->parity : nullptr;
     {
-        long long warps = (long long)n_tiles * BLOCK_M;                          // one warp per board
-        int grid = (int)std::max<long long>(1, std::min<long long>((warps * 32 + 255) / 256, (long long)num_sms() * 8));
-        stem_kernel<<<grid, 256, 0, st>>>(tokens, n, bpad, N->stem_table, N->stem_bias, N->act[0], count, (uint32_t)row_base);
+        const long long squares = (long long)n * NPOS;                           // one thread per (board, square)
+        int grid = (int)std::max<long long>(1, std::min<long long>((squares + 255) / 256, (long long)num_sms() * 8));
+        stem_onehot_kernel<<<grid, 256, 0, st>>>(tokens, n, bpad, N->stem_in, count, (uint32_t)row_base);
         MCAZ_CHECK_LAUNCH();
     }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1074,31 +1087,33 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
         cudaEventRecord(ev0, st);
     }
     TowerParams T;
-    T.bias = N->bias; T.act0 = N->act[0]; T.act1 = N->act[1];
+    T.bias = N->bias; T.act0 = N->act[0]; T.act1 = N->act[1]; T.head_w = N->heads.hw4; T.head_in = N->head_in;
     T.bpad = bpad; T.n_pairs = n_pairs; T.count = count; T.row_base = (uint32_t)row_base;
     if (N->per_layer) {
         if (int rc = build_schedule(e, n_pairs)) return rc;
         T.flags = nullptr; T.epoch = 0; T.sched_stride = 0;
         const size_t per_layer = (size_t)(N->sched_grid / 2) * TOWER_MAX_ITEMS;
-        for (int L = 0; L < NLAYERS; ++L) {
+        for (int L = 0; L < NLEVELS; ++L) {
             T.sched = N->sched + L * per_layer;
-            tower_tc_kernel<<<N->sched_grid, CONV_THREADS, TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, T);
+            tower_tc_kernel<<<N->sched_grid, CONV_THREADS, TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in,
+                                                                             N->map_stem_w, T);
             MCAZ_CHECK_LAUNCH();
         }
-        e->launches += NLAYERS - 1;
+        e->launches += NLEVELS - 1;
     } else {
         if (int rc = build_tower_schedule(e, n_pairs)) return rc;
         T.sched = N->tower_sched; T.flags = N->tower_flags; T.epoch = ++N->epoch;
         T.sched_stride = (size_t)(N->tower_grid / 2) * TOWER_MAX_ITEMS;
-        tower_tc_kernel<<<N->tower_grid, CONV_THREADS, TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, T);
+        tower_tc_kernel<<<N->tower_grid, CONV_THREADS, TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in,
+                                                                         N->map_stem_w, T);
         MCAZ_CHECK_LAUNCH();
     }
     if (ev1) cudaEventRecord(ev1, st);
     if (search_view)
-        heads_legal_kernel<<<std::min(num_sms() * 3, (n + HEADS_WARPS - 1) / HEADS_WARPS), HEADS_THREADS, 0, st>>>(N->act[0], bpad, N->heads, *search_view, values,
+        heads_legal_kernel<<<std::min(num_sms() * 4, (n + HEADS_WARPS - 1) / HEADS_WARPS), HEADS_THREADS, 0, st>>>(N->head_in, N->heads, *search_view, values,
                                                                                                                      row_base, n);
     else
-        heads_kernel<<<std::min(num_sms() * 3, (n + HEADS_WARPS - 1) / HEADS_WARPS), HEADS_THREADS, 0, st>>>(N->act[0], clocks, n, bpad, N->heads, logits, values);
+        heads_kernel<<<std::min(num_sms() * 4, (n + HEADS_WARPS - 1) / HEADS_WARPS), HEADS_THREADS, 0, st>>>(N->head_in, clocks, n, N->heads, logits, values);
     MCAZ_CHECK_LAUNCH();
     e->launches += 3;
     return MCAZ_OK;
@@ -1133,7 +1148,7 @@ int network_profile(az_engine* e, int on, double* avg_ms_per_tower, int* n_forwa
         *avg_ms_per_tower = N->events_used ? total / (double)N->events_used : 0.0;
         if (n_forwards) *n_forwards = (int)N->events_used;
     }
-    if (launches_per_forward) *launches_per_forward = N->per_layer ? NLAYERS : 1;
+    if (launches_per_forward) *launches_per_forward = N->per_layer ? NLEVELS : 1;
     N->events_used = 0;
     N->profiling = on != 0;
     return MCAZ_OK;
