@@ -329,6 +329,9 @@ def run_ours(args):
         cpu = {'value': s, 'unit': 'sims/s', 'cores': threads, 'kind': 'port',
                'sample': 'BASELINE.json configs[0]: one process, %d torch threads, self-play from STARTING_FEN at 36 sims/move for %.1f s '
                          '(%.2f positions/s); oracle/ref_selfplay.py' % (threads, wall, m)}
+    dropin = None
+    if rank == 0 and world == 1 and builtin and not args.no_cpu_baseline:
+        dropin = measure_dropin()
     if rank == 0:
         out = {
             'metric': METRIC, 'value': value, 'unit': 'sims/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -350,11 +353,59 @@ def run_ours(args):
             'sims_breakdown': {'network_rows': evals_all / max(sims_all, 1), 'cache_hits': cached_all / max(sims_all, 1),
                                'terminal': terminal_all / max(sims_all, 1)},
             'roofline': roof, 'tree_roofline': tree, 'without_cache_lockstep': plain,
-            'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+            'cpu_baseline': cpu, 'dropin_config1': dropin, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
         }
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_dropin(seconds=4.0, sims=36):
+    """BASELINE.json configs[0] through the drop-in classes exactly as app/base.py:113-120 wires the reference's: one game at a
+    time, two SimpleAlphaZeroAgent sharing one policy, RoundRobinReferee, per-episode init_mcts, 36 simulations per move,
+    numpy RNG on the host.  Strictly sequential search (one tree, one leaf per network pass): this is the latency-bound
+    use of the engine, reported beside the CPU baseline of the same configuration."""
+    import numpy as np
+    import torch
+    from minitchess_alphazero_b200.agent import RoundRobinReferee, SimpleAlphaZeroAgent
+    from minitchess_alphazero_b200.environment import MinitChessEnvironment
+    from minitchess_alphazero_b200.erlyx_compat import BaseCallback, run_episodes
+    from minitchess_alphazero_b200.policy import Network, SimpleAlphaZeroPolicy
+
+    class Init(BaseCallback):                                   # exp/callbacks.py:57-62
+        def __init__(self, agent):
+            self.agent = agent
+
+        def on_episode_begin(self, initial_observation):
+            self.agent.init_mcts()
+
+    class Count(BaseCallback):
+        plies = 0
+
+        def on_step_end(self, action, observation, reward, done):
+            Count.plies += 1
+
+    torch.manual_seed(0)
+    np.random.seed(0)
+    env = MinitChessEnvironment()
+    policy = SimpleAlphaZeroPolicy(Network().eval())
+    agents = [SimpleAlphaZeroAgent(environment=env, policy=policy, num_simulations=sims) for _ in range(2)]
+    referee = RoundRobinReferee(agent_tuple=tuple(agents))
+    cbs = [Count(), Init(agents[0]), Init(agents[1])]
+    with torch.no_grad():
+        run_episodes(env, referee, 1, callbacks=cbs, use_tqdm=False)          # warm-up episode
+        Count.plies, episodes = 0, 0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            referee.reset()
+            run_episodes(env, referee, 1, callbacks=cbs, use_tqdm=False)
+            episodes += 1
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    return {'value': Count.plies * sims / dt, 'unit': 'sims/s', 'positions_per_second': Count.plies / dt, 'sims_per_move': sims,
+            'episodes': episodes, 'seconds': dt,
+            'api': 'SimpleAlphaZeroAgent.select_action x 2 + RoundRobinReferee + MinitChessEnvironment + run_episodes, one game at a time'}
 
 
 def measure_e2e(sp, args, world):

@@ -156,6 +156,14 @@ typedef struct az_config {
                                   arena (6 x max_sims_per_move + 64).  For engines whose positions only move forward
                                   (az_play / az_play_device / az_selfplay); leave 0 when az_set_positions may jump back
                                   to an earlier position of a kept tree (the per-agent facade).  Default 0              */
+    int32_t lookahead_rows;    /* > 0 (needs eval_cache_log2 > 0, leaves_per_step = 1): for engines with few games.  A pass
+                                  of the network costs the same for one row as for a tile of 256, so every new unfinished
+                                  node also queues its children as rows of the batch (at most this many per batch); their
+                                  priors and values go to the exact cache only, where the later simulation that expands
+                                  such a child finds the very bits a pass would give it then.  az_search / az_search_noise
+                                  then run a game's simulations back to back inside one launch until one needs the
+                                  network and return as soon as no game waits for a row.  The order of a game's simulations
+                                  and every number in its tree are unchanged (exp/agent.py:41-45).  Default 0             */
 } az_config;
 
 void az_default_config(az_config* out);

@@ -43,7 +43,8 @@ class Config(ctypes.Structure):
                 ('numpy1_dtype_flow', ctypes.c_int32), ('device_rng', ctypes.c_int32),
                 ('seed', ctypes.c_uint64), ('rules', Rules), ('network', ctypes.c_int32),
                 ('leaves_per_step', ctypes.c_int32), ('own_stream', ctypes.c_int32),
-                ('eval_cache_log2', ctypes.c_int32), ('free_sims', ctypes.c_int32), ('recycle', ctypes.c_int32)]
+                ('eval_cache_log2', ctypes.c_int32), ('free_sims', ctypes.c_int32), ('recycle', ctypes.c_int32),
+                ('lookahead_rows', ctypes.c_int32)]
 
 
 _lib = None

@@ -81,7 +81,9 @@ class MonteCarloTreeSearch:
     they change.  `evaluator` may instead be any callable object with `.forward(tokens_u8, clocks)` ->
     (logits, values) CUDA tensors (e.g. `policy.TorchEvaluator(net, dtype=torch.float32)` for fp32 checks)."""
 
-    def __init__(self, environment, model, cpuct, epsilon=0.25, alpha=0.6, evaluator=None, rules_switches=None, _reuse=None):
+    def __init__(self, environment, model, cpuct, epsilon=0.25, alpha=0.6, evaluator=None, rules_switches=None, _reuse=None,
+                 engine_options=None):
+        self._engine_options = dict(engine_options or {})      # overrides for the built-in evaluator's engine (tests)
         self._environment = environment
         self._model = model
         self._cpuct = cpuct
@@ -111,6 +113,11 @@ class MonteCarloTreeSearch:
             opts = dict(max_sims_per_move=max(int(num_simulations), 1), cpuct=float(self._cpuct),
                         dirichlet_epsilon=float(self._epsilon), dirichlet_alpha=float(self._alpha),
                         network=0 if self._evaluator is not None else 1)
+            if self._evaluator is None:
+                # one tree, one leaf per network pass: let every pass also evaluate the children of the new nodes into
+                # the exact cache (a pass costs the same for 1 row as for 256) -- same trees, far fewer passes
+                opts.update(eval_cache_log2=16, lookahead_rows=255)
+                opts.update(self._engine_options)
             if self._rules is not None:
                 opts['rules'] = self._rules
             self._engine = Engine(1, **opts)
@@ -189,8 +196,9 @@ class SimpleAlphaZeroAgent(PolicyAgent):                    # exp/agent.py:91-11
 
     def init_mcts(self):
         evaluator = getattr(getattr(self, '_mcts', None), '_evaluator', None)    # an injected evaluator survives resets
+        old = getattr(self, '_mcts', None)
         self._mcts = MonteCarloTreeSearch(self._environment, self.policy.model, self._cpuct, evaluator=evaluator,
-                                          _reuse=getattr(self, '_mcts', None))
+                                          _reuse=old, engine_options=getattr(old, '_engine_options', None))
         self._count = 0
 
     def select_action(self, observation):
@@ -228,6 +236,8 @@ class BatchedAlphaZeroAgent:
         else:
             engine_options.setdefault('recycle', 1)             # positions only move forward within a game
             engine_options.setdefault('eval_cache_log2', 20)
+            if self.n_games <= 128:                             # the network tile is mostly empty: fill it with look-ahead rows
+                engine_options.setdefault('lookahead_rows', 256 - self.n_games)
             self._engine = Engine(self.n_games, max_sims_per_move=self._num_simulations, cpuct=float(cpuct), tau_change=self._tau_change,
                                   device_rng=1, network=1, seed=int(seed), **engine_options)
         self._rng = rng if rng is not None else np.random

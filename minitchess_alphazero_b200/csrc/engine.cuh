@@ -35,6 +35,8 @@ struct az_engine {
     uint32_t cache_mask = 0;
     uint32_t cache_epoch = 1;              // bumped by az_set_weights
     int parity = 0;                        // row counter of the last search launch
+    int lookahead_rows = 0;                // look-ahead rows per batch (cfg.lookahead_rows when the cache is on)
+    uint32_t* d_pending = nullptr;         // [2] games waiting for a network row after a launch
     // az_profile_tree: CUDA events around every search_step_kernel launch
     bool tree_profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tree_events;

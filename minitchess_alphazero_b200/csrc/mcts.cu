@@ -170,10 +170,12 @@ __device__ __forceinline__ bool play_device_one(const View& V, int g, int lane) 
 // straight on (at most free_max descents per launch); the first leaf that needs the network takes a row of the
 // batch V.batch and ends the game's turn.  The order of a game's simulations -- all that the reference's
 // sequential search depends on -- is unchanged (exp/agent.py:41-45).
+template <bool LOOKAHEAD>
 __device__ __forceinline__ void search_one(const View& V, int g, int lane, const float* values, const mc_state& start) {
     az::backup_one(V, g, lane, nullptr, values, nullptr, 0);
     __syncwarp();
     int left = V.new_budget >= 0 ? V.new_budget : V.sims_left[g];
+    bool waiting = false;
     for (int it = 0; it < V.free_max; ++it) {
         if (left <= 0) {
             if (!V.async_play) break;
@@ -182,24 +184,33 @@ __device__ __forceinline__ void search_one(const View& V, int g, int lane, const
             left = V.sims_per_move;
         }
         if (V.game_result[g] != MC_ONGOING) break;
+        // caller-supplied root noise (az_search_noise): simulation number i of this call mixes row i of the block
+        const double* noise = V.noise_block ? V.noise_block + (size_t)(V.noise_budget - left) * V.G * MC_MAX_MOVES : nullptr;
         --left;
-        const uint8_t kind = az::select_expand_one(V, g, lane, nullptr, nullptr, 0);
+        const uint8_t kind = az::select_expand_one<LOOKAHEAD>(V, g, lane, noise, nullptr, 0);
         __syncwarp();
-        if (kind != az::LEAF_TERMINAL && kind != az::LEAF_CACHED) break;
+        if (kind != az::LEAF_TERMINAL && kind != az::LEAF_CACHED) { waiting = kind == az::LEAF_EVAL; break; }
         az::backup_one(V, g, lane, nullptr, values, nullptr, 0);
         __syncwarp();
     }
-    if (lane == 0) V.sims_left[g] = left;
+    if (lane == 0) {
+        V.sims_left[g] = left;
+        if (waiting && V.pending_count) atomicAdd(&V.pending_count[V.parity], 1u);
+    }
 }
 
 // az_search / az_selfplay inner step.  leaves_per_step = K > 1 keeps the fixed form: back up the K descents of
 // the previous launch, start K new ones (virtual loss keeps them apart), one row per slot.
-__global__ void __launch_bounds__(128, 8) search_step_kernel(View V, const float* values, mc_state start) {
+template <bool LOOKAHEAD>
+__global__ void __launch_bounds__(128, LOOKAHEAD ? 4 : 8) search_step_kernel(View V, const float* values, mc_state start) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
-    if (V.compact && blockIdx.x == 0 && threadIdx.x == 0) V.row_count[V.parity ^ 1] = 0u;   // the next launch's counter
+    if (V.compact && blockIdx.x == 0 && threadIdx.x == 0) {     // the next launch's counters
+        V.row_count[V.parity ^ 1] = 0u;
+        if (V.pending_count) V.pending_count[V.parity ^ 1] = 0u;
+    }
     for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < V.G; g += warps) {
-        if (V.K == 1) { search_one(V, g, lane, values, start); continue; }
+        if (V.K == 1) { search_one<LOOKAHEAD>(V, g, lane, values, start); continue; }
         for (int j = 0; j < V.K; ++j) {
             az::backup_one(V, g, lane, nullptr, values, nullptr, j);
             __syncwarp();
@@ -545,6 +556,7 @@ void az_default_config(az_config* c) {
     c->eval_cache_log2 = 0;
     c->free_sims = 0;
     c->recycle = 0;
+    c->lookahead_rows = 0;
 }
 
 int az_create(const az_config* cfg, az_engine** out) {
@@ -576,6 +588,11 @@ int az_create(const az_config* cfg, az_engine** out) {
     V.numpy1 = cfg->numpy1_dtype_flow; V.tau_change = cfg->tau_change; V.rules = cfg->rules; V.seed = cfg->seed;
     V.device_rng = 0; V.sim_counter = 0;   // set per launch by az_search
     const size_t G = V.G, T = 2 * G, N = T * V.NC, E = T * V.EC, S = G * V.K;   // S: leaf slots
+    // look-ahead rows need the exact cache (their results live nowhere else) and the sequential search
+    if (cfg->lookahead_rows < 0 || cfg->lookahead_rows > 65536) { delete e; return fail(MCAZ_EINVAL, "az_create: lookahead_rows must be in [0, 65536]"); }
+    e->lookahead_rows = (cfg->lookahead_rows > 0 && cfg->eval_cache_log2 > 0 && cfg->network && V.K == 1) ? cfg->lookahead_rows : 0;
+    const size_t R = S + (size_t)e->lookahead_rows;                              // rows of the dense batch
+    V.row_cap = (int)R; V.spec_rows = 0; V.noise_block = nullptr; V.noise_budget = 0; V.pending_count = nullptr;
     int rc = MCAZ_OK;
 #define A(ptr, n) if (!rc) rc = dev_alloc(e, &ptr, (n))
     A(V.game_state, G); A(V.game_result, G); A(V.game_ply, G); A(V.game_hist, G * az::HIST); A(V.game_hist_len, G); A(V.game_start_ply, G);
@@ -585,11 +602,14 @@ int az_create(const az_config* cfg, az_engine** out) {
     A(V.ht, T * V.HC);
     A(V.path_len, S); A(V.path_edge, S * az::MAX_DEPTH); A(V.path_node, S * az::MAX_DEPTH);
     A(V.leaf_node, S); A(V.leaf_kind, S); A(V.leaf_value, S);
-    A(V.tokens, S * MC_TOKENS); A(V.clocks, S); A(V.needs_eval, S); A(V.leaf_states, S);
+    A(V.tokens, R * MC_TOKENS); A(V.clocks, R); A(V.needs_eval, S); A(V.leaf_states, S);
+    V.row_state = nullptr; V.row_n = nullptr; V.row_codes = nullptr;
+    if (e->lookahead_rows > 0) { A(V.row_state, R); A(V.row_n, R); A(V.row_codes, R * az::CACHE_MAX_E); }
+    A(e->d_pending, 2);
     V.edge_vl = nullptr;
     if (V.K > 1) { A(V.edge_vl, E); }
     A(V.counters, AZ_NUM_COUNTERS); A(V.error_flag, 1);
-    A(V.sim_serial, G); A(V.move_serial, G); A(V.sims_left, G); A(V.row_count, 2); A(V.row_slot, S);
+    A(V.sim_serial, G); A(V.move_serial, G); A(V.sims_left, G); A(V.row_count, 2); A(V.row_slot, R);
     V.sims_per_move = cfg->max_sims_per_move; V.new_budget = -1; V.free_max = 1; V.async_play = 0; V.compact = 0; V.parity = 0;
     V.cache = nullptr; V.cache_mask = 0; V.cache_epoch = 1;
     if (cfg->eval_cache_log2 < 0 || cfg->eval_cache_log2 > 28) rc = fail(MCAZ_EINVAL, "az_create: eval_cache_log2 must be in [0, 28]");
@@ -751,6 +771,7 @@ static View search_view(az_engine* e) {
     V.parity = V.compact ? (e->parity ^= 1) : 0;
     V.cache = e->d_cache; V.cache_mask = e->cache_mask; V.cache_epoch = e->cache_epoch;
     V.free_max = V.K == 1 ? (e->cfg.free_sims > 0 ? e->cfg.free_sims : 1) : 1;
+    V.spec_rows = (V.compact && V.cache) ? e->lookahead_rows : 0;
     return V;
 }
 
@@ -766,7 +787,10 @@ static int search_launch(az_engine* e, const View& V) {
         e->tree_events_used++;
         cudaEventRecord(ev0, e->stream);
     }
-    search_step_kernel<<<warp_grid(V.G, 128), 128, 0, e->stream>>>(V, e->d_values, start_state());   // priors: written by the policy head
+    if (V.spec_rows > 0)     // few games: the variant that also queues look-ahead rows
+        search_step_kernel<true><<<warp_grid(V.G, 128), 128, 0, e->stream>>>(V, e->d_values, start_state());
+    else
+        search_step_kernel<false><<<warp_grid(V.G, 128), 128, 0, e->stream>>>(V, e->d_values, start_state());   // priors: written by the policy head
     MCAZ_CHECK_LAUNCH();
     if (ev1) cudaEventRecord(ev1, e->stream);
     e->launches++;
@@ -791,19 +815,34 @@ static int maybe_recycle(az_engine* e, long long need) {
     return MCAZ_OK;
 }
 
-static int run_search(az_engine* e, int n_batches, int new_budget, bool async, int sims_per_move) {
+// noise != nullptr: caller-supplied root noise, one row per simulation of the call (az_search_noise).
+// Engines with look-ahead rows (few games) chain a game's simulations inside one launch until one needs the network, and
+// every such call -- like every call with caller noise -- stops as soon as no game is waiting for a row: the device
+// counts the waiting games per launch and the host reads that one word back.
+static int run_search(az_engine* e, int n_batches, int new_budget, bool async, int sims_per_move, const double* noise = nullptr) {
     {
         const long long per_game = (long long)n_batches * (e->v.K == 1 ? std::max(1, e->cfg.free_sims) : e->v.K);
         if (int rc = maybe_recycle(e, new_budget >= 0 ? std::min<long long>(per_game, new_budget) : per_game)) return rc;
     }
+    const bool chained = e->lookahead_rows > 0 && !async && e->v.K == 1 && new_budget >= 0;
+    const bool early_exit = chained || noise != nullptr;
     for (int s = 0; s <= n_batches; ++s) {
         View V = search_view(e);
         V.new_budget = s == 0 ? new_budget : -1;
         V.async_play = async ? 1 : 0;
         V.sims_per_move = sims_per_move;
+        if (noise) { V.noise_block = noise; V.noise_budget = new_budget; }
+        if (chained) V.free_max = new_budget + 1;
+        if (early_exit) V.pending_count = e->d_pending;
         if (s == n_batches) V.free_max = 0;       // closing launch: back up what the last batch evaluated, start nothing
         if (int rc = search_launch(e, V)) return rc;
         if (s == n_batches) break;
+        if (early_exit && V.compact) {
+            uint32_t waiting = 0;
+            MCAZ_CUDA(cudaMemcpyAsync(&waiting, e->d_pending + V.parity, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+            MCAZ_CUDA(cudaStreamSynchronize(e->stream));
+            if (waiting == 0) break;              // every game has spent its budget and nothing is left to back up
+        }
         if (int rc = network_forward_search(e, V, e->d_values)) return rc;
     }
     return engine_check_errors(e);
@@ -828,6 +867,10 @@ int az_search_noise(az_engine* e, int n_sims, const double* root_noise) {
     e->scratch.begin();
     In<double> noise;
     if (int rc = noise.init(root_noise, per_sim * n_sims, e->stream, e->scratch)) return rc;
+    if (V.K == 1)
+        // the search loop of az_search with the caller's noise: simulation i of every game mixes row i (exact cache, dense
+        // rows, look-ahead rows and early exit as configured); same trees as n_sims rounds of select / evaluate / backup
+        return run_search(e, n_sims, n_sims, false, e->cfg.max_sims_per_move, noise.ptr);
     const int grid = warp_grid(V.G, 128);
     for (int s = 0; s < n_sims; ++s) {
         // exp/agent.py:54-88 once per game: descent with this simulation's noise, evaluation, backup

@@ -96,6 +96,17 @@ struct View {
     int32_t* row_slot;              // [S] row -> slot
     // exact evaluation cache (nullptr = off)
     CacheEntry* cache; uint32_t cache_mask; uint32_t cache_epoch;
+    // look-ahead rows (engines with few games): a tower pass costs the same for 1 row as for 256, so every new
+    // unfinished node also queues its children as rows of the batch; their (priors, value) only go to the exact cache,
+    // where the later simulation that expands such a child finds the very bits the network would give it then
+    int row_cap;                    // rows the dense batch holds: slots + look-ahead rows
+    int spec_rows;                  // look-ahead rows admitted per batch (0 = off)
+    mc_state* row_state;            // [row_cap] position of a look-ahead row (row_slot = -1)
+    int32_t* row_n;                 // [row_cap] its number of legal moves
+    uint16_t* row_codes;            // [row_cap][CACHE_MAX_E] its sorted legal codes
+    uint32_t* pending_count;        // [2] games that ended this launch waiting for a network row (per parity)
+    // caller-supplied root noise of a chained search (az_search_noise): block [noise_budget][G][MC_MAX_MOVES]
+    const double* noise_block; int noise_budget;
     // replay recording of the device move choice
     az_replay_tuple* record; az_replay_tuple* replay; unsigned long long* replay_count; unsigned long long replay_cap;
 };
@@ -361,15 +372,21 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {      // L2-co
     return v;
 }
 
-__device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, int lane, const mc_state& s, uint8_t* kind,
-                                                double* value, const uint32_t* pnode, int depth) {
-    const bool white = mc::white_to_move(s);
-    const mc::Sets st = mc::sets_of(s);
+// Warp-cooperative move generation of one position (lane = square in the mover's view): legal target sets, the
+// prefix sums that place each lane's codes in ascending order, the number of legal moves and the result by the rules.
+struct WarpGen {
+    mc::Sets st; bool white, knight, pawn; uint32_t tg; int fv, emit_n, off_q, off_n, tot_q, qb, nb, E, res;
+};
+__device__ __forceinline__ WarpGen warp_generate(const View& V, const mc_state& s, int lane) {
+    WarpGen w;
+    w.white = mc::white_to_move(s);
+    w.st = mc::sets_of(s);
     const int fv = lane;                                   // view square of this lane (30, 31: none)
-    const int sq = white ? fv : 29 - fv;
+    w.fv = fv;
+    const int sq = w.white ? fv : 29 - fv;
     int type = 0;
-    if (fv < 30 && ((st.own >> sq) & 1u)) type = mc::piece_at(s, sq);
-    const uint32_t tg = legal_targets_warp(st, white, type, sq & 31, lane, V.rules);
+    if (fv < 30 && ((w.st.own >> sq) & 1u)) type = mc::piece_at(s, sq);
+    w.tg = legal_targets_warp(w.st, w.white, type, sq & 31, lane, V.rules);
     const int r = fv < 30 ? fv / 5 : 0, f = fv < 30 ? fv % 5 : 0;
     // width of this square's slice of the queen / knight code blocks (for the base code) and codes emitted
     int qwidth = 0, nwidth = 0;
@@ -378,18 +395,109 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, 
 #pragma unroll
         for (int d = 0; d < 8; ++d) nwidth += mc::n_on(r, f, d) ? 1 : 0;
     }
-    const bool knight = type == mc::KNIGHT;
-    int emit_n = mc::popc(tg);
-    if (type == mc::PAWN && V.rules.promo_multiplicity > 1)
-        emit_n += (V.rules.promo_multiplicity - 1) * mc::popc(tg & (white ? mc::RANK_6 : mc::RANK_1));
-    int tot_q, tot_n, tot_qw, tot_nw, tot_moves;
-    const int off_q = warp_excl_scan(knight ? 0 : emit_n, lane, &tot_q);
-    const int off_n = warp_excl_scan(knight ? emit_n : 0, lane, &tot_n);
-    const int qb = warp_excl_scan(qwidth, lane, &tot_qw);
-    const int nb = 430 + warp_excl_scan(nwidth, lane, &tot_nw);
-    warp_excl_scan(mc::popc(tg), lane, &tot_moves);
-    int E = tot_q + tot_n;
-    int res = mc::result_of(s, st, tot_moves, V.rules);
+    w.knight = type == mc::KNIGHT;
+    w.pawn = type == mc::PAWN;
+    w.emit_n = mc::popc(w.tg);
+    if (w.pawn && V.rules.promo_multiplicity > 1)
+        w.emit_n += (V.rules.promo_multiplicity - 1) * mc::popc(w.tg & (w.white ? mc::RANK_6 : mc::RANK_1));
+    int tot_n, tot_qw, tot_nw, tot_moves;
+    w.off_q = warp_excl_scan(w.knight ? 0 : w.emit_n, lane, &w.tot_q);
+    w.off_n = warp_excl_scan(w.knight ? w.emit_n : 0, lane, &tot_n);
+    w.qb = warp_excl_scan(qwidth, lane, &tot_qw);
+    w.nb = 430 + warp_excl_scan(nwidth, lane, &tot_nw);
+    warp_excl_scan(mc::popc(w.tg), lane, &tot_moves);
+    w.E = w.tot_q + tot_n;
+    w.res = mc::result_of(s, w.st, tot_moves, V.rules);
+    return w;
+}
+// This lane's codes, in order, to emit(index within the position's sorted list, code).
+template <typename Emit>
+__device__ __forceinline__ void warp_emit_codes(const View& V, const WarpGen& w, Emit&& emit) {
+    if (w.emit_n <= 0) return;
+    int k = w.knight ? w.tot_q + w.off_n : w.off_q;
+    mc::emit_square_codes(w.fv, w.white, w.knight, w.tg, w.knight ? w.nb : w.qb, w.pawn, V.rules.promo_multiplicity,
+                          [&](uint16_t c) { emit(k, c); ++k; });
+}
+
+// Exact evaluation cache lookup: same (board, side, fullmove, number of legal moves) evaluated before with these
+// weights?  On a hit every lane gets the value and the priors of edges lane and lane + 32.
+__device__ __forceinline__ bool cache_lookup(const View& V, const mc_state& s, int E, int lane, float* value, float* p0, float* p1) {
+    bool hit = false;
+    const CacheEntry* c = V.cache + (cache_hash(s) & V.cache_mask);
+    const uint32_t s1 = ld_cg_u32(&c->seq);
+    if (!(s1 & 1u)) {
+        __threadfence();
+        const bool key_ok = ld_cg_u32(&c->epoch) == V.cache_epoch && ld_cg_u32(&c->pl0) == s.pl0 && ld_cg_u32(&c->pl1) == s.pl1 &&
+                            ld_cg_u32(&c->pl2) == s.pl2 && ld_cg_u32(&c->white) == s.white &&
+                            ld_cg_u32(&c->meta_n) == ((s.meta & CACHE_KEY_META) | ((uint32_t)E << 8));
+        if (key_ok) {        // the same on every lane unless a writer is at work, which the seq check below catches
+            *value = __uint_as_float(ld_cg_u32(reinterpret_cast<const uint32_t*>(&c->value)));
+            if (lane < E) *p0 = __uint_as_float(ld_cg_u32(reinterpret_cast<const uint32_t*>(&c->priors[lane])));
+            if (lane + 32 < E) *p1 = __uint_as_float(ld_cg_u32(reinterpret_cast<const uint32_t*>(&c->priors[lane + 32])));
+            __threadfence();
+            hit = ld_cg_u32(&c->seq) == s1;
+        }
+    }
+    return __all_sync(0xffffffffu, hit);
+}
+
+// tokens of FEN-order cell i = lane and the clock input: Network.process_observation (exp/policy.py:96-105)
+__device__ __forceinline__ void write_network_row(const View& V, int row, int lane, const mc_state& s, const mc::Sets& st, bool white) {
+    if (lane < 30) {
+        int cell = 5 * (5 - lane / 5) + lane % 5;
+        if (!white) cell = 29 - cell;
+        const int ty = mc::piece_at(s, cell);
+        const bool mine = (st.own >> cell) & 1u;
+        V.tokens[(size_t)row * MC_TOKENS + lane] = (uint8_t)(mine ? ty : 0);
+        V.tokens[(size_t)row * MC_TOKENS + 30 + lane] = (uint8_t)(mine ? 0 : ty);
+    }
+    if (lane == 0) {
+        const double c = (double)mc::fullmove(s) + (white ? 0.0 : 0.5);
+        V.clocks[row] = (float)(c / 30.0);
+    }
+}
+
+// Look-ahead: queue the children of a new node (its E codes start at edge e0) as rows of the batch, unless they are
+// finished, already cached or the batch is full.  Nothing of the tree is touched.
+__device__ __forceinline__ void queue_children(const View& V, int lane, const mc_state& s, bool white, size_t e0, int E) {
+    uint16_t prev = 0xffffu;
+    for (int i = 0; i < E; ++i) {
+        const uint16_t code = V.edge_code[e0 + i];
+        if (code == prev) continue;                      // promo_multiplicity > 1 repeats a code
+        prev = code;
+        int fv, tv;
+        mc::code_to_view(code, fv, tv);
+        const mc_state cs = mc::apply_move(s, white ? fv : 29 - fv, white ? tv : 29 - tv);
+        const WarpGen w = warp_generate(V, cs, lane);
+        if (w.res != MC_ONGOING || w.E <= 0 || w.E > CACHE_MAX_E) continue;
+        float v, p0, p1;
+        if (cache_lookup(V, cs, w.E, lane, &v, &p0, &p1)) continue;
+        // admit while fewer than spec_rows rows are taken: the slots' own rows (atomicAdd, at most G*K) always fit
+        int row = -1;
+        if (lane == 0) {
+            uint32_t old = *reinterpret_cast<volatile uint32_t*>(&V.row_count[V.parity]);
+            while (old < (uint32_t)V.spec_rows) {
+                const uint32_t seen = atomicCAS(&V.row_count[V.parity], old, old + 1u);
+                if (seen == old) { row = (int)old; break; }
+                old = seen;
+            }
+        }
+        row = __shfl_sync(0xffffffffu, row, 0);
+        if (row < 0) return;                             // batch full
+        write_network_row(V, row, lane, cs, w.st, w.white);
+        warp_emit_codes(V, w, [&](int k, uint16_t c) { V.row_codes[(size_t)row * CACHE_MAX_E + k] = c; });
+        if (lane == 0) { V.row_slot[row] = -1; V.row_state[row] = cs; V.row_n[row] = w.E; }
+    }
+}
+
+template <bool LOOKAHEAD>
+__device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, int lane, const mc_state& s, uint8_t* kind,
+                                                double* value, const uint32_t* pnode, int depth) {
+    const WarpGen w = warp_generate(V, s, lane);
+    const bool white = w.white;
+    const mc::Sets& st = w.st;
+    int E = w.E;
+    int res = w.res;
     if (res == MC_ONGOING && V.rules.fivefold_repetition && depth >= 16) {
         int same = 0;
         for (int d = lane; d < depth; d += 32) {
@@ -422,32 +530,14 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, 
     // exact evaluation cache: same (board, side, fullmove) evaluated before with these weights?
     bool hit = false;
     float hit_value = 0.f, hit_p0 = 0.f, hit_p1 = 0.f;      // priors of edges lane and lane + 32
-    if (!terminal && V.cache && E <= CACHE_MAX_E) {
-        const CacheEntry* c = V.cache + (cache_hash(s) & V.cache_mask);
-        const uint32_t s1 = ld_cg_u32(&c->seq);
-        if (!(s1 & 1u)) {
-            __threadfence();
-            const bool key_ok = ld_cg_u32(&c->epoch) == V.cache_epoch && ld_cg_u32(&c->pl0) == s.pl0 && ld_cg_u32(&c->pl1) == s.pl1 &&
-                                ld_cg_u32(&c->pl2) == s.pl2 && ld_cg_u32(&c->white) == s.white &&
-                                ld_cg_u32(&c->meta_n) == ((s.meta & CACHE_KEY_META) | ((uint32_t)E << 8));
-            if (key_ok) {        // the same on every lane unless a writer is at work, which the seq check below catches
-                hit_value = __uint_as_float(ld_cg_u32(reinterpret_cast<const uint32_t*>(&c->value)));
-                if (lane < E) hit_p0 = __uint_as_float(ld_cg_u32(reinterpret_cast<const uint32_t*>(&c->priors[lane])));
-                if (lane + 32 < E) hit_p1 = __uint_as_float(ld_cg_u32(reinterpret_cast<const uint32_t*>(&c->priors[lane + 32])));
-                __threadfence();
-                hit = ld_cg_u32(&c->seq) == s1;
-            }
-        }
-        hit = __all_sync(0xffffffffu, hit);
-    }
-    if (!terminal && emit_n > 0) {
-        size_t w = (size_t)t * V.EC + off + (knight ? tot_q + off_n : off_q);
-        mc::emit_square_codes(fv, white, knight, tg, knight ? nb : qb, type == mc::PAWN, V.rules.promo_multiplicity,
-                              [&](uint16_t c) {
-                                  V.edge_Q[w] = 0.0; V.edge_N[w] = 0u; V.edge_P[w] = 0.0f; V.edge_child[w] = NONE; V.edge_code[w] = c;
-                                  if (V.edge_vl) V.edge_vl[w] = 0;
-                                  ++w;
-                              });
+    if (!terminal && V.cache && E <= CACHE_MAX_E) hit = cache_lookup(V, s, E, lane, &hit_value, &hit_p0, &hit_p1);
+    if (!terminal) {
+        const size_t w0 = (size_t)t * V.EC + off;
+        warp_emit_codes(V, w, [&](int k, uint16_t c) {
+            const size_t x = w0 + k;
+            V.edge_Q[x] = 0.0; V.edge_N[x] = 0u; V.edge_P[x] = 0.0f; V.edge_child[x] = NONE; V.edge_code[x] = c;
+            if (V.edge_vl) V.edge_vl[x] = 0;
+        });
     }
     if (hit) {
         __syncwarp();            // the zeroed priors above are overwritten by the cached ones
@@ -462,15 +552,7 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, 
         if (lane == 0) { row = (int)atomicAdd(&V.row_count[V.parity], 1u); V.row_slot[row] = slot; }
         row = __shfl_sync(0xffffffffu, row, 0);
     }
-    if (needs_net && fv < 30) {
-        // tokens of FEN-order cell i = lane: Network.process_observation
-        int cell = 5 * (5 - lane / 5) + lane % 5;
-        if (!white) cell = 29 - cell;
-        const int ty = mc::piece_at(s, cell);
-        const bool mine = (st.own >> cell) & 1u;
-        V.tokens[(size_t)row * MC_TOKENS + lane] = (uint8_t)(mine ? ty : 0);
-        V.tokens[(size_t)row * MC_TOKENS + 30 + lane] = (uint8_t)(mine ? 0 : ty);
-    }
+    if (needs_net) write_network_row(V, row, lane, s, st, white);
     if (lane == 0) {
         V.node_board[gi] = board_of(s);
         V.node_meta[gi] = s.meta;
@@ -480,21 +562,18 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, 
         V.tree_nodes[t] = node + 1;
         V.tree_edges[t] = off + (uint32_t)E;
         ht_insert(V, t, s, node);
-        if (needs_net) {
-            const double c = (double)mc::fullmove(s) + (white ? 0.0 : 0.5);
-            V.clocks[row] = (float)(c / 30.0);
-            V.leaf_states[slot] = s;
-        }
+        if (needs_net) V.leaf_states[slot] = s;
         count(V, C_NODES, 1);
         count(V, C_EDGES, (unsigned long long)E);
     }
     __syncwarp();
+    if (LOOKAHEAD && !terminal && V.spec_rows > 0 && V.cache) queue_children(V, lane, s, white, (size_t)t * V.EC + off, E);
     if (terminal) { *kind = LEAF_TERMINAL; *value = decisive ? -1.0 : -0.0; }
     else if (hit) { *kind = LEAF_CACHED; *value = (double)hit_value; }
     else { *kind = LEAF_EVAL; *value = 0.0; }
     return node;
 }
-#define AZ_EXPAND expand_warp
+#define AZ_EXPAND expand_warp<LOOKAHEAD>
 #else
 #define AZ_EXPAND expand
 #endif
@@ -502,6 +581,7 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, 
 // One simulation of game g down to its leaf (exp/agent.py:54-88 without the backup).
 // `noise`: per-game Dirichlet sample [MC_MAX_MOVES] or nullptr.
 // Returns the leaf kind (the same on every lane).
+template <bool LOOKAHEAD = false>
 MC_HD uint8_t select_expand_one(const View& V, int g, int lane, const double* noise, uint8_t* noise_used, int j = 0) {
     const int slot = g * V.K + j;
     if (lane == 0) {

@@ -699,7 +699,7 @@ heads_legal_kernel(const float* __restrict__ head_in, HeadWeights H, az::View V,
                    int row_base, int chunk_rows) {
     // rows of the batch: dense (row -> slot through row_slot, az_search) or one row per slot with a needs_eval mask;
     // this launch covers rows [row_base, row_base + chunk_rows) of it, which sit in act rows [0, chunk_rows)
-    const int total = V.compact ? min((int)__ldg(V.row_count + V.parity), V.G * V.K) : V.G * V.K;
+    const int total = V.compact ? min((int)__ldg(V.row_count + V.parity), V.row_cap) : V.G * V.K;
     const int n_rows = max(0, min(chunk_rows, total - row_base));
     __shared__ float s_in[HEADS_WARPS][96];
     const float pb0 = __ldg(H.pb), pb1 = __ldg(H.pb + 1), vb = __ldg(H.vb), v2b = __ldg(H.v2b);
@@ -707,8 +707,9 @@ heads_legal_kernel(const float* __restrict__ head_in, HeadWeights H, az::View V,
     float* in = s_in[warp];
     for (int r = blockIdx.x * HEADS_WARPS + warp; r < n_rows; r += gridDim.x * HEADS_WARPS) {
         const int slot = V.compact ? V.row_slot[row_base + r] : row_base + r;
+        // slot < 0: a look-ahead row -- a position no tree holds yet; its priors and value only go to the cache
+        const bool lookahead = slot < 0;
         if (!V.compact && !V.needs_eval[slot]) continue;
-        const int g = slot / V.K;
         float d0, d1, d2;
         heads_load_sums(head_in, r, lane, d0, d1, d2);
         if (lane < NPOS) {
@@ -722,15 +723,25 @@ heads_legal_kernel(const float* __restrict__ head_in, HeadWeights H, az::View V,
         }
         __syncwarp();
         // ---- legal logits -> softmax -> edge_P of the leaf
-        const int t = 2 * g + (V.game_ply[g] & 1);
-        const uint32_t node = V.leaf_node[slot];
-        const size_t gi = (size_t)t * V.NC + node;
-        const int E = (int)(V.node_info[gi] & 0xffffu);
-        const size_t e0 = (size_t)t * V.EC + V.node_edge_off[gi];
+        int E;
+        size_t e0 = 0;
+        const uint16_t* codes;
+        if (lookahead) {
+            E = V.row_n[row_base + r];
+            codes = V.row_codes + (size_t)(row_base + r) * az::CACHE_MAX_E;
+        } else {
+            const int g = slot / V.K;
+            const int t = 2 * g + (V.game_ply[g] & 1);
+            const uint32_t node = V.leaf_node[slot];
+            const size_t gi = (size_t)t * V.NC + node;
+            E = (int)(V.node_info[gi] & 0xffffu);
+            e0 = (size_t)t * V.EC + V.node_edge_off[gi];
+            codes = V.edge_code + e0;
+        }
         float lg[3] = {-INFINITY, -INFINITY, -INFINITY};
         float m = -INFINITY;
         for (int i = lane, kk = 0; i < E && kk < 3; i += 32, ++kk) {
-            const int code = V.edge_code[e0 + i];
+            const int code = codes[i];
             float acc = __ldg(H.plb + code);
 #pragma unroll
             for (int j = 0; j < 61; ++j) acc += in[j] * __ldg(H.plt + j * 554 + code);   // 61 independent gathers in flight
@@ -743,7 +754,10 @@ heads_legal_kernel(const float* __restrict__ head_in, HeadWeights H, az::View V,
         for (int i = lane, kk = 0; i < E && kk < 3; i += 32, ++kk) sum += expf(lg[kk] - m);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        for (int i = lane, kk = 0; i < E && kk < 3; i += 32, ++kk) { lg[kk] = expf(lg[kk] - m) / sum; V.edge_P[e0 + i] = lg[kk]; }
+        for (int i = lane, kk = 0; i < E && kk < 3; i += 32, ++kk) {
+            lg[kk] = expf(lg[kk] - m) / sum;
+            if (!lookahead) V.edge_P[e0 + i] = lg[kk];
+        }
         // ---- value
         float hv[8];
 #pragma unroll
@@ -761,11 +775,11 @@ heads_legal_kernel(const float* __restrict__ head_in, HeadWeights H, az::View V,
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         const float value = tanhf(part + v2b);
-        if (lane == 0) values[slot] = value;
+        if (lane == 0 && !lookahead) values[slot] = value;
         // ---- remember the evaluation (exact cache: key = everything the network saw).  Tree kernels of the other
         // stream may be reading the entry: seqlock (odd seq = being written)
         if (V.cache && E <= az::CACHE_MAX_E) {
-            const mc_state s = V.leaf_states[slot];
+            const mc_state s = lookahead ? V.row_state[row_base + r] : V.leaf_states[slot];
             az::CacheEntry* c = V.cache + (az::cache_hash(s) & V.cache_mask);
             // a row whose key is already stored was evaluated twice in this batch (or since its lookup): count them
             if (lane == 0 && c->epoch == V.cache_epoch && c->pl0 == s.pl0 && c->pl1 == s.pl1 && c->pl2 == s.pl2 && c->white == s.white &&
@@ -912,7 +926,7 @@ int network_create(az_engine* e) {
             }
         }
     }
-    return net_alloc_acts(e, std::min(e->v.G * e->v.K, MAX_CHUNK_BOARDS));   // grows on demand (network_forward batches)
+    return net_alloc_acts(e, std::min(std::max(e->v.G * e->v.K, e->v.row_cap), MAX_CHUNK_BOARDS));   // grows on demand (network_forward batches)
 }
 
 void network_destroy(az_engine* e) {
@@ -1124,7 +1138,7 @@ int network_forward_search(az_engine* e, const az::View& V, float* values) {
     Network* N = e->net;
     if (!N->have_weights) return fail(MCAZ_ESTATE, "network weights have not been set (az_set_weights)");
     // more rows than one pass holds: chunks of 8192 rows of the (dense) batch, one after the other
-    const int rows = V.G * V.K;
+    const int rows = V.compact ? std::max(V.row_cap, V.G * V.K) : V.G * V.K;    // dense batch: slots + look-ahead rows
     const int n_chunks = (rows + MAX_CHUNK_BOARDS - 1) / MAX_CHUNK_BOARDS;
     const int chunk = (((rows + n_chunks - 1) / n_chunks + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (2 * BLOCK_M);
     for (int base = 0; base < rows; base += chunk) {

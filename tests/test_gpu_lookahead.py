@@ -1,0 +1,113 @@
+"""GPU: look-ahead rows (`lookahead_rows`, the option the per-agent facade turns on).  With one tree and one leaf per
+network pass the tower's tile is empty but for one row, so every new node also queues its children as rows; their
+evaluations go to the exact cache only.  The search must not notice: same order of simulations, same noise rows, same
+visit counts and Q bits as the plain one-pass-per-simulation loop (exp/agent.py:41-45), with far fewer passes."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def net(mcaz_lib):
+    from minitchess_alphazero_b200.policy import Network
+    torch.manual_seed(0)
+    return Network().eval()
+
+
+def make(net, n_games, sims, **kw):
+    from minitchess_alphazero_b200.engine import Engine
+    from minitchess_alphazero_b200.policy import flatten_state_dict
+    eng = Engine(n_games, max_sims_per_move=sims, network=1, **kw)
+    eng.set_weights(flatten_state_dict(net.state_dict(), device='cuda'))
+    return eng
+
+
+def snapshot(eng):
+    codes, visits, q, n_legal = eng.root_stats()
+    states, results = eng.game_states()
+    return codes, visits, q, n_legal, states, results
+
+
+def same(a, b):
+    return all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize('n_games', [1, 5])
+def test_caller_noise_search_is_unchanged_by_lookahead_rows(net, n_games):
+    from minitchess_alphazero_b200._lib import MC_MAX_MOVES
+    sims = 36
+    plain = make(net, n_games, sims)
+    ahead = make(net, n_games, sims, eval_cache_log2=14, lookahead_rows=255)
+    small = make(net, n_games, sims, eval_cache_log2=14, lookahead_rows=7)      # the batch fills up: rows are dropped
+    manual = make(net, n_games, sims)                                           # the loop spelt out: select / evaluate / backup
+    engines = (plain, ahead, small, manual)
+    rng = np.random.RandomState(3)
+    for move in range(14):
+        noise = np.zeros((sims, n_games, MC_MAX_MOVES))
+        noise[:, :, :40] = rng.dirichlet([0.6] * 40, size=(sims, n_games))     # any positive rows do: only the legal prefix is read
+        for e in engines[:3]:
+            e.search_noise(noise)
+        for k in range(sims):
+            manual.select_expand(noise[k])
+            manual.eval_backup()
+        ref = snapshot(plain)
+        for e in engines[1:]:
+            assert same(ref, snapshot(e)), move
+        codes, visits, _, n_legal = ref[:4]
+        pick = np.array([codes[g, visits[g, :max(n_legal[g], 1)].argmax()] for g in range(n_games)], dtype=np.uint16)
+        live = np.nonzero(ref[5] == 0)[0].astype(np.int32)
+        if len(live) == 0:
+            break
+        for e in engines:
+            e.play(pick[live], game_ids=live)
+    c = [e.counters() for e in engines]
+    assert c[0]['simulations'] == c[1]['simulations'] == c[2]['simulations']
+    assert c[0]['nodes'] == c[1]['nodes'] and c[0]['edges'] == c[1]['edges']
+    assert c[0]['cached_evaluations'] == 0
+    # most simulations found their leaf evaluated ahead of time
+    assert c[1]['evaluations'] < 0.35 * c[0]['evaluations'], (c[0]['evaluations'], c[1]['evaluations'])
+    assert c[1]['evaluations'] <= c[2]['evaluations'] < c[0]['evaluations']
+
+
+def test_device_noise_search_is_unchanged_by_lookahead_rows(net):
+    sims = 24
+    plain = make(net, 3, sims, device_rng=1, seed=9)
+    ahead = make(net, 3, sims, device_rng=1, seed=9, eval_cache_log2=14, lookahead_rows=200)
+    for move in range(10):
+        plain.search(sims)
+        ahead.search(sims)
+        assert same(snapshot(plain), snapshot(ahead)), move
+        plain.play_device()
+        ahead.play_device()
+    a, b = plain.counters(), ahead.counters()
+    assert a['simulations'] == b['simulations'] and b['evaluations'] < 0.5 * a['evaluations']
+
+
+def test_facade_uses_lookahead_rows_and_plays_the_same_game(net):
+    """The drop-in agent with and without the option: identical visit distributions and moves under one numpy seed."""
+    from minitchess_alphazero_b200.agent import MonteCarloTreeSearch, SimpleAlphaZeroAgent
+    from minitchess_alphazero_b200.environment import MinitChessEnvironment
+    from minitchess_alphazero_b200.policy import SimpleAlphaZeroPolicy
+    env = MinitChessEnvironment()
+    policy = SimpleAlphaZeroPolicy(net)
+    games = []
+    for options in ({}, {'lookahead_rows': 0, 'eval_cache_log2': 0}):
+        np.random.seed(11)
+        agents = [SimpleAlphaZeroAgent(env, policy, 20) for _ in range(2)]
+        for a in agents:
+            a._mcts = MonteCarloTreeSearch(env, policy.model, 1, engine_options=options)
+        episode, obs = env.new_episode()
+        trace = []
+        for ply in range(10):
+            act = agents[ply & 1].select_action(obs)
+            trace.append((int(act.action), act.info['pi'].tolist()))
+            obs, _, done = episode.step(act.action)
+            if done:
+                break
+        games.append(trace)
+        evals = sum(a._mcts.engine.counters()['evaluations'] for a in agents)
+        games.append(evals)
+    assert games[0] == games[2]
+    assert games[1] < 0.5 * games[3]
