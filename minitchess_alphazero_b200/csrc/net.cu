@@ -45,6 +45,8 @@ constexpr int STAGES = 6;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB: this CTA's 128 boards x 64 input channels
 constexpr int B_BYTES = (C / 2) * BLOCK_K * 2;   // 16 KB: this CTA's half of the 256 output channels
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int STEM_K = 16;         // channels of a one-hot stem row (14 live): one K = 16 MMA, one 32-byte swizzle row
+constexpr int STEM_TILE_BYTES = BLOCK_M * STEM_K * 2;   // 4 KB: 128 boards (or 128 output channels) x 16 channels
 constexpr int CONV_THREADS = 256;                // TMA, MMA, TMEM-alloc, spare + 4 epilogue warps
 constexpr uint32_t SCHED_END = 0xffffffffu;
 constexpr int MAX_CHUNK_BOARDS = 8192;           // boards per forward pass (keeps the per-pair schedule within TOWER_MAX_ITEMS)
@@ -139,6 +141,15 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// The stem level's operands: rows of 16 channels = 32 bytes, SWIZZLE_32B (layout type 6), 8-row groups 256 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;
+    return d;
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10),
 // both K-major, N >> 3 in [17,23), M >> 4 in [24,29).
 // cta_group::2: one instruction spans the CTA pair, M = 256 boards (128 per CTA), N = 256.
@@ -186,6 +197,8 @@ struct TowerParams {
     int bpad;
     int n_pairs;
     uint32_t epoch;
+    int first_level;              // levels below this one are not in the schedule (0; MCAZ_DEBUG_TOWER timing experiments only)
+    int fuse_heads;               // 1: the last level's epilogue takes the head convolutions (0 only in timing experiments)
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
@@ -211,15 +224,22 @@ __device__ __forceinline__ uint4 ld_cg_v4(const uint4* p) {   // L2-coherent: ne
 }
 
 // Epilogue of the last level for one accumulator row (this thread's board at one position): 8 chunks of 32 channels.
-// Kept out of line so that its registers do not weigh on the common epilogue.
-__device__ __noinline__ void epilogue_heads(uint32_t taddr, const float* bias, const float4* s_hw, const __nv_bfloat16* res_row, float* h) {
-    float h0 = 0.f, h1 = 0.f, h2 = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < C / 32; ++c) {
-        uint4 res[4];
+// Kept out of line so that its registers do not weigh on the common epilogue.  The residual row is published before
+// the item's MMAs start, so four chunks of it are fetched ahead of the accumulator and refilled as they are used.
+__device__ __noinline__ void epilogue_heads(uint32_t taddr, const float* bias, const float4* s_hw, const __nv_bfloat16* res_row,
+                                            uint64_t* acc_full, uint32_t acc_phase, float* h) {
+    uint4 res[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
         const uint4* rp = reinterpret_cast<const uint4*>(res_row + c * 32);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) res[j] = ld_cg_v4(rp + j);
+        for (int j = 0; j < 4; ++j) res[c][j] = ld_cg_v4(rp + j);
+    }
+    mbar_wait(acc_full, acc_phase);
+    tc_fence_after();
+    float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < C / 32; ++c) {
         uint32_t v[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -237,13 +257,18 @@ __device__ __noinline__ void epilogue_heads(uint32_t taddr, const float* bias, c
 #pragma unroll
             for (int hh = 0; hh < 4; ++hh) {
                 const int e = j * 8 + hh * 2;
-                const uint32_t r = (&res[j].x)[hh];
+                const uint32_t r = (&res[c & 3][j].x)[hh];
                 const float x0 = fmaxf(__uint_as_float(v[e]) + bias[c * 32 + e] + __uint_as_float(r << 16), 0.f);
                 const float x1 = fmaxf(__uint_as_float(v[e + 1]) + bias[c * 32 + e + 1] + __uint_as_float(r & 0xffff0000u), 0.f);
                 const float4 w0 = s_hw[c * 32 + e], w1 = s_hw[c * 32 + e + 1];
                 h0 = fmaf(x0, w0.x, h0); h1 = fmaf(x0, w0.y, h1); h2 = fmaf(x0, w0.z, h2);
                 h0 = fmaf(x1, w1.x, h0); h1 = fmaf(x1, w1.y, h1); h2 = fmaf(x1, w1.z, h2);
             }
+        }
+        if (c + 4 < C / 32) {
+            const uint4* rp = reinterpret_cast<const uint4*>(res_row + (c + 4) * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) res[c & 3][j] = ld_cg_v4(rp + j);
         }
     }
     h[0] = h0; h[1] = h1; h[2] = h2;
@@ -304,12 +329,12 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             const int pos = item & 0xff, tp = (item >> 8) & 0xffff, L = item >> 24;
             if (tp >= live_pairs) continue;
             const int tile = 2 * tp + (int)rank;
-            if (L > 0 && P.flags) {
+            if (L > P.first_level && P.flags) {
                 // inputs published? (warp 3 polls the global flags ahead of us)
                 while (ld_acquire_cta_shared(&s_deps_ok) <= (uint32_t)k) __nanosleep(SPIN_NS);
                 asm volatile("fence.proxy.async;" ::: "memory");   // order the acquired writes before our TMA reads
             }
-            // level 0 (stem): one-hot rows x folded embedding/conv table, one 64-channel chunk per tap;
+            // level 0 (stem): one-hot rows x folded embedding/conv table, one 16-channel chunk (32-byte rows) per tap;
             // level L >= 1: convolution L - 1 reads act0 (even) / act1 (odd), four chunks per tap
             const int conv = L - 1, chunks = L == 0 ? 1 : C / BLOCK_K;
             const CUtensorMap* map_in = L == 0 ? &map_stem_in : ((conv & 1) ? &map_act1 : &map_act0);
@@ -321,7 +346,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                 for (int kc = 0; kc < chunks; ++kc, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
-                    if (leader) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
+                    if (leader) mbar_expect_tx(&full[s], L == 0 ? 4 * STEM_TILE_BYTES : 2 * STAGE_BYTES);
                     else mbar_arrive_remote(&full[s], 0);
                     uint8_t* st = smem + s * STAGE_BYTES;
                     tma_load_3d_2sm(st, map_in, &full[s], kc * BLOCK_K, tile * BLOCK_M, src);
@@ -353,7 +378,8 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                     mbar_wait(&full[s], (it / STAGES) & 1);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-                    const uint64_t da = umma_desc(a_addr), db = umma_desc(a_addr + A_BYTES);
+                    const uint64_t da = stem ? umma_desc_sw32(a_addr) : umma_desc(a_addr);
+                    const uint64_t db = stem ? umma_desc_sw32(a_addr + A_BYTES) : umma_desc(a_addr + A_BYTES);
 #pragma unroll
                     for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
                         if (kk < ksteps) {
@@ -375,7 +401,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             const uint32_t item = __ldg(&sched[k]);
             if (item == SCHED_END) break;
             const int pos = item & 0xff, tp = (item >> 8) & 0xffff, L = item >> 24;
-            if (tp < live_pairs && L > 0 && P.flags && lane < 9) {
+            if (tp < live_pairs && L > P.first_level && P.flags && lane < 9) {
                 int src;
                 if (tap_valid(pos, lane, src)) {
                     const uint32_t* fl = P.flags + (((size_t)(L - 1) * P.n_pairs + tp) * NPOS + src) * 2 + rank;
@@ -404,7 +430,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             const uint32_t acc = j & 1, acc_phase = (j >> 1) & 1;
             ++j;
             const bool odd = L >= 2 && (L & 1) == 0;           // second conv of a residual block
-            const bool last = L == NLAYERS;                    // its output only feeds the three 1x1 head convolutions
+            const bool last = L == NLAYERS && P.fuse_heads;    // its output only feeds the three 1x1 head convolutions
             __nv_bfloat16* out = (odd || L == 0) ? P.act0 : P.act1;
             const float* bias = s_bias + L * C;
             const size_t row_off = ((size_t)pos * P.bpad + (size_t)tile * BLOCK_M + q * 32 + lane) * C;
@@ -412,10 +438,8 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                 // the tower's output row never leaves the SM: bias + residual + ReLU in fp32, then the three 1x1 head
                 // filters as dot products over the row this thread holds
                 if (P.flags) while (ld_acquire_cta_shared(&s_deps_ok) <= (uint32_t)k) __nanosleep(SPIN_NS);
-                mbar_wait(&acc_full[acc], acc_phase);
-                tc_fence_after();
                 float h[3];
-                epilogue_heads(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C, bias, s_hw, out + row_off, h);
+                epilogue_heads(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C, bias, s_hw, out + row_off, &acc_full[acc], acc_phase, h);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
@@ -524,7 +548,7 @@ __global__ void prep_tower_kernel(const float* __restrict__ flat, __nv_bfloat16*
     if (k == 0) bias[L * C + n] = (cb[n] - mean[n]) * scale + beta[n];
 }
 
-// stem level weights: Ws[tap][cout][64] bf16.  The stem's input row of a square is one-hot: channel k < 7 = "the mover's
+// stem level weights: Ws[tap][cout][16] bf16.  The stem's input row of a square is one-hot: channel k < 7 = "the mover's
 // token is k", channel 7 + k = "the opponent's token is k" (token 0 = none there; Embedding(7,4) gives it a vector too),
 // so Embedding + Conv3x3(8->256) + BatchNorm collapse into one table per tap -- the MMA then just adds two of its rows.
 __global__ void prep_stem_kernel(const float* __restrict__ flat, __nv_bfloat16* __restrict__ ws, float* __restrict__ bias) {
@@ -533,13 +557,13 @@ __global__ void prep_stem_kernel(const float* __restrict__ flat, __nv_bfloat16* 
     const float *sb = sw + 18432, *gamma = sb + 256, *beta = gamma + 256, *mean = beta + 256, *var = mean + 256;
     const float* emb = flat + OFF_EMB;
     const float scale = gamma[c] / sqrtf(var[c] + BN_EPS);
-    for (int k = 0; k < BLOCK_K; ++k) {
+    for (int k = 0; k < STEM_K; ++k) {
         float acc = 0.f;
         if (k < 14) {
             const int ch = k / 7, tok = k % 7;
             for (int e = 0; e < 4; ++e) acc += sw[((size_t)c * 8 + ch * 4 + e) * 9 + t] * emb[tok * 4 + e];
         }
-        ws[((size_t)t * C + c) * BLOCK_K + k] = __float2bfloat16(acc * scale);
+        ws[((size_t)t * C + c) * STEM_K + k] = __float2bfloat16(acc * scale);
     }
     if (t == 0) bias[c] = (sb[c] - mean[c]) * scale + beta[c];
 }
@@ -590,7 +614,7 @@ __global__ void prep_heads_kernel(const float* __restrict__ flat, HeadWeights H)
 
 // ---------------------------------------------------------------------------------- stem input
 // One thread per (board, square): the square's two tokens become the 16 leading channels of its one-hot row
-// (32 bytes; channels 16..63 of the 128-byte row stay zero from the allocation).  Rows past the live ones keep
+// (32 bytes = the whole row).  Rows past the live ones keep
 // whatever an earlier batch left there: rows never mix, and nobody reads the results of dead rows.
 __global__ void __launch_bounds__(256) stem_onehot_kernel(const uint8_t* __restrict__ tokens, int n, int bpad,
                                                           __nv_bfloat16* __restrict__ stem_in, const uint32_t* __restrict__ count,
@@ -607,7 +631,7 @@ __global__ void __launch_bounds__(256) stem_onehot_kernel(const uint8_t* __restr
 #pragma unroll
         for (int k = 0; k < 8; ++k)
             w[k] = ((mine == 2 * k || theirs == 2 * k) ? 0x3F80u : 0u) | ((mine == 2 * k + 1 || theirs == 2 * k + 1) ? 0x3F800000u : 0u);
-        uint4* dst = reinterpret_cast<uint4*>(stem_in + ((size_t)pos * bpad + board) * BLOCK_K);
+        uint4* dst = reinterpret_cast<uint4*>(stem_in + ((size_t)pos * bpad + board) * STEM_K);
         dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
         dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
@@ -672,7 +696,7 @@ heads_kernel(const float* __restrict__ head_in, const float* __restrict__ clocks
         float hv[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) hv[k] = __ldg(H.v1b + lane + 32 * k);
-#pragma unroll 2
+#pragma unroll 8
         for (int j = 0; j < 31; ++j) {
             const float xj = in[61 + j];
             const float* wr = H.v1t + j * 256 + lane;
@@ -762,7 +786,7 @@ heads_legal_kernel(const float* __restrict__ head_in, HeadWeights H, az::View V,
         float hv[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) hv[k] = __ldg(H.v1b + lane + 32 * k);
-#pragma unroll 2
+#pragma unroll 8
         for (int j = 0; j < 31; ++j) {
             const float xj = in[61 + j];
             const float* wr = H.v1t + j * 256 + lane;
@@ -809,7 +833,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_map_3d(CUtensorMap* map, void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1) {
+int make_map_3d(CUtensorMap* map, void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -823,7 +848,7 @@ int make_map_3d(CUtensorMap* map, void* ptr, uint64_t d0, uint64_t d1, uint64_t 
     cuuint32_t box[3] = {b0, b1, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(MCAZ_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     return MCAZ_OK;
 }
@@ -835,8 +860,8 @@ struct Network {
     __nv_bfloat16 *act[2] = {nullptr, nullptr};
     __nv_bfloat16* w = nullptr;        // [18][9][256][256]
     float* bias = nullptr;             // [18][256]
-    __nv_bfloat16* stem_w = nullptr;       // [9 taps][256 cout][64] bf16: folded embedding x stem conv x BN table (14 live channels)
-    __nv_bfloat16* stem_in = nullptr;      // [30 pos][capacity][64] bf16 one-hot token rows
+    __nv_bfloat16* stem_w = nullptr;       // [9 taps][256 cout][16] bf16: folded embedding x stem conv x BN table (14 live channels)
+    __nv_bfloat16* stem_in = nullptr;      // [30 pos][capacity][16] bf16 one-hot token rows
     float* head_in = nullptr;              // [capacity][HEAD_IN]
     float* head_pool = nullptr;
     HeadWeights heads{};
@@ -870,11 +895,11 @@ static int net_alloc_acts(az_engine* e, int boards) {
     if (N->stem_in) cudaFree(N->stem_in);
     if (N->head_in) cudaFree(N->head_in);
     N->stem_in = nullptr; N->head_in = nullptr;
-    MCAZ_CUDA(cudaMalloc(&N->stem_in, (size_t)NPOS * cap * BLOCK_K * sizeof(__nv_bfloat16)));
-    MCAZ_CUDA(cudaMemset(N->stem_in, 0, (size_t)NPOS * cap * BLOCK_K * sizeof(__nv_bfloat16)));
+    MCAZ_CUDA(cudaMalloc(&N->stem_in, (size_t)NPOS * cap * STEM_K * sizeof(__nv_bfloat16)));
+    MCAZ_CUDA(cudaMemset(N->stem_in, 0, (size_t)NPOS * cap * STEM_K * sizeof(__nv_bfloat16)));
     MCAZ_CUDA(cudaMalloc(&N->head_in, (size_t)cap * HEAD_IN * sizeof(float)));
     MCAZ_CUDA(cudaMemset(N->head_in, 0, (size_t)cap * HEAD_IN * sizeof(float)));
-    if (int rc = make_map_3d(&N->map_stem_in, N->stem_in, BLOCK_K, cap, NPOS, BLOCK_K, BLOCK_M)) return rc;
+    if (int rc = make_map_3d(&N->map_stem_in, N->stem_in, STEM_K, cap, NPOS, STEM_K, BLOCK_M, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
     N->capacity = cap;
     return MCAZ_OK;
 }
@@ -888,7 +913,7 @@ int network_create(az_engine* e) {
     e->net = N;
     MCAZ_CUDA(cudaMalloc(&N->w, (size_t)NLAYERS * 9 * C * C * sizeof(__nv_bfloat16)));
     MCAZ_CUDA(cudaMalloc(&N->bias, (size_t)NLEVELS * C * sizeof(float)));
-    MCAZ_CUDA(cudaMalloc(&N->stem_w, (size_t)9 * C * BLOCK_K * sizeof(__nv_bfloat16)));
+    MCAZ_CUDA(cudaMalloc(&N->stem_w, (size_t)9 * C * STEM_K * sizeof(__nv_bfloat16)));
     const size_t head_floats = 512 + 4 + 256 + 4 + 61 * 554 + 554 + 31 * 256 + 256 + 256 + 4 + 4 * 256 + 16;
     MCAZ_CUDA(cudaMalloc(&N->head_pool, head_floats * sizeof(float)));
     float* p = N->head_pool;
@@ -905,7 +930,7 @@ int network_create(az_engine* e) {
     p += (4 - ((p - N->head_pool) & 3)) & 3;                 // float4 reads
     N->heads.hw4 = p;
     if (int rc = make_map_3d(&N->map_w, N->w, C, C, (uint64_t)NLAYERS * 9, BLOCK_K, C / 2)) return rc;
-    if (int rc = make_map_3d(&N->map_stem_w, N->stem_w, BLOCK_K, C, 9, BLOCK_K, C / 2)) return rc;
+    if (int rc = make_map_3d(&N->map_stem_w, N->stem_w, STEM_K, C, 9, STEM_K, C / 2, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
     MCAZ_CUDA(cudaFuncSetAttribute(tower_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_SMEM));
     {
         // Default: the fused data-flow tower, provided every CTA pair of its grid can be resident at once (its
@@ -1001,6 +1026,14 @@ static int build_schedule(az_engine* e, int n_pairs) {
 // CTA pair with the least accumulated work (list scheduling).  Every pair therefore walks the layers in
 // order and the tile pairs in ascending order within a layer, so an item's inputs -- produced one layer
 // earlier at the same place of that order -- are normally long finished when it starts.
+// MCAZ_DEBUG_TOWER (timing experiments, results are then wrong): bit 0 = the last level stores its activations like
+// any other instead of taking the head convolutions, bit 1 = no stem level in the schedule.
+static int tower_debug() {
+    static int v = -1;
+    if (v < 0) { const char* s = getenv("MCAZ_DEBUG_TOWER"); v = s ? atoi(s) : 0; }
+    return v;
+}
+
 static int build_tower_schedule(az_engine* e, int n_pairs) {
     Network* N = e->net;
     const int clusters = std::max(1, std::min(num_sms() / 2, n_pairs * NPOS));
@@ -1030,7 +1063,7 @@ static int build_tower_schedule(az_engine* e, int n_pairs) {
         const int n_groups = (live + group_max - 1) / group_max;
         for (int gi = 0; gi < n_groups; ++gi) {
             const int g0 = (int)((long long)live * gi / n_groups), g1 = (int)((long long)live * (gi + 1) / n_groups);
-            for (int L = 0; L < NLEVELS; ++L)       // level 0 = stem: nine K = 16 MMAs at most, its cost is the epilogue
+            for (int L = tower_debug() & 2 ? 1 : 0; L < NLEVELS; ++L)       // level 0 = stem: nine K = 16 MMAs at most, its cost is the epilogue
                 for (int tp = g0; tp < g1; ++tp)
                     for (int pos : order) {
                         int best = 0;
@@ -1103,6 +1136,7 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
     TowerParams T;
     T.bias = N->bias; T.act0 = N->act[0]; T.act1 = N->act[1]; T.head_w = N->heads.hw4; T.head_in = N->head_in;
     T.bpad = bpad; T.n_pairs = n_pairs; T.count = count; T.row_base = (uint32_t)row_base;
+    T.first_level = (tower_debug() & 2) ? 1 : 0; T.fuse_heads = (tower_debug() & 1) ? 0 : 1;
     if (N->per_layer) {
         if (int rc = build_schedule(e, n_pairs)) return rc;
         T.flags = nullptr; T.epoch = 0; T.sched_stride = 0;

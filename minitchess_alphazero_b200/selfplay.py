@@ -153,15 +153,17 @@ class BatchedSelfPlay:
         if n == 0 or ms <= 0:
             return None
         rows = self.engine.n_slots if evaluations is None else evaluations / n     # mean rows per forward
-        flop = rows * self.CONV_FLOP_PER_EVAL * 18 / per_forward     # algorithmic FLOP of one launch
+        # algorithmic FLOP of one launch: 18 convolutions 256->256, plus the stem (8->256) and the heads' three 1x1
+        # convolutions (256->3) that run as level 0 and in the last epilogue of the same kernel
+        flop = rows * (self.CONV_FLOP_PER_EVAL * 18 + 2 * 552960 + 2 * 23040) / per_forward
         ms_launch = ms / per_forward
         fused = per_forward == 1
         return {'bound': 'tensor',
-                'kernel': ('tower_tc_kernel (18 x [3x3 conv 256->256] in one data-flow ordered launch, tcgen05 cta_group::2)' if fused
+                'kernel': ('tower_tc_kernel (stem + 18 x [3x3 conv 256->256] + head 1x1 convs in one data-flow ordered launch, tcgen05 cta_group::2)' if fused
                            else 'tower_tc_kernel (tcgen05 cta_group::2 3x3 conv 256->256, launched once per layer: MCAZ_TOWER=layers)'),
                 'achieved': flop / (ms_launch / 1e3) / 1e12, 'unit': 'TFLOP/s',
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/ (ncu --set full)
-                'traffic': 934e6 if fused else 151e6, 'ms_per_launch': ms_launch, 'launches_timed': n * per_forward,
+                'traffic': 888e6 if fused else 151e6, 'ms_per_launch': ms_launch, 'launches_timed': n * per_forward,
                 'rows_per_launch': rows, 'flop_per_launch': flop,
                 # the kernel skips the 62 of 270 tap-positions that multiply zero padding: MMAs actually issued
                 'achieved_mma': flop * 208 / 270 / (ms_launch / 1e3) / 1e12,

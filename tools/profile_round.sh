@@ -11,7 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 2300 -c 300 --csv -
 python tools/launch_summary.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launches_summary.txt
 # full sections of the tree / stem / head kernels inside a 200-simulation search
 $B --sims 200 --steps 1 --warmup 1 > gpurun_out/${TAG}_plain200.json 2> gpurun_out/${TAG}_plain200.err || exit 1
-ncu --set full --clock-control none --import-source on -k "regex:search_step_kernel|heads_legal_kernel|stem_kernel" -s 2400 -c 6 \
+ncu --set full --clock-control none --import-source on -k "regex:search_step_kernel|heads_legal_kernel|stem_onehot_kernel" -s 2400 -c 6 \
     -f -o gpurun_out/${TAG}_aux $B --sims 200 --steps 1 --warmup 1 > gpurun_out/${TAG}_ncu_aux.log 2>&1
 # the tower on a full 4096-row batch
 python tools/net_bench.py 4096 10 > gpurun_out/${TAG}_netbench.log 2>&1 || exit 1
