@@ -603,8 +603,12 @@ int az_create(const az_config* cfg, az_engine** out) {
     A(V.path_len, S); A(V.path_edge, S * az::MAX_DEPTH); A(V.path_node, S * az::MAX_DEPTH);
     A(V.leaf_node, S); A(V.leaf_kind, S); A(V.leaf_value, S);
     A(V.tokens, R * MC_TOKENS); A(V.clocks, R); A(V.needs_eval, S); A(V.leaf_states, S);
-    V.row_state = nullptr; V.row_n = nullptr; V.row_codes = nullptr;
-    if (e->lookahead_rows > 0) { A(V.row_state, R); A(V.row_n, R); A(V.row_codes, R * az::CACHE_MAX_E); }
+    V.row_state = nullptr; V.seen = nullptr; V.seen_mask = 0;
+    if (e->lookahead_rows > 0) {
+        A(V.row_state, R);
+        A(V.seen, (size_t)1 << cfg->eval_cache_log2);
+        V.seen_mask = (1u << cfg->eval_cache_log2) - 1u;
+    }
     A(e->d_pending, 2);
     V.edge_vl = nullptr;
     if (V.K > 1) { A(V.edge_vl, E); }

@@ -101,9 +101,8 @@ struct View {
     // where the later simulation that expands such a child finds the very bits the network would give it then
     int row_cap;                    // rows the dense batch holds: slots + look-ahead rows
     int spec_rows;                  // look-ahead rows admitted per batch (0 = off)
-    mc_state* row_state;            // [row_cap] position of a look-ahead row (row_slot = -1)
-    int32_t* row_n;                 // [row_cap] its number of legal moves
-    uint16_t* row_codes;            // [row_cap][CACHE_MAX_E] its sorted legal codes
+    mc_state* row_state;            // [row_cap] position of a look-ahead row (row_slot = -1); the policy head generates its moves
+    uint32_t* seen; uint32_t seen_mask;   // tag per cache slot: this position was queued or evaluated (skip it as a child)
     uint32_t* pending_count;        // [2] games that ended this launch waiting for a network row (per parity)
     // caller-supplied root noise of a chained search (az_search_noise): block [noise_budget][G][MC_MAX_MOVES]
     const double* noise_block; int noise_budget;
@@ -457,36 +456,62 @@ __device__ __forceinline__ void write_network_row(const View& V, int row, int la
     }
 }
 
-// Look-ahead: queue the children of a new node (its E codes start at edge e0) as rows of the batch, unless they are
-// finished, already cached or the batch is full.  Nothing of the tree is touched.
+// Tag of a position in the `seen` table (one word per cache slot): "queued or evaluated under these weights".  A stale
+// or colliding tag only costs a look-ahead row that is not queued (or one queued twice); results never depend on it.
+__device__ __forceinline__ uint32_t seen_tag(const View& V, const mc_state& s) {
+    mc_state k = s;
+    k.meta = s.meta & CACHE_KEY_META;
+    return ((hash_state(k) * 0x2545F491u) ^ (V.cache_epoch * 0x9E3779B1u)) | 0x80000000u;
+}
+
+// Look-ahead: queue the children of a new node (its E codes start at edge e0) as rows of the batch, unless they were
+// queued or evaluated before or the batch is full.  Lane = child: every lane applies its move, probes the tag table and,
+// if its child is new, writes the child's network row (tokens, clock) and position; the legal moves of such a row are
+// generated later by the policy head, a warp per row, off this tree's critical path.  Nothing of the tree is touched.
 __device__ __forceinline__ void queue_children(const View& V, int lane, const mc_state& s, bool white, size_t e0, int E) {
-    uint16_t prev = 0xffffu;
-    for (int i = 0; i < E; ++i) {
-        const uint16_t code = V.edge_code[e0 + i];
-        if (code == prev) continue;                      // promo_multiplicity > 1 repeats a code
-        prev = code;
-        int fv, tv;
-        mc::code_to_view(code, fv, tv);
-        const mc_state cs = mc::apply_move(s, white ? fv : 29 - fv, white ? tv : 29 - tv);
-        const WarpGen w = warp_generate(V, cs, lane);
-        if (w.res != MC_ONGOING || w.E <= 0 || w.E > CACHE_MAX_E) continue;
-        float v, p0, p1;
-        if (cache_lookup(V, cs, w.E, lane, &v, &p0, &p1)) continue;
+    for (int base = 0; base < E; base += 32) {
+        const int i = base + lane;
+        bool want = false;
+        mc_state cs = s;
+        uint32_t idx = 0, tag = 0;
+        if (i < E) {
+            const uint16_t code = V.edge_code[e0 + i];
+            if (i == 0 || V.edge_code[e0 + i - 1] != code) {             // promo_multiplicity > 1 repeats a code
+                int fv, tv;
+                mc::code_to_view(code, fv, tv);
+                cs = mc::apply_move(s, white ? fv : 29 - fv, white ? tv : 29 - tv);
+                if (mc::fullmove(cs) <= V.rules.max_fullmoves) {          // else the move cap ends the game there
+                    idx = cache_hash(cs) & V.seen_mask;
+                    tag = seen_tag(V, cs);
+                    want = ld_cg_u32(&V.seen[idx]) != tag;
+                }
+            }
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, want);
+        const int n = mc::popc(ballot);
+        if (n == 0) continue;
         // admit while fewer than spec_rows rows are taken: the slots' own rows (atomicAdd, at most G*K) always fit
-        int row = -1;
+        int first = 0, take = 0;
         if (lane == 0) {
             uint32_t old = *reinterpret_cast<volatile uint32_t*>(&V.row_count[V.parity]);
             while (old < (uint32_t)V.spec_rows) {
-                const uint32_t seen = atomicCAS(&V.row_count[V.parity], old, old + 1u);
-                if (seen == old) { row = (int)old; break; }
-                old = seen;
+                const uint32_t t = min((uint32_t)n, (uint32_t)V.spec_rows - old);
+                const uint32_t got = atomicCAS(&V.row_count[V.parity], old, old + t);
+                if (got == old) { first = (int)old; take = (int)t; break; }
+                old = got;
             }
         }
-        row = __shfl_sync(0xffffffffu, row, 0);
-        if (row < 0) return;                             // batch full
-        write_network_row(V, row, lane, cs, w.st, w.white);
-        warp_emit_codes(V, w, [&](int k, uint16_t c) { V.row_codes[(size_t)row * CACHE_MAX_E + k] = c; });
-        if (lane == 0) { V.row_slot[row] = -1; V.row_state[row] = cs; V.row_n[row] = w.E; }
+        first = __shfl_sync(0xffffffffu, first, 0);
+        take = __shfl_sync(0xffffffffu, take, 0);
+        const int rank = mc::popc(ballot & ((1u << lane) - 1u));
+        if (want && rank < take) {
+            const int row = first + rank;
+            mc::tokenize(cs, V.tokens + (size_t)row * MC_TOKENS, &V.clocks[row]);
+            V.row_slot[row] = -1;
+            V.row_state[row] = cs;
+            V.seen[idx] = tag;
+        }
+        if (take < n) return;                            // batch full
     }
 }
 
@@ -567,7 +592,10 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, 
         count(V, C_EDGES, (unsigned long long)E);
     }
     __syncwarp();
-    if (LOOKAHEAD && !terminal && V.spec_rows > 0 && V.cache) queue_children(V, lane, s, white, (size_t)t * V.EC + off, E);
+    if (LOOKAHEAD && !terminal && V.spec_rows > 0 && V.cache) {
+        if (lane == 0) V.seen[cache_hash(s) & V.seen_mask] = seen_tag(V, s);      // evaluated now, or found in the cache
+        queue_children(V, lane, s, white, (size_t)t * V.EC + off, E);
+    }
     if (terminal) { *kind = LEAF_TERMINAL; *value = decisive ? -1.0 : -0.0; }
     else if (hit) { *kind = LEAF_CACHED; *value = (double)hit_value; }
     else { *kind = LEAF_EVAL; *value = 0.0; }

@@ -718,7 +718,8 @@ heads_kernel(const float* __restrict__ head_in, const float* __restrict__ clocks
 // p[0][legal_moves].softmax(0)), ~9 of 554.  This variant computes just those, applies the legal-move
 // softmax and writes the priors straight into the new node's edges; the value goes to values[g].
 // One warp per game slot.
-__global__ void __launch_bounds__(HEADS_THREADS, 4)
+template <bool LOOKAHEAD>
+__global__ void __launch_bounds__(HEADS_THREADS, LOOKAHEAD ? 2 : 4)
 heads_legal_kernel(const float* __restrict__ head_in, HeadWeights H, az::View V, float* __restrict__ values,
                    int row_base, int chunk_rows) {
     // rows of the batch: dense (row -> slot through row_slot, az_search) or one row per slot with a needs_eval mask;
@@ -726,13 +727,14 @@ heads_legal_kernel(const float* __restrict__ head_in, HeadWeights H, az::View V,
     const int total = V.compact ? min((int)__ldg(V.row_count + V.parity), V.row_cap) : V.G * V.K;
     const int n_rows = max(0, min(chunk_rows, total - row_base));
     __shared__ float s_in[HEADS_WARPS][96];
+    __shared__ uint16_t s_codes[LOOKAHEAD ? HEADS_WARPS : 1][az::CACHE_MAX_E];
     const float pb0 = __ldg(H.pb), pb1 = __ldg(H.pb + 1), vb = __ldg(H.vb), v2b = __ldg(H.v2b);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* in = s_in[warp];
     for (int r = blockIdx.x * HEADS_WARPS + warp; r < n_rows; r += gridDim.x * HEADS_WARPS) {
         const int slot = V.compact ? V.row_slot[row_base + r] : row_base + r;
         // slot < 0: a look-ahead row -- a position no tree holds yet; its priors and value only go to the cache
-        const bool lookahead = slot < 0;
+        const bool lookahead = LOOKAHEAD && slot < 0;
         if (!V.compact && !V.needs_eval[slot]) continue;
         float d0, d1, d2;
         heads_load_sums(head_in, r, lane, d0, d1, d2);
@@ -751,8 +753,18 @@ heads_legal_kernel(const float* __restrict__ head_in, HeadWeights H, az::View V,
         size_t e0 = 0;
         const uint16_t* codes;
         if (lookahead) {
-            E = V.row_n[row_base + r];
-            codes = V.row_codes + (size_t)(row_base + r) * az::CACHE_MAX_E;
+#if defined(__CUDA_ARCH__)
+            // the row was queued by its position alone: generate its legal moves here (lane = square), a warp per row
+            const az::WarpGen w = az::warp_generate(V, V.row_state[row_base + r], lane);
+            E = w.E;
+            if (w.res != MC_ONGOING || E <= 0 || E > az::CACHE_MAX_E) { __syncwarp(); continue; }   // finished there: never evaluated
+            uint16_t* sc = s_codes[LOOKAHEAD ? warp : 0];
+            az::warp_emit_codes(V, w, [&](int k, uint16_t c) { sc[k] = c; });
+            __syncwarp();
+            codes = sc;
+#else
+            E = 0; codes = nullptr;
+#endif
         } else {
             const int g = slot / V.K;
             const int t = 2 * g + (V.game_ply[g] & 1);
@@ -1158,8 +1170,13 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
     }
     if (ev1) cudaEventRecord(ev1, st);
     if (search_view)
-        heads_legal_kernel<<<std::min(num_sms() * 4, (n + HEADS_WARPS - 1) / HEADS_WARPS), HEADS_THREADS, 0, st>>>(N->head_in, N->heads, *search_view, values,
-                                                                                                                     row_base, n);
+    {
+        const int grid = std::min(num_sms() * 4, (n + HEADS_WARPS - 1) / HEADS_WARPS);
+        if (search_view->spec_rows > 0)
+            heads_legal_kernel<true><<<grid, HEADS_THREADS, 0, st>>>(N->head_in, N->heads, *search_view, values, row_base, n);
+        else
+            heads_legal_kernel<false><<<grid, HEADS_THREADS, 0, st>>>(N->head_in, N->heads, *search_view, values, row_base, n);
+    }
     else
         heads_kernel<<<std::min(num_sms() * 4, (n + HEADS_WARPS - 1) / HEADS_WARPS), HEADS_THREADS, 0, st>>>(N->head_in, clocks, n, N->heads, logits, values);
     MCAZ_CHECK_LAUNCH();

@@ -28,6 +28,8 @@ for ep in range(6):
         plies = 0; t_all = time.perf_counter()
         l0 = _lib.lib().mcaz_kernel_launches()
         c0 = [a._mcts.engine.counters() for a in agents]
+        for a in agents:
+            a._mcts.engine.profile_network(True, read=True); a._mcts.engine.profile_tree(True, read=True)
     for a in agents: a.init_mcts()
     episode, obs = env.new_episode()
     done, turn = False, 0
@@ -36,6 +38,11 @@ for ep in range(6):
         t = time.perf_counter(); obs, r, done = episode.step(act.action); T['step'] += time.perf_counter() - t
         turn ^= 1; plies += 1
 dt = time.perf_counter() - t_all
+net_ms = tree_ms = 0.0; n_fwd = n_tree = 0
+for a in agents:
+    ms, n, _ = a._mcts.engine.profile_network(False, read=True); net_ms += ms * n; n_fwd += n
+    ms, n = a._mcts.engine.profile_tree(False, read=True); tree_ms += ms; n_tree += n
+print('per move: %.1f tower launches %.3f ms, %.1f search launches %.3f ms' % (n_fwd / plies, net_ms / plies, n_tree / plies, tree_ms / plies))
 c1 = [a._mcts.engine.counters() for a in agents]
 ev = sum(b['evaluations'] - a['evaluations'] for a, b in zip(c0, c1))
 ch = sum(b['cached_evaluations'] - a['cached_evaluations'] for a, b in zip(c0, c1))
