@@ -468,7 +468,7 @@ __device__ __forceinline__ uint32_t seen_tag(const View& V, const mc_state& s) {
 // queued or evaluated before or the batch is full.  Lane = child: every lane applies its move, probes the tag table and,
 // if its child is new, writes the child's network row (tokens, clock) and position; the legal moves of such a row are
 // generated later by the policy head, a warp per row, off this tree's critical path.  Nothing of the tree is touched.
-__device__ __forceinline__ void queue_children(const View& V, int lane, const mc_state& s, bool white, size_t e0, int E) {
+__device__ __forceinline__ void queue_children(const View& V, int lane, const mc_state& s, bool white, size_t e0, int E, bool deep) {
     for (int base = 0; base < E; base += 32) {
         const int i = base + lane;
         bool want = false;
@@ -504,7 +504,8 @@ __device__ __forceinline__ void queue_children(const View& V, int lane, const mc
         first = __shfl_sync(0xffffffffu, first, 0);
         take = __shfl_sync(0xffffffffu, take, 0);
         const int rank = mc::popc(ballot & ((1u << lane) - 1u));
-        if (want && rank < take) {
+        const bool queued = want && rank < take;
+        if (queued) {
             const int row = first + rank;
             mc::tokenize(cs, V.tokens + (size_t)row * MC_TOKENS, &V.clocks[row]);
             V.row_slot[row] = -1;
@@ -512,6 +513,38 @@ __device__ __forceinline__ void queue_children(const View& V, int lane, const mc
             V.seen[idx] = tag;
         }
         if (take < n) return;                            // batch full
+        // A pass is certain (the new node itself needs the network): fill its tile further with the grandchildren.
+        // Every lane that queued a child generates that child's moves on its own (scalar code) and queues their
+        // positions one by one.
+        if (deep && queued) {
+            uint16_t codes[MC_MAX_MOVES];
+            int res;
+            int m = mc::generate(cs, V.rules, codes, &res);
+            if (res != MC_ONGOING) m = 0;
+            const bool cwhite = mc::white_to_move(cs);
+            for (int k = 0; k < m; ++k) {
+                if (k > 0 && codes[k] == codes[k - 1]) continue;
+                int fv, tv;
+                mc::code_to_view(codes[k], fv, tv);
+                const mc_state gs = mc::apply_move(cs, cwhite ? fv : 29 - fv, cwhite ? tv : 29 - tv);
+                if (mc::fullmove(gs) > V.rules.max_fullmoves) continue;
+                const uint32_t gidx = cache_hash(gs) & V.seen_mask, gtag = seen_tag(V, gs);
+                if (ld_cg_u32(&V.seen[gidx]) == gtag) continue;
+                int row = -1;
+                uint32_t old = *reinterpret_cast<volatile uint32_t*>(&V.row_count[V.parity]);
+                while (old < (uint32_t)V.spec_rows) {
+                    const uint32_t got = atomicCAS(&V.row_count[V.parity], old, old + 1u);
+                    if (got == old) { row = (int)old; break; }
+                    old = got;
+                }
+                if (row < 0) break;                      // batch full
+                mc::tokenize(gs, V.tokens + (size_t)row * MC_TOKENS, &V.clocks[row]);
+                V.row_slot[row] = -1;
+                V.row_state[row] = gs;
+                V.seen[gidx] = gtag;
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -594,7 +627,9 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, 
     __syncwarp();
     if (LOOKAHEAD && !terminal && V.spec_rows > 0 && V.cache) {
         if (lane == 0) V.seen[cache_hash(s) & V.seen_mask] = seen_tag(V, s);      // evaluated now, or found in the cache
-        queue_children(V, lane, s, white, (size_t)t * V.EC + off, E);
+        // grandchildren too when a pass is certain and the node sits at most two plies below the root, where the
+        // search is dense enough to come by them (deeper down they mostly go unvisited and only cost time)
+        queue_children(V, lane, s, white, (size_t)t * V.EC + off, E, needs_net && depth <= 2);
     }
     if (terminal) { *kind = LEAF_TERMINAL; *value = decisive ? -1.0 : -0.0; }
     else if (hit) { *kind = LEAF_CACHED; *value = (double)hit_value; }

@@ -17,4 +17,4 @@ ncu --set full --clock-control none --import-source on -k "regex:search_step_ker
 python tools/net_bench.py 4096 10 > gpurun_out/${TAG}_netbench.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:tower_tc_kernel -s 5 -c 2 -f -o gpurun_out/${TAG}_tower \
     python tools/net_bench.py 4096 10 > gpurun_out/${TAG}_ncu_tower.log 2>&1
-tail -2 gpurun_out/${TAG}_launches_summary.txt gpurun_out/${TAG}_ncu_aux.log gpurun_out/${TAG}_ncu_tower.log
+tail -n 2 gpurun_out/${TAG}_launches_summary.txt; tail -n 2 gpurun_out/${TAG}_ncu_aux.log; tail -n 2 gpurun_out/${TAG}_ncu_tower.log
