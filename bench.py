@@ -167,7 +167,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = sum(sims_s) / len(sims_s)
     sample = '%d processes x 1 torch thread, each playing self-play moves at %d sims/move for %.1f s per step' % (procs, args.sims, per_step)
-    print(json.dumps({
+    emit(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'sims/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1000 * dt / max(args.steps, 1), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -355,7 +355,7 @@ def run_ours(args):
             'roofline': roof, 'tree_roofline': tree, 'without_cache_lockstep': plain,
             'cpu_baseline': cpu, 'dropin_config1': dropin, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
         }
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -466,7 +466,17 @@ def measure_e2e(sp, args, world):
                    'host (pinned) buffers'}
 
 
+def emit(line):
+    """The one JSON line goes to the process's original stdout."""
+    os.write(_REAL_STDOUT, (line + '\n').encode())
+
+
 if __name__ == '__main__':
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner under torchrun, ...)
+    # is sent to stderr instead
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse_args()
     if a.impl == 'reference':
         run_reference(a)
