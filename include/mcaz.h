@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MCAZ_ABI_VERSION 2
+#define MCAZ_ABI_VERSION 3   /* 3: az_config.lookahead_rows */
 
 /* ---- geometry and action indexing (exp/generate_moves_list.py:5-57, exp/moves_dict.json) */
 #define MC_FILES 5

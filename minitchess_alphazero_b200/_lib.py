@@ -26,7 +26,7 @@ class McazError(RuntimeError):
         self.code = code
 
 
-ABI_VERSION = 2      # MCAZ_ABI_VERSION of include/mcaz.h
+ABI_VERSION = 3      # MCAZ_ABI_VERSION of include/mcaz.h
 
 
 class Rules(ctypes.Structure):
