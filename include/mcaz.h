@@ -181,6 +181,9 @@ int az_set_weights(az_engine* e, const float* flat, size_t n);
 /* (Re)start games: game_ids[i] gets position states[i] (NULL = STARTING_FEN) and two empty
  * trees -- MonteCarloInit.on_episode_begin (exp/callbacks.py:57-62).                        */
 int az_reset_games(az_engine* e, const int32_t* game_ids, int n, const mc_state* states);
+/* Empty single trees (tree id = 2 * game + k, k = 0 / 1) without touching the game or its other tree: init_mcts() of ONE
+ * of the two agents that share an engine (exp/agent.py:105-108).  No simulation may be pending.                          */
+int az_reset_trees(az_engine* e, const int32_t* tree_ids, int n);
 /* Overwrite the current position of running games without touching their trees (used by the
  * per-agent facade, where the environment owns the game line).                              */
 int az_set_positions(az_engine* e, const int32_t* game_ids, int n, const mc_state* states,

@@ -7,6 +7,8 @@ RNG once per simulation whose root is expanded (exp/agent.py:81-82), move choice
 `np.random.choice` (exp/agent.py:113-118).  For thousands of concurrent games use
 `selfplay.BatchedSelfPlay`.
 """
+import weakref
+
 import numpy as np
 
 from . import rules
@@ -75,6 +77,27 @@ class _Visited:
         return self._tree._node(fen) is not None
 
 
+class _SharedEngine:
+    """One engine (one game slot, two trees) serving up to two per-agent searches that evaluate with the same `Network`
+    object -- the reference's actor wiring: two agents, one policy (app/base.py:113).  Each search owns one tree; the
+    uploaded weights and the exact evaluation cache are common, so what one agent's search (or its look-ahead rows)
+    evaluated, the other's finds in the cache.  Trees never mix: results are those of two separate engines."""
+
+    def __init__(self, engine, capacity_sims, model):
+        self.engine, self.capacity_sims, self.fingerprint = engine, capacity_sims, None
+        self.model = weakref.ref(model)                # the pool key holds id(model): make sure it is still that object
+        self.owners = [None, None]                     # weak references to the searches holding tree 0 / tree 1
+
+    def free_tree(self):
+        for k, ref in enumerate(self.owners):
+            if ref is None or ref() is None:
+                return k
+        return None
+
+
+_ENGINE_POOL = {}      # (id(model), simulations, search parameters) -> [_SharedEngine, ...]
+
+
 class MonteCarloTreeSearch:
     """exp/agent.py:24-88 over one GPU-resident tree.  `model` is the torch `Network` (`policy.model`); its
     weights are mirrored into the engine's built-in sm_100a network (az_set_weights) and re-read whenever
@@ -89,54 +112,75 @@ class MonteCarloTreeSearch:
         self._cpuct = cpuct
         self._epsilon, self._alpha = epsilon, alpha
         self._rules = rules_switches
-        self._engine = None
-        self._capacity_sims = 0
+        self._shared, self._tree = None, 0
         self._evaluator = evaluator
-        self._fingerprint = None
-        if _reuse is not None and _reuse._engine is not None and _reuse._evaluator is evaluator:
-            # a new game of the same agent: keep the engine (arenas, uploaded weights), empty its trees
-            self._engine, self._capacity_sims, self._fingerprint = _reuse._engine, _reuse._capacity_sims, _reuse._fingerprint
-            self._engine.reset_games()
+        if _reuse is not None and _reuse._shared is not None and _reuse._evaluator is evaluator:
+            # a new game of the same agent: keep the engine (arenas, uploaded weights, cache), empty this agent's tree
+            self._shared, self._tree = _reuse._shared, _reuse._tree
+            self._shared.owners[self._tree] = weakref.ref(self)
+            self._engine.reset_trees([self._tree])
         self._fields = {k: _NodeField(self, k) for k in ('Q', 'N', 'P', 'legal_moves', 'terminal')}
         self._fields['visited'] = _Visited(self)
 
     def __getitem__(self, item):
         return self._fields.get(item, None)
 
+    @property
+    def _engine(self):
+        return self._shared.engine if self._shared is not None else None
+
     def _node(self, fen):
         if self._engine is None:
             return None
-        return self._engine.node_stats(0, 0, rules.state_from_fen(fen))
+        return self._engine.node_stats(0, self._tree, rules.state_from_fen(fen))
 
     def _ensure(self, num_simulations):
-        if self._engine is None:
+        if self._shared is None:
             opts = dict(max_sims_per_move=max(int(num_simulations), 1), cpuct=float(self._cpuct),
                         dirichlet_epsilon=float(self._epsilon), dirichlet_alpha=float(self._alpha),
                         network=0 if self._evaluator is not None else 1)
+            share = False
             if self._evaluator is None:
                 # one tree, one leaf per network pass: let every pass also evaluate the children of the new nodes into
                 # the exact cache (a pass costs the same for 1 row as for 256) -- same trees, far fewer passes
                 opts.update(eval_cache_log2=16, lookahead_rows=255)
                 opts.update(self._engine_options)
+                share = bool(opts.pop('share_engine', True))
             if self._rules is not None:
                 opts['rules'] = self._rules
-            self._engine = Engine(1, **opts)
-            self._capacity_sims = int(num_simulations)
-        elif int(num_simulations) > self._capacity_sims:
+            # a second search over the same Network object (the reference's two agents share one policy) takes the free
+            # tree of the first one's engine: one copy of the weights, one evaluation cache
+            key = (id(self._model), repr(sorted((k, repr(v)) for k, v in opts.items() if k != 'rules')), id(self._rules))
+            holder = None
+            if share:
+                pool = _ENGINE_POOL.setdefault(key, [])
+                pool[:] = [h for h in pool if h.model() is not None]         # engines of models that are gone
+                for h in pool:
+                    if h.model() is self._model and h.free_tree() is not None:
+                        holder = h
+                        break
+            if holder is None:
+                holder = _SharedEngine(Engine(1, **opts), int(num_simulations), self._model)
+                if share:
+                    _ENGINE_POOL.setdefault(key, []).append(holder)
+            self._shared, self._tree = holder, holder.free_tree()
+            holder.owners[self._tree] = weakref.ref(self)
+            holder.engine.reset_trees([self._tree])
+        elif int(num_simulations) > self._shared.capacity_sims:
             raise ValueError('num_simulations grew from %d to %d: the tree arenas were sized for the first value'
-                             % (self._capacity_sims, num_simulations))
+                             % (self._shared.capacity_sims, num_simulations))
         fp = weights_fingerprint(self._model)
-        if fp != self._fingerprint:                 # first use, load_state_dict or an optimiser step
+        if fp != self._shared.fingerprint:          # first use, load_state_dict or an optimiser step
             if self._evaluator is None:
                 self._engine.set_weights(flatten_state_dict(self._model.state_dict(), device='cuda'))
             elif hasattr(self._evaluator, 'load'):
                 self._evaluator.load(self._model)
-            self._fingerprint = fp
+            self._shared.fingerprint = fp
 
     def simulate(self, num_simulations, observation):       # exp/agent.py:41-45
         self._ensure(num_simulations)
         eng, ev = self._engine, self._evaluator
-        eng.set_positions(rules.state_from_fen(observation), trees=[0])
+        eng.set_positions(rules.state_from_fen(observation), trees=[self._tree])
         if ev is not None:
             tokens, clocks, _needs = eng.leaf_batch_device()
         if ev is None:

@@ -255,6 +255,17 @@ __global__ void __launch_bounds__(256) reset_games_kernel(View V, const int32_t*
     }
 }
 
+// empty single trees (block per listed tree)
+__global__ void __launch_bounds__(256) reset_trees_kernel(View V, const int32_t* tree_ids, int n) {
+    for (int k = blockIdx.x; k < n; k += gridDim.x) {
+        const int t = tree_ids[k];
+        if (t < 0 || t >= 2 * V.G) continue;
+        uint32_t* tab = V.ht + (size_t)t * V.HC;
+        for (int i = threadIdx.x; i < V.HC; i += blockDim.x) tab[i] = 0u;
+        if (threadIdx.x == 0) { V.tree_nodes[t] = 0; V.tree_edges[t] = 0; V.tree_root[t] = az::NONE; }
+    }
+}
+
 __global__ void set_positions_kernel(View V, const int32_t* game_ids, int n, const mc_state* states, const int32_t* tree_of_game) {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const int g = game_ids ? game_ids[k] : k;
@@ -671,6 +682,20 @@ int az_reset_games(az_engine* e, const int32_t* game_ids, int n, const mc_state*
     MCAZ_CHECK_LAUNCH();
     e->launches++;
     e->leaf_pending = false;
+    MCAZ_CUDA(cudaStreamSynchronize(e->stream));
+    return MCAZ_OK;
+}
+
+int az_reset_trees(az_engine* e, const int32_t* tree_ids, int n) {
+    if (!e || n < 0 || (n > 0 && !tree_ids)) return fail(MCAZ_EINVAL, "az_reset_trees: bad argument");
+    if (e->leaf_pending) return fail(MCAZ_ESTATE, "az_reset_trees: a simulation is pending (call az_backup first)");
+    if (n == 0) return MCAZ_OK;
+    e->scratch.begin();
+    In<int32_t> ids;
+    if (int rc = ids.init(tree_ids, n, e->stream, e->scratch)) return rc;
+    reset_trees_kernel<<<std::min(n, num_sms() * 8), 256, 0, e->stream>>>(e->v, ids.ptr, n);
+    MCAZ_CHECK_LAUNCH();
+    e->launches++;
     MCAZ_CUDA(cudaStreamSynchronize(e->stream));
     return MCAZ_OK;
 }

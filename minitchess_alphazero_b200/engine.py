@@ -97,6 +97,11 @@ class Engine:
         st = None if states is None else np.ascontiguousarray(states, dtype=STATE_DTYPE)
         self._check(self._L.az_reset_games(self._h, ptr(ids), n, ptr(st)))
 
+    def reset_trees(self, tree_ids):
+        """Empty single trees (tree id = 2 * game + k): `init_mcts()` of one of two agents sharing the engine."""
+        ids = np.ascontiguousarray(np.atleast_1d(tree_ids), dtype=np.int32)
+        self._check(self._L.az_reset_trees(self._h, ptr(ids), len(ids)))
+
     def set_positions(self, states, game_ids=None, trees=None):
         ids = self._ids(game_ids)
         st = np.ascontiguousarray(np.atleast_1d(states), dtype=STATE_DTYPE)

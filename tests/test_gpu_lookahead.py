@@ -92,22 +92,26 @@ def test_facade_uses_lookahead_rows_and_plays_the_same_game(net):
     from minitchess_alphazero_b200.policy import SimpleAlphaZeroPolicy
     env = MinitChessEnvironment()
     policy = SimpleAlphaZeroPolicy(net)
-    games = []
-    for options in ({}, {'lookahead_rows': 0, 'eval_cache_log2': 0}):
+    games, evals = [], []
+    for options in ({}, {'share_engine': False}, {'lookahead_rows': 0, 'eval_cache_log2': 0, 'share_engine': False}):
         np.random.seed(11)
         agents = [SimpleAlphaZeroAgent(env, policy, 20) for _ in range(2)]
         for a in agents:
             a._mcts = MonteCarloTreeSearch(env, policy.model, 1, engine_options=options)
         episode, obs = env.new_episode()
         trace = []
-        for ply in range(10):
+        for ply in range(12):
+            if ply == 6:
+                agents[0].init_mcts()           # one agent starts a new tree; the other's, in the same engine, must survive
             act = agents[ply & 1].select_action(obs)
             trace.append((int(act.action), act.info['pi'].tolist()))
             obs, _, done = episode.step(act.action)
             if done:
                 break
         games.append(trace)
-        evals = sum(a._mcts.engine.counters()['evaluations'] for a in agents)
-        games.append(evals)
-    assert games[0] == games[2]
-    assert games[1] < 0.5 * games[3]
+        engines = {id(a._mcts.engine): a._mcts.engine for a in agents}
+        assert len(engines) == (1 if options.get('share_engine', True) else 2)
+        evals.append(sum(e.counters()['evaluations'] for e in engines.values()))
+    assert games[0] == games[1] == games[2]
+    # shared engine (one cache for both agents) <= separate engines with look-ahead rows < plain
+    assert evals[0] <= evals[1] < 0.5 * evals[2], evals

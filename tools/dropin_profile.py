@@ -27,9 +27,10 @@ for ep in range(6):
         for k in T: T[k] = 0.0
         plies = 0; t_all = time.perf_counter()
         l0 = _lib.lib().mcaz_kernel_launches()
-        c0 = [a._mcts.engine.counters() for a in agents]
-        for a in agents:
-            a._mcts.engine.profile_network(True, read=True); a._mcts.engine.profile_tree(True, read=True)
+        engines = list({id(a._mcts.engine): a._mcts.engine for a in agents}.values())
+        c0 = [e.counters() for e in engines]
+        for e in engines:
+            e.profile_network(True, read=True); e.profile_tree(True, read=True)
     for a in agents: a.init_mcts()
     episode, obs = env.new_episode()
     done, turn = False, 0
@@ -39,11 +40,11 @@ for ep in range(6):
         turn ^= 1; plies += 1
 dt = time.perf_counter() - t_all
 net_ms = tree_ms = 0.0; n_fwd = n_tree = 0
-for a in agents:
-    ms, n, _ = a._mcts.engine.profile_network(False, read=True); net_ms += ms * n; n_fwd += n
-    ms, n = a._mcts.engine.profile_tree(False, read=True); tree_ms += ms; n_tree += n
+for e in engines:
+    ms, n, _ = e.profile_network(False, read=True); net_ms += ms * n; n_fwd += n
+    ms, n = e.profile_tree(False, read=True); tree_ms += ms; n_tree += n
 print('per move: %.1f tower launches %.3f ms, %.1f search launches %.3f ms' % (n_fwd / plies, net_ms / plies, n_tree / plies, tree_ms / plies))
-c1 = [a._mcts.engine.counters() for a in agents]
+c1 = [e.counters() for e in engines]
 ev = sum(b['evaluations'] - a['evaluations'] for a, b in zip(c0, c1))
 ch = sum(b['cached_evaluations'] - a['cached_evaluations'] for a, b in zip(c0, c1))
 print('%d plies, %.2f ms/move (%.0f sims/s): simulate %.2f, rest of select_action %.2f, env.step %.2f ms; network rows/move %.1f, cache hits/move %.1f, launches/move %.1f' % (
