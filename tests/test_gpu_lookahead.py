@@ -115,3 +115,18 @@ def test_facade_uses_lookahead_rows_and_plays_the_same_game(net):
     assert games[0] == games[1] == games[2]
     # shared engine (one cache for both agents) <= separate engines with look-ahead rows < plain
     assert evals[0] <= evals[1] < 0.5 * evals[2], evals
+
+
+def test_lookahead_rows_beyond_one_network_pass(net):
+    """More rows than one pass of the tower holds (8192): the dense batch runs as chunks, look-ahead rows included."""
+    sims = 12
+    plain = make(net, 40, sims, device_rng=1, seed=4)
+    ahead = make(net, 40, sims, device_rng=1, seed=4, eval_cache_log2=16, lookahead_rows=9000)
+    for move in range(5):
+        plain.search(sims)
+        ahead.search(sims)
+        assert same(snapshot(plain), snapshot(ahead)), move
+        plain.play_device()
+        ahead.play_device()
+    a, b = plain.counters(), ahead.counters()
+    assert a['simulations'] == b['simulations'] and b['evaluations'] < a['evaluations']
