@@ -40,7 +40,9 @@ class _NodeField:
     """`mcts['N'][fen]`-style access to one per-node array of the GPU tree."""
 
     def __init__(self, tree, field):
-        self._tree, self._field = tree, field
+        # weak: the search owns its fields, not the other way round -- no reference cycle, so a dropped agent frees
+        # its tree slot (and, with the last user, the engine) at once instead of at the next garbage collection
+        self._tree, self._field = weakref.proxy(tree), field
 
     def _fetch(self, fen):
         st = self._tree._node(fen)
@@ -71,7 +73,7 @@ class _NodeField:
 
 class _Visited:
     def __init__(self, tree):
-        self._tree = tree
+        self._tree = weakref.proxy(tree)
 
     def __contains__(self, fen):
         return self._tree._node(fen) is not None

@@ -130,3 +130,22 @@ def test_lookahead_rows_beyond_one_network_pass(net):
         ahead.play_device()
     a, b = plain.counters(), ahead.counters()
     assert a['simulations'] == b['simulations'] and b['evaluations'] < a['evaluations']
+
+
+def test_dropped_agents_free_their_tree_slots(net):
+    """app/base.py:113 builds two new agents per batch of episodes: they must land on the engine the previous pair used."""
+    from minitchess_alphazero_b200.agent import SimpleAlphaZeroAgent
+    from minitchess_alphazero_b200.environment import MinitChessEnvironment
+    from minitchess_alphazero_b200.policy import SimpleAlphaZeroPolicy
+    env = MinitChessEnvironment()
+    policy = SimpleAlphaZeroPolicy(net)
+    seen = set()
+    for batch in range(3):
+        agents = [SimpleAlphaZeroAgent(env, policy, 6) for _ in range(2)]
+        _, obs = env.new_episode()
+        for a in agents:
+            a.select_action(obs)
+        assert agents[0]._mcts.engine is agents[1]._mcts.engine and agents[0]._mcts._tree != agents[1]._mcts._tree
+        seen.add(id(agents[0]._mcts.engine))
+        del agents, a
+    assert len(seen) == 1
