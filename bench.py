@@ -322,6 +322,37 @@ def run_ours(args):
                  'steps': n_plain, 'mode': 'lockstep, eval_cache off'}
         sp2.engine.close()
 
+    # the engine's own production loop beside the lock-step headline: continuous self-play (az_selfplay: every game searches,
+    # moves, records and restarts on its own inside the search kernel) with up to four chained simulations per launch
+    cont = None
+    if builtin and not args.no_plain and not continuous:
+        sp3 = BatchedSelfPlay(net, n_games=G, num_simulations=S, seed=1234 + rank, evaluator='builtin', eval_cache_log2=args.eval_cache,
+                              free_sims=4)
+        if not args.no_stagger:
+            sp3.stagger()
+        for _ in range(2):
+            sp3.run_continuous(S)
+        barrier()
+        q0 = sp3.engine.counters()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        n_cont = max(1, min(args.steps, 2))
+        for _ in range(n_cont):
+            sp3.run_continuous(S)
+        t1.record()
+        barrier()
+        q1 = sp3.engine.counters()
+        ct = torch.tensor([t0.elapsed_time(t1), float(q1['simulations'] - q0['simulations']), float(q1['evaluations'] - q0['evaluations'])],
+                          dtype=torch.float64, device='cuda')
+        if world > 1:
+            cmax = ct.clone()
+            dist.all_reduce(cmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ct)
+            ct[0] = cmax[0]
+        cont = {'value': float(ct[1]) / (float(ct[0]) / 1000.0), 'unit': 'sims/s', 'evals_per_second': float(ct[2]) / (float(ct[0]) / 1000.0),
+                'steps': n_cont, 'mode': 'continuous (az_selfplay), free_sims 4, eval_cache as the headline; a step = %d network batches' % S}
+        sp3.engine.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = torch.get_num_threads()
@@ -352,7 +383,7 @@ def run_ours(args):
             'positions_per_second': moves_all / (ms / 1000.0), 'evals_per_second': evals_all / (ms / 1000.0),
             'sims_breakdown': {'network_rows': evals_all / max(sims_all, 1), 'cache_hits': cached_all / max(sims_all, 1),
                                'terminal': terminal_all / max(sims_all, 1)},
-            'roofline': roof, 'tree_roofline': tree, 'without_cache_lockstep': plain,
+            'roofline': roof, 'tree_roofline': tree, 'without_cache_lockstep': plain, 'continuous_selfplay': cont,
             'cpu_baseline': cpu, 'dropin_config1': dropin, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
         }
         emit(json.dumps(out))
