@@ -115,6 +115,7 @@ class MonteCarloTreeSearch:
         self._epsilon, self._alpha = epsilon, alpha
         self._rules = rules_switches
         self._shared, self._tree = None, 0
+        self._last_node = None                                  # (fen, node statistics) read since the last search
         self._evaluator = evaluator
         if _reuse is not None and _reuse._shared is not None and _reuse._evaluator is evaluator:
             # a new game of the same agent: keep the engine (arenas, uploaded weights, cache), empty this agent's tree
@@ -134,7 +135,12 @@ class MonteCarloTreeSearch:
     def _node(self, fen):
         if self._engine is None:
             return None
-        return self._engine.node_stats(0, self._tree, rules.state_from_fen(fen))
+        # policy.get_distribution reads two fields of the root right after a search: one read-back serves both
+        if self._last_node is not None and self._last_node[0] == fen:
+            return self._last_node[1]
+        stats = self._engine.node_stats(0, self._tree, rules.state_from_fen(fen))
+        self._last_node = (fen, stats)
+        return stats
 
     def _ensure(self, num_simulations):
         if self._shared is None:
@@ -180,6 +186,7 @@ class MonteCarloTreeSearch:
             self._shared.fingerprint = fp
 
     def simulate(self, num_simulations, observation):       # exp/agent.py:41-45
+        self._last_node = None
         self._ensure(num_simulations)
         eng, ev = self._engine, self._evaluator
         eng.set_positions(rules.state_from_fen(observation), trees=[self._tree])

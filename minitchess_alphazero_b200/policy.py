@@ -103,8 +103,9 @@ def flatten_state_dict(state_dict, device=None):
 
 
 def weights_fingerprint(module):
-    """Cheap staleness check: torch bumps `_version` on every in-place update / load_state_dict."""
-    return tuple(p._version for p in module.state_dict().values())
+    """Cheap staleness check: torch bumps `_version` on every in-place update / load_state_dict.  Walks the module's own
+    parameter and buffer objects (same version counters as the state_dict aliases, without building the dict)."""
+    return tuple(p._version for p in module.parameters()) + tuple(b._version for b in module.buffers())
 
 
 class TorchEvaluator:
