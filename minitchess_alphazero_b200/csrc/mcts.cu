@@ -199,6 +199,20 @@ __device__ __forceinline__ void search_one(const View& V, int g, int lane, const
     }
 }
 
+// A search that ends while look-ahead rows are queued never evaluates them: take their tags back, so that a later
+// expansion queues those positions again instead of meeting each of them as a miss.
+__global__ void __launch_bounds__(256) untag_rows_kernel(View V) {
+    const int rows = min((int)V.row_count[V.parity], V.row_cap);
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+        if (V.row_slot[r] >= 0) continue;
+        const mc_state s = V.row_state[r];
+        const uint32_t idx = az::cache_hash(s) & V.seen_mask;
+#if defined(__CUDA_ARCH__)
+        if (V.seen[idx] == az::seen_tag(V, s)) V.seen[idx] = 0u;
+#endif
+    }
+}
+
 // az_search / az_selfplay inner step.  leaves_per_step = K > 1 keeps the fixed form: back up the K descents of
 // the previous launch, start K new ones (virtual loss keeps them apart), one row per slot.
 template <bool LOOKAHEAD>
@@ -870,7 +884,14 @@ static int run_search(az_engine* e, int n_batches, int new_budget, bool async, i
             uint32_t waiting = 0;
             MCAZ_CUDA(cudaMemcpyAsync(&waiting, e->d_pending + V.parity, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
             MCAZ_CUDA(cudaStreamSynchronize(e->stream));
-            if (waiting == 0) break;              // every game has spent its budget and nothing is left to back up
+            if (waiting == 0) {                   // every game has spent its budget and nothing is left to back up
+                if (V.spec_rows > 0) {
+                    untag_rows_kernel<<<std::max(1, std::min((V.row_cap + 255) / 256, num_sms())), 256, 0, e->stream>>>(V);
+                    MCAZ_CHECK_LAUNCH();
+                    e->launches++;
+                }
+                break;
+            }
         }
         if (int rc = network_forward_search(e, V, e->d_values)) return rc;
     }
