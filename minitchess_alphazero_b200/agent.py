@@ -151,7 +151,7 @@ class MonteCarloTreeSearch:
             if self._evaluator is None:
                 # one tree, one leaf per network pass: let every pass also evaluate the children of the new nodes into
                 # the exact cache (a pass costs the same for 1 row as for 256) -- same trees, far fewer passes
-                opts.update(eval_cache_log2=16, lookahead_rows=255)
+                opts.update(eval_cache_log2=18, lookahead_rows=255)
                 opts.update(self._engine_options)
                 share = bool(opts.pop('share_engine', True))
             if self._rules is not None:
