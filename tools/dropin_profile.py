@@ -9,6 +9,8 @@ from minitchess_alphazero_b200.policy import Network, SimpleAlphaZeroPolicy
 
 sims = int(sys.argv[1]) if len(sys.argv) > 1 else 36
 opts = {} if len(sys.argv) < 3 or sys.argv[2] != 'plain' else {'lookahead_rows': 0, 'eval_cache_log2': 0}
+if len(sys.argv) > 2 and sys.argv[2].startswith('la='):
+    opts = {'lookahead_rows': int(sys.argv[2][3:])}
 torch.manual_seed(0); np.random.seed(0)
 env = MinitChessEnvironment()
 policy = SimpleAlphaZeroPolicy(Network().eval())
