@@ -215,6 +215,8 @@ struct TowerParams {
     int first_level;              // levels below this one are not in the schedule (0; MCAZ_DEBUG_TOWER timing experiments only)
     int fuse_heads;               // 1: the last level's epilogue takes the head convolutions (0 only in timing experiments)
     uint32_t wait_hint;           // suspend-time hint (ns) of the epilogue warps' waits for an accumulator; 0 = plain try_wait spin
+    unsigned long long* stats;    // MCAZ_TOWER_STATS=1: per CTA {MMA issuer: total, waiting for operands, waiting for an accumulator;
+                                  // TMA producer: total, waiting for dependencies, waiting for a free stage} in clock cycles; else nullptr
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
@@ -339,6 +341,8 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
     if (warp == 0 && lane == 0) {
         // ---------------------------------------------------------------- TMA producer (both CTAs)
         uint32_t it = 0;
+        const long long p_start = clock64();
+        long long p_deps = 0, p_slot = 0;
         for (int k = 0; k < TOWER_MAX_ITEMS; ++k) {
             const uint32_t item = __ldg(&sched[k]);
             if (item == SCHED_END) break;
@@ -347,7 +351,9 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             const int tile = 2 * tp + (int)rank;
             if (L > P.first_level && P.flags) {
                 // inputs published? (warp 3 polls the global flags ahead of us)
+                const long long t0 = clock64();
                 while (ld_acquire_cta_shared(&s_deps_ok) <= (uint32_t)k) __nanosleep(SPIN_NS);
+                p_deps += clock64() - t0;
                 asm volatile("fence.proxy.async;" ::: "memory");   // order the acquired writes before our TMA reads
             }
             // level 0 (stem): one-hot rows x folded embedding/conv table, one 16-channel chunk (32-byte rows) per tap;
@@ -361,7 +367,9 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                 if (!tap_valid(pos, tap, src)) continue;
                 for (int kc = 0; kc < chunks; ++kc, ++it) {
                     const int s = it % STAGES;
+                    const long long t1 = clock64();
                     mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    p_slot += clock64() - t1;
                     if (leader) mbar_expect_tx(&full[s], L == 0 ? 4 * STEM_TILE_BYTES : 2 * STAGE_BYTES);
                     else mbar_arrive_remote(&full[s], 0);
                     uint8_t* st = smem + s * STAGE_BYTES;
@@ -370,9 +378,15 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                 }
             }
         }
+        if (P.stats) {
+            unsigned long long* st = P.stats + (size_t)blockIdx.x * 6;
+            st[3] = (unsigned long long)(clock64() - p_start); st[4] = (unsigned long long)p_deps; st[5] = (unsigned long long)p_slot;
+        }
     } else if (warp == 1 && lane == 0 && leader) {
         // ---------------------------------------------------------------- MMA issuer (leader CTA)
         uint32_t it = 0, j = 0;                       // j: items actually computed (accumulator ring position)
+        const long long m_start = clock64();
+        long long m_full = 0, m_acc = 0;
         for (int k = 0; k < TOWER_MAX_ITEMS; ++k) {
             const uint32_t item = __ldg(&sched[k]);
             if (item == SCHED_END) break;
@@ -381,7 +395,9 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             const bool stem = (item >> 24) == 0;          // K = 16 per tap: the 14 one-hot channels
             const int chunks = stem ? 1 : C / BLOCK_K, ksteps = stem ? 1 : BLOCK_K / 16;
             const uint32_t acc = j & 1;
+            const long long t0 = clock64();
             mbar_wait(&acc_empty[acc], ((j >> 1) & 1) ^ 1);
+            m_acc += clock64() - t0;
             ++j;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * C;
@@ -391,7 +407,9 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                 if (!tap_valid(pos, tap, src)) continue;
                 for (int kc = 0; kc < chunks; ++kc, ++it) {
                     const int s = it % STAGES;
+                    const long long t1 = clock64();
                     mbar_wait(&full[s], (it / STAGES) & 1);
+                    m_full += clock64() - t1;
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
                     const uint64_t da = stem ? umma_desc_sw32(a_addr) : umma_desc(a_addr);
@@ -407,6 +425,10 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                 }
             }
             umma_commit_2sm(&acc_full[acc]);
+        }
+        if (P.stats) {
+            unsigned long long* st = P.stats + (size_t)blockIdx.x * 6;
+            st[0] = (unsigned long long)(clock64() - m_start); st[1] = (unsigned long long)m_full; st[2] = (unsigned long long)m_acc;
         }
     } else if (warp == 3) {
         // ---------------------------------------------------------------- dependency watcher
@@ -904,6 +926,7 @@ struct Network {
     bool per_layer = false;            // false: tower_tc_kernel (one data-flow ordered launch for the 18 layers, default);
                                        // true: the same kernel launched once per layer (MCAZ_TOWER=layers, or no co-residency)
     // profiling (az_profile_network)
+    unsigned long long* stats = nullptr;   // MCAZ_TOWER_STATS=1: [grid][6] wait-cycle counters of the last tower launch
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
     size_t events_used = 0;
@@ -995,6 +1018,7 @@ void network_destroy(az_engine* e) {
     if (N->sched) cudaFree(N->sched);
     if (N->tower_sched) cudaFree(N->tower_sched);
     if (N->tower_flags) cudaFree(N->tower_flags);
+    if (N->stats) cudaFree(N->stats);
     for (auto& ev : N->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     delete N;
     e->net = nullptr;
@@ -1166,6 +1190,15 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
     T.bpad = bpad; T.n_pairs = n_pairs; T.count = count; T.row_base = (uint32_t)row_base;
     T.first_level = (tower_debug() & 2) ? 1 : 0; T.fuse_heads = (tower_debug() & 1) ? 0 : 1;
     {
+        static int want_stats = -1;
+        if (want_stats < 0) { const char* ss = getenv("MCAZ_TOWER_STATS"); want_stats = ss && atoi(ss) > 0; }
+        if (want_stats && !N->stats) {
+            MCAZ_CUDA(cudaMalloc(&N->stats, (size_t)num_sms() * 6 * sizeof(unsigned long long)));
+            MCAZ_CUDA(cudaMemset(N->stats, 0, (size_t)num_sms() * 6 * sizeof(unsigned long long)));
+        }
+        T.stats = N->stats;
+    }
+    {
         static int hint = -1;
         if (hint < 0) { const char* hs = getenv("MCAZ_WAIT_HINT"); hint = hs ? atoi(hs) : 2000; }     // A/B on one box: 267.2 -> 266.1 ms per 200 batches; 20000 ns: 266.8
         T.wait_hint = (uint32_t)hint;
@@ -1241,6 +1274,16 @@ int network_profile(az_engine* e, int on, double* avg_ms_per_tower, int* n_forwa
 }
 
 }  // namespace mcaz
+
+extern "C" int az_tower_stats(az_engine* e, unsigned long long* out, int capacity) {
+    if (!e || !e->net || !out) return mcaz::fail(MCAZ_EINVAL, "az_tower_stats: bad argument");
+    if (!e->net->stats) return mcaz::fail(MCAZ_ESTATE, "az_tower_stats: run with MCAZ_TOWER_STATS=1");
+    const int n = std::min(capacity, mcaz::num_sms() * 6);
+    cudaStreamSynchronize(e->stream);
+    if (cudaMemcpy(out, e->net->stats, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return mcaz::fail(MCAZ_ECUDA, "az_tower_stats: copy failed");
+    return n;
+}
 
 extern "C" int az_profile_network(az_engine* e, int on, double* avg_ms_per_tower, int* n_forwards, int* launches_per_forward) {
     if (!e) return mcaz::fail(MCAZ_EINVAL, "az_profile_network: null engine");

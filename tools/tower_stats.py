@@ -1,0 +1,44 @@
+"""Where the tower's MMA issuer and TMA producer wait (MCAZ_TOWER_STATS=1): per-CTA clock-cycle counters of one launch.
+    MCAZ_TOWER_STATS=1 python tools/tower_stats.py [rows]"""
+import ctypes
+import os
+import sys
+
+os.environ.setdefault('MCAZ_TOWER_STATS', '1')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from minitchess_alphazero_b200 import _lib
+from minitchess_alphazero_b200.engine import Engine
+from minitchess_alphazero_b200.policy import Network, flatten_state_dict
+
+G = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+eng = Engine(G, max_sims_per_move=4, network=1)
+torch.manual_seed(0)
+eng.set_weights(flatten_state_dict(Network().state_dict()).numpy())
+tok = torch.randint(0, 7, (G, 60), dtype=torch.uint8, device='cuda')
+clk = torch.rand(G, device='cuda')
+lg = torch.empty(G, 554, device='cuda')
+vl = torch.empty(G, device='cuda')
+L = _lib.lib()
+for _ in range(20):
+    _lib.check(L.az_network_forward(eng._h, _lib.ptr(tok), _lib.ptr(clk), G, _lib.ptr(lg), _lib.ptr(vl)))
+torch.cuda.synchronize()
+out = np.zeros(148 * 6, dtype=np.uint64)
+L.az_tower_stats.restype = ctypes.c_int
+n = L.az_tower_stats(eng._h, _lib.ptr(out), len(out))
+assert n > 0, L.mcaz_last_error()
+st = out[:n].reshape(-1, 6).astype(np.float64)
+lead = st[0::2]
+print('rows %d, %d CTA pairs' % (G, len(lead)))
+print('MMA issuer : %.0f k cycles; waiting for operands (TMA) %.1f %%, for a free accumulator (epilogue) %.1f %%, issuing %.1f %%' % (
+    lead[:, 0].mean() / 1e3, 100 * lead[:, 1].sum() / lead[:, 0].sum(), 100 * lead[:, 2].sum() / lead[:, 0].sum(),
+    100 * (1 - (lead[:, 1].sum() + lead[:, 2].sum()) / lead[:, 0].sum())))
+print('TMA producer: %.0f k cycles; waiting for dependencies %.1f %%, for a free stage %.1f %%, issuing %.1f %%' % (
+    st[:, 3].mean() / 1e3, 100 * st[:, 4].sum() / st[:, 3].sum(), 100 * st[:, 5].sum() / st[:, 3].sum(),
+    100 * (1 - (st[:, 4].sum() + st[:, 5].sum()) / st[:, 3].sum())))
+if G >= 512:
+    print('per pair, operand-wait share: min %.1f %% max %.1f %%; dependency-wait share: min %.1f %% max %.1f %%' % (
+    100 * (lead[:, 1] / lead[:, 0]).min(), 100 * (lead[:, 1] / lead[:, 0]).max(),
+    100 * (st[:, 4] / st[:, 3]).min(), 100 * (st[:, 4] / st[:, 3]).max()))
