@@ -23,6 +23,6 @@ N = int(sys.argv[2]) if len(sys.argv) > 2 else 600
 for _ in range(N): fwd()
 torch.cuda.synchronize(); dt = (time.perf_counter() - t) / N
 ms, n, lpf = eng.profile_network(False, read=True)
-ms = ms / 18
+ms = ms / 18          # per convolution (the tower's time also holds the stem level and the head epilogue)
 print('G=%d forward %.3f ms (%.2f M evals/s); conv launch avg %.1f us over %d forwards; nominal %.0f TFLOP/s' % (
     G, dt * 1e3, G / dt / 1e6, ms * 1e3, n, G * 2 * 17694720 / (ms / 1e3) / 1e12))
