@@ -48,3 +48,25 @@ def test_no_cpu_fallback(mcaz_lib):
     with pytest.raises(_lib.McazError) as e:
         rules.legal_moves(rules.state_from_fen(rules.STARTING_FEN))
     assert e.value.code == -2
+
+
+def test_integration_md_stub_matches_the_abi(mcaz_lib):
+    """The raw ctypes stub INTEGRATION.md shows a maintainer must describe the structs the library was built with
+    (field order and sizes), or the documented binding would corrupt az_config."""
+    import ctypes
+    text = open(os.path.join(REPO, 'INTEGRATION.md')).read()
+    block = re.search(r'## 3\. Raw ctypes stub.*?```python\n(.*?)```', text, flags=re.S).group(1)
+    # only the declarations: stop before the first call that needs a device
+    decl = block.split('def check(rc)')[0].replace("L = ctypes.CDLL('minitchess_alphazero_b200/libmcaz.so')", 'L = _L')
+    ns = {'_L': mcaz_lib}
+    exec(decl, ns)
+    mcaz_lib.mcaz_struct_size.restype = ctypes.c_size_t
+    assert ns['STATE'].itemsize == mcaz_lib.mcaz_struct_size(0)
+    assert ctypes.sizeof(ns['McRules']) == mcaz_lib.mcaz_struct_size(1)
+    assert ctypes.sizeof(ns['AzConfig']) == mcaz_lib.mcaz_struct_size(2)
+    # same field names, order and types as the package's own mirror
+    from minitchess_alphazero_b200 import _lib
+    assert [(n, t) for n, t in ns['McRules']._fields_] == [(n, t) for n, t in _lib.Rules._fields_]
+    ours = [(n, ctypes.sizeof(t)) for n, t in _lib.Config._fields_]
+    theirs = [(n, ctypes.sizeof(t)) for n, t in ns['AzConfig']._fields_]
+    assert ours == theirs
