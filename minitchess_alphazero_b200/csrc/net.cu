@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -1082,7 +1083,11 @@ static int build_schedule(az_engine* e, int n_pairs) {
 // any other instead of taking the head convolutions, bit 1 = no stem level in the schedule.
 static int tower_debug() {
     static int v = -1;
-    if (v < 0) { const char* s = getenv("MCAZ_DEBUG_TOWER"); v = s ? atoi(s) : 0; }
+    if (v < 0) {
+        const char* s = getenv("MCAZ_DEBUG_TOWER");
+        v = s ? atoi(s) : 0;
+        if (v) fprintf(stderr, "libmcaz: MCAZ_DEBUG_TOWER=%d -- timing experiment, NETWORK OUTPUTS ARE WRONG\n", v);
+    }
     return v;
 }
 
