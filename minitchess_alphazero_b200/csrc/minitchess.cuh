@@ -48,6 +48,20 @@ MC_HD int lsb(uint32_t x) {
 #endif
 }
 
+// a square set seen from the mover's side (black: rotated by 180 degrees, view square = 29 - real square)
+MC_HD uint32_t view_of(uint32_t b, bool white) {
+    if (white) return b;
+#if defined(__CUDA_ARCH__)
+    return __brev(b) >> 2;
+#else
+    b = ((b >> 1) & 0x55555555u) | ((b & 0x55555555u) << 1);
+    b = ((b >> 2) & 0x33333333u) | ((b & 0x33333333u) << 2);
+    b = ((b >> 4) & 0x0f0f0f0fu) | ((b & 0x0f0f0f0fu) << 4);
+    b = ((b >> 8) & 0x00ff00ffu) | ((b & 0x00ff00ffu) << 8);
+    return ((b >> 16) | (b << 16)) >> 2;
+#endif
+}
+
 struct Sets {
     uint32_t occ, own, opp, pawns, rooks, bishops, knights, queens, kings;
 };
@@ -166,7 +180,10 @@ MC_HD bool leaves_king_safe(const Sets& t, bool white, int type, int from, int t
     return (att & own_king) == 0;
 }
 
-MC_HD uint32_t legal_targets(const Sets& t, bool white, int type, int from, const mc_rules& R) {
+// Legal targets by definition: one king-safety test (a full opponent attack set) per candidate move.  Kept as the
+// statement of what `Guard` below must reproduce (tests/host_harness compares the two square by square) and for the
+// warp-cooperative expansion, which deals these tests out one per lane.
+MC_HD uint32_t legal_targets_by_test(const Sets& t, bool white, int type, int from, const mc_rules& R) {
     uint32_t tg = pseudo_targets(t, white, type, from, R), out = 0;
     while (tg) {
         int to = lsb(tg);
@@ -174,6 +191,64 @@ MC_HD uint32_t legal_targets(const Sets& t, bool white, int type, int from, cons
         if (leaves_king_safe(t, white, type, from, to)) out |= 1u << to;
     }
     return out;
+}
+
+// Everything the king-safety test depends on, worked out once per position: 17 ray fills and one attack set
+// instead of one attack set (8 ray fills) per candidate move.  MinitChess has no castling and no en passant, so a
+// move is legal iff
+//   king:   the target is not attacked once the king is lifted off the board (`danger`);
+//   others: the target is on `check_mask` (anywhere when not in check; the checker or a square between it and the
+//           king in single check; nowhere in double check) and, if the piece is the first own piece on a line from
+//           the king to an enemy slider of that line's kind, on that line (`pin[d]`: the squares from the king
+//           up to and including the pinner).
+struct Guard {
+    uint32_t danger, check_mask, checkers;
+    uint32_t pin[8];
+};
+
+template <int SHIFT, bool UP>
+MC_HD void guard_line(uint32_t kb, uint32_t keep, uint32_t occ, uint32_t own, uint32_t sliders, uint32_t& checkers,
+                      uint32_t& lines, uint32_t& pin) {
+    const uint32_t e = ~occ;
+    const uint32_t r1 = ray<SHIFT, UP>(kb, keep, e);            // up to and including the first piece
+    const uint32_t b1 = r1 & occ;
+    const uint32_t hit = b1 & sliders;
+    checkers |= hit;
+    lines |= hit ? r1 : 0u;
+    const uint32_t r2 = ray<SHIFT, UP>(b1 & own, keep, e);      // from an own first piece on to the next one
+    pin = (r2 & occ & sliders) ? (r1 | r2) : 0u;
+}
+
+MC_HD Guard make_guard(const Sets& t, bool white) {
+    Guard g;
+    const uint32_t kb = t.kings & t.own;
+    g.danger = attacked_by(t.opp, !white, t.occ & ~kb, t.pawns, t.rooks, t.bishops, t.knights, t.queens, t.kings);
+    const uint32_t straight = t.opp & (t.rooks | t.queens), diagonal = t.opp & (t.bishops | t.queens);
+    uint32_t checkers = (knight_attacks(kb) & t.opp & t.knights) | (pawn_attacks(kb, white) & t.opp & t.pawns) |
+                        (king_attacks(kb) & t.opp & t.kings);
+    uint32_t lines = checkers;
+    guard_line<5, true>(kb, FULL, t.occ, t.own, straight, checkers, lines, g.pin[0]);
+    guard_line<5, false>(kb, FULL, t.occ, t.own, straight, checkers, lines, g.pin[1]);
+    guard_line<1, true>(kb, ~FILE_E, t.occ, t.own, straight, checkers, lines, g.pin[2]);
+    guard_line<1, false>(kb, ~FILE_A, t.occ, t.own, straight, checkers, lines, g.pin[3]);
+    guard_line<6, true>(kb, ~FILE_E, t.occ, t.own, diagonal, checkers, lines, g.pin[4]);
+    guard_line<4, true>(kb, ~FILE_A, t.occ, t.own, diagonal, checkers, lines, g.pin[5]);
+    guard_line<4, false>(kb, ~FILE_E, t.occ, t.own, diagonal, checkers, lines, g.pin[6]);
+    guard_line<6, false>(kb, ~FILE_A, t.occ, t.own, diagonal, checkers, lines, g.pin[7]);
+    g.checkers = checkers;
+    const int n = popc(checkers);
+    g.check_mask = n == 0 ? FULL : (n == 1 ? lines : 0u);
+    return g;
+}
+
+MC_HD uint32_t legal_targets(const Sets& t, const Guard& g, bool white, int type, int from, const mc_rules& R) {
+    const uint32_t ps = pseudo_targets(t, white, type, from, R);
+    if (type == KING) return ps & ~g.danger;
+    const uint32_t fb = 1u << from;
+    uint32_t allowed = g.check_mask;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) allowed &= (g.pin[d] & fb) ? g.pin[d] : FULL;
+    return ps & allowed;
 }
 
 // ---- action codes (exp/generate_moves_list.py:11-36) -----------------------------------------
@@ -211,14 +286,15 @@ template <typename Emit>
 MC_HD int emit_square_codes(int fv, bool white, bool knight, uint32_t tg, int base, bool promo_piece, int promo_rep,
                             Emit&& emit) {
     int r = fv / 5, f = fv % 5, n = 0, code = base;
+    const uint32_t tgv = view_of(tg, white);               // targets as view squares
     if (!knight) {
         for (int d = 0; d < 8; ++d) {
-            int dr = qdir_dr(d), df = qdir_df(d), reach = qreach(r, f, d);
+            const int reach = qreach(r, f, d), stride = 5 * qdir_dr(d) + qdir_df(d);
+            int tv = fv;
             for (int k = 1; k <= reach; ++k, ++code) {
-                int tv = 5 * (r + k * dr) + f + k * df;
-                int to = white ? tv : 29 - tv;
-                if ((tg >> to) & 1u) {
-                    int rep = (promo_piece && (tv / 5 == 5)) ? promo_rep : 1;
+                tv += stride;
+                if ((tgv >> tv) & 1u) {
+                    int rep = (promo_piece && tv >= 25) ? promo_rep : 1;
                     for (int j = 0; j < rep; ++j) { emit((uint16_t)code); ++n; }
                 }
             }
@@ -227,52 +303,85 @@ MC_HD int emit_square_codes(int fv, bool white, bool knight, uint32_t tg, int ba
         for (int d = 0; d < 8; ++d) {
             if (!n_on(r, f, d)) continue;
             int tv = 5 * (r + ndir_dr(d)) + f + ndir_df(d);
-            int to = white ? tv : 29 - tv;
-            if ((tg >> to) & 1u) { emit((uint16_t)code); ++n; }
+            if ((tgv >> tv) & 1u) { emit((uint16_t)code); ++n; }
             ++code;
         }
     }
     return n;
 }
 
-// Base code of view-square fv in the queen block / knight block (prefix sums, computed).
+// Base code of view-square fv in the queen block / knight block: prefix sums of the per-square widths, worked out by
+// the compiler from the same direction lists and packed into 64-bit immediates (qbase - 13 fv in 6 bits, ten squares a
+// word; nbase - 430 in 7 bits, nine squares a word) -- a shift and a mask at run time, still no table in memory.
+namespace detail {
+constexpr int c_abs(int x) { return x < 0 ? -x : x; }
+constexpr int c_qwidth(int r, int f) {
+    int n = 0;
+    for (int dr = -1; dr <= 1; ++dr)
+        for (int df = -1; df <= 1; ++df) {
+            if (dr == 0 && df == 0) continue;
+            int nr = dr > 0 ? 5 - r : (dr < 0 ? r : 5), nf = df > 0 ? 4 - f : (df < 0 ? f : 5);
+            n += nr < nf ? nr : nf;
+        }
+    return n;
+}
+constexpr int c_nwidth(int r, int f) {
+    int n = 0;
+    for (int dr = -2; dr <= 2; ++dr)
+        for (int df = -2; df <= 2; ++df)
+            if (c_abs(dr) + c_abs(df) == 3 && dr != 0 && df != 0 && r + dr >= 0 && r + dr < 6 && f + df >= 0 && f + df < 5) ++n;
+    return n;
+}
+constexpr int c_qbase(int fv) { int b = 0; for (int s = 0; s < fv; ++s) b += c_qwidth(s / 5, s % 5); return b; }
+constexpr int c_nbase(int fv) { int b = 0; for (int s = 0; s < fv; ++s) b += c_nwidth(s / 5, s % 5); return b; }
+constexpr uint64_t c_pack_q(int word) {
+    uint64_t v = 0;
+    for (int i = 0; i < 10; ++i) v |= (uint64_t)(c_qbase(word * 10 + i) - 13 * (word * 10 + i)) << (6 * i);
+    return v;
+}
+constexpr uint64_t c_pack_n(int word) {
+    uint64_t v = 0;
+    for (int i = 0; i < 9 && word * 9 + i < 30; ++i) v |= (uint64_t)c_nbase(word * 9 + i) << (7 * i);
+    return v;
+}
+static_assert(c_qbase(30) == 430 && c_nbase(30) == 124, "554 action codes (exp/generate_moves_list.py)");
+static_assert(c_qbase(29) - 13 * 29 < 64 && c_nbase(29) < 128, "packing widths");
+constexpr uint64_t QB0 = c_pack_q(0), QB1 = c_pack_q(1), QB2 = c_pack_q(2);
+constexpr uint64_t NB0 = c_pack_n(0), NB1 = c_pack_n(1), NB2 = c_pack_n(2), NB3 = c_pack_n(3);
+}  // namespace detail
 MC_HD int qbase(int fv) {
-    int b = 0;
-    for (int s = 0; s < fv; ++s) b += qcount(s / 5, s % 5);
-    return b;
+    const int w = fv >= 20 ? 2 : (fv >= 10 ? 1 : 0);
+    const uint64_t v = w == 2 ? detail::QB2 : (w == 1 ? detail::QB1 : detail::QB0);
+    return 13 * fv + (int)((v >> (6 * (fv - 10 * w))) & 63u);
 }
 MC_HD int nbase(int fv) {
-    int b = 430;
-    for (int s = 0; s < fv; ++s)
-        for (int d = 0; d < 8; ++d) b += n_on(s / 5, s % 5, d) ? 1 : 0;
-    return b;
+    const int w = fv >= 27 ? 3 : (fv >= 18 ? 2 : (fv >= 9 ? 1 : 0));
+    const uint64_t v = w == 3 ? detail::NB3 : (w == 2 ? detail::NB2 : (w == 1 ? detail::NB1 : detail::NB0));
+    return 430 + (int)((v >> (7 * (fv - 9 * w))) & 127u);
 }
 
 // code -> view squares.  Returns false for code >= 554.
 MC_HD bool code_to_view(int code, int& fv, int& tv) {
     if (code < 0 || code >= MC_NUM_ACTIONS) return false;
     if (code < 430) {
-        int base = 0;
-        for (int s = 0; s < 30; ++s) {
-            int r = s / 5, f = s % 5, c = qcount(r, f);
-            if (code < base + c) {
-                int off = code - base;
-                for (int d = 0; d < 8; ++d) {
-                    int reach = qreach(r, f, d);
-                    if (off < reach) { fv = s; tv = 5 * (r + (off + 1) * qdir_dr(d)) + f + (off + 1) * qdir_df(d); return true; }
-                    off -= reach;
-                }
-            }
-            base += c;
+        int s = 0;
+        for (int q = 1; q < 30; ++q) s += qbase(q) <= code ? 1 : 0;      // the last square whose base is <= code
+        const int r = s / 5, f = s % 5;
+        int off = code - qbase(s);
+        for (int d = 0; d < 8; ++d) {
+            int reach = qreach(r, f, d);
+            if (off < reach) { fv = s; tv = 5 * (r + (off + 1) * qdir_dr(d)) + f + (off + 1) * qdir_df(d); return true; }
+            off -= reach;
         }
     } else {
-        int c = 430;
-        for (int s = 0; s < 30; ++s)
-            for (int d = 0; d < 8; ++d)
-                if (n_on(s / 5, s % 5, d)) {
-                    if (c == code) { fv = s; tv = 5 * (s / 5 + ndir_dr(d)) + s % 5 + ndir_df(d); return true; }
-                    ++c;
-                }
+        int s = 0;
+        for (int q = 1; q < 30; ++q) s += nbase(q) <= code ? 1 : 0;
+        int c = nbase(s);
+        for (int d = 0; d < 8; ++d)
+            if (n_on(s / 5, s % 5, d)) {
+                if (c == code) { fv = s; tv = 5 * (s / 5 + ndir_dr(d)) + s % 5 + ndir_df(d); return true; }
+                ++c;
+            }
     }
     return false;
 }
@@ -331,29 +440,24 @@ MC_HD int result_of(const mc_state& s, const Sets& t, int n_legal, const mc_rule
 MC_HD int generate(const mc_state& s, const mc_rules& R, uint16_t* codes, int* result) {
     Sets t = sets_of(s);
     bool white = white_to_move(s);
+    const Guard g = make_guard(t, white);
     int n = 0, n_moves = 0;
+    const uint32_t own_knights = t.own & t.knights;
     for (int pass = 0; pass < 2; ++pass) {
-        int base = pass ? 430 : 0;
-        for (int fv = 0; fv < 30; ++fv) {
-            int sq = white ? fv : 29 - fv;
-            int r = fv / 5, f = fv % 5;
-            int width;
-            if (pass == 0) width = qcount(r, f);
-            else { width = 0; for (int d = 0; d < 8; ++d) width += n_on(r, f, d) ? 1 : 0; }
-            if ((t.own >> sq) & 1u) {
-                int type = piece_at(s, sq);
-                if ((type == KNIGHT) == (pass == 1)) {
-                    uint32_t tg = legal_targets(t, white, type, sq, R);
-                    if (tg) {
-                        n_moves += popc(tg);
-                        int w = n;
-                        emit_square_codes(fv, white, pass == 1, tg, base, type == PAWN, R.promo_multiplicity,
-                                          [&](uint16_t c) { if (w < MC_MAX_MOVES) codes[w] = c; ++w; });
-                        n = w;
-                    }
-                }
+        uint32_t left = view_of(pass ? own_knights : (t.own & ~own_knights), white);      // ascending view squares
+        while (left) {
+            const int fv = lsb(left);
+            left &= left - 1;
+            const int sq = white ? fv : 29 - fv;
+            const int type = piece_at(s, sq);
+            const uint32_t tg = legal_targets(t, g, white, type, sq, R);
+            if (tg) {
+                n_moves += popc(tg);
+                int w = n;
+                emit_square_codes(fv, white, pass == 1, tg, pass ? nbase(fv) : qbase(fv), type == PAWN, R.promo_multiplicity,
+                                  [&](uint16_t c) { if (w < MC_MAX_MOVES) codes[w] = c; ++w; });
+                n = w;
             }
-            base += width;
         }
     }
     if (result) *result = result_of(s, t, n_moves, R);
@@ -388,12 +492,13 @@ MC_HD int step(const mc_state& s, int code, const mc_rules& R, mc_state* out) {
     Sets t = sets_of(s);
     bool white = white_to_move(s);
     // result needs the legal-move count
+    const Guard g = make_guard(t, white);
     int n_moves = 0;
     uint32_t own = t.own;
     while (own) {
         int sq = lsb(own);
         own &= own - 1;
-        n_moves += popc(legal_targets(t, white, piece_at(s, sq), sq, R));
+        n_moves += popc(legal_targets(t, g, white, piece_at(s, sq), sq, R));
     }
     if (result_of(s, t, n_moves, R) != MC_ONGOING) return 2;
     int fv, tv;
@@ -402,7 +507,7 @@ MC_HD int step(const mc_state& s, int code, const mc_rules& R, mc_state* out) {
     if (!((t.own >> from) & 1u)) return 1;
     int type = piece_at(s, from);
     // a knight-shaped code needs a knight, a queen-shaped code anything else (uci is the same)
-    if (!((legal_targets(t, white, type, from, R) >> to) & 1u)) return 1;
+    if (!((legal_targets(t, g, white, type, from, R) >> to) & 1u)) return 1;
     *out = apply_move(s, from, to);
     return 0;
 }

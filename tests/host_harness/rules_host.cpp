@@ -25,6 +25,26 @@ void hh_apply(const mc_state* s, const uint16_t* codes, int n, const mc_rules* r
 void hh_tokenize(const mc_state* s, int n, uint8_t* tokens, float* clocks) {
     for (int i = 0; i < n; ++i) mc::tokenize(s[i], tokens + (size_t)i * 60, clocks + i);
 }
+// Legal target sets of every own piece, by the per-position Guard (what generate/step use) and by the definition
+// (one king-safety test per candidate move): out[i*30 + square].
+void hh_targets_both(const mc_state* s, int n, const mc_rules* rules, uint32_t* by_guard, uint32_t* by_test) {
+    mc_rules R = rules_or_default(rules);
+    for (int i = 0; i < n; ++i) {
+        mc::Sets t = mc::sets_of(s[i]);
+        bool white = mc::white_to_move(s[i]);
+        mc::Guard g = mc::make_guard(t, white);
+        for (int sq = 0; sq < 30; ++sq) {
+            uint32_t a = 0, b = 0;
+            if ((t.own >> sq) & 1u) {
+                int type = mc::piece_at(s[i], sq);
+                a = mc::legal_targets(t, g, white, type, sq, R);
+                b = mc::legal_targets_by_test(t, white, type, sq, R);
+            }
+            by_guard[(size_t)i * 30 + sq] = a;
+            by_test[(size_t)i * 30 + sq] = b;
+        }
+    }
+}
 int hh_view_to_code(int fv, int tv) { return mc::view_to_code(fv, tv); }
 int hh_code_to_view(int code, int* fv, int* tv) { return mc::code_to_view(code, *fv, *tv) ? 0 : -1; }
 }
