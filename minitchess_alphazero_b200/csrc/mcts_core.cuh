@@ -317,8 +317,8 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
 
 // Legal targets of the piece on this lane's square (lane = square in the mover's view), warp-cooperative: every lane
 // lists the pseudo-legal targets of its own piece, the (piece, target) pairs of the whole position are dealt out one per
-// lane, each lane runs the king-safety test of its pair (mc::leaves_king_safe, the same predicate mc::legal_targets
-// applies target by target), and a ballot carries the verdicts back.  A position has 15-30 pseudo-legal moves, so one
+// lane, each lane runs the king-safety test of its pair (mc::leaves_king_safe, the predicate mc::legal_targets_by_test
+// applies target by target and mc::Guard reproduces per position), and a ballot carries the verdicts back.  A position has 15-30 pseudo-legal moves, so one
 // round of ~250 instructions replaces up to ten on the lane that holds the queen.
 __device__ __forceinline__ uint32_t legal_targets_warp(const mc::Sets& st, bool white, int type, int sq, int lane, const mc_rules& R) {
     const uint32_t ps = type ? mc::pseudo_targets(st, white, type, sq, R) : 0u;
