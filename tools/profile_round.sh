@@ -17,4 +17,8 @@ ncu --set full --clock-control none --import-source on -k "regex:search_step_ker
 python tools/net_bench.py 4096 10 > gpurun_out/${TAG}_netbench.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:tower_tc_kernel -s 5 -c 2 -f -o gpurun_out/${TAG}_tower \
     python tools/net_bench.py 4096 10 > gpurun_out/${TAG}_ncu_tower.log 2>&1
+# the stateless rules kernels (BASELINE.json configs[1]): 1 M positions plain, then full sections on 65 536 positions
+python tools/rules_bench.py > gpurun_out/${TAG}_rules_bench.json 2> gpurun_out/${TAG}_rules_bench.err || exit 1
+ncu --set full --clock-control none --import-source on -k "regex:legal_moves_kernel|apply_kernel" -s 90 -c 2 -f -o gpurun_out/${TAG}_rules \
+    python tools/rules_bench.py 65536 > gpurun_out/${TAG}_ncu_rules.log 2>&1
 tail -n 2 gpurun_out/${TAG}_launches_summary.txt; tail -n 2 gpurun_out/${TAG}_ncu_aux.log; tail -n 2 gpurun_out/${TAG}_ncu_tower.log
