@@ -170,11 +170,21 @@ def test_guard_matches_move_by_move_king_safety(host_rules):
             bad = np.nonzero((a != b).any(1))[0]
             assert len(bad) == 0, rc.state_to_fen(pos[bad[0]])
             assert b.any()
-    # and the full generator against the mailbox oracle on the synthetic set (checks, pins and mates galore)
-    c0, n0, r0 = rc.legal_moves(synth)
-    c1, n1, r1 = np.zeros_like(c0), np.zeros_like(n0), np.zeros_like(r0)
-    host_rules.hh_legal_moves(vp(synth), len(synth), None, vp(c1), vp(n1), vp(r1))
-    assert np.array_equal(n0, n1) and np.array_equal(r0, r1) and np.array_equal(c0, c1)
+    # and the full generator and the step against the mailbox oracle on the synthetic set (checks, pins and mates
+    # galore), under the default rules and every switch
+    for rules in (None, rc.Rules(1, 1, 30, 1, 1), rc.Rules(0, 4, 30, 1, 1), rc.Rules(0, 1, 12, 0, 1)):
+        rp = ctypes.byref(rules) if rules is not None else None
+        c0, n0, r0 = rc.legal_moves(synth, rules)
+        c1, n1, r1 = np.zeros_like(c0), np.zeros_like(n0), np.zeros_like(r0)
+        host_rules.hh_legal_moves(vp(synth), len(synth), rp, vp(c1), vp(n1), vp(r1))
+        assert np.array_equal(n0, n1) and np.array_equal(r0, r1) and np.array_equal(c0, c1)
+        rnd = np.random.RandomState(1).randint(0, 554, len(synth)).astype(np.uint16)
+        first = np.ascontiguousarray(c0[:, 0])
+        for codes in (first, rnd):
+            o0, s0 = rc.apply(synth, codes, rules)
+            o1, s1 = np.zeros_like(o0), np.zeros_like(s0)
+            host_rules.hh_apply(vp(synth), vp(codes), len(synth), rp, vp(o1), vp(s1))
+            assert np.array_equal(o0, o1) and np.array_equal(s0, s1)
 
 
 def test_tokeniser_matches_golden(host_rules):
