@@ -12,6 +12,30 @@ from minitchess_alphazero_b200._lib import MC_MAX_MOVES
 ALPHA = 0.6
 
 
+def synthetic_positions(seed, n):
+    """Random piece placements (one king each, up to 10 other pieces, any mix): far denser in pins, double checks,
+    adjacent kings and pieces en prise than reachable play -- inputs for the rules parity tests (CPU host build and GPU)."""
+    rng = np.random.RandomState(seed)
+    out = np.zeros(n, dtype=rc.STATE_DTYPE)
+    for i in range(n):
+        k = rng.randint(2, 12)
+        sq = rng.permutation(30)[:k + 2]
+        types = [6, 6] + list(rng.choice([1, 2, 3, 4, 5], size=k, p=[0.3, 0.2, 0.15, 0.15, 0.2]))
+        white = [1, 0] + list(rng.randint(0, 2, size=k))
+        pl = [0, 0, 0]
+        w = 0
+        for s_, t_, c_ in zip(sq, types, white):
+            if t_ == 1 and (s_ < 5 or s_ >= 25):
+                t_ = 4                                   # no pawns on the first or last rank
+            for b in range(3):
+                if (t_ >> b) & 1:
+                    pl[b] |= 1 << int(s_)
+            if c_:
+                w |= 1 << int(s_)
+        out[i] = (pl[0], pl[1], pl[2], w, int(rng.randint(0, 2)) | (int(rng.randint(0, 20)) << 8) | (int(rng.randint(1, 30)) << 16))
+    return out
+
+
 def host_backend():
     """CDLL of tests/host_harness/mcts_host.cpp (built on demand)."""
     import ctypes

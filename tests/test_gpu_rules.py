@@ -113,3 +113,17 @@ def test_empty_and_device_buffers(rules):
     c0, n0, r0 = rc.legal_moves(pos)
     assert np.array_equal(d_counts.cpu().numpy(), n0)
     assert np.array_equal(d_codes.cpu().numpy().view(np.uint16), c0)
+
+
+def test_synthetic_positions(rules):
+    """Random piece placements (dense in pins, double checks, mates): the CUDA kernels against the mailbox oracle."""
+    from parity_common import synthetic_positions
+    pos = synthetic_positions(3, 50000)
+    c0, n0, r0 = rc.legal_moves(pos)
+    c1, n1, r1 = rules.legal_moves(pos)
+    assert np.array_equal(n0, n1) and np.array_equal(r0, r1) and np.array_equal(c0, c1)
+    rnd = np.random.RandomState(1).randint(0, 554, len(pos)).astype(np.uint16)
+    for codes in (np.ascontiguousarray(c0[:, 0]), rnd):
+        o0, s0 = rc.apply(pos, codes)
+        o1, s1 = rules.apply(pos, codes)
+        assert np.array_equal(o0, o1) and np.array_equal(s0, s1)

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from conftest import load_golden, vp
+from parity_common import synthetic_positions
 from oracle import rules_c as rc
 
 RES = {'*': 0, '1-0': 1, '0-1': 2, '1/2-1/2': 3}
@@ -132,36 +133,12 @@ def test_bitboard_header_matches_oracle(host_rules):
         assert np.array_equal(n0, n1) and np.array_equal(r0, r1) and np.array_equal(c0, c1)
 
 
-def _synthetic_positions(seed, n):
-    """Random piece placements (one king each, up to 8 other pieces per side, any mix): far denser in pins, double
-    checks, adjacent kings and pieces en prise than reachable play -- inputs for the Guard-vs-definition comparison."""
-    rng = np.random.RandomState(seed)
-    out = np.zeros(n, dtype=rc.STATE_DTYPE)
-    for i in range(n):
-        k = rng.randint(2, 12)
-        sq = rng.permutation(30)[:k + 2]
-        types = [6, 6] + list(rng.choice([1, 2, 3, 4, 5], size=k, p=[0.3, 0.2, 0.15, 0.15, 0.2]))
-        white = [1, 0] + list(rng.randint(0, 2, size=k))
-        pl = [0, 0, 0]
-        w = 0
-        for s_, t_, c_ in zip(sq, types, white):
-            if t_ == 1 and (s_ < 5 or s_ >= 25):
-                t_ = 4                                   # no pawns on the first or last rank
-            for b in range(3):
-                if (t_ >> b) & 1:
-                    pl[b] |= 1 << int(s_)
-            if c_:
-                w |= 1 << int(s_)
-        out[i] = (pl[0], pl[1], pl[2], w, int(rng.randint(0, 2)) | (int(rng.randint(0, 20)) << 8) | (int(rng.randint(1, 30)) << 16))
-    return out
-
-
 def test_guard_matches_move_by_move_king_safety(host_rules):
     """mc::legal_targets (pins, check mask and king danger worked out once per position) == one king-safety test per
     candidate move, for every piece of 100 k reachable and 100 k synthetic positions, under both pawn rules."""
     import ctypes
     reach = np.ascontiguousarray(rc.random_positions(9, 100000))
-    synth = _synthetic_positions(3, 100000)
+    synth = synthetic_positions(3, 100000)
     for pos in (reach, synth):
         for rules in (None, rc.Rules(1, 1, 30, 1, 1)):
             a = np.zeros((len(pos), 30), dtype=np.uint32)
