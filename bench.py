@@ -43,7 +43,6 @@ def parse_args():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--games', type=int, default=4096, help='concurrent games per GPU')
     ap.add_argument('--sims', type=int, default=200, help='simulations per move')
-    ap.add_argument('--evaluator', default='builtin', choices=['builtin', 'torch'])
     ap.add_argument('--cpu-seconds', type=float, default=15.0, help='budget of the CPU baseline sample')
     ap.add_argument('--mode', default='lockstep', choices=['continuous', 'lockstep'],
                     help='continuous: az_selfplay, every game moves as soon as its own simulations are done (a step = '
@@ -55,6 +54,9 @@ def parse_args():
     ap.add_argument('--no-plain', action='store_true', help='skip the comparison pass without cache / continuous mode')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-legs', action='store_true', help='N > 1 only: skip the config4 (32768 games x 800 sims/move sharded) and '
+                    'loop (self-play + gather + learner step + weight broadcast) legs')
+    ap.add_argument('--loop-moves', type=int, default=6, help='moves of self-play per loop iteration in the loop leg')
     return ap.parse_args()
 
 
@@ -200,11 +202,11 @@ def run_ours(args):
     G, S = args.games, args.sims
     torch.manual_seed(0)
     net = Network().eval()
-    builtin = args.evaluator == 'builtin'
-    opts = {'eval_cache_log2': args.eval_cache, 'free_sims': args.free_sims} if builtin else {}
-    sp = BatchedSelfPlay(net, n_games=G, num_simulations=S, seed=1234 + rank, evaluator=args.evaluator, **opts)
+    builtin = True
+    opts = {'eval_cache_log2': args.eval_cache, 'free_sims': args.free_sims}
+    sp = BatchedSelfPlay(net, n_games=G, num_simulations=S, seed=1234 + rank, **opts)
     eng = sp.engine
-    continuous = builtin and args.mode == 'continuous'
+    continuous = args.mode == 'continuous'
 
     def barrier():
         torch.cuda.synchronize()
@@ -267,19 +269,7 @@ def run_ours(args):
         tree.update({'peak': pk['hbm_gbs'], 'frac': tree['achieved'] / pk['hbm_gbs'],
                      'note': 'latency-bound pointer chasing: one warp walks one tree; see profiles/ for warp efficiency'})
     if prof is None:
-        # library evaluator: time the whole forward over the resident leaf batch
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(20):
-            sp.evaluator.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        fwd_ms = e0.elapsed_time(e1) / 20
-        achieved = G * FLOP_PER_EVAL / (fwd_ms / 1000.0) / 1e12
-        roof = {'bound': 'tensor', 'kernel': 'network forward (cuDNN/cuBLAS via PyTorch, all layers)', 'achieved': achieved,
-                'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'], 'traffic': None, 'peak_source': pk['which'],
-                'ms_per_launch': fwd_ms}
+        roof = None
     else:
         roof = prof
         roof.update({'peak': pk['tflops'], 'frac': roof['achieved'] / pk['tflops'], 'mma_frac': roof['achieved_mma'] / pk['tflops'],
@@ -295,7 +285,7 @@ def run_ours(args):
     plain = None
     if builtin and not args.no_plain and (args.eval_cache > 0 or continuous):
         eng.close()                     # frees the first engine's arenas
-        sp2 = BatchedSelfPlay(net, n_games=G, num_simulations=S, seed=1234 + rank, evaluator='builtin', eval_cache_log2=0)
+        sp2 = BatchedSelfPlay(net, n_games=G, num_simulations=S, seed=1234 + rank, eval_cache_log2=0)
         if not args.no_stagger:
             sp2.stagger()
         for _ in range(min(args.warmup, 3)):
@@ -326,7 +316,7 @@ def run_ours(args):
     # moves, records and restarts on its own inside the search kernel) with up to four chained simulations per launch
     cont = None
     if builtin and not args.no_plain and not continuous:
-        sp3 = BatchedSelfPlay(net, n_games=G, num_simulations=S, seed=1234 + rank, evaluator='builtin', eval_cache_log2=args.eval_cache,
+        sp3 = BatchedSelfPlay(net, n_games=G, num_simulations=S, seed=1234 + rank, eval_cache_log2=args.eval_cache,
                               free_sims=4)
         if not args.no_stagger:
             sp3.stagger()
@@ -371,7 +361,7 @@ def run_ours(args):
             'config': {'workload': '%s: batched self-play, %d concurrent games x %d sims/move per GPU, random-init reference-size net' % (
                            'BASELINE.json configs[3] (32768 games x 800 sims/move sharded over the GPUs)' if (G * world == 32768 and S == 800)
                            else 'BASELINE.json configs[2]' if (G == 4096 and S == 200) else 'custom size', G, S),
-                       'games_per_gpu': G, 'sims_per_move': S, 'evaluator': args.evaluator,
+                       'games_per_gpu': G, 'sims_per_move': S, 'evaluator': 'builtin (tower_tc_kernel)',
                        'mode': ('continuous (az_selfplay): a step = %d network batches; games move on their own' % S) if continuous
                                else 'lockstep (az_search + az_play_device): a step = one move in every game',
                        'eval_cache': ('exact, 2^%d entries' % args.eval_cache) if builtin and args.eval_cache > 0 else 'off',

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MCAZ_ABI_VERSION 3   /* 3: az_config.lookahead_rows */
+#define MCAZ_ABI_VERSION 4   /* 4: az_replay_tuple.weights_version, az_set_weights_version, az_tree_dump, counter 14 */
 
 /* ---- geometry and action indexing (exp/generate_moves_list.py:5-57, exp/moves_dict.json) */
 #define MC_FILES 5
@@ -71,7 +71,8 @@ typedef struct mc_state {
 typedef struct mc_rules {
     int32_t pawn_double_step;      /* default 0                                            */
     int32_t promo_multiplicity;    /* default 1 (queen only); 4 = q,r,b,n share one code   */
-    int32_t max_fullmoves;         /* default 30: draw once fullmove number > this         */
+    int32_t max_fullmoves;         /* default 30: draw once fullmove number > this; an engine
+                                      (az_create) takes at most 31: a game line is <= 64 plies */
     int32_t insufficient_material; /* default 1                                            */
     int32_t fivefold_repetition;   /* default 1 (episode-level only: needs history)        */
 } mc_rules;
@@ -177,6 +178,11 @@ int az_destroy(az_engine* e);
 #define AZ_NUM_BN_STATS 9734
 #define AZ_NUM_WEIGHT_FLOATS (AZ_NUM_PARAMS + AZ_NUM_BN_STATS)
 int az_set_weights(az_engine* e, const float* flat, size_t n);
+/* Version stamp of the weights in use -- LearnPuppet.weights_version (app/base.py:171-174), which the actor sends
+ * along with every episode (app/base.py:63-68) so that the learner can drop episodes played with other weights
+ * (app/learner.py:51-53).  Every replay tuple carries the stamp in force when its game finished.  az_set_weights
+ * adds 1 to the stamp (0 at creation); a learner that numbers its weights itself sets its own value afterwards.  */
+int az_set_weights_version(az_engine* e, uint32_t version);
 
 /* (Re)start games: game_ids[i] gets position states[i] (NULL = STARTING_FEN) and two empty
  * trees -- MonteCarloInit.on_episode_begin (exp/callbacks.py:57-62).                        */
@@ -250,6 +256,16 @@ int az_play_device(az_engine* e);
 
 int az_game_states(az_engine* e, const int32_t* game_ids, int n, mc_state* states, int8_t* results);
 
+/* Every node of one tree at once -- the whole dicts of MonteCarloTreeSearch (exp/agent.py:25-36: Q, N, P, legal_moves,
+ * terminal, visited), in creation order.  HOST output buffers.  Node i: position states[i], info[i] = number of
+ * edges | MC_NODE_TERMINAL | MC_NODE_DECISIVE, its edges at [edge_off[i], edge_off[i] + n_edges) of codes / visits /
+ * q / priors.  *n_nodes / *n_edges receive the totals; when they exceed max_nodes / max_edges only that many entries
+ * are written (call again with larger buffers).  Any of the array pointers may be NULL.                             */
+#define MC_NODE_TERMINAL (1u << 16)   /* finished position: no edges; exp/agent.py:59-63 `terminal[fen]`        */
+#define MC_NODE_DECISIVE (1u << 17)   /* ... won by the side that moved into it (terminal value -1, else -0)   */
+int az_tree_dump(az_engine* e, int game_id, int tree, int max_nodes, mc_state* states, uint32_t* info, uint32_t* edge_off,
+                 int* n_nodes, int max_edges, uint16_t* codes, uint32_t* visits, double* q, float* priors, int* n_edges);
+
 /* Replay tuples (exp/callbacks.py:31-54 -> exp/learner.py:23-41), packed per ply.           */
 typedef struct az_replay_tuple {
     mc_state observation;            /* position before the move                            */
@@ -257,10 +273,14 @@ typedef struct az_replay_tuple {
     uint16_t action;
     int8_t reward;                   /* +1 / 0 / -1 from the mover's point of view, back-filled */
     uint8_t pad[3];
+    uint32_t weights_version;        /* az_set_weights_version stamp when the game finished (app/base.py:66) */
     uint16_t codes[MC_MAX_MOVES];
     float pi[MC_MAX_MOVES];
 } az_replay_tuple;
-/* Moves up to `max` finished-game tuples into out (host or device); *n_out = count.         */
+/* Moves up to `max` finished-game tuples into out (host or device); *n_out = count.  Tuples beyond `max` stay
+ * queued for the next call, in order.  The queue holds 64 * n_games tuples; a finished game is queued whole or, when
+ * it does not fit, dropped whole and counted in counter [14] -- so drain at least once per 32 moves of every game
+ * (one game is at most 62 plies under the default 30-move cap).                                                   */
 int az_drain_replay(az_engine* e, az_replay_tuple* out, int max, int* n_out);
 
 /* Learner-side collate on the device (exp/learner.py:23-41 collate_fn): n packed tuples -> dense pi
@@ -273,8 +293,9 @@ int az_collate(const az_replay_tuple* tuples, int n, float* pi, int64_t* tokens,
  * [9] simulations whose leaf evaluation came from the evaluation cache ([0] = [1] + [2] + [9]),
  * [10] tree levels descended and [11] edges read on the way (bytes-per-simulation accounting),
  * [12] nodes dropped by the recycler (recycle = 1), [13] network rows whose position was already in the
- * evaluation cache when they were stored (evaluated more than once within one batch).                  */
-#define AZ_NUM_COUNTERS 14
+ * evaluation cache when they were stored (evaluated more than once within one batch),
+ * [14] replay tuples dropped because the replay queue was full (whole games; see az_drain_replay).      */
+#define AZ_NUM_COUNTERS 15
 int az_counters(az_engine* e, uint64_t* out);
 
 /* Stand-alone network forward (exp/policy.py:71-80) on n positions with the engine's weights:

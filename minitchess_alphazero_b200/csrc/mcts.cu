@@ -14,11 +14,13 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "engine.cuh"
 
 using namespace mcaz;
 using az::View;
+static_assert(MC_NODE_TERMINAL == az::INFO_TERMINAL && MC_NODE_DECISIVE == az::INFO_DECISIVE, "az_tree_dump info bits");
 
 namespace mcaz {
 int num_sms();
@@ -135,7 +137,7 @@ __device__ __forceinline__ bool play_device_one(const View& V, int g, int lane) 
     // replay tuple of this ply
     az_replay_tuple* rec = V.record + (size_t)g * az::MAX_DEPTH + min(ply - V.game_start_ply[g], az::MAX_DEPTH - 1);
     for (int i = lane; i < E; i += 32) { rec->codes[i] = V.edge_code[e0 + i]; rec->pi[i] = (float)((double)V.edge_N[e0 + i] / (double)nsum); }
-    if (lane == 0) { rec->observation = s; rec->n_legal = (uint16_t)E; rec->action = (uint16_t)code; rec->reward = 0; }
+    if (lane == 0) { rec->observation = s; rec->n_legal = (uint16_t)E; rec->action = (uint16_t)code; rec->reward = 0; rec->weights_version = 0u; }
     __syncwarp();
     play_chosen_move(V, g, lane, code);
     const int res = V.game_result[g];
@@ -144,20 +146,30 @@ __device__ __forceinline__ bool play_device_one(const View& V, int g, int lane) 
         // tuples go to the replay ring (lanes copy the 604-byte tuples word by word)
         static_assert(sizeof(az_replay_tuple) % 4 == 0, "az_replay_tuple is copied by words");
         const int n_rec = min(V.game_ply[g] - V.game_start_ply[g], az::MAX_DEPTH);
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(V.replay_count, (unsigned long long)n_rec);
+        // the whole game or nothing: reserve its n_rec slots in one step; a game that does not fit is dropped and counted
+        // (a partly written game would break the reward chain of its episode)
+        unsigned long long base = ~0ull;
+        if (lane == 0) {
+            unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(V.replay_count);
+            while (old + (unsigned long long)n_rec <= V.replay_cap) {
+                const unsigned long long got = atomicCAS(V.replay_count, old, old + (unsigned long long)n_rec);
+                if (got == old) { base = old; break; }
+                old = got;
+            }
+            if (base == ~0ull) az::count(V, az::C_REPLAY_DROPPED, (unsigned long long)n_rec);
+        }
         base = __shfl_sync(0xffffffffu, base, 0);
         const int last_reward = (res == MC_DRAW) ? 0 : 1;
-        for (int p = n_rec - 1; p >= 0; --p) {
+        for (int p = n_rec - 1; p >= 0 && base != ~0ull; --p) {
             az_replay_tuple* r = V.record + (size_t)g * az::MAX_DEPTH + p;
-            if (lane == 0) r->reward = (int8_t)(((n_rec - 1 - p) & 1) ? -last_reward : last_reward);
-            __syncwarp();
-            const unsigned long long dst = base + (unsigned long long)p;
-            if (dst < V.replay_cap) {
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(r);
-                uint32_t* out = reinterpret_cast<uint32_t*>(V.replay + dst);
-                for (int w = lane; w < (int)(sizeof(az_replay_tuple) / 4); w += 32) out[w] = src[w];
+            if (lane == 0) {
+                r->reward = (int8_t)(((n_rec - 1 - p) & 1) ? -last_reward : last_reward);
+                r->weights_version = V.weights_version;          // the stamp at push time (app/base.py:63-68)
             }
+            __syncwarp();
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(r);
+            uint32_t* out = reinterpret_cast<uint32_t*>(V.replay + base + (unsigned long long)p);
+            for (int w = lane; w < (int)(sizeof(az_replay_tuple) / 4); w += 32) out[w] = src[w];
         }
     }
     __syncwarp();
@@ -195,7 +207,9 @@ __device__ __forceinline__ void search_one(const View& V, int g, int lane, const
     }
     if (lane == 0) {
         V.sims_left[g] = left;
-        if (waiting && V.pending_count) atomicAdd(&V.pending_count[V.parity], 1u);
+        // the host stops the batch loop when this stays 0: a game counts while it waits for a row OR still has budget
+        // (a launch whose descents all ended on finished / cached leaves leaves nobody waiting with simulations unspent)
+        if (V.pending_count && (waiting || (left > 0 && V.game_result[g] == MC_ONGOING))) atomicAdd(&V.pending_count[V.parity], 1u);
     }
 }
 
@@ -587,6 +601,10 @@ void az_default_config(az_config* c) {
 int az_create(const az_config* cfg, az_engine** out) {
     if (!cfg || !out) return fail(MCAZ_EINVAL, "az_create: null argument");
     if (cfg->n_games <= 0 || cfg->max_sims_per_move <= 0) return fail(MCAZ_EINVAL, "az_create: n_games and max_sims_per_move must be positive");
+    // a game line of 2 * max_fullmoves plies (+ 2 for a start position with black to move) must fit the per-game records:
+    // replay tuples, simulation paths and the repetition history are MAX_DEPTH = HIST = 64 entries each
+    if (cfg->rules.max_fullmoves < 1 || 2 * cfg->rules.max_fullmoves + 2 > az::MAX_DEPTH)
+        return fail(MCAZ_EINVAL, "az_create: rules.max_fullmoves must be in [1, 31] (per-game records hold 64 plies)");
     if (int rc = require_device()) return rc;
     az_engine* e = new az_engine();
     e->cfg = *cfg;
@@ -654,6 +672,7 @@ int az_create(const az_config* cfg, az_engine** out) {
 #undef A
     V.record = e->d_record; V.replay = e->d_replay; V.replay_count = e->d_replay_count;
     V.replay_cap = (unsigned long long)e->replay_capacity;
+    V.weights_version = 0u;
     if (!rc && cfg->network) rc = network_create(e);
     if (rc) { az_destroy(e); return rc; }
     *out = e;
@@ -682,7 +701,14 @@ int az_set_weights(az_engine* e, const float* flat, size_t n) {
     int rc = network_set_weights(e, in.ptr);
     if (!rc) MCAZ_CUDA(cudaStreamSynchronize(e->stream));
     if (++e->cache_epoch == 0) e->cache_epoch = 1;   // cached evaluations belong to the old weights (0 = never written)
+    e->v.weights_version += 1u;                      // a learner with its own numbering overrides this (az_set_weights_version)
     return rc;
+}
+
+int az_set_weights_version(az_engine* e, uint32_t version) {
+    if (!e) return fail(MCAZ_EINVAL, "az_set_weights_version: null engine");
+    e->v.weights_version = version;
+    return MCAZ_OK;
 }
 
 int az_reset_games(az_engine* e, const int32_t* game_ids, int n, const mc_state* states) {
@@ -941,7 +967,15 @@ int az_selfplay(az_engine* e, int n_steps, int sims_per_move) {
     if (e->v.K != 1) return fail(MCAZ_ESTATE, "az_selfplay: leaves_per_step must be 1");
     if (sims_per_move > e->cfg.max_sims_per_move) return fail(MCAZ_EINVAL, "az_selfplay: sims_per_move exceeds max_sims_per_move (arena size)");
     if (e->leaf_pending) return fail(MCAZ_ESTATE, "az_selfplay: a simulation is pending (call az_backup first)");
-    return run_search(e, n_steps, -1, true, sims_per_move);
+    // recycle = 1: the arenas hold a few moves' worth of nodes, and games keep moving inside this call.  Run it in segments
+    // in which a tree takes at most sims_per_move new nodes; every segment starts by compacting the trees that could not
+    // take that many (run_search) and ends with the closing launch, after which no simulation is pending.  Same games as
+    // one long call: only the order of a game's own simulations matters.
+    const int fm = std::max(1, e->cfg.free_sims);
+    const int seg = e->cfg.recycle ? std::max(1, sims_per_move / fm) : std::max(1, n_steps);
+    for (int done = 0; done < n_steps; done += seg)
+        if (int rc = run_search(e, std::min(seg, n_steps - done), -1, true, sims_per_move)) return rc;
+    return MCAZ_OK;
 }
 
 int az_profile_tree(az_engine* e, int on, double* total_ms, int* n_launches) {
@@ -1024,6 +1058,42 @@ int az_node_stats(az_engine* e, int game_id, int tree, const mc_state* state, in
     return MCAZ_OK;
 }
 
+int az_tree_dump(az_engine* e, int game_id, int tree, int max_nodes, mc_state* states, uint32_t* info, uint32_t* edge_off, int* n_nodes,
+                 int max_edges, uint16_t* codes, uint32_t* visits, double* q, float* priors, int* n_edges) {
+    if (!e || game_id < 0 || game_id >= e->v.G || tree < 0 || tree > 1 || max_nodes < 0 || max_edges < 0 || !n_nodes || !n_edges)
+        return fail(MCAZ_EINVAL, "az_tree_dump: bad argument");
+    const View& V = e->v;
+    const size_t t = 2 * (size_t)game_id + (size_t)tree;
+    uint32_t n = 0, m = 0;
+    MCAZ_CUDA(cudaStreamSynchronize(e->stream));
+    MCAZ_CUDA(cudaMemcpy(&n, V.tree_nodes + t, sizeof(n), cudaMemcpyDeviceToHost));
+    MCAZ_CUDA(cudaMemcpy(&m, V.tree_edges + t, sizeof(m), cudaMemcpyDeviceToHost));
+    *n_nodes = (int)n; *n_edges = (int)m;
+    const size_t nn = std::min<size_t>(n, (size_t)max_nodes), mm = std::min<size_t>(m, (size_t)max_edges);
+    const size_t nb = t * V.NC, eb = t * V.EC;
+    if (nn) {
+        if (states) {
+            std::vector<az::Board4> board(nn);
+            std::vector<uint32_t> meta(nn);
+            MCAZ_CUDA(cudaMemcpy(board.data(), V.node_board + nb, nn * sizeof(az::Board4), cudaMemcpyDeviceToHost));
+            MCAZ_CUDA(cudaMemcpy(meta.data(), V.node_meta + nb, nn * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < nn; ++i) states[i] = az::state_of(board[i], meta[i]);
+        }
+        if (info) {
+            MCAZ_CUDA(cudaMemcpy(info, V.node_info + nb, nn * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < nn; ++i) info[i] &= 0xffffu | az::INFO_TERMINAL | az::INFO_DECISIVE;
+        }
+        if (edge_off) MCAZ_CUDA(cudaMemcpy(edge_off, V.node_edge_off + nb, nn * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    }
+    if (mm) {
+        if (codes) MCAZ_CUDA(cudaMemcpy(codes, V.edge_code + eb, mm * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+        if (visits) MCAZ_CUDA(cudaMemcpy(visits, V.edge_N + eb, mm * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (q) MCAZ_CUDA(cudaMemcpy(q, V.edge_Q + eb, mm * sizeof(double), cudaMemcpyDeviceToHost));
+        if (priors) MCAZ_CUDA(cudaMemcpy(priors, V.edge_P + eb, mm * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return MCAZ_OK;
+}
+
 int az_play(az_engine* e, const int32_t* game_ids, const uint16_t* codes, int n, int8_t* results) {
     if (!e || n < 0 || (n > 0 && !codes)) return fail(MCAZ_EINVAL, "az_play: bad argument");
     if (e->leaf_pending) return fail(MCAZ_ESTATE, "az_play: a simulation is pending (call az_backup first)");
@@ -1076,12 +1146,20 @@ int az_drain_replay(az_engine* e, az_replay_tuple* out, int max, int* n_out) {
     unsigned long long count = 0;
     MCAZ_CUDA(cudaMemcpyAsync(&count, e->d_replay_count, sizeof(count), cudaMemcpyDeviceToHost, e->stream));
     MCAZ_CUDA(cudaStreamSynchronize(e->stream));
-    size_t have = (size_t)std::min<unsigned long long>(count, e->replay_capacity);
-    size_t take = std::min<size_t>(have, (size_t)max);
-    if (take && out)
+    const size_t have = (size_t)std::min<unsigned long long>(count, e->replay_capacity);   // reservations never pass the capacity
+    const size_t take = out ? std::min<size_t>(have, (size_t)max) : 0;
+    if (take)
         MCAZ_CUDA(cudaMemcpyAsync(out, e->d_replay, take * sizeof(az_replay_tuple),
                                   is_device_pointer(out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
-    MCAZ_CUDA(cudaMemsetAsync(e->d_replay_count, 0, sizeof(unsigned long long), e->stream));
+    // what was not taken stays queued, in order: move it to the front in pieces no longer than the gap (no overlap)
+    const size_t rest = out ? have - take : 0;              // out == NULL discards everything
+    for (size_t done = 0; done < rest && take > 0; done += take) {
+        const size_t n = std::min(take, rest - done);
+        MCAZ_CUDA(cudaMemcpyAsync(e->d_replay + done, e->d_replay + take + done, n * sizeof(az_replay_tuple), cudaMemcpyDeviceToDevice,
+                                  e->stream));
+    }
+    const unsigned long long left = (unsigned long long)(take > 0 ? rest : (out ? have : 0));
+    MCAZ_CUDA(cudaMemcpyAsync(e->d_replay_count, &left, sizeof(left), cudaMemcpyHostToDevice, e->stream));
     MCAZ_CUDA(cudaStreamSynchronize(e->stream));
     *n_out = (int)take;
     return MCAZ_OK;

@@ -37,7 +37,7 @@ constexpr int MAX_LEAVES = 16;                // leaves_per_step limit
 // LEAF_CACHED: a new position whose priors and value were found in the exact evaluation cache -- the
 // simulation is complete without a network row, like a terminal one.
 enum LeafKind : uint8_t { LEAF_NONE = 0, LEAF_EVAL = 1, LEAF_TERMINAL = 2, LEAF_COLLISION = 3, LEAF_CACHED = 4 };
-enum Counter : int { C_SIMS = 0, C_EVALS, C_TERMINAL, C_MOVES, C_GAMES, C_NODES, C_EDGES, C_LAUNCHES, C_COLLISIONS, C_CACHED, C_DEPTH, C_PATH_EDGES, C_RECYCLED, C_DUP_ROWS };
+enum Counter : int { C_SIMS = 0, C_EVALS, C_TERMINAL, C_MOVES, C_GAMES, C_NODES, C_EDGES, C_LAUNCHES, C_COLLISIONS, C_CACHED, C_DEPTH, C_PATH_EDGES, C_RECYCLED, C_DUP_ROWS, C_REPLAY_DROPPED };
 enum ErrorBit : int { ERR_NODE_CAP = 1, ERR_EDGE_CAP = 2, ERR_HASH_CAP = 4, ERR_DEPTH = 8, ERR_ILLEGAL = 16 };
 
 struct alignas(16) Board4 { uint32_t x, y, z, w; };
@@ -103,11 +103,12 @@ struct View {
     int spec_rows;                  // look-ahead rows admitted per batch (0 = off)
     mc_state* row_state;            // [row_cap] position of a look-ahead row (row_slot = -1); the policy head generates its moves
     uint32_t* seen; uint32_t seen_mask;   // tag per cache slot: this position was queued or evaluated (skip it as a child)
-    uint32_t* pending_count;        // [2] games that ended this launch waiting for a network row (per parity)
+    uint32_t* pending_count;        // [2] games that ended this launch waiting for a network row or with budget left (per parity)
     // caller-supplied root noise of a chained search (az_search_noise): block [noise_budget][G][MC_MAX_MOVES]
     const double* noise_block; int noise_budget;
     // replay recording of the device move choice
     az_replay_tuple* record; az_replay_tuple* replay; unsigned long long* replay_count; unsigned long long replay_cap;
+    uint32_t weights_version;       // stamp of the weights in use (az_set_weights_version), written into finished games' tuples
 };
 
 #if defined(__CUDA_ARCH__)

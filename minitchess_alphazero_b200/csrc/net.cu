@@ -924,6 +924,7 @@ struct Network {
     uint32_t* tower_flags = nullptr;   // [19][n_pairs][30][2]
     int tower_pairs = -1, tower_grid = 0;
     uint32_t epoch = 0;
+    bool cooperative = true;           // fused form: launched with cudaLaunchAttributeCooperative (all CTA pairs resident or none)
     bool per_layer = false;            // false: tower_tc_kernel (one data-flow ordered launch for the 18 layers, default);
                                        // true: the same kernel launched once per layer (MCAZ_TOWER=layers, or no co-residency)
     // profiling (az_profile_network)
@@ -1081,6 +1082,9 @@ static int build_schedule(az_engine* e, int n_pairs) {
 // earlier at the same place of that order -- are normally long finished when it starts.
 // MCAZ_DEBUG_TOWER (timing experiments, results are then wrong): bit 0 = the last level stores its activations like
 // any other instead of taking the head convolutions, bit 1 = no stem level in the schedule.
+// Only in builds made with -DMCAZ_TIMING_EXPERIMENTS (never the shipped library): there the environment also sets the L2
+// group size and the epilogue's wait hint.
+#ifdef MCAZ_TIMING_EXPERIMENTS
 static int tower_debug() {
     static int v = -1;
     if (v < 0) {
@@ -1090,6 +1094,11 @@ static int tower_debug() {
     }
     return v;
 }
+static int env_or(const char* name, int dflt) { const char* s = getenv(name); return (s && atoi(s) > 0) ? atoi(s) : dflt; }
+#else
+static constexpr int tower_debug() { return 0; }
+static constexpr int env_or(const char*, int dflt) { return dflt; }
+#endif
 
 static int build_tower_schedule(az_engine* e, int n_pairs) {
     Network* N = e->net;
@@ -1109,8 +1118,7 @@ static int build_tower_schedule(az_engine* e, int n_pairs) {
     // resident in the 126 MB L2 from layer to layer: at most 12 pairs per group (3072 boards, 2 x 47 MB), split
     // evenly (16 pairs -> 8 + 8).  Small groups leave too few items per layer to hide the waits on the previous
     // layer (measured on 2 800-row batches: groups of <= 4 pairs 1.40 ms, <= 6: 1.27, <= 8: 1.17, <= 12: 1.165, 16: 1.19).
-    int group_max = 12;
-    { const char* gs = getenv("MCAZ_TOWER_GROUP"); if (gs && atoi(gs) > 0) group_max = atoi(gs); }
+    const int group_max = env_or("MCAZ_TOWER_GROUP", 12);
     const size_t per_table = (size_t)clusters * TOWER_MAX_ITEMS;
     std::vector<uint32_t> table(per_table * n_pairs, SCHED_END);
     for (int live = 1; live <= n_pairs; ++live) {
@@ -1203,11 +1211,7 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
         }
         T.stats = N->stats;
     }
-    {
-        static int hint = -1;
-        if (hint < 0) { const char* hs = getenv("MCAZ_WAIT_HINT"); hint = hs ? atoi(hs) : 2000; }     // A/B on one box: 267.2 -> 266.1 ms per 200 batches; 20000 ns: 266.8
-        T.wait_hint = (uint32_t)hint;
-    }
+    T.wait_hint = (uint32_t)env_or("MCAZ_WAIT_HINT", 2000);     // A/B on one box: 267.2 -> 266.1 ms per 200 batches; 20000 ns: 266.8
     if (N->per_layer) {
         if (int rc = build_schedule(e, n_pairs)) return rc;
         T.flags = nullptr; T.epoch = 0; T.sched_stride = 0;
@@ -1223,8 +1227,25 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
         if (int rc = build_tower_schedule(e, n_pairs)) return rc;
         T.sched = N->tower_sched; T.flags = N->tower_flags; T.epoch = ++N->epoch;
         T.sched_stride = (size_t)(N->tower_grid / 2) * TOWER_MAX_ITEMS;
-        tower_tc_kernel<<<N->tower_grid, CONV_THREADS, TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in,
-                                                                         N->map_stem_w, T);
+        // The CTA pairs of this launch wait on one another's flags, so they must all be resident at once.  A cooperative
+        // launch makes the hardware guarantee that whatever else runs on the GPU (another engine's stream, the caller's
+        // torch kernels): the grid starts only when all of it fits.  (network_create checked that it can fit at all.)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(N->tower_grid); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = TOWER_SMEM; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+        cfg.attrs = attr; cfg.numAttrs = N->cooperative ? 1 : 0;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, tower_tc_kernel, N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in, N->map_stem_w, T);
+        if (le != cudaSuccess && N->cooperative) {
+            // this driver does not take the cooperative attribute together with a cluster launch: engines that share the GPU
+            // with other streams must then not overlap their towers (own_stream engines fall back to one launch per level)
+            cudaGetLastError();
+            N->cooperative = false;
+            if (e->cfg.own_stream) { N->per_layer = true; return forward_chunk(e, tokens, clocks, n, logits, values, search_view, row_base, sched_rows); }
+            cfg.numAttrs = 0;
+            le = cudaLaunchKernelEx(&cfg, tower_tc_kernel, N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in, N->map_stem_w, T);
+        }
+        if (le != cudaSuccess) return fail(MCAZ_ECUDA, std::string("tower launch: ") + cudaGetErrorString(le));
         MCAZ_CHECK_LAUNCH();
     }
     if (ev1) cudaEventRecord(ev1, st);

@@ -15,13 +15,15 @@ from ._lib import (AZ_NUM_COUNTERS, AZ_NUM_WEIGHT_FLOATS, MC_MAX_MOVES, MC_NUM_A
                    check, ptr)
 
 COUNTER_NAMES = ('simulations', 'evaluations', 'terminal_leaves', 'moves', 'games_finished', 'nodes', 'edges',
-                 'kernel_launches', 'collisions', 'cached_evaluations', 'path_depth', 'path_edges', 'recycled_nodes', 'duplicate_rows')
+                 'kernel_launches', 'collisions', 'cached_evaluations', 'path_depth', 'path_edges', 'recycled_nodes', 'duplicate_rows',
+                 'replay_dropped')
 
 REPLAY_DTYPE = np.dtype([('observation', STATE_DTYPE), ('n_legal', '<u2'), ('action', '<u2'), ('reward', 'i1'),
-                         ('pad', 'u1', 3), ('codes', '<u2', MC_MAX_MOVES), ('pi', '<f4', MC_MAX_MOVES)])
+                         ('pad', 'u1', 3), ('weights_version', '<u4'), ('codes', '<u2', MC_MAX_MOVES), ('pi', '<f4', MC_MAX_MOVES)])
+NODE_TERMINAL, NODE_DECISIVE = 1 << 16, 1 << 17      # MC_NODE_* bits of az_tree_dump's info words
 
 
-assert REPLAY_DTYPE.itemsize == 604          # az_replay_tuple; checked against the library in Engine.__init__
+assert REPLAY_DTYPE.itemsize == 608          # az_replay_tuple; checked against the library in Engine.__init__
 
 
 class _CudaView:
@@ -232,20 +234,44 @@ class Engine:
         return {'legal_moves': codes[:E].astype(int).tolist(), 'N': visits[:E].astype(np.float64), 'Q': q[:E].copy(),
                 'P': pri[:E].copy(), 'terminal': tval.value if term.value else None}
 
+    def tree_dump(self, game_id=0, tree=0):
+        """Every node of one tree (az_tree_dump) -- the whole dicts of MonteCarloTreeSearch (exp/agent.py:25-36) in creation
+        order: {'states' STATE_DTYPE[n], 'info' uint32[n] (edges | NODE_TERMINAL | NODE_DECISIVE), 'edge_off' uint32[n],
+        'codes' uint16[m], 'N' uint32[m], 'Q' float64[m], 'P' float32[m]}."""
+        n, m = ctypes.c_int(), ctypes.c_int()
+        self._check(self._L.az_tree_dump(self._h, int(game_id), int(tree), 0, None, None, None, ctypes.byref(n), 0, None, None, None,
+                                         None, ctypes.byref(m)))
+        nn, mm = n.value, m.value
+        states = np.zeros(nn, dtype=STATE_DTYPE)
+        info, off = np.zeros(nn, dtype=np.uint32), np.zeros(nn, dtype=np.uint32)
+        codes, visits = np.zeros(mm, dtype=np.uint16), np.zeros(mm, dtype=np.uint32)
+        q, pri = np.zeros(mm, dtype=np.float64), np.zeros(mm, dtype=np.float32)
+        self._check(self._L.az_tree_dump(self._h, int(game_id), int(tree), nn, ptr(states), ptr(info), ptr(off), ctypes.byref(n), mm,
+                                         ptr(codes), ptr(visits), ptr(q), ptr(pri), ctypes.byref(m)))
+        assert (n.value, m.value) == (nn, mm)
+        return {'states': states, 'info': info, 'edge_off': off, 'codes': codes, 'N': visits, 'Q': q, 'P': pri}
+
     def counters(self):
         out = np.zeros(AZ_NUM_COUNTERS, dtype=np.uint64)
         self._check(self._L.az_counters(self._h, ptr(out)))
         return dict(zip(COUNTER_NAMES, (int(x) for x in out)))
 
     # ------------------------------------------------------------------ network
-    def set_weights(self, flat):
-        """flat: float32 [AZ_NUM_WEIGHT_FLOATS] numpy array or CUDA tensor (policy.flatten_state_dict)."""
+    def set_weights(self, flat, version=None):
+        """flat: float32 [AZ_NUM_WEIGHT_FLOATS] numpy array or CUDA tensor (policy.flatten_state_dict).  `version`: the
+        learner's stamp of these weights (LearnPuppet.weights_version, app/base.py:171-174) as an unsigned 32-bit number;
+        default: the engine counts its uploads.  Finished games' replay tuples carry it (`weights_version`)."""
         n = flat.numel() if hasattr(flat, 'numel') else flat.size
         assert n == AZ_NUM_WEIGHT_FLOATS, n
         if hasattr(flat, 'is_cuda') and flat.is_cuda:      # produced on torch's stream, consumed on the engine's
             import torch
             torch.cuda.current_stream().synchronize()
         self._check(self._L.az_set_weights(self._h, ptr(flat), ctypes.c_size_t(n)))
+        if version is not None:
+            self.set_weights_version(version)
+
+    def set_weights_version(self, version):
+        self._check(self._L.az_set_weights_version(self._h, ctypes.c_uint32(int(version) & 0xffffffff)))
 
     def network_forward(self, tokens, clocks):
         tokens = np.ascontiguousarray(tokens, dtype=np.uint8).reshape(-1, MC_TOKENS)

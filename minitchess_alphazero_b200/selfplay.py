@@ -9,7 +9,7 @@ import torch
 from . import rules
 from ._lib import MC_MAX_MOVES
 from .engine import Engine
-from .policy import TorchEvaluator, flatten_state_dict
+from .policy import flatten_state_dict
 
 
 def replay_to_episode_dicts(tuples):
@@ -47,51 +47,35 @@ def collate_device(tuples, device='cuda'):
 
 class BatchedSelfPlay:
     """`n_games` concurrent games x `num_simulations` per move in throughput mode: Philox Dirichlet
-    noise, move sampling, replay recording and game restarts all on the device.
-
-    evaluator='builtin' uses the hand-written sm_100a network inside libmcaz.so (`az_search`);
-    evaluator='torch' evaluates the leaf batch with cuDNN/cuBLAS through PyTorch (library baseline).
-    """
+    noise, move sampling, replay recording and game restarts all on the device, leaves evaluated by the
+    hand-written sm_100a network inside libmcaz.so (`az_search` / `az_selfplay`)."""
 
     def __init__(self, network, n_games, num_simulations, cpuct=1.0, tau_change=6, epsilon=0.25, alpha=0.6, seed=0,
-                 evaluator='builtin', dtype=torch.bfloat16, **engine_options):
+                 **engine_options):
         self.n_games, self.num_simulations = int(n_games), int(num_simulations)
-        self.mode = evaluator
         # with leaves_per_step = K every search step runs K descents per tree: size the arenas for all of them
         leaves = int(engine_options.get('leaves_per_step', 1) or 1)
         engine_options.setdefault('recycle', 1)       # games only move forward here: plies behind them can be dropped
-        if evaluator == 'builtin' and leaves == 1:
+        if leaves == 1:
             # exact evaluation cache sized for a few moves' worth of evaluations (192 B per entry; 4096 x 200 -> 2^23 = 1.6 GB)
             want = max(1, self.n_games * self.num_simulations * 8)
             engine_options.setdefault('eval_cache_log2', min(24, max(12, (want - 1).bit_length())))
         self.engine = Engine(n_games, max_sims_per_move=num_simulations * leaves, cpuct=float(cpuct), tau_change=int(tau_change),
                              dirichlet_epsilon=float(epsilon), dirichlet_alpha=float(alpha), seed=int(seed),
-                             device_rng=1, network=1 if evaluator == 'builtin' else 0, **engine_options)
+                             device_rng=1, network=1, **engine_options)
         self.network = network
-        if evaluator == 'builtin':
-            self.sync_weights()
-        else:
-            self.evaluator = TorchEvaluator(network, dtype=dtype)
-            self._tokens, self._clocks, self._needs = self.engine.leaf_batch_device()
-            self.evaluator.capture(self._tokens, self._clocks)
+        self.weights_version = 0
+        self.sync_weights()
 
-    def sync_weights(self, flat=None):
-        """Push the torch Network's weights to the engine (SimulatePuppet.load_weights, app/base.py:126-129)."""
-        if self.mode == 'builtin':
-            self.engine.set_weights(flatten_state_dict(self.network.state_dict(), device='cuda') if flat is None else flat)
-        else:
-            self.evaluator.load(self.network)
-            self.evaluator.capture(self._tokens, self._clocks)
+    def sync_weights(self, flat=None, version=None):
+        """Push the torch Network's weights to the engine (SimulatePuppet.load_weights, app/base.py:126-129); `version` is
+        the learner's stamp that finished games' replay tuples will carry (app/base.py:63-68; default: previous + 1)."""
+        self.weights_version = int(version) if version is not None else self.weights_version + 1
+        self.engine.set_weights(flatten_state_dict(self.network.state_dict(), device='cuda') if flat is None else flat,
+                                version=self.weights_version)
 
     def search(self):
-        if self.mode == 'builtin':
-            self.engine.search(self.num_simulations)
-        else:
-            eng, ev = self.engine, self.evaluator
-            for _ in range(self.num_simulations):
-                eng.select_expand()
-                logits, values = ev.replay()
-                eng.backup(values, logits=logits)
+        self.engine.search(self.num_simulations)
 
     def step(self):
         """One move in every game: search, choose, record, play, restart finished games."""
@@ -108,8 +92,6 @@ class BatchedSelfPlay:
         instead of n_games copies of the start position marching through the opening together.  `sims` must be
         large enough for the visit counts to spread over the root's moves (with 2 simulations every game would play
         edge 0, exp/agent.py:84-85 on an all-zero u), or all games of one ply would share one position."""
-        import numpy as np
-        assert self.mode == 'builtin'
         target = (np.arange(self.n_games, dtype=np.int64) * max_ply) // self.n_games
         for step in range(max_ply):
             ids = np.nonzero(target == max_ply - step)[0].astype(np.int32)
@@ -126,7 +108,6 @@ class BatchedSelfPlay:
         """Continuous self-play (az_selfplay): `n_batches` network batches; every game searches, chooses, records,
         plays and restarts on its own inside the search kernel, so a game whose move needed fewer network rows
         (terminal or cached leaves) simply moves earlier and the batch stays full."""
-        assert self.mode == 'builtin', 'continuous self-play runs on the built-in network'
         self.engine.selfplay(int(n_batches), self.num_simulations)
 
     def drain(self):
@@ -137,8 +118,6 @@ class BatchedSelfPlay:
 
     def reset_kernel_timer(self):
         """Start bracketing the tower-convolution launches with CUDA events on the engine's stream."""
-        if self.mode != 'builtin':
-            return None
         self.engine.profile_network(True, read=True)
         self.engine.profile_tree(True, read=True)
         return True
@@ -147,8 +126,6 @@ class BatchedSelfPlay:
         """Roofline record of the dominant kernel (tower_tc_kernel) from the events recorded since
         reset_kernel_timer(): algorithmic FLOP of the rows it evaluated / the time it ran.  `evaluations` = rows
         evaluated in that window (the engine's evaluation counter); default: every launch had a full batch."""
-        if self.mode != 'builtin':
-            return None
         ms, n, per_forward = self.engine.profile_network(False, read=True)
         if n == 0 or ms <= 0:
             return None

@@ -13,6 +13,10 @@ What is recorded, and from what:
                            game with the torch-free hash evaluator, np.random.seed(0), 36 sims
   mcts_net_game.json       same with the real random-init Network (config 1 of BASELINE.json)
   restatement_pin.json     record that oracle/ref_selfplay.py reproduced both games exactly
+  learner_golden.json.gz   reference SimpleAlphaZeroLearner.update (exp/learner.py:72-94) on a fixed 256-tuple dataset,
+                           CPU (`.cuda()` patched to a no-op IN THIS GENERATOR ONLY), torch.manual_seed(0): the batches
+                           the DataLoader drew, every mini-batch loss, per-tensor sums of the trained state_dict --
+                           for lr 0.2 (app/learner.py:69) and lr 1e-3
 
 The rules fixtures pin the *oracle stack* (shim + reference wrapper), not the absent
 python-chess fork: rules parity with the fork stays UNPINNED.
@@ -226,7 +230,84 @@ def gen_mcts(net):
     dump('restatement_pin.json', pins)
 
 
+class LoggingDataset:
+    """What SimpleAlphaZeroDataset is to the DataLoader (exp/dataset.py:6-20), remembering the order of the reads."""
+
+    def __init__(self, items):
+        self.items, self.reads = items, []
+
+    def __len__(self):
+        return len(self.items)
+
+    def __getitem__(self, i):
+        self.reads.append(int(i))
+        return self.items[i]
+
+
+def learner_dataset(fens, n=256, seed=5):
+    """Replay tuples in InfoRecorder's format (exp/callbacks.py:40-53) on golden positions: pi a seeded Dirichlet over the
+    legal moves, rewards from {-1, 0, 1}.  The learner does not care where tuples come from."""
+    rng = np.random.RandomState(seed)
+    items = []
+    for fen in fens:
+        ep = env_mod.MinitChessEpisode(fen)
+        legal = list(ep.get_legal_moves())
+        if ep.is_done() or not legal:
+            continue
+        pi = rng.dirichlet([0.6] * len(legal))
+        items.append({'observation': fen, 'legal_moves': legal, 'pi': pi.tolist(), 'action': int(rng.choice(legal)),
+                      'reward': float(rng.choice([-1.0, 0.0, 1.0]))})
+        if len(items) == n:
+            break
+    assert len(items) == n
+    return items
+
+
+def gen_learner(fens):
+    import importlib
+    cwd = os.getcwd()
+    os.chdir('/tmp')                               # exp/learner.py:3-6 opens a log file in the cwd
+    try:
+        learner_mod = importlib.import_module('exp.learner')
+    finally:
+        os.chdir(cwd)
+    items = learner_dataset(fens)
+    runs = {}
+    orig_module_cuda, orig_tensor_cuda = torch.nn.Module.cuda, torch.Tensor.cuda
+    torch.nn.Module.cuda = lambda self, *a, **k: self          # exp/learner.py:79,86 -- no GPU in the build container
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        for lr in (0.2, 1e-3):
+            torch.manual_seed(0)
+            net = policy_mod.Network()
+            data = LoggingDataset(items)
+            learner = learner_mod.SimpleAlphaZeroLearner(env_mod.MinitChessEnvironment(), 36, net, batch_size=32, epochs=1,
+                                                         optim_params={'lr': lr})
+            losses = []
+            orig_acc = learner_mod.AvgSmoothLoss.accumulate
+
+            def acc(self, v, _l=losses, _o=orig_acc):
+                _l.append(float(v))
+                return _o(self, v)
+            learner_mod.AvgSmoothLoss.accumulate = acc
+            try:
+                learner.update(data)
+            finally:
+                learner_mod.AvgSmoothLoss.accumulate = orig_acc
+            sd = net.state_dict()
+            runs[repr(lr)] = {'lr': lr, 'batches': [data.reads[i:i + 32] for i in range(0, len(data.reads), 32)], 'losses': losses,
+                              'sums': {k: [float(v.double().sum()), float(v.double().abs().sum())] for k, v in sd.items()
+                                       if not k.endswith('num_batches_tracked')}}
+    finally:
+        torch.nn.Module.cuda, torch.Tensor.cuda = orig_module_cuda, orig_tensor_cuda
+    dump('learner_golden.json.gz', {'items': items, 'seed': 0, 'batch_size': 32, 'runs': runs}, gz=True)
+
+
 def main():
+    if '--only-learner' in sys.argv:
+        recs = json.load(gzip.open(os.path.join(HERE, 'rules_positions.json.gz'), 'rt'))
+        gen_learner([r['fen'] for r in recs])
+        return
     with open(os.path.join(REFERENCE_ROOT, 'exp', 'moves_dict.json'), 'rb') as f:
         blob = f.read()
     dump('moves_dict.json.sha256', {'sha256': hashlib.sha256(blob).hexdigest(), 'bytes': len(blob)})
@@ -235,6 +316,7 @@ def main():
     gen_tokens(fens)
     net = gen_network(fens)
     gen_mcts(net)
+    gen_learner(fens)
 
 
 if __name__ == '__main__':

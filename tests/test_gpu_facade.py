@@ -54,7 +54,7 @@ def test_golden_game_through_environment_facade(mcaz_lib):
 
 def test_network_parity_torch_evaluator(net):
     """T2: fp32 within 1e-5 relative of the reference Network's output; bf16 tower within 1e-2."""
-    from minitchess_alphazero_b200.policy import TorchEvaluator
+    from torch_evaluator import TorchEvaluator
     g = load_golden('network_seed0.npz')
     tok = torch.from_numpy(g['tokens'].reshape(-1, 60)).cuda()
     clk = torch.from_numpy(g['clocks'].reshape(-1)).cuda()
@@ -75,7 +75,8 @@ def test_agent_facade_first_moves_match_reference_game(net, evaluator):
     compared as distributions (they are checked bit-exactly with shared priors in test_gpu_mcts)."""
     from minitchess_alphazero_b200.agent import SimpleAlphaZeroAgent, RoundRobinReferee, MonteCarloTreeSearch
     from minitchess_alphazero_b200.environment import MinitChessEnvironment
-    from minitchess_alphazero_b200.policy import SimpleAlphaZeroPolicy, TorchEvaluator
+    from minitchess_alphazero_b200.policy import SimpleAlphaZeroPolicy
+    from torch_evaluator import TorchEvaluator
     g = load_golden('mcts_net_game.json')
     env = MinitChessEnvironment()
     policy = SimpleAlphaZeroPolicy(net)
@@ -130,13 +131,13 @@ def test_weights_reload_is_seen(net):
     assert not np.allclose(p0, p1)
 
 
-def test_batched_selfplay_torch_evaluator(net):
+def test_batched_selfplay_replay_format(net):
     from minitchess_alphazero_b200.selfplay import BatchedSelfPlay, replay_to_episode_dicts
-    sp = BatchedSelfPlay(net, n_games=96, num_simulations=6, evaluator='torch', seed=1)
+    sp = BatchedSelfPlay(net, n_games=96, num_simulations=6, seed=1)
     sp.run(70)                                                   # > 60 plies: every game finishes at least once
     c = sp.engine.counters()
     assert c['simulations'] > 0 and c['evaluations'] > 0 and c['games_finished'] >= 96
-    assert c['simulations'] == c['evaluations'] + c['terminal_leaves']
+    assert c['simulations'] == c['evaluations'] + c['terminal_leaves'] + c['cached_evaluations']
     tuples = sp.drain()
     assert len(tuples) >= 96
     eps = replay_to_episode_dicts(tuples[:400])

@@ -78,6 +78,6 @@ def test_arena_bookkeeping(mcaz_lib):
     # both networks were really used: their evaluations of the start position differ
     from oracle import rules_c as rc
     tok, clk = rc.tokenize(rc.start_state())
-    l0, _ = arena._nets[0].network_forward(tok, clk)
-    l1, _ = arena._nets[1].network_forward(tok, clk)
+    l0, _ = arena._sides[0].engine.network_forward(tok, clk)
+    l1, _ = arena._sides[1].engine.network_forward(tok, clk)
     assert not np.allclose(l0, l1)

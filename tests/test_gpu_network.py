@@ -102,7 +102,8 @@ def test_search_with_builtin_network_matches_torch_evaluator(mcaz_lib):
     """az_search (built-in net) and the external-evaluator path build the same kind of tree: root visit
     distributions agree closely on a no-noise search from the start position."""
     from minitchess_alphazero_b200.engine import Engine
-    from minitchess_alphazero_b200.policy import Network, flatten_state_dict, TorchEvaluator
+    from minitchess_alphazero_b200.policy import Network, flatten_state_dict
+    from torch_evaluator import TorchEvaluator
     torch.manual_seed(0)
     net = Network().eval()
     sims = 64
