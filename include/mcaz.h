@@ -319,6 +319,12 @@ int az_profile_network(az_engine* e, int on, double* avg_ms_per_tower, int* n_fo
  * the previous read.                                                                                            */
 int az_profile_tree(az_engine* e, int on, double* total_ms, int* n_launches);
 
+/* Measurement hook for the statistical tests: n samples of the root noise that throughput mode (device_rng = 1) mixes into
+ * a root with n_edges edges -- Philox4x32-10 -> single-precision Marsaglia-Tsang gamma(alpha) -> normalise, the very
+ * device function the search calls -- in place of np.random.dirichlet([alpha] * n_edges) (exp/agent.py:82).
+ * out[n x n_edges] float64, host or device.                                                                      */
+int az_sample_root_noise(uint64_t seed, float alpha, int n_edges, int n, double* out);
+
 /* Kernels launched by this library in this process (all engines and mc_* calls).               */
 uint64_t mcaz_kernel_launches(void);
 

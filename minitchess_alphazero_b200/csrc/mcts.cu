@@ -534,6 +534,17 @@ __global__ void __launch_bounds__(RECYCLE_THREADS) recycle_kernel(View V, int ne
     }
 }
 
+// n samples of the root noise a root with E edges gets (measurement hook: the sampler itself, outside any search)
+__global__ void __launch_bounds__(128) sample_root_noise_kernel(unsigned long long seed, float alpha, int E, int n, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += warps) {
+        double gam[3] = {0.0, 0.0, 0.0};
+        const double gsum = az::root_noise_gammas(seed, k & 0xffff, (unsigned long long)(k >> 16), E, lane, alpha, gam);
+        for (int i = lane, kk = 0; i < E && kk < 3; i += 32, ++kk) out[(size_t)k * E + i] = gam[kk] / gsum;
+    }
+}
+
 int warp_grid(int n_warps, int block) {
     int per = block / 32;
     int want = (n_warps + per - 1) / per;
@@ -975,6 +986,22 @@ int az_selfplay(az_engine* e, int n_steps, int sims_per_move) {
     const int seg = e->cfg.recycle ? std::max(1, sims_per_move / fm) : std::max(1, n_steps);
     for (int done = 0; done < n_steps; done += seg)
         if (int rc = run_search(e, std::min(seg, n_steps - done), -1, true, sims_per_move)) return rc;
+    return MCAZ_OK;
+}
+
+int az_sample_root_noise(uint64_t seed, float alpha, int n_edges, int n, double* out) {
+    if (n < 0 || n_edges < 1 || n_edges > MC_MAX_MOVES || !(alpha > 0.f) || (n > 0 && !out)) return fail(MCAZ_EINVAL, "az_sample_root_noise: bad argument");
+    if (int rc = require_device()) return rc;
+    if (n == 0) return MCAZ_OK;
+    cudaStream_t st = 0;
+    Scratch& sc = thread_scratch();
+    sc.begin();
+    Out<double> o;
+    if (int rc = o.init(out, (size_t)n * n_edges, st, sc)) return rc;
+    sample_root_noise_kernel<<<warp_grid(n, 128), 128, 0, st>>>((unsigned long long)seed, alpha, n_edges, n, o.ptr);
+    MCAZ_CHECK_LAUNCH();
+    if (int rc = o.finish(st)) return rc;
+    MCAZ_CUDA(cudaStreamSynchronize(st));
     return MCAZ_OK;
 }
 

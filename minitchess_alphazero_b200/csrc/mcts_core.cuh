@@ -642,6 +642,24 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, 
 #define AZ_EXPAND expand
 #endif
 
+#if defined(__CUDACC__)
+// Throughput mode's root noise (exp/agent.py:81-82 without numpy's stream): Dirichlet(alpha) over the root's E edges = gamma(alpha)
+// draws over their sum.  Warp-cooperative: this lane draws the gammas of edges lane, lane + 32, lane + 64 (Philox keyed by
+// seed, game slot, the slot's simulation serial and the edge, so a sample does not depend on how descents are batched into
+// launches); returns the sum over all edges.  az_sample_root_noise draws from this very function for the statistical tests.
+__device__ __forceinline__ double root_noise_gammas(unsigned long long seed, int g, unsigned long long counter, int E, int lane,
+                                                    float alpha, double gam[3]) {
+    double part = 0.0;
+    for (int i = lane, kk = 0; i < E && kk < 3; i += 32, ++kk) {
+        mcaz::Philox rng(seed, (uint32_t)g, (uint32_t)counter, (uint32_t)(counter >> 32) ^ ((uint32_t)i << 16));
+        gam[kk] = rng.gamma((double)alpha);
+        part += gam[kk];
+    }
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    return part;
+}
+#endif
+
 // One simulation of game g down to its leaf (exp/agent.py:54-88 without the backup).
 // `noise`: per-game Dirichlet sample [MC_MAX_MOVES] or nullptr.
 // Returns the leaf kind (the same on every lane).
@@ -709,14 +727,7 @@ MC_HD uint8_t select_expand_one(const View& V, int g, int lane, const double* no
         double gam[3] = {0.0, 0.0, 0.0}, gsum = 1.0;
         const bool dev_noise = (depth == 0) && (noise == nullptr) && V.device_rng && (V.eps > 0.0f);
         if (dev_noise) {
-            double part = 0.0;
-            for (int i = lane, kk = 0; i < E && kk < 3; i += AZ_LANES, ++kk) {
-                mcaz::Philox rng(V.seed, (uint32_t)g, (uint32_t)rng_counter, (uint32_t)(rng_counter >> 32) ^ ((uint32_t)i << 16));
-                gam[kk] = rng.gamma((double)V.alpha);
-                part += gam[kk];
-            }
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-            gsum = part;
+            gsum = root_noise_gammas(V.seed, g, rng_counter, E, lane, V.alpha, gam);
             mix = true;
         }
 #endif

@@ -290,6 +290,13 @@ class Engine:
         return out[:n.value]
 
 
+def sample_root_noise(seed, alpha, n_edges, n):
+    """n Dirichlet(alpha) samples over n_edges edges from the device sampler of throughput mode (az_sample_root_noise)."""
+    out = np.zeros((int(n), int(n_edges)), dtype=np.float64)
+    check(_lib.lib().az_sample_root_noise(ctypes.c_uint64(int(seed)), ctypes.c_float(float(alpha)), int(n_edges), int(n), ptr(out)))
+    return out
+
+
 def _profile_network(self, on=True, read=False):
     """bench hook: (avg ms per residual tower, forwards measured, kernel launches per tower) since the last call."""
     ms, n, lpf = ctypes.c_double(), ctypes.c_int(), ctypes.c_int()

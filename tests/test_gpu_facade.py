@@ -71,8 +71,9 @@ def test_network_parity_torch_evaluator(net):
 @pytest.mark.parametrize('evaluator', ['builtin', 'torch_fp32'])
 def test_agent_facade_first_moves_match_reference_game(net, evaluator):
     """T3: the reference's config-1 game (random-init net, seed 0, 36 sims) through the drop-in
-    agent classes.  fp32 GPU evaluation differs from the CPU in the last bits, so visit counts are
-    compared as distributions (they are checked bit-exactly with shared priors in test_gpu_mcts)."""
+    agent classes.  fp32 GPU evaluation differs from the CPU in the last bits (and the bf16 tower within 1e-2), so
+    visit counts are compared as distributions -- at most 3 of the 36 visits may sit elsewhere, and at least one ply must
+    be identical (they are checked bit-exactly with shared evaluator bits in test_gpu_mcts / test_gpu_production_pin)."""
     from minitchess_alphazero_b200.agent import SimpleAlphaZeroAgent, RoundRobinReferee, MonteCarloTreeSearch
     from minitchess_alphazero_b200.environment import MinitChessEnvironment
     from minitchess_alphazero_b200.policy import SimpleAlphaZeroPolicy
@@ -95,12 +96,12 @@ def test_agent_facade_first_moves_match_reference_game(net, evaluator):
         assert action.info['legal_moves'] == ply['legal_moves']
         pi = action.info['pi']
         assert isinstance(pi, np.ndarray) and pi.dtype == np.float64 and abs(pi.sum() - 1) < 1e-12
-        assert np.abs(pi - np.array(ply['pi'])).max() <= (3.0 if evaluator == 'torch_fp32' else 6.0) / g['sims']
+        assert np.abs(pi - np.array(ply['pi'])).max() <= 3.0 / g['sims'], (evaluator, pi.tolist(), ply['pi'])
         same += int(np.array_equal(pi, np.array(ply['pi'])))
         if int(action.action) != ply['action']:
             break                                   # the lines diverged; later plies are not comparable
         obs, _, _ = ep.step(int(action.action))
-    assert same >= 1 or evaluator == 'builtin'
+    assert same >= 1, evaluator                     # at least one ply with the very visit counts of the reference's game
     # dict-style access like the reference's MonteCarloTreeSearch.__getitem__
     tree = agents[0]._mcts
     assert isinstance(tree, MonteCarloTreeSearch)

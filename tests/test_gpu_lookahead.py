@@ -149,3 +149,35 @@ def test_dropped_agents_free_their_tree_slots(net):
         seen.add(id(agents[0]._mcts.engine))
         del agents, a
     assert len(seen) == 1
+
+
+@pytest.mark.parametrize('cache', [0, 14])
+@pytest.mark.parametrize('fen', ['2nQ1/1Q1p1/pk3/1qBqK/1q3/1qQ2 w 6 4',        # every legal move mates: all leaves below the root are finished
+                                 '1Q3/pR3/k1PbR/R4/K2q1/1Br2 w 12 23',
+                                 'k4/5/1QK2/5/5/5 w 2 20'])                   # mates and stalemates one ply down
+def test_caller_noise_search_spends_its_whole_budget_on_finished_leaves(net, fen, cache):
+    """One game, no look-ahead rows: once a mate is in the tree PUCT keeps coming back to it, so whole launches end with
+    nobody waiting for a network row while simulations are still unspent.  The call must run all of them (it used to stop
+    at the first such launch) and build the tree of the loop spelt out call by call (exp/agent.py:41-45)."""
+    from minitchess_alphazero_b200._lib import MC_MAX_MOVES
+    from minitchess_alphazero_b200 import rules
+    sims = 36
+    start = np.array([rules.state_from_fen(fen)])
+    one = make(net, 1, sims, eval_cache_log2=cache, lookahead_rows=0)
+    manual = make(net, 1, sims)
+    rng = np.random.RandomState(5)
+    for e in (one, manual):
+        e.reset_games(states=start)
+    for call in range(3):                                   # the later calls start with the mates already in the tree
+        noise = np.zeros((sims, 1, MC_MAX_MOVES))
+        noise[:, :, :40] = rng.dirichlet([0.6] * 40, size=(sims, 1))
+        before = one.counters()['simulations']
+        one.search_noise(noise)
+        assert one.counters()['simulations'] - before == sims
+        for k in range(sims):
+            manual.select_expand(noise[k])
+            manual.eval_backup()
+        assert same(snapshot(one), snapshot(manual)), call
+    c = one.counters()
+    assert c['terminal_leaves'] > c['evaluations']          # most simulations ended on finished positions
+    assert c['simulations'] == c['evaluations'] + c['terminal_leaves'] + c['cached_evaluations'] == 3 * sims
