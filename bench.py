@@ -68,6 +68,19 @@ def peaks():
     return {'hbm_gbs': 6650.0, 'tflops': 1400.0, 'which': 'fallback'}
 
 
+def tower_traffic(rows):
+    """DRAM bytes of one tower launch from the committed ncu captures: the entry whose batch size is nearest to `rows`."""
+    path = os.path.join(REPO, 'profiles', 'tower_traffic.json')
+    if not os.path.exists(path):
+        return None, None
+    table = json.load(open(path)).get('fused', [])
+    if not table:
+        return None, None
+    best = min(table, key=lambda e: abs(e['rows'] - rows))
+    return best['read_bytes'] + best['write_bytes'], 'ncu dram__bytes_read.sum + dram__bytes_write.sum of a %d-row launch (%s); this run averaged %.0f rows per launch' % (
+        best['rows'], best['source'], rows)
+
+
 # --------------------------------------------------------------------------- clocks sampling
 class ClockSampler:
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
@@ -255,10 +268,11 @@ def run_ours(args):
     moves = c1['moves'] - c0['moves']
     cached = c1['cached_evaluations'] - c0['cached_evaluations']
     terminal = c1['terminal_leaves'] - c0['terminal_leaves']
-    tot = torch.tensor([sims, evals, moves, cached, terminal], dtype=torch.float64, device='cuda')
+    dup = c1['duplicate_rows'] - c0['duplicate_rows']
+    tot = torch.tensor([sims, evals, moves, cached, terminal, dup], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(tot)
-    sims_all, evals_all, moves_all, cached_all, terminal_all = (float(x) for x in tot.tolist())
+    sims_all, evals_all, moves_all, cached_all, terminal_all, dup_all = (float(x) for x in tot.tolist())
     value = sims_all / (ms / 1000.0)
 
     # roofline of the dominant kernel: the network tower (tensor-bound), from the rows it actually evaluated
@@ -272,6 +286,7 @@ def run_ours(args):
         roof = None
     else:
         roof = prof
+        roof['traffic'], roof['traffic_source'] = tower_traffic(roof['rows_per_launch'])
         roof.update({'peak': pk['tflops'], 'frac': roof['achieved'] / pk['tflops'], 'mma_frac': roof['achieved_mma'] / pk['tflops'],
                      'peak_source': pk['which']})
 
@@ -343,6 +358,14 @@ def run_ours(args):
                 'steps': n_cont, 'mode': 'continuous (az_selfplay), free_sims 4, eval_cache as the headline; a step = %d network batches' % S}
         sp3.engine.close()
 
+    # N > 1: the two multi-GPU configurations of BASELINE.json beside the headline -- configs[3] at its full size sharded over
+    # the ranks, and one iteration of the full loop of configs[4]
+    config4 = loop_leg = None
+    if world > 1 and not args.no_legs:
+        eng.close()
+        config4 = leg_config4(net, rank, world, args, barrier)
+        loop_leg = leg_loop(net, rank, world, args, barrier)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = torch.get_num_threads()
@@ -372,13 +395,99 @@ def run_ours(args):
                            int(c1['edges'] * 22 / 1e6), int(G * 30 * 256 * 2 * 2 / 1e6))},
             'positions_per_second': moves_all / (ms / 1000.0), 'evals_per_second': evals_all / (ms / 1000.0),
             'sims_breakdown': {'network_rows': evals_all / max(sims_all, 1), 'cache_hits': cached_all / max(sims_all, 1),
-                               'terminal': terminal_all / max(sims_all, 1)},
+                               'terminal': terminal_all / max(sims_all, 1),
+                               'rows_evaluated_twice_in_one_batch': dup_all / max(sims_all, 1)},
             'roofline': roof, 'tree_roofline': tree, 'without_cache_lockstep': plain, 'continuous_selfplay': cont,
+            'config4': config4, 'loop': loop_leg,
             'cpu_baseline': cpu, 'dropin_config1': dropin, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
         }
         emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def leg_config4(net, rank, world, args, barrier, total_games=32768, sims=800, steps=2):
+    """BASELINE.json configs[3]: 32768 concurrent games x 800 simulations per move sharded over the ranks (game g on rank
+    g mod world: 16384 / 8192 / 4096 games per GPU at 2 / 4 / 8), the finished games' replay tuples all-gathered every step."""
+    import torch
+    import torch.distributed as dist
+    from minitchess_alphazero_b200.parallel import gather_replay
+    from minitchess_alphazero_b200.selfplay import BatchedSelfPlay
+    G = total_games // world
+    sp = BatchedSelfPlay(net, n_games=G, num_simulations=sims, seed=4321 + rank, eval_cache_log2=args.eval_cache)
+    sp.stagger()
+    gathered_tuples = 0
+
+    def one_step():
+        nonlocal gathered_tuples
+        sp.step()
+        _, counts = gather_replay(sp.engine, world, max_tuples=2 * G)
+        gathered_tuples += int(counts.sum())
+    one_step()
+    barrier()
+    gathered_tuples = 0
+    c0 = sp.engine.counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one_step()
+    e1.record()
+    barrier()
+    c1 = sp.engine.counters()
+    d = {k: c1[k] - c0[k] for k in c1}
+    t = torch.tensor([e0.elapsed_time(e1), float(d['simulations']), float(d['evaluations']), float(d['cached_evaluations']),
+                      float(d['terminal_leaves']), float(d['moves'])], dtype=torch.float64, device='cuda')
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t)
+    ms, simsum = float(tmax[0]), float(t[1])
+    sp.engine.close()
+    return {'workload': 'BASELINE.json configs[3]: %d concurrent games x %d sims/move sharded over %d GPUs (%d per GPU), replay all_gather '
+                        'every step (counts first, then max(count) rows)' % (total_games, sims, world, G),
+            'value': simsum / (ms / 1e3), 'unit': 'sims/s', 'steps': steps, 'ms_per_step': ms / steps,
+            'evals_per_second': float(t[2]) / (ms / 1e3), 'positions_per_second': float(t[5]) / (ms / 1e3),
+            'sims_breakdown': {'network_rows': float(t[2]) / max(simsum, 1), 'cache_hits': float(t[3]) / max(simsum, 1),
+                               'terminal': float(t[4]) / max(simsum, 1)},
+            'replay_tuples_gathered': gathered_tuples, 'games_total': total_games, 'games_per_gpu': G, 'sims_per_move': sims}
+
+
+def leg_loop(net, rank, world, args, barrier, learner_batches=256):
+    """BASELINE.json configs[4]: one iteration of the full loop -- self-play on every GPU (4096 games x 200 sims/move each,
+    `--loop-moves` moves), replay all_gather, the learner's update on rank 0 (exp/learner.py:72-94: AdamW lr 0.2, batch 32,
+    app/learner.py:65-69; bounded to `learner_batches` mini-batches of the gathered tuples so that the bench stays short),
+    NCCL weight broadcast with the version stamp, engines reload.  Seconds per iteration, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from minitchess_alphazero_b200.loop import iteration
+    from minitchess_alphazero_b200.selfplay import BatchedSelfPlay
+    G, S = args.games, args.sims
+    sp = BatchedSelfPlay(net, n_games=G, num_simulations=S, seed=777 + rank, eval_cache_log2=args.eval_cache)
+    sp.stagger()
+    kw = dict(batch_size=32, optim_params={'lr': 0.2}, max_batches=learner_batches)
+    iteration(sp, net, 2, **dict(kw, max_batches=8))                 # warm-up: every phase once
+    barrier()
+    c0 = sp.engine.counters()
+    t0 = time.perf_counter()
+    out = iteration(sp, net, args.loop_moves, **kw)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    c1 = sp.engine.counters()
+    phases = ['selfplay', 'gather', 'learner', 'arena', 'broadcast']
+    t = torch.tensor([dt] + [float(out['seconds'].get(k, 0.0)) for k in phases], dtype=torch.float64, device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    s = torch.tensor([float(c1['simulations'] - c0['simulations'])], dtype=torch.float64, device='cuda')
+    dist.all_reduce(s)
+    info = torch.tensor([float(out['tuples']), float(out['used']), float(out['stale']), float(len(out['losses'])), float(out['version'])],
+                        dtype=torch.float64, device='cuda')
+    dist.broadcast(info, src=0)
+    sp.engine.close()
+    sec = {k: float(v) for k, v in zip(phases, t[1:].tolist())}
+    return {'workload': 'BASELINE.json configs[4]: self-play on %d GPUs (%d games x %d sims/move each, %d moves) -> replay all_gather -> '
+                        'learner update on rank 0 (AdamW lr 0.2, batch 32, first %d mini-batches) -> NCCL weight broadcast -> engines reload'
+                        % (world, G, S, args.loop_moves, learner_batches),
+            'seconds_per_iteration': float(t[0]), 'seconds': sec, 'selfplay_sims_per_second': float(s[0]) / max(sec['selfplay'], 1e-9),
+            'tuples_gathered': int(info[0]), 'tuples_used': int(info[1]), 'stale_dropped': int(info[2]), 'learner_steps': int(info[3]),
+            'weights_version': int(info[4]), 'moves_per_iteration': args.loop_moves}
 
 
 def measure_dropin(seconds=4.0, sims=36):

@@ -217,7 +217,8 @@ struct TowerParams {
     int fuse_heads;               // 1: the last level's epilogue takes the head convolutions (0 only in timing experiments)
     uint32_t wait_hint;           // suspend-time hint (ns) of the epilogue warps' waits for an accumulator; 0 = plain try_wait spin
     unsigned long long* stats;    // MCAZ_TOWER_STATS=1: per CTA {MMA issuer: total, waiting for operands, waiting for an accumulator;
-                                  // TMA producer: total, waiting for dependencies, waiting for a free stage} in clock cycles; else nullptr
+                                  // TMA producer: total, waiting for dependencies, waiting for a free stage; MMA issuer: operand wait
+                                  // at the first stage of an item, items} in clock cycles; else nullptr
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
@@ -380,14 +381,14 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             }
         }
         if (P.stats) {
-            unsigned long long* st = P.stats + (size_t)blockIdx.x * 6;
+            unsigned long long* st = P.stats + (size_t)blockIdx.x * 8;
             st[3] = (unsigned long long)(clock64() - p_start); st[4] = (unsigned long long)p_deps; st[5] = (unsigned long long)p_slot;
         }
     } else if (warp == 1 && lane == 0 && leader) {
         // ---------------------------------------------------------------- MMA issuer (leader CTA)
         uint32_t it = 0, j = 0;                       // j: items actually computed (accumulator ring position)
         const long long m_start = clock64();
-        long long m_full = 0, m_acc = 0;
+        long long m_full = 0, m_acc = 0, m_first = 0, m_items = 0;
         for (int k = 0; k < TOWER_MAX_ITEMS; ++k) {
             const uint32_t item = __ldg(&sched[k]);
             if (item == SCHED_END) break;
@@ -403,6 +404,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * C;
             uint32_t accumulate = 0;
+            ++m_items;
             for (int tap = 0; tap < 9; ++tap) {
                 int src;
                 if (!tap_valid(pos, tap, src)) continue;
@@ -410,7 +412,9 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                     const int s = it % STAGES;
                     const long long t1 = clock64();
                     mbar_wait(&full[s], (it / STAGES) & 1);
-                    m_full += clock64() - t1;
+                    const long long waited = clock64() - t1;
+                    m_full += waited;
+                    if (!accumulate) m_first += waited;       // the item's first stage: dependency stalls and ring refills show up here
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
                     const uint64_t da = stem ? umma_desc_sw32(a_addr) : umma_desc(a_addr);
@@ -428,8 +432,9 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             umma_commit_2sm(&acc_full[acc]);
         }
         if (P.stats) {
-            unsigned long long* st = P.stats + (size_t)blockIdx.x * 6;
+            unsigned long long* st = P.stats + (size_t)blockIdx.x * 8;
             st[0] = (unsigned long long)(clock64() - m_start); st[1] = (unsigned long long)m_full; st[2] = (unsigned long long)m_acc;
+            st[6] = (unsigned long long)m_first; st[7] = (unsigned long long)m_items;
         }
     } else if (warp == 3) {
         // ---------------------------------------------------------------- dependency watcher
@@ -928,7 +933,7 @@ struct Network {
     bool per_layer = false;            // false: tower_tc_kernel (one data-flow ordered launch for the 18 layers, default);
                                        // true: the same kernel launched once per layer (MCAZ_TOWER=layers, or no co-residency)
     // profiling (az_profile_network)
-    unsigned long long* stats = nullptr;   // MCAZ_TOWER_STATS=1: [grid][6] wait-cycle counters of the last tower launch
+    unsigned long long* stats = nullptr;   // MCAZ_TOWER_STATS=1: [grid][8] wait-cycle counters of the last tower launch
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
     size_t events_used = 0;
@@ -1206,8 +1211,8 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
         static int want_stats = -1;
         if (want_stats < 0) { const char* ss = getenv("MCAZ_TOWER_STATS"); want_stats = ss && atoi(ss) > 0; }
         if (want_stats && !N->stats) {
-            MCAZ_CUDA(cudaMalloc(&N->stats, (size_t)num_sms() * 6 * sizeof(unsigned long long)));
-            MCAZ_CUDA(cudaMemset(N->stats, 0, (size_t)num_sms() * 6 * sizeof(unsigned long long)));
+            MCAZ_CUDA(cudaMalloc(&N->stats, (size_t)num_sms() * 8 * sizeof(unsigned long long)));
+            MCAZ_CUDA(cudaMemset(N->stats, 0, (size_t)num_sms() * 8 * sizeof(unsigned long long)));
         }
         T.stats = N->stats;
     }
@@ -1304,7 +1309,7 @@ int network_profile(az_engine* e, int on, double* avg_ms_per_tower, int* n_forwa
 extern "C" int az_tower_stats(az_engine* e, unsigned long long* out, int capacity) {
     if (!e || !e->net || !out) return mcaz::fail(MCAZ_EINVAL, "az_tower_stats: bad argument");
     if (!e->net->stats) return mcaz::fail(MCAZ_ESTATE, "az_tower_stats: run with MCAZ_TOWER_STATS=1");
-    const int n = std::min(capacity, mcaz::num_sms() * 6);
+    const int n = std::min(capacity, mcaz::num_sms() * 8);
     cudaStreamSynchronize(e->stream);
     if (cudaMemcpy(out, e->net->stats, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
         return mcaz::fail(MCAZ_ECUDA, "az_tower_stats: copy failed");

@@ -139,8 +139,8 @@ class BatchedSelfPlay:
                 'kernel': ('tower_tc_kernel (stem + 18 x [3x3 conv 256->256] + head 1x1 convs in one data-flow ordered launch, tcgen05 cta_group::2)' if fused
                            else 'tower_tc_kernel (tcgen05 cta_group::2 3x3 conv 256->256, launched once per layer: MCAZ_TOWER=layers)'),
                 'achieved': flop / (ms_launch / 1e3) / 1e12, 'unit': 'TFLOP/s',
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/ (ncu --set full)
-                'traffic': 875e6 if fused else 151e6, 'ms_per_launch': ms_launch, 'launches_timed': n * per_forward,
+                'traffic': None,          # bench.py fills this in from the committed ncu pages (profiles/tower_traffic.json)
+                'ms_per_launch': ms_launch, 'launches_timed': n * per_forward,
                 'rows_per_launch': rows, 'flop_per_launch': flop,
                 # the kernel skips the 62 of 270 tap-positions that multiply zero padding: MMAs actually issued
                 'achieved_mma': flop * 208 / 270 / (ms_launch / 1e3) / 1e12,
