@@ -67,8 +67,23 @@ class _NodeField:
     def __contains__(self, fen):
         return self._fetch(fen) is not None
 
+    # the whole dict, like the reference's (exp/agent.py:25-36): one read-back of the tree (az_tree_dump)
     def keys(self):
-        raise NotImplementedError('the GPU tree is addressed by position; enumerate via Engine.node_stats')
+        term = self._field == 'terminal'
+        return [fen for fen, rec in self._tree._all_nodes().items() if (rec['terminal'] is not None) == term]
+
+    def items(self):
+        term = self._field == 'terminal'
+        return [(fen, rec[self._field]) for fen, rec in self._tree._all_nodes().items() if (rec['terminal'] is not None) == term]
+
+    def values(self):
+        return [v for _, v in self.items()]
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return len(self.keys())
 
 
 class _Visited:
@@ -77,6 +92,12 @@ class _Visited:
 
     def __contains__(self, fen):
         return self._tree._node(fen) is not None
+
+    def __iter__(self):
+        return iter(self._tree._all_nodes())
+
+    def __len__(self):
+        return len(self._tree._all_nodes())
 
 
 class _SharedEngine:
@@ -116,6 +137,7 @@ class MonteCarloTreeSearch:
         self._rules = rules_switches
         self._shared, self._tree = None, 0
         self._last_node = None                                  # (fen, node statistics) read since the last search
+        self._dump = None                                       # the whole tree, read since the last search
         self._evaluator = evaluator
         if _reuse is not None and _reuse._shared is not None and _reuse._evaluator is evaluator:
             # a new game of the same agent: keep the engine (arenas, uploaded weights, cache), empty this agent's tree
@@ -141,6 +163,24 @@ class MonteCarloTreeSearch:
         stats = self._engine.node_stats(0, self._tree, rules.state_from_fen(fen))
         self._last_node = (fen, stats)
         return stats
+
+    def _all_nodes(self):
+        """{fen: {'legal_moves', 'N', 'Q', 'P', 'terminal'}} of every node of this agent's tree, in creation order."""
+        if self._engine is None:
+            return {}
+        if self._dump is None:
+            from .engine import NODE_DECISIVE, NODE_TERMINAL
+            d = self._engine.tree_dump(0, self._tree)
+            out = {}
+            for i, st in enumerate(d['states']):
+                info, off = int(d['info'][i]), int(d['edge_off'][i])
+                E = 0 if info & NODE_TERMINAL else info & 0xffff
+                out[rules.state_to_fen(st)] = {
+                    'legal_moves': d['codes'][off:off + E].astype(int).tolist(), 'N': d['N'][off:off + E].astype(np.float64),
+                    'Q': d['Q'][off:off + E].copy(), 'P': d['P'][off:off + E].copy(),
+                    'terminal': ((-1.0 if info & NODE_DECISIVE else -0.0) if info & NODE_TERMINAL else None)}
+            self._dump = out
+        return self._dump
 
     def _ensure(self, num_simulations):
         if self._shared is None:
@@ -188,7 +228,7 @@ class MonteCarloTreeSearch:
             self._shared.fingerprint = fp
 
     def simulate(self, num_simulations, observation):       # exp/agent.py:41-45
-        self._last_node = None
+        self._last_node = self._dump = None
         self._ensure(num_simulations)
         eng, ev = self._engine, self._evaluator
         eng.set_positions(rules.state_from_fen(observation), trees=[self._tree])

@@ -109,6 +109,12 @@ def test_agent_facade_first_moves_match_reference_game(net, evaluator):
     assert tree['legal_moves'][root] == g['plies'][0]['legal_moves']
     assert root in tree['visited'] and tree['N'][root].sum() >= g['sims'] - 1
     assert tree['P'][root].dtype == np.float32 and abs(tree['P'][root].sum() - 1) < 1e-5
+    # ... and as whole dicts (exp/agent.py:25-36): every key of N answers the point lookups with the same arrays
+    keys = tree['N'].keys()
+    assert root in keys and len(keys) == len(tree['Q']) == len(tree['legal_moves']) and len(tree['visited']) == len(keys) + len(tree['terminal'])
+    for fen, n in tree['N'].items():
+        assert np.array_equal(n, tree['N'][fen]) and len(n) == len(tree['legal_moves'][fen])
+    assert sum(n.sum() for n in tree['N'].values()) >= g['sims'] - 1
     # a second game reuses the engine with empty trees (MonteCarloInit.on_episode_begin)
     eng = agents[0]._mcts.engine
     agents[0].init_mcts()

@@ -51,17 +51,19 @@ def pack_tuples(items):
     return out
 
 
-def check(run, losses, net, later_tol, sum_tol):
+def check(run, losses, net, later_tol, sum_tol, skip=()):
     want = run['losses']
     assert len(losses) == len(want) == 8
     assert abs(losses[0] - want[0]) <= 1e-5 * abs(want[0])                      # same weights, same batch: forward only
     assert np.allclose(losses, want, rtol=later_tol, atol=0), (losses, want)
     sd = net.state_dict()
-    worst = 0.0
+    worst = (0.0, None)
     for k, (s, a) in run['sums'].items():
+        if k.endswith(skip) if skip else False:
+            continue
         v = sd[k].double().cpu()
-        worst = max(worst, abs(float(v.sum()) - s) / max(a, 1e-12), abs(float(v.abs().sum()) - a) / max(a, 1e-12))
-    assert worst <= sum_tol, worst
+        worst = max(worst, (abs(float(v.sum()) - s) / max(a, 1e-12), k), (abs(float(v.abs().sum()) - a) / max(a, 1e-12), k))
+    assert worst[0] <= sum_tol, worst
 
 
 @pytest.mark.parametrize('lr', ['0.2', '0.001'])
@@ -94,4 +96,8 @@ def test_learner_update_on_packed_tuples_matches_reference_update_gpu(mcaz_lib, 
                                 device='cuda', order=run['batches'])
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
-    check(run, losses, net, later_tol=2e-2, sum_tol=2e-2)
+    # A convolution bias that feeds a BatchNorm in train mode has a gradient of exactly zero (the batch mean absorbs it); what
+    # reaches AdamW is rounding noise, which Adam normalises to steps of +-lr whatever its size, so those 20 tensors wander
+    # differently under cuDNN than under oneDNN (bit-identical on the CPU, above) without touching any output -- the losses
+    # still agree.  They are left out of the weight comparison here.
+    check(run, losses, net, later_tol=2e-2, sum_tol=2e-2, skip=('layers.0.bias',))
