@@ -57,7 +57,7 @@ def check(run, losses, net, later_tol, sum_tol, skip=()):
     assert abs(losses[0] - want[0]) <= 1e-5 * abs(want[0])                      # same weights, same batch: forward only
     assert np.allclose(losses, want, rtol=later_tol, atol=0), (losses, want)
     sd = net.state_dict()
-    worst = (0.0, None)
+    worst = (0.0, '')
     for k, (s, a) in run['sums'].items():
         if k.endswith(skip) if skip else False:
             continue
