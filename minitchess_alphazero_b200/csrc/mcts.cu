@@ -107,12 +107,12 @@ __device__ __forceinline__ bool play_device_one(const View& V, int g, int lane) 
     uint32_t root = V.tree_root[t];
     if (root == az::NONE) root = az::ht_find(V, t, V.game_state[g]);
     if (root == az::NONE) return false;
-    const size_t gi = (size_t)t * V.NC + root;
-    const int E = (int)(V.node_info[gi] & 0xffffu);
-    const size_t e0 = (size_t)t * V.EC + V.node_edge_off[gi];
+    const az::NodeHead rh = az::load_head(&V.nodes[(size_t)t * V.NC + root]);
+    const int E = (int)(rh.info & 0xffffu);
+    const az::Edge* re = V.edges + (size_t)t * V.EC + rh.edge_off;          // the root's edges
     const mc_state s = V.game_state[g];
     unsigned int nsum = 0, nmax = 0;
-    for (int i = lane; i < E; i += 32) { unsigned int c = V.edge_N[e0 + i]; nsum += c; nmax = max(nmax, c); }
+    for (int i = lane; i < E; i += 32) { unsigned int c = re[i].stat.N; nsum += c; nmax = max(nmax, c); }
     for (int o = 16; o > 0; o >>= 1) { nsum += __shfl_xor_sync(0xffffffffu, nsum, o); nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o)); }
     if (nsum == 0) return false;
     const uint32_t serial = V.move_serial[g];          // the game slot's own move counter keys the RNG
@@ -125,18 +125,18 @@ __device__ __forceinline__ bool play_device_one(const View& V, int g, int lane) 
         // sample proportionally to N (np.random.choice(legal, p=pi))
         const double target = u * (double)nsum;
         double acc = 0;
-        for (int i = 0; i < E && choice < 0; ++i) { acc += (double)V.edge_N[e0 + i]; if (target < acc) choice = i; }
+        for (int i = 0; i < E && choice < 0; ++i) { acc += (double)re[i].stat.N; if (target < acc) choice = i; }
         if (choice < 0) choice = E - 1;
     } else {
         int n_best = 0;
-        for (int i = 0; i < E; ++i) n_best += (V.edge_N[e0 + i] == nmax);
+        for (int i = 0; i < E; ++i) n_best += (re[i].stat.N == nmax);
         int pick = min((int)(u * n_best), n_best - 1);
-        for (int i = 0; i < E; ++i) if (V.edge_N[e0 + i] == nmax) { if (pick == 0) { choice = i; break; } --pick; }
+        for (int i = 0; i < E; ++i) if (re[i].stat.N == nmax) { if (pick == 0) { choice = i; break; } --pick; }
     }
-    const int code = V.edge_code[e0 + choice];
+    const int code = re[choice].link.code;
     // replay tuple of this ply
     az_replay_tuple* rec = V.record + (size_t)g * az::MAX_DEPTH + min(ply - V.game_start_ply[g], az::MAX_DEPTH - 1);
-    for (int i = lane; i < E; i += 32) { rec->codes[i] = V.edge_code[e0 + i]; rec->pi[i] = (float)((double)V.edge_N[e0 + i] / (double)nsum); }
+    for (int i = lane; i < E; i += 32) { rec->codes[i] = re[i].link.code; rec->pi[i] = (float)((double)re[i].stat.N / (double)nsum); }
     if (lane == 0) { rec->observation = s; rec->n_legal = (uint16_t)E; rec->action = (uint16_t)code; rec->reward = 0; rec->weights_version = 0u; }
     __syncwarp();
     play_chosen_move(V, g, lane, code);
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(256) untag_rows_kernel(View V) {
 // az_search / az_selfplay inner step.  leaves_per_step = K > 1 keeps the fixed form: back up the K descents of
 // the previous launch, start K new ones (virtual loss keeps them apart), one row per slot.
 template <bool LOOKAHEAD>
-__global__ void __launch_bounds__(128, LOOKAHEAD ? 4 : 8) search_step_kernel(View V, const float* values, mc_state start) {
+__global__ void __launch_bounds__(128, LOOKAHEAD ? 4 : 7) search_step_kernel(View V, const float* values, mc_state start) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     if (V.compact && blockIdx.x == 0 && threadIdx.x == 0) {     // the next launch's counters
@@ -342,14 +342,14 @@ __global__ void __launch_bounds__(128) root_stats_kernel(View V, const int32_t* 
         uint32_t root = V.tree_root[t];
         if (root == az::NONE) root = az::ht_find(V, t, V.game_state[g]);
         if (root == az::NONE) { if (lane == 0) n_legal[k] = -1; continue; }
-        const size_t gi = (size_t)t * V.NC + root;
-        const uint32_t info = V.node_info[gi];
-        const int E = (info & az::INFO_TERMINAL) ? 0 : (int)(info & 0xffffu);
-        const size_t e0 = (size_t)t * V.EC + V.node_edge_off[gi];
+        const az::NodeHead h = az::load_head(&V.nodes[(size_t)t * V.NC + root]);
+        const int E = (h.info & az::INFO_TERMINAL) ? 0 : (int)(h.info & 0xffffu);
+        const az::Edge* re = V.edges + (size_t)t * V.EC + h.edge_off;
         for (int i = lane; i < E; i += 32) {
-            codes[(size_t)k * MC_MAX_MOVES + i] = V.edge_code[e0 + i];
-            visits[(size_t)k * MC_MAX_MOVES + i] = V.edge_N[e0 + i];
-            if (q) q[(size_t)k * MC_MAX_MOVES + i] = V.edge_Q[e0 + i];
+            const az::EdgeStat st = az::load_stat(&re[i]);
+            codes[(size_t)k * MC_MAX_MOVES + i] = re[i].link.code;
+            visits[(size_t)k * MC_MAX_MOVES + i] = st.N;
+            if (q) q[(size_t)k * MC_MAX_MOVES + i] = st.Q;
         }
         if (lane == 0) n_legal[k] = E;
     }
@@ -366,16 +366,17 @@ __global__ void node_stats_kernel(View V, int g, int tree, mc_state s, NodeStats
     const int t = 2 * g + (tree & 1);
     uint32_t node = az::ht_find(V, t, s);
     if (node == az::NONE) { if (lane == 0) { out->found = 0; out->n_legal = 0; out->is_terminal = 0; out->terminal_value = 0; } return; }
-    const size_t gi = (size_t)t * V.NC + node;
-    const uint32_t info = V.node_info[gi];
+    const az::NodeHead h = az::load_head(&V.nodes[(size_t)t * V.NC + node]);
+    const uint32_t info = h.info;
     const bool term = (info & az::INFO_TERMINAL) != 0;
     const int E = term ? 0 : (int)(info & 0xffffu);
-    const size_t e0 = (size_t)t * V.EC + V.node_edge_off[gi];
+    const az::Edge* re = V.edges + (size_t)t * V.EC + h.edge_off;
     for (int i = lane; i < E; i += 32) {
-        codes[i] = V.edge_code[e0 + i];
-        visits[i] = V.edge_N[e0 + i];
-        q[i] = V.edge_Q[e0 + i];
-        priors[i] = V.edge_P[e0 + i];
+        const az::EdgeStat st = az::load_stat(&re[i]);
+        codes[i] = re[i].link.code;
+        visits[i] = st.N;
+        q[i] = st.Q;
+        priors[i] = st.P;
     }
     if (lane == 0) {
         out->found = 1; out->n_legal = E; out->is_terminal = term ? 1 : 0;
@@ -434,20 +435,22 @@ __global__ void __launch_bounds__(RECYCLE_THREADS) recycle_kernel(View V, int ne
         const mc_state cur = V.game_state[g];
         const int cur_ply = ply_of_meta(cur.meta);
         const size_t nb = (size_t)t * V.NC, eb = (size_t)t * V.EC;
-        uint32_t* map = V.ht + (size_t)t * V.HC;            // old node -> new node (HC >= 2 NC)
+        uint32_t* map = V.ht + (size_t)t * V.HC;            // [0, NC): old node -> new node; [NC, 2 NC): where new node j's edges were (HC >= 2 NC)
+        uint32_t* old_off_of = map + V.NC;
         if (tid == 0) { s_tot[0] = 0; s_tot[1] = 0; }
         __syncthreads();
-        // ---- pass 1: node headers (chunks of 256 nodes: read, scan, barrier, write)
+        // ---- pass 1: node headers (chunks of 256 nodes: read, scan, barrier, write).  The scan over the edge counts gives
+        // every live node its new first edge at once, so pass 2 can point the links at their children's final places.
         for (uint32_t base = 0; base < n; base += RECYCLE_THREADS) {
             const uint32_t i = base + tid;
-            az::Board4 board{}; uint32_t meta = 0, off = 0, info = 0;
+            az::Board4 board{}; az::NodeHead head{};
             bool live = false;
             if (i < n) {
-                board = V.node_board[nb + i]; meta = V.node_meta[nb + i]; off = V.node_edge_off[nb + i]; info = V.node_info[nb + i];
-                const int ply = ply_of_meta(meta);
-                live = ply > cur_ply || (meta == cur.meta && board.x == cur.pl0 && board.y == cur.pl1 && board.z == cur.pl2 && board.w == cur.white);
+                board = az::load_board(&V.nodes[nb + i]); head = az::load_head(&V.nodes[nb + i]);
+                const int ply = ply_of_meta(head.meta);
+                live = ply > cur_ply || (head.meta == cur.meta && board.x == cur.pl0 && board.y == cur.pl1 && board.z == cur.pl2 && board.w == cur.white);
             }
-            const uint32_t E = live && !(info & az::INFO_TERMINAL) ? (info & 0xffffu) : 0u;
+            const uint32_t E = live && !(head.info & az::INFO_TERMINAL) ? (head.info & 0xffffu) : 0u;
             // block-wide exclusive scan of (live, E)
             uint32_t a = live ? 1u : 0u, b = E;
             for (int o = 1; o < 32; o <<= 1) {
@@ -458,58 +461,50 @@ __global__ void __launch_bounds__(RECYCLE_THREADS) recycle_kernel(View V, int ne
             __syncthreads();
             uint32_t pa = s_tot[0], pb = s_tot[1];
             for (int w = 0; w < warp; ++w) { pa += s_scan[w][0]; pb += s_scan[w][1]; }
-            const uint32_t new_i = pa + a - (live ? 1u : 0u);
+            const uint32_t new_i = pa + a - (live ? 1u : 0u), new_off = pb + b - E;
             __syncthreads();
             if (tid == RECYCLE_THREADS - 1) { s_tot[0] = pa + a; s_tot[1] = pb + b; }
             if (i < n) map[i] = live ? new_i : az::NONE;
             if (live) {                                     // new_i <= i and every older chunk is already moved
-                V.node_board[nb + new_i] = board; V.node_meta[nb + new_i] = meta; V.node_info[nb + new_i] = info;
-                V.node_edge_off[nb + new_i] = off;          // old offset for now: pass 2 moves the edges and fixes it
+                az::store_node(&V.nodes[nb + new_i], board, head.meta, new_off, head.info);
+                old_off_of[new_i] = head.edge_off;
             }
             __syncthreads();
         }
         const uint32_t n_live = s_tot[0], m_live = s_tot[1];
         __syncthreads();
-        if (tid == 0) s_tot[0] = 0;                          // edges placed so far
-        // ---- pass 2: edge blocks, one node per warp and round: all warps read, barrier, all write
+        // ---- pass 2: edge records, one node per warp and round: all warps read, barrier, all write.  Order-preserving: a node's
+        // new place ends where its old one does at the latest, and everything before that has been read by then.
         for (uint32_t base = 0; base < n_live; base += WARPS) {
             const uint32_t j = base + warp;
-            uint32_t old_off = 0, E = 0;
-            double q[3]; uint32_t nn[3], ch[3]; float pp[3]; uint16_t cd[3], vl[3];
+            uint32_t old_off = 0, new_off = 0, E = 0;
+            az::EdgeStat st[3]; az::EdgeLink lk[3];
             if (j < n_live) {
-                old_off = V.node_edge_off[nb + j];
-                const uint32_t info = V.node_info[nb + j];
-                E = (info & az::INFO_TERMINAL) ? 0u : (info & 0xffffu);
+                const az::NodeHead h = az::load_head(&V.nodes[nb + j]);
+                old_off = old_off_of[j]; new_off = h.edge_off;
+                E = (h.info & az::INFO_TERMINAL) ? 0u : (h.info & 0xffffu);
             }
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const uint32_t i = lane + 32 * k;
-                if (i < E) {
-                    const size_t e = eb + old_off + i;
-                    q[k] = V.edge_Q[e]; nn[k] = V.edge_N[e]; pp[k] = V.edge_P[e]; ch[k] = V.edge_child[e]; cd[k] = V.edge_code[e];
-                    vl[k] = V.edge_vl ? V.edge_vl[e] : (uint16_t)0;
-                }
+                if (i < E) { st[k] = az::load_stat(&V.edges[eb + old_off + i]); lk[k] = az::load_link(&V.edges[eb + old_off + i]); }
             }
-            if (lane == 0) s_scan[warp][0] = E;
-            __syncthreads();                                  // this round's reads are done, its sizes published
-            uint32_t new_off = s_tot[0], round_total = 0;
-            for (int w = 0; w < WARPS; ++w) {
-                if (w < warp) new_off += s_scan[w][0];
-                round_total += s_scan[w][0];
-            }
+            __syncthreads();                                  // this round's reads are done
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const uint32_t i = lane + 32 * k;
                 if (i < E) {
-                    const size_t e = eb + new_off + i;
-                    V.edge_Q[e] = q[k]; V.edge_N[e] = nn[k]; V.edge_P[e] = pp[k]; V.edge_code[e] = cd[k];
-                    V.edge_child[e] = ch[k] == az::NONE ? az::NONE : map[ch[k]];    // children are deeper: always live
-                    if (V.edge_vl) V.edge_vl[e] = vl[k];
+                    az::Edge* e = &V.edges[eb + new_off + i];
+                    uint32_t child = lk[k].child, child_off = 0;
+                    if (child != az::NONE) {                  // children are deeper: always live; their headers are final since pass 1
+                        child = map[child];
+                        child_off = V.nodes[nb + child].head.edge_off;
+                    }
+                    *reinterpret_cast<uint4*>(&e->stat) = make_uint4((uint32_t)__double2loint(st[k].Q), (uint32_t)__double2hiint(st[k].Q), st[k].N, __float_as_uint(st[k].P));
+                    *reinterpret_cast<uint4*>(&e->link) = make_uint4(child, child_off, lk[k].child_info, (uint32_t)lk[k].code | ((uint32_t)lk[k].vl << 16));
                 }
             }
-            if (j < n_live && lane == 0) V.node_edge_off[nb + j] = new_off;
-            __syncthreads();                                  // this round's writes are done, s_tot[0] has been read
-            if (tid == 0) s_tot[0] += round_total;
+            __syncthreads();                                  // this round's writes are done
         }
         __syncthreads();
         // ---- roots, then the hash table
@@ -526,7 +521,7 @@ __global__ void __launch_bounds__(RECYCLE_THREADS) recycle_kernel(View V, int ne
         __syncthreads();
         const uint32_t mask = (uint32_t)V.HC - 1u;
         for (uint32_t i = tid; i < n_live; i += RECYCLE_THREADS) {
-            const mc_state s = az::state_of(V.node_board[nb + i], V.node_meta[nb + i]);
+            const mc_state s = az::state_of(az::load_board(&V.nodes[nb + i]), V.nodes[nb + i].head.meta);
             uint32_t h = az::hash_state(s) & mask;
             while (atomicCAS(&tab[h], 0u, i + 1u) != 0u) h = (h + 1u) & mask;
         }
@@ -651,8 +646,7 @@ int az_create(const az_config* cfg, az_engine** out) {
 #define A(ptr, n) if (!rc) rc = dev_alloc(e, &ptr, (n))
     A(V.game_state, G); A(V.game_result, G); A(V.game_ply, G); A(V.game_hist, G * az::HIST); A(V.game_hist_len, G); A(V.game_start_ply, G);
     A(V.tree_nodes, T); A(V.tree_edges, T); A(V.tree_root, T);
-    A(V.node_board, N); A(V.node_meta, N); A(V.node_edge_off, N); A(V.node_info, N);
-    A(V.edge_Q, E); A(V.edge_N, E); A(V.edge_P, E); A(V.edge_child, E); A(V.edge_code, E);
+    A(V.nodes, N); A(V.edges, E);
     A(V.ht, T * V.HC);
     A(V.path_len, S); A(V.path_edge, S * az::MAX_DEPTH); A(V.path_node, S * az::MAX_DEPTH);
     A(V.leaf_node, S); A(V.leaf_kind, S); A(V.leaf_value, S);
@@ -664,8 +658,6 @@ int az_create(const az_config* cfg, az_engine** out) {
         V.seen_mask = (1u << cfg->eval_cache_log2) - 1u;
     }
     A(e->d_pending, 2);
-    V.edge_vl = nullptr;
-    if (V.K > 1) { A(V.edge_vl, E); }
     A(V.counters, AZ_NUM_COUNTERS); A(V.error_flag, 1);
     A(V.sim_serial, G); A(V.move_serial, G); A(V.sims_left, G); A(V.row_count, 2); A(V.row_slot, R);
     V.sims_per_move = cfg->max_sims_per_move; V.new_budget = -1; V.free_max = 1; V.async_play = 0; V.compact = 0; V.parity = 0;
@@ -1099,24 +1091,23 @@ int az_tree_dump(az_engine* e, int game_id, int tree, int max_nodes, mc_state* s
     const size_t nn = std::min<size_t>(n, (size_t)max_nodes), mm = std::min<size_t>(m, (size_t)max_edges);
     const size_t nb = t * V.NC, eb = t * V.EC;
     if (nn) {
-        if (states) {
-            std::vector<az::Board4> board(nn);
-            std::vector<uint32_t> meta(nn);
-            MCAZ_CUDA(cudaMemcpy(board.data(), V.node_board + nb, nn * sizeof(az::Board4), cudaMemcpyDeviceToHost));
-            MCAZ_CUDA(cudaMemcpy(meta.data(), V.node_meta + nb, nn * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-            for (size_t i = 0; i < nn; ++i) states[i] = az::state_of(board[i], meta[i]);
+        std::vector<az::Node> nodes(nn);
+        MCAZ_CUDA(cudaMemcpy(nodes.data(), V.nodes + nb, nn * sizeof(az::Node), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < nn; ++i) {
+            if (states) states[i] = az::state_of(nodes[i].board, nodes[i].head.meta);
+            if (info) info[i] = nodes[i].head.info & (0xffffu | az::INFO_TERMINAL | az::INFO_DECISIVE);
+            if (edge_off) edge_off[i] = nodes[i].head.edge_off;
         }
-        if (info) {
-            MCAZ_CUDA(cudaMemcpy(info, V.node_info + nb, nn * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-            for (size_t i = 0; i < nn; ++i) info[i] &= 0xffffu | az::INFO_TERMINAL | az::INFO_DECISIVE;
-        }
-        if (edge_off) MCAZ_CUDA(cudaMemcpy(edge_off, V.node_edge_off + nb, nn * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     }
-    if (mm) {
-        if (codes) MCAZ_CUDA(cudaMemcpy(codes, V.edge_code + eb, mm * sizeof(uint16_t), cudaMemcpyDeviceToHost));
-        if (visits) MCAZ_CUDA(cudaMemcpy(visits, V.edge_N + eb, mm * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        if (q) MCAZ_CUDA(cudaMemcpy(q, V.edge_Q + eb, mm * sizeof(double), cudaMemcpyDeviceToHost));
-        if (priors) MCAZ_CUDA(cudaMemcpy(priors, V.edge_P + eb, mm * sizeof(float), cudaMemcpyDeviceToHost));
+    if (mm && (codes || visits || q || priors)) {
+        std::vector<az::Edge> edges(mm);
+        MCAZ_CUDA(cudaMemcpy(edges.data(), V.edges + eb, mm * sizeof(az::Edge), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < mm; ++i) {
+            if (codes) codes[i] = edges[i].link.code;
+            if (visits) visits[i] = edges[i].stat.N;
+            if (q) q[i] = edges[i].stat.Q;
+            if (priors) priors[i] = edges[i].stat.P;
+        }
     }
     return MCAZ_OK;
 }

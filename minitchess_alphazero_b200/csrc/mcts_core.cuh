@@ -8,13 +8,16 @@
 // One warp walks one tree; lanes split the edges of a node.  The same source compiles for the
 // host with one "lane" so CPU tests can drive it; the product only launches the kernels.
 //
-// Layout in HBM (per engine; T = 2*G trees, fixed per-tree arenas of NC nodes / EC edges):
-//   node_board[T*NC] 16 B  piece planes + colour plane      node_meta[T*NC] 4 B  turn/clocks
-//   node_edge_off[T*NC] 4 B first edge (tree-relative)      node_info[T*NC] 4 B  n_edges | flags
-//   edge_Q[T*EC] f64, edge_N[T*EC] u32, edge_P[T*EC] f32, edge_child[T*EC] u32, edge_code[T*EC] u16
+// Layout in HBM (per engine; T = 2*G trees, fixed per-tree arenas of NC nodes / EC edges), records of two 128-bit words:
+//   nodes[T*NC]  Node 32 B: {board: piece planes + colour plane | meta, first edge (tree-relative), n_edges | flags, -}
+//   edges[T*EC]  Edge 32 B: {stat: Q f64, N u32, P f32 -- all that PUCT reads | link: child node, and, cached from the child's
+//                header when the edge is first traversed, the child's first edge and info word, then code u16, virtual loss u16}
 //   ht[T*HC] u32  open-addressing table: position -> node (the reference keys its dicts by the
 //                 FEN string, so one position reached by two paths is ONE node: a DAG)
-// A node's edges are contiguous in every edge array, so a warp reads them coalesced.
+// A node's edges are contiguous, lane i of the tree's warp loads edge i with two 128-bit loads, and because the link word
+// tells where the child's edges are, a descent costs ONE dependent memory round trip per level (round 1: header, then
+// statistics, then child index = three).  The node header is only read at the root, at an untraversed edge (the move has
+// to be applied to the parent's position) and by the read-back calls.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -41,6 +44,12 @@ enum Counter : int { C_SIMS = 0, C_EVALS, C_TERMINAL, C_MOVES, C_GAMES, C_NODES,
 enum ErrorBit : int { ERR_NODE_CAP = 1, ERR_EDGE_CAP = 2, ERR_HASH_CAP = 4, ERR_DEPTH = 8, ERR_ILLEGAL = 16 };
 
 struct alignas(16) Board4 { uint32_t x, y, z, w; };
+struct alignas(16) NodeHead { uint32_t meta, edge_off, info, pad; };
+struct alignas(32) Node { Board4 board; NodeHead head; };
+struct alignas(16) EdgeStat { double Q; uint32_t N; float P; };
+struct alignas(16) EdgeLink { uint32_t child, child_off, child_info; uint16_t code, vl; };
+struct alignas(32) Edge { EdgeStat stat; EdgeLink link; };
+static_assert(sizeof(Node) == 32 && sizeof(Edge) == 32 && sizeof(EdgeStat) == 16 && sizeof(EdgeLink) == 16, "tree record layout");
 
 // Exact evaluation cache (SURVEY.md 7.3 point 6): the network sees (tokens, clock) = board, side to move and
 // fullmove number -- not the halfmove clock -- so two nodes with that key get bit-identical priors and value,
@@ -64,9 +73,7 @@ struct View {
     Board4* game_hist; int32_t* game_hist_len;     // [G*HIST] positions since the last irreversible move
     // trees
     uint32_t* tree_nodes; uint32_t* tree_edges; uint32_t* tree_root;
-    Board4* node_board; uint32_t* node_meta; uint32_t* node_edge_off; uint32_t* node_info;
-    double* edge_Q; uint32_t* edge_N; float* edge_P; uint32_t* edge_child; uint16_t* edge_code;
-    uint16_t* edge_vl;              // virtual-loss counts of descents in flight (K > 1 only, else nullptr)
+    Node* nodes; Edge* edges;       // [T*NC], [T*EC]; Edge::link.vl = virtual-loss count of descents in flight (K > 1 only)
     uint32_t* ht;
     // per-slot simulation scratch (slot = game * K + leaf index)
     int32_t* path_len; uint32_t* path_edge; uint32_t* path_node;   // [G*MAX_DEPTH]
@@ -155,6 +162,59 @@ MC_HD float fmul(float a, float b) {
 #endif
 }
 
+// 128-bit accesses to the tree records: one LDG.128 / STG.128 each on the device, plain struct copies on the host
+MC_HD NodeHead load_head(const Node* n) {
+#if defined(__CUDA_ARCH__)
+    const uint4 r = *reinterpret_cast<const uint4*>(&n->head);
+    return NodeHead{r.x, r.y, r.z, r.w};
+#else
+    return n->head;
+#endif
+}
+MC_HD Board4 load_board(const Node* n) {
+#if defined(__CUDA_ARCH__)
+    const uint4 r = *reinterpret_cast<const uint4*>(&n->board);
+    return Board4{r.x, r.y, r.z, r.w};
+#else
+    return n->board;
+#endif
+}
+MC_HD void store_node(Node* n, const Board4& b, uint32_t meta, uint32_t edge_off, uint32_t info) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint4*>(&n->board) = make_uint4(b.x, b.y, b.z, b.w);
+    *reinterpret_cast<uint4*>(&n->head) = make_uint4(meta, edge_off, info, 0u);
+#else
+    n->board = b;
+    n->head = NodeHead{meta, edge_off, info, 0u};
+#endif
+}
+MC_HD EdgeStat load_stat(const Edge* e) {
+#if defined(__CUDA_ARCH__)
+    const uint4 r = *reinterpret_cast<const uint4*>(&e->stat);
+    return EdgeStat{__hiloint2double((int)r.y, (int)r.x), r.z, __uint_as_float(r.w)};
+#else
+    return e->stat;
+#endif
+}
+MC_HD EdgeLink load_link(const Edge* e) {
+#if defined(__CUDA_ARCH__)
+    const uint4 r = *reinterpret_cast<const uint4*>(&e->link);
+    return EdgeLink{r.x, r.y, r.z, (uint16_t)(r.w & 0xffffu), (uint16_t)(r.w >> 16)};
+#else
+    return e->link;
+#endif
+}
+// A fresh edge: no visits, no prior yet, leads nowhere yet (exp/agent.py:64-65: Q = N = zeros)
+MC_HD void store_new_edge(Edge* e, uint16_t code) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint4*>(&e->stat) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(&e->link) = make_uint4(0xffffffffu, 0u, 0u, (uint32_t)code);
+#else
+    e->stat = EdgeStat{0.0, 0u, 0.0f};
+    e->link = EdgeLink{0xffffffffu, 0u, 0u, code, 0};
+#endif
+}
+
 MC_HD void raise(const View& V, int bit) {
 #if defined(__CUDA_ARCH__)
     atomicOr(V.error_flag, bit);
@@ -198,9 +258,9 @@ MC_HD uint32_t ht_find(const View& V, int t, const mc_state& s) {
         uint32_t e = tab[h];
         if (e == 0) return NONE;
         uint32_t n = e - 1;
-        size_t gi = (size_t)t * V.NC + n;
-        Board4 b = V.node_board[gi];
-        if (b.x == s.pl0 && b.y == s.pl1 && b.z == s.pl2 && b.w == s.white && V.node_meta[gi] == s.meta) return n;
+        const Node* nd = V.nodes + (size_t)t * V.NC + n;
+        const Board4 b = load_board(nd);
+        if (b.x == s.pl0 && b.y == s.pl1 && b.z == s.pl2 && b.w == s.white && nd->head.meta == s.meta) return n;
         h = (h + 1) & mask;
     }
     return NONE;
@@ -225,8 +285,8 @@ MC_HD bool same_position(const Board4& b, uint32_t meta, const mc_state& s) {
 MC_HD int path_repetitions(const View& V, int t, const uint32_t* pnode, int depth, const mc_state& s) {
     int same = 0;
     for (int d = 0; d < depth; ++d) {
-        const size_t gi = (size_t)t * V.NC + pnode[d];
-        same += same_position(V.node_board[gi], V.node_meta[gi], s) ? 1 : 0;
+        const Node* nd = V.nodes + (size_t)t * V.NC + pnode[d];
+        same += same_position(load_board(nd), nd->head.meta, s) ? 1 : 0;
     }
     return same;
 }
@@ -234,9 +294,10 @@ MC_HD int path_repetitions(const View& V, int t, const uint32_t* pnode, int dept
 // Create the node for an unvisited position (exp/agent.py:57-66).  Lane 0 writes; every lane
 // gets the node index, its kind and, for a finished position, the value to back up.
 MC_HD uint32_t expand(const View& V, int slot, int t, int lane, const mc_state& s, uint8_t* kind, double* value,
-                      const uint32_t* pnode, int depth) {
+                      const uint32_t* pnode, int depth, uint32_t* out_off, uint32_t* out_info) {
     uint32_t node = NONE;
     int is_terminal = 0, decisive = 0;
+    *out_off = 0; *out_info = 0;
 #if defined(__CUDA_ARCH__)
     if (lane == 0)
 #endif
@@ -261,20 +322,12 @@ MC_HD uint32_t expand(const View& V, int slot, int t, int lane, const mc_state& 
                 E = 0;
                 is_terminal = 1;  // keeps the tree consistent; the error flag fails the call
             }
-            V.node_board[gi] = board_of(s);
-            V.node_meta[gi] = s.meta;
-            V.node_edge_off[gi] = off;
-            V.node_info[gi] = (uint32_t)E | (is_terminal ? INFO_TERMINAL : 0u) | (decisive ? INFO_DECISIVE : 0u) |
-                              ((!is_terminal && V.K > 1) ? INFO_PENDING : 0u);
+            const uint32_t info = (uint32_t)E | (is_terminal ? INFO_TERMINAL : 0u) | (decisive ? INFO_DECISIVE : 0u) |
+                                  ((!is_terminal && V.K > 1) ? INFO_PENDING : 0u);
+            store_node(&V.nodes[gi], board_of(s), s.meta, off, info);
+            *out_off = off; *out_info = info;
             size_t ge = (size_t)t * V.EC + off;
-            for (int k = 0; k < E; ++k) {
-                V.edge_Q[ge + k] = 0.0;
-                V.edge_N[ge + k] = 0u;
-                V.edge_P[ge + k] = 0.0f;
-                V.edge_child[ge + k] = NONE;
-                V.edge_code[ge + k] = codes[k];
-                if (V.edge_vl) V.edge_vl[ge + k] = 0;
-            }
+            for (int k = 0; k < E; ++k) store_new_edge(&V.edges[ge + k], codes[k]);
             V.tree_nodes[t] = n + 1;
             V.tree_edges[t] = off + (uint32_t)E;
             ht_insert(V, t, s, n);
@@ -476,8 +529,8 @@ __device__ __forceinline__ void queue_children(const View& V, int lane, const mc
         mc_state cs = s;
         uint32_t idx = 0, tag = 0;
         if (i < E) {
-            const uint16_t code = V.edge_code[e0 + i];
-            if (i == 0 || V.edge_code[e0 + i - 1] != code) {             // promo_multiplicity > 1 repeats a code
+            const uint16_t code = V.edges[e0 + i].link.code;
+            if (i == 0 || V.edges[e0 + i - 1].link.code != code) {       // promo_multiplicity > 1 repeats a code
                 int fv, tv;
                 mc::code_to_view(code, fv, tv);
                 cs = mc::apply_move(s, white ? fv : 29 - fv, white ? tv : 29 - tv);
@@ -551,7 +604,8 @@ __device__ __forceinline__ void queue_children(const View& V, int lane, const mc
 
 template <bool LOOKAHEAD>
 __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, int lane, const mc_state& s, uint8_t* kind,
-                                                double* value, const uint32_t* pnode, int depth) {
+                                                double* value, const uint32_t* pnode, int depth, uint32_t* out_off, uint32_t* out_info) {
+    *out_off = 0; *out_info = 0;
     const WarpGen w = warp_generate(V, s, lane);
     const bool white = w.white;
     const mc::Sets& st = w.st;
@@ -560,8 +614,8 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, 
     if (res == MC_ONGOING && V.rules.fivefold_repetition && depth >= 16) {
         int same = 0;
         for (int d = lane; d < depth; d += 32) {
-            const size_t pi = (size_t)t * V.NC + pnode[d];
-            same += same_position(V.node_board[pi], V.node_meta[pi], s) ? 1 : 0;
+            const Node* pn = V.nodes + (size_t)t * V.NC + pnode[d];
+            same += same_position(load_board(pn), pn->head.meta, s) ? 1 : 0;
         }
         for (int o = 16; o > 0; o >>= 1) same += __shfl_xor_sync(0xffffffffu, same, o);
         if (same >= 4) res = MC_DRAW;
@@ -592,17 +646,13 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, 
     if (!terminal && V.cache && E <= CACHE_MAX_E) hit = cache_lookup(V, s, E, lane, &hit_value, &hit_p0, &hit_p1);
     if (!terminal) {
         const size_t w0 = (size_t)t * V.EC + off;
-        warp_emit_codes(V, w, [&](int k, uint16_t c) {
-            const size_t x = w0 + k;
-            V.edge_Q[x] = 0.0; V.edge_N[x] = 0u; V.edge_P[x] = 0.0f; V.edge_child[x] = NONE; V.edge_code[x] = c;
-            if (V.edge_vl) V.edge_vl[x] = 0;
-        });
+        warp_emit_codes(V, w, [&](int k, uint16_t c) { store_new_edge(&V.edges[w0 + k], c); });
     }
     if (hit) {
         __syncwarp();            // the zeroed priors above are overwritten by the cached ones
         const size_t w0 = (size_t)t * V.EC + off;
-        if (lane < E) V.edge_P[w0 + lane] = hit_p0;
-        if (lane + 32 < E) V.edge_P[w0 + lane + 32] = hit_p1;
+        if (lane < E) V.edges[w0 + lane].stat.P = hit_p0;
+        if (lane + 32 < E) V.edges[w0 + lane + 32].stat.P = hit_p1;
     }
     // network row of this leaf: dense (az_search) or the slot itself
     int row = slot;
@@ -612,12 +662,11 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, 
         row = __shfl_sync(0xffffffffu, row, 0);
     }
     if (needs_net) write_network_row(V, row, lane, s, st, white);
-    if (lane == 0) {
-        V.node_board[gi] = board_of(s);
-        V.node_meta[gi] = s.meta;
-        V.node_edge_off[gi] = off;
-        V.node_info[gi] = (uint32_t)E | (terminal ? INFO_TERMINAL : 0u) | ((terminal && decisive) ? INFO_DECISIVE : 0u) |
+    const uint32_t info = (uint32_t)E | (terminal ? INFO_TERMINAL : 0u) | ((terminal && decisive) ? INFO_DECISIVE : 0u) |
                           ((needs_net && V.K > 1) ? INFO_PENDING : 0u);
+    *out_off = off; *out_info = info;
+    if (lane == 0) {
+        store_node(&V.nodes[gi], board_of(s), s.meta, off, info);
         V.tree_nodes[t] = node + 1;
         V.tree_edges[t] = off + (uint32_t)E;
         ht_insert(V, t, s, node);
@@ -692,15 +741,19 @@ MC_HD uint8_t select_expand_one(const View& V, int g, int lane, const double* no
     uint32_t node = V.tree_root[t];
     int depth = 0;
     unsigned int path_edges = 0;       // edges read on the way down (bytes-per-simulation accounting)
+    uint32_t info = 0, off = 0;        // header words of `node`: from its own header at the root, from the parent's link below
     if (node == NONE) {
         mc_state s = V.game_state[g];
         node = ht_find(V, t, s);
-        if (node == NONE) node = AZ_EXPAND(V, slot, t, lane, s, &kind, &value, pnode, 0);
+        if (node == NONE) node = AZ_EXPAND(V, slot, t, lane, s, &kind, &value, pnode, 0, &off, &info);
         if (lane == 0 && node != NONE) V.tree_root[t] = node;
         AZ_SYNCWARP();
     }
+    if (kind == LEAF_NONE) {
+        const NodeHead h = load_head(&V.nodes[nbase + node]);
+        info = h.info; off = h.edge_off;
+    }
     while (kind == LEAF_NONE) {
-        uint32_t info = V.node_info[nbase + node];
         if (info & INFO_TERMINAL) {  // exp/agent.py:75-77: revisit backs up -terminal[node]
             kind = LEAF_TERMINAL;
             value = (info & INFO_DECISIVE) ? 1.0 : 0.0;
@@ -713,10 +766,25 @@ MC_HD uint8_t select_expand_one(const View& V, int g, int lane, const double* no
         }
         const int E = (int)(info & 0xffffu);
         path_edges += (unsigned int)E;
-        const size_t e0 = ebase + V.node_edge_off[nbase + node];
+        const size_t e0 = ebase + off;
+        // this lane's edges: both 128-bit words of edge `lane` stay in registers (positions with more than 32 legal moves are rare:
+        // their edges 32.. are read where they are used, and again from L1); the host build reads everything in place
+#if defined(__CUDA_ARCH__)
+        EdgeStat est0{0.0, 0u, 0.0f};
+        EdgeLink elk0{NONE, 0u, 0u, 0, 0};
+        if (lane < E) { est0 = load_stat(&V.edges[e0 + lane]); elk0 = load_link(&V.edges[e0 + lane]); }
+#define AZ_STAT(i, kk) ((kk) == 0 ? est0 : load_stat(&V.edges[e0 + (i)]))
+#define AZ_LINK(i, kk) ((kk) == 0 ? elk0 : load_link(&V.edges[e0 + (i)]))
+#define AZ_MY_EDGES_BEGIN _Pragma("unroll") for (int kk = 0; kk < 3; ++kk) { const int i = lane + 32 * kk; if (i < E) {
+#else
+#define AZ_STAT(i, kk) V.edges[e0 + (i)].stat
+#define AZ_LINK(i, kk) V.edges[e0 + (i)].link
+#define AZ_MY_EDGES_BEGIN for (int i = 0; i < E; ++i) { {
+#endif
+#define AZ_MY_EDGES_END }}
         // sum of visit counts (exact in float64: small integers)
         unsigned int nsum_u = 0;
-        for (int i = lane; i < E; i += AZ_LANES) nsum_u += V.edge_N[e0 + i] + (vloss ? (unsigned int)V.edge_vl[e0 + i] : 0u);
+        AZ_MY_EDGES_BEGIN nsum_u += AZ_STAT(i, kk).N + (vloss ? (unsigned int)AZ_LINK(i, kk).vl : 0u); AZ_MY_EDGES_END
 #if defined(__CUDA_ARCH__)
         for (int o = 16; o > 0; o >>= 1) nsum_u += __shfl_xor_sync(0xffffffffu, nsum_u, o);
 #endif
@@ -733,13 +801,14 @@ MC_HD uint8_t select_expand_one(const View& V, int g, int lane, const double* no
 #endif
         double best_u = 0.0;
         int best_i = 0x7fffffff;
-        for (int i = lane; i < E; i += AZ_LANES) {
-            const float p = V.edge_P[e0 + i];
+        AZ_MY_EDGES_BEGIN
+            const EdgeStat es = AZ_STAT(i, kk);
+            const float p = es.P;
             double x;
             if (mix) {
                 // P = (1-eps)*P + eps*dirichlet: float32 product, float64 sum (exp/agent.py:82 under NEP 50)
 #if defined(__CUDA_ARCH__)
-                const double nz = dev_noise ? gam[(i - lane) / AZ_LANES] / gsum : noise[(size_t)g * MC_MAX_MOVES + i];
+                const double nz = dev_noise ? gam[kk] / gsum : noise[(size_t)g * MC_MAX_MOVES + i];
 #else
                 const double nz = noise[(size_t)g * MC_MAX_MOVES + i];
 #endif
@@ -751,14 +820,14 @@ MC_HD uint8_t select_expand_one(const View& V, int g, int lane, const double* no
             } else {
                 x = dmul((double)fmul(V.cpuct, p), root_n);
             }
-            double q_i = V.edge_Q[e0 + i], n_i = (double)V.edge_N[e0 + i];
+            double q_i = es.Q, n_i = (double)es.N;
             if (vloss) {   // descents in flight count as visits that lost (virtual loss)
-                const double vl = (double)V.edge_vl[e0 + i];
+                const double vl = (double)AZ_LINK(i, kk).vl;
                 if (vl > 0.0) { q_i = (n_i * q_i - vl) / (n_i + vl); n_i += vl; }
             }
             const double u = dadd(q_i, ddiv(x, dadd(1.0, n_i)));
             if (best_i == 0x7fffffff || u > best_u) { best_u = u; best_i = i; }  // first max within the lane
-        }
+        AZ_MY_EDGES_END
 #if defined(__CUDA_ARCH__)
         for (int o = 16; o > 0; o >>= 1) {
             double ou = __shfl_xor_sync(0xffffffffu, best_u, o);
@@ -772,25 +841,54 @@ MC_HD uint8_t select_expand_one(const View& V, int g, int lane, const double* no
         if (mix && lane == 0 && noise_used) noise_used[g] = 1;
         if (depth >= MAX_DEPTH) { raise(V, ERR_DEPTH); kind = LEAF_TERMINAL; value = 0.0; break; }
         const size_t e = e0 + (size_t)best_i;
+        // where the chosen edge leads: its link word is already in the registers of the lane that owns it
+#if defined(__CUDA_ARCH__)
+        EdgeLink lk = elk0;
+        if (best_i >= 32) lk = load_link(&V.edges[e]);          // every lane reads the same record
+        else {
+            const int owner = best_i;
+            lk.child = __shfl_sync(0xffffffffu, lk.child, owner);
+            lk.child_off = __shfl_sync(0xffffffffu, lk.child_off, owner);
+            lk.child_info = __shfl_sync(0xffffffffu, lk.child_info, owner);
+            lk.code = (uint16_t)__shfl_sync(0xffffffffu, (uint32_t)lk.code, owner);
+        }
+#else
+        const EdgeLink lk = V.edges[e].link;
+#endif
+#undef AZ_STAT
+#undef AZ_LINK
+#undef AZ_MY_EDGES_BEGIN
+#undef AZ_MY_EDGES_END
         if (lane == 0) {
             pedge[depth] = (uint32_t)(e - ebase);
             pnode[depth] = node;
-            if (vloss) V.edge_vl[e] += 1;
+            if (vloss) V.edges[e].link.vl += 1;
         }
         ++depth;
-        uint32_t child = V.edge_child[e];
+        uint32_t child = lk.child;
         if (child == NONE) {
-            // first traversal of this edge: apply the move and look the position up
-            mc_state ps = state_of(V.node_board[nbase + node], V.node_meta[nbase + node]);
+            // first traversal of this edge: apply the move to the parent's position and look the result up
+            const Node* pn = &V.nodes[nbase + node];
+            mc_state ps = state_of(load_board(pn), pn->head.meta);
             int fv, tv;
-            mc::code_to_view(V.edge_code[e], fv, tv);
+            mc::code_to_view(lk.code, fv, tv);
             const bool white = mc::white_to_move(ps);
             mc_state cs = mc::apply_move(ps, white ? fv : 29 - fv, white ? tv : 29 - tv);
             child = ht_find(V, t, cs);
-            if (child == NONE) { AZ_SYNCWARP(); child = AZ_EXPAND(V, slot, t, lane, cs, &kind, &value, pnode, depth); }
-            if (lane == 0 && child != NONE) V.edge_child[e] = child;
+            uint32_t c_off = 0, c_info = 0;
+            if (child == NONE) { AZ_SYNCWARP(); child = AZ_EXPAND(V, slot, t, lane, cs, &kind, &value, pnode, depth, &c_off, &c_info); }
+            else { const NodeHead h = load_head(&V.nodes[nbase + child]); c_off = h.edge_off; c_info = h.info; }    // a transposition
+            if (lane == 0 && child != NONE) {
+                // the link caches what a descent needs of the child's header (its edge count and terminal flags never change)
+                EdgeLink* l = &V.edges[e].link;
+                l->child = child; l->child_off = c_off; l->child_info = c_info & ~INFO_PENDING;
+            }
             AZ_SYNCWARP();
             if (child == NONE) break;
+            info = c_info; off = c_off;
+        } else {
+            info = lk.child_info; off = lk.child_off;
+            if (vloss) info = load_head(&V.nodes[nbase + child]).info;    // INFO_PENDING comes and goes: the header has it
         }
         node = child;
     }
@@ -816,38 +914,40 @@ MC_HD void backup_one(const View& V, int g, int lane, const float* logits, const
     double value = V.leaf_value[slot];
     if (kind == LEAF_EVAL) {
         const uint32_t node = V.leaf_node[slot];
-        const int E = (int)(V.node_info[nbase + node] & 0xffffu);
-        const size_t e0 = ebase + V.node_edge_off[nbase + node];
+        const NodeHead h = load_head(&V.nodes[nbase + node]);
+        const int E = (int)(h.info & 0xffffu);
+        const size_t e0 = ebase + h.edge_off;
         if (priors) {
-            for (int i = lane; i < E; i += AZ_LANES) V.edge_P[e0 + i] = priors[(size_t)slot * MC_MAX_MOVES + i];
+            for (int i = lane; i < E; i += AZ_LANES) V.edges[e0 + i].stat.P = priors[(size_t)slot * MC_MAX_MOVES + i];
         } else if (logits) {
             const float* lg = logits + (size_t)slot * MC_NUM_ACTIONS;
             float m = -INFINITY;
-            for (int i = lane; i < E; i += AZ_LANES) m = fmaxf(m, lg[V.edge_code[e0 + i]]);
+            for (int i = lane; i < E; i += AZ_LANES) m = fmaxf(m, lg[V.edges[e0 + i].link.code]);
 #if defined(__CUDA_ARCH__)
             for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
 #endif
             float sum = 0.f;
-            for (int i = lane; i < E; i += AZ_LANES) sum += expf(lg[V.edge_code[e0 + i]] - m);
+            for (int i = lane; i < E; i += AZ_LANES) sum += expf(lg[V.edges[e0 + i].link.code] - m);
 #if defined(__CUDA_ARCH__)
             for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
 #endif
-            for (int i = lane; i < E; i += AZ_LANES) V.edge_P[e0 + i] = expf(lg[V.edge_code[e0 + i]] - m) / sum;
-        }   // else: the policy head already wrote the priors into edge_P (heads_legal_kernel)
+            for (int i = lane; i < E; i += AZ_LANES) V.edges[e0 + i].stat.P = expf(lg[V.edges[e0 + i].link.code] - m) / sum;
+        }   // else: the policy head already wrote the priors into the edges (heads_legal_kernel)
         value = (double)values[slot];
-        if (V.K > 1 && lane == 0) V.node_info[nbase + node] &= ~INFO_PENDING;
+        if (V.K > 1 && lane == 0) V.nodes[nbase + node].head.info &= ~INFO_PENDING;
     }
     if (lane == 0) {
         const uint32_t* pedge = V.path_edge + (size_t)slot * MAX_DEPTH;
         const bool vloss = V.K > 1;
         for (int d = V.path_len[slot] - 1; d >= 0; --d) {
-            const size_t e = ebase + pedge[d];
-            if (vloss) V.edge_vl[e] -= 1;
+            Edge* ed = &V.edges[ebase + pedge[d]];
+            if (vloss) ed->link.vl -= 1;
             if (kind == LEAF_COLLISION) continue;      // dropped descent: only its virtual loss is undone
             value = -value;
-            const double n = (double)V.edge_N[e];
-            V.edge_Q[e] = ddiv(dadd(dmul(n, V.edge_Q[e]), value), dadd(n, 1.0));
-            V.edge_N[e] += 1u;
+            const EdgeStat st = load_stat(ed);          // one 128-bit read; Q and N go back (the prior is someone else's to write)
+            const double n = (double)st.N;
+            ed->stat.Q = ddiv(dadd(dmul(n, st.Q), value), dadd(n, 1.0));
+            ed->stat.N = st.N + 1u;
         }
         if (kind == LEAF_COLLISION) count(V, C_COLLISIONS, 1);
         else {

@@ -6,7 +6,7 @@
 //                      CTA pair, bf16 in, fp32 accumulate in TMEM), operands staged by TMA (SWIZZLE_128B,
 //                      K-major), 6-stage mbarrier pipeline, double-buffered TMEM accumulators, fused
 //                      bias(+BN) / residual / ReLU / bf16 epilogue; one data-flow ordered launch; works on the
-//                      tile pairs that hold rows of the (dense) leaf batch, one list schedule per count; the epilogue
+//                      tile pairs that hold rows of the (dense) leaf batch, work items claimed at run time; the epilogue
 //                      of the last level also takes the three 1x1 head convolutions (fp32 dot products of the row it
 //                      holds) and writes 90 floats per board instead of the 15 KB activation rows
 //   heads_kernel       policy head (61->554 linear) and value head (31->256 -> 1, tanh) on those sums, fp32;
@@ -42,15 +42,17 @@ constexpr int NLEVELS = NLAYERS + 1;   // work-item levels of the tower kernel: 
 constexpr int HEAD_IN = 96;       // floats per board handed to the heads: p0[30], p1[30], -, v[30] at 0 / 30 / 61 (raw 1x1 sums)
 constexpr int BLOCK_M = 128;      // boards per tile
 constexpr int BLOCK_K = 64;       // bf16 elements = one 128-byte swizzle row
-constexpr int STAGES = 6;
+#ifndef TOWER_STAGES
+#define TOWER_STAGES 6      // measured: a seventh stage (225 KB of shared memory, no L1 left) slows the epilogue by more than it saves
+#endif
+constexpr int STAGES = TOWER_STAGES;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB: this CTA's 128 boards x 64 input channels
 constexpr int B_BYTES = (C / 2) * BLOCK_K * 2;   // 16 KB: this CTA's half of the 256 output channels
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int STEM_K = 16;         // channels of a one-hot stem row (14 live): one K = 16 MMA, one 32-byte swizzle row
 constexpr int STEM_TILE_BYTES = BLOCK_M * STEM_K * 2;   // 4 KB: 128 boards (or 128 output channels) x 16 channels
 constexpr int CONV_THREADS = 256;                // TMA, MMA, TMEM-alloc, spare + 4 epilogue warps
-constexpr uint32_t SCHED_END = 0xffffffffu;
-constexpr int MAX_CHUNK_BOARDS = 8192;           // boards per forward pass (keeps the per-pair schedule within TOWER_MAX_ITEMS)
+constexpr int MAX_CHUNK_BOARDS = 8192;           // boards per forward pass (32 tile pairs: three L2 groups)
 
 // flat state_dict offsets (floats), exp/policy.py:56-69 order without num_batches_tracked
 constexpr size_t OFF_EMB = 0;
@@ -178,47 +180,61 @@ __device__ __forceinline__ bool tap_valid(int pos, int tap, int& src) {
 }
 
 // ---------------------------------------------------------------------------------- residual tower
-// One work item = (layer, output position, pair of 128-board tiles), computed by a CTA pair with
+// One work item = (level, output position, pair of 128-board tiles), computed by a CTA pair with
 // tcgen05.mma.cta_group::2: each CTA stages its own boards (A) and half of the output channels (B), so every
 // SM reads and writes half the weight bytes of the single-CTA form -- the shared-memory port, not the tensor
 // pipe, is what limits a 1-CTA 128x256 SS-mode MMA.  Roles per CTA: warp 0 lane 0 TMA producer, warp 1 lane 0
-// MMA issuer (leader CTA only), warp 2 TMEM allocator, warp 3 dependency watcher, warps 4-7 epilogue of this
-// CTA's 128 accumulator rows.  6-stage smem ring, double-buffered TMEM accumulators.
+// MMA issuer (leader CTA only), warp 2 TMEM allocator, warp 3 work-item scheduler (leader) + dependency watcher,
+// warps 4-7 epilogue of this CTA's 128 accumulator rows.  TOWER_STAGES-deep smem ring, double-buffered TMEM accumulators.
 //
-// Default form: the 18 convolutions are ONE persistent launch.  Layers are ordered by data flow instead of
-// by kernel boundaries: item (L, p, tp) may start once the items (L-1, p', tp) for the valid taps p' of p
-// have published their outputs (per-item epoch flags in global memory, release/acquire at gpu scope); that
-// one rule also covers the write-after-read hazards of the two ping-pong activation buffers.  CTA pairs
-// that finish a layer early move on instead of idling at a grid-wide barrier.
-// Fallback form (MCAZ_TOWER=layers, or when the pairs cannot all be resident): the same kernel is launched
-// once per layer with that layer's items and flags == nullptr -- kernel boundaries order the layers.
-constexpr int TOWER_MAX_ITEMS = 320;
+// Default form: stem + 18 convolutions are ONE persistent launch.  The items of a launch form one list in data-flow order
+// (groups of tile pairs that fit the L2 together; within a group level by level, tile pair by tile pair, the positions with
+// the most taps first), and the CTA pairs CLAIM items from it at run time with one atomicAdd per item: a pair that runs
+// faster (nearer L2 slice, cheaper items) simply takes more.  Item (L, p, tp) may start once the items (L-1, p', tp) for
+// the valid taps p' of p have published their outputs (per-item epoch flags in global memory, release/acquire at gpu
+// scope); that one rule also covers the write-after-read hazards of the two ping-pong activation buffers.  Because an
+// item is only ever claimed by a pair that is running, and its inputs are items claimed earlier, the waits cannot
+// deadlock whatever part of the grid is resident: nothing has to be co-resident.  (Round 1 dealt the items out
+// ahead of time by estimated cost, one table per batch size; measured, 4-8 % of the kernel went into waits on
+// pairs that had fallen behind their share, and a launch next to another kernel could hang.)
+// Per-level form (MCAZ_TOWER=layers): the same kernel launched once per level with flags == nullptr --
+// kernel boundaries order the levels.  Bit-identical: an item's arithmetic does not depend on who runs it when.
 #ifndef SPIN_NS
 #define SPIN_NS 40     // back-off of the waits on the dependency watcher: a hot spin costs issue slots and power
 #endif
-constexpr int TOWER_SMEM = STAGES * STAGE_BYTES + 1024 + 256 + NLEVELS * C * 4 + C * 16;
+constexpr int TOWER_SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+static_assert(TOWER_SMEM <= 227 * 1024, "tower shared memory");
 constexpr unsigned long long WATCHDOG_CYCLES = 20ull * 1000 * 1000 * 1000;   // ~10 s: a dependency that never arrives
+constexpr int ITEM_RING = 16;          // claimed items in flight per CTA (scheduler -> producer / MMA / epilogue); see tower_scheduler
+#ifndef TOWER_GROUP_PAIRS
+#define TOWER_GROUP_PAIRS 12
+#endif
+constexpr int GROUP_MAX_PAIRS = TOWER_GROUP_PAIRS;    // tile pairs that walk the levels together (their ping-pong buffers stay in the 126 MB L2)
 
 struct TowerParams {
-    const float* bias;            // [19][256]: stem, then the 18 convolutions
-    const float* head_w;          // [256][4]: folded 1x1 filters policy 0, policy 1, value, 0
+    float bias[NLEVELS * C];      // [19][256]: stem, then the 18 convolutions.  In the kernel's parameter space (constant
+                                  // bank): every epilogue thread reads the same word at the same time
+    const float* bias_g;          // the same in global memory, for the out-of-line head epilogue
+    const float4* head_w;         // [256]: folded 1x1 filters policy 0, policy 1, value, 0 per input channel
     float* head_in;               // [bpad][HEAD_IN]: written by the last level's epilogue
     __nv_bfloat16* act0;          // layer input of even layers / residual + output of odd layers
     __nv_bfloat16* act1;
-    const uint32_t* sched;        // [clusters][TOWER_MAX_ITEMS]: level << 24 | tile pair << 8 | position
     uint32_t* flags;              // [19][n_pairs][30][2] epoch stamps; nullptr = one level per launch, no dependencies
+    uint32_t* claim;              // [2]: next item of the list, CTA pairs that have left the kernel (resets both)
     const uint32_t* count;        // device row count of this forward (dense leaf batch) or nullptr: all n_pairs are live
-    size_t sched_stride;          // words between the schedules for k and k + 1 live pairs (0: one schedule, dead pairs skipped)
     uint32_t row_base;            // first row of this chunk within the batch that `count` counts
     int bpad;
     int n_pairs;
     uint32_t epoch;
-    int first_level;              // levels below this one are not in the schedule (0; MCAZ_DEBUG_TOWER timing experiments only)
+    int first_level;              // levels below this one are not in the list (0; timing experiments only)
+    int n_levels;                 // levels in the list from first_level on (19; 1 in the per-level form)
     int fuse_heads;               // 1: the last level's epilogue takes the head convolutions (0 only in timing experiments)
+    int group_max;                // tile pairs per L2 group
     uint32_t wait_hint;           // suspend-time hint (ns) of the epilogue warps' waits for an accumulator; 0 = plain try_wait spin
     unsigned long long* stats;    // MCAZ_TOWER_STATS=1: per CTA {MMA issuer: total, waiting for operands, waiting for an accumulator;
                                   // TMA producer: total, waiting for dependencies, waiting for a free stage; MMA issuer: operand wait
                                   // at the first stage of an item, items} in clock cycles; else nullptr
+    uint8_t pos_order[32];        // the 30 positions, those with the most valid taps first
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
@@ -242,18 +258,67 @@ __device__ __forceinline__ uint4 ld_cg_v4(const uint4* p) {   // L2-coherent: ne
     asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
+// 256-bit forms (sm_100: LDG.256 / STG.256): a thread's 32 channels of a row are 64 contiguous bytes = two whole 32-byte
+// sectors, so the activation rows travel as full sectors in half as many L2 requests as with 128-bit accesses
+__device__ __forceinline__ void ld_cg_v8(const void* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.cg.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_v8(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
+// ---- claimed work items: a ring of 64-bit slots per CTA, slot k % ITEM_RING = (item << 32) | (k + 1).  One aligned
+// 64-bit store publishes an item (item and sequence number can never be seen apart), to this CTA and to its peer.
+constexpr uint32_t ITEM_END = 0xffffffffu;
+__device__ __forceinline__ void ring_put(unsigned long long* ring, uint32_t k, uint32_t item, uint32_t peer) {
+    const unsigned long long v = ((unsigned long long)item << 32) | (unsigned long long)(k + 1u);
+    const uint32_t addr = smem_u32(&ring[k % ITEM_RING]);
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "st.volatile.shared::cta.b64 [%0], %1;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %2;\n\t"
+        "st.volatile.shared::cluster.b64 [ra], %1;\n\t}"
+        ::"r"(addr), "l"(v), "r"(peer)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t ring_get(const unsigned long long* ring, uint32_t k) {
+    const uint32_t addr = smem_u32(&ring[k % ITEM_RING]);
+    unsigned long long v;
+    for (;;) {
+        asm volatile("ld.volatile.shared::cta.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+        if ((uint32_t)v == k + 1u) break;
+        __nanosleep(SPIN_NS);
+    }
+    return (uint32_t)(v >> 32);
+}
+// Item number idx of the launch's list -> level << 24 | tile pair << 8 | position, or ITEM_END past the end.
+__device__ __forceinline__ uint32_t tower_item(const TowerParams& P, int live_pairs, uint32_t idx) {
+    const int n_groups = (live_pairs + P.group_max - 1) / P.group_max;
+    for (int gi = 0; gi < n_groups; ++gi) {
+        const int g0 = (int)((long long)live_pairs * gi / n_groups), g1 = (int)((long long)live_pairs * (gi + 1) / n_groups);
+        const uint32_t per_level = (uint32_t)(g1 - g0) * NPOS, cnt = per_level * (uint32_t)P.n_levels;
+        if (idx < cnt) {
+            const uint32_t L = (uint32_t)P.first_level + idx / per_level, r = idx % per_level;
+            return (L << 24) | ((uint32_t)(g0 + (int)(r / NPOS)) << 8) | (uint32_t)P.pos_order[r % NPOS];
+        }
+        idx -= cnt;
+    }
+    return ITEM_END;
+}
 
 // Epilogue of the last level for one accumulator row (this thread's board at one position): 8 chunks of 32 channels.
 // Kept out of line so that its registers do not weigh on the common epilogue.  The residual row is published before
 // the item's MMAs start, so four chunks of it are fetched ahead of the accumulator and refilled as they are used.
-__device__ __noinline__ void epilogue_heads(uint32_t taddr, const float* bias, const float4* s_hw, const __nv_bfloat16* res_row,
-                                            uint64_t* acc_full, uint32_t acc_phase, uint32_t wait_hint, float* h) {
+__device__ __noinline__ void epilogue_heads(uint32_t taddr, const float* __restrict__ bias, const float4* __restrict__ hw,
+                                            const __nv_bfloat16* res_row, uint64_t* acc_full, uint32_t acc_phase, uint32_t wait_hint,
+                                            float* h) {
     uint4 res[4][4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        const uint4* rp = reinterpret_cast<const uint4*>(res_row + c * 32);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) res[c][j] = ld_cg_v4(rp + j);
+        ld_cg_v8(res_row + c * 32, res[c][0], res[c][1]);
+        ld_cg_v8(res_row + c * 32 + 16, res[c][2], res[c][3]);
     }
     if (wait_hint) mbar_wait_hint(acc_full, acc_phase, wait_hint); else mbar_wait(acc_full, acc_phase);
     tc_fence_after();
@@ -278,17 +343,16 @@ __device__ __noinline__ void epilogue_heads(uint32_t taddr, const float* bias, c
             for (int hh = 0; hh < 4; ++hh) {
                 const int e = j * 8 + hh * 2;
                 const uint32_t r = (&res[c & 3][j].x)[hh];
-                const float x0 = fmaxf(__uint_as_float(v[e]) + bias[c * 32 + e] + __uint_as_float(r << 16), 0.f);
-                const float x1 = fmaxf(__uint_as_float(v[e + 1]) + bias[c * 32 + e + 1] + __uint_as_float(r & 0xffff0000u), 0.f);
-                const float4 w0 = s_hw[c * 32 + e], w1 = s_hw[c * 32 + e + 1];
+                const float x0 = fmaxf(__uint_as_float(v[e]) + __ldg(bias + c * 32 + e) + __uint_as_float(r << 16), 0.f);
+                const float x1 = fmaxf(__uint_as_float(v[e + 1]) + __ldg(bias + c * 32 + e + 1) + __uint_as_float(r & 0xffff0000u), 0.f);
+                const float4 w0 = __ldg(hw + c * 32 + e), w1 = __ldg(hw + c * 32 + e + 1);
                 h0 = fmaf(x0, w0.x, h0); h1 = fmaf(x0, w0.y, h1); h2 = fmaf(x0, w0.z, h2);
                 h0 = fmaf(x1, w1.x, h0); h1 = fmaf(x1, w1.y, h1); h2 = fmaf(x1, w1.z, h2);
             }
         }
         if (c + 4 < C / 32) {
-            const uint4* rp = reinterpret_cast<const uint4*>(res_row + (c + 4) * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) res[c & 3][j] = ld_cg_v4(rp + j);
+            ld_cg_v8(res_row + (c + 4) * 32, res[c & 3][0], res[c & 3][1]);
+            ld_cg_v8(res_row + (c + 4) * 32 + 16, res[c & 3][2], res[c & 3][3]);
         }
     }
     h[0] = h0; h[1] = h1; h[2] = h2;
@@ -297,7 +361,7 @@ __device__ __noinline__ void epilogue_heads(uint32_t taddr, const float* bias, c
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
 tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_constant__ CUtensorMap map_act1,
                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_stem_in,
-                const __grid_constant__ CUtensorMap map_stem_w, const TowerParams P) {
+                const __grid_constant__ CUtensorMap map_stem_w, const __grid_constant__ TowerParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -306,25 +370,22 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
     uint64_t* acc_full = bars + 2 * STAGES;
     uint64_t* acc_empty = bars + 2 * STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-    float* s_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // [19][256]
-    float4* s_hw = reinterpret_cast<float4*>(s_bias + NLEVELS * C);                // [256] head filters per channel
+    __shared__ unsigned long long s_ring[ITEM_RING];   // claimed items (written by the leader's scheduler, here and in the peer)
     __shared__ uint32_t s_deps_ok;            // items [0, s_deps_ok) have all their inputs published (written by warp 3)
+    __shared__ uint32_t s_prod_at;            // item the TMA producer of this CTA is loading (flow control of the scheduler)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
-    // dense leaf batch: only the tile pairs that hold rows are computed.  The fused form has one schedule per number
-    // of live pairs (sched_stride apart); in the per-layer form every role skips the items of the dead pairs.
+    // dense leaf batch: only the tile pairs that hold rows are in the list
     int live_pairs = P.n_pairs;
     if (P.count) {
         const uint32_t total = __ldg(P.count), rows = total > P.row_base ? total - P.row_base : 0u;
         live_pairs = (int)min((uint32_t)P.n_pairs, (rows + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
     }
-    const uint32_t* sched = P.sched + (size_t)max(live_pairs - 1, 0) * P.sched_stride + (size_t)(blockIdx.x >> 1) * TOWER_MAX_ITEMS;
 
-    for (int i = threadIdx.x; i < NLEVELS * C; i += CONV_THREADS) s_bias[i] = P.bias[i];
-    for (int i = threadIdx.x; i < C; i += CONV_THREADS) s_hw[i] = reinterpret_cast<const float4*>(P.head_w)[i];
-    if (threadIdx.x == 0) s_deps_ok = 0;
+    if (threadIdx.x < ITEM_RING) s_ring[threadIdx.x] = 0ull;
+    if (threadIdx.x == 0) { s_deps_ok = 0; s_prod_at = 0; }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
@@ -345,16 +406,16 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
         uint32_t it = 0;
         const long long p_start = clock64();
         long long p_deps = 0, p_slot = 0;
-        for (int k = 0; k < TOWER_MAX_ITEMS; ++k) {
-            const uint32_t item = __ldg(&sched[k]);
-            if (item == SCHED_END) break;
+        for (uint32_t k = 0;; ++k) {
+            const uint32_t item = ring_get(s_ring, k);
+            if (item == ITEM_END) break;
+            *reinterpret_cast<volatile uint32_t*>(&s_prod_at) = k;
             const int pos = item & 0xff, tp = (item >> 8) & 0xffff, L = item >> 24;
-            if (tp >= live_pairs) continue;
             const int tile = 2 * tp + (int)rank;
             if (L > P.first_level && P.flags) {
                 // inputs published? (warp 3 polls the global flags ahead of us)
                 const long long t0 = clock64();
-                while (ld_acquire_cta_shared(&s_deps_ok) <= (uint32_t)k) __nanosleep(SPIN_NS);
+                while (ld_acquire_cta_shared(&s_deps_ok) <= k) __nanosleep(SPIN_NS);
                 p_deps += clock64() - t0;
                 asm volatile("fence.proxy.async;" ::: "memory");   // order the acquired writes before our TMA reads
             }
@@ -386,21 +447,19 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
         }
     } else if (warp == 1 && lane == 0 && leader) {
         // ---------------------------------------------------------------- MMA issuer (leader CTA)
-        uint32_t it = 0, j = 0;                       // j: items actually computed (accumulator ring position)
+        uint32_t it = 0;
         const long long m_start = clock64();
         long long m_full = 0, m_acc = 0, m_first = 0, m_items = 0;
-        for (int k = 0; k < TOWER_MAX_ITEMS; ++k) {
-            const uint32_t item = __ldg(&sched[k]);
-            if (item == SCHED_END) break;
+        for (uint32_t k = 0;; ++k) {
+            const uint32_t item = ring_get(s_ring, k);
+            if (item == ITEM_END) break;
             const int pos = item & 0xff;
-            if ((int)((item >> 8) & 0xffff) >= live_pairs) continue;
             const bool stem = (item >> 24) == 0;          // K = 16 per tap: the 14 one-hot channels
             const int chunks = stem ? 1 : C / BLOCK_K, ksteps = stem ? 1 : BLOCK_K / 16;
-            const uint32_t acc = j & 1;
+            const uint32_t acc = k & 1;
             const long long t0 = clock64();
-            mbar_wait(&acc_empty[acc], ((j >> 1) & 1) ^ 1);
+            mbar_wait(&acc_empty[acc], ((k >> 1) & 1) ^ 1);
             m_acc += clock64() - t0;
-            ++j;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * C;
             uint32_t accumulate = 0;
@@ -437,53 +496,65 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             st[6] = (unsigned long long)m_first; st[7] = (unsigned long long)m_items;
         }
     } else if (warp == 3) {
-        // ---------------------------------------------------------------- dependency watcher
-        // Item (L, p, tp) reads the previous layer's output at the valid taps of p (rows of this CTA's
-        // tile): lanes 0-8 each poll one of those flags, so a check costs one L2 round trip and runs
-        // ahead of the TMA producer instead of stalling it.
-        for (int k = 0; k < TOWER_MAX_ITEMS; ++k) {
-            const uint32_t item = __ldg(&sched[k]);
-            if (item == SCHED_END) break;
+        // ---------------------------------------------------------------- scheduler (leader) + dependency watcher
+        // The leader's lane 0 claims the pair's next item -- one atomicAdd on the launch's list -- as soon as the producer
+        // has begun the item before it, and publishes it to both CTAs.  The producer never runs more than a few items
+        // ahead of the epilogue (ring stages, two accumulators), so a ring slot is long read by everyone when it is reused.
+        // Then item (L, p, tp) reads the previous level's output at the valid taps of p (rows of this CTA's tile): lanes
+        // 0-8 each poll one of those flags, so a check costs one L2 round trip and runs ahead of the TMA producer.
+        for (uint32_t k = 0;; ++k) {
+            uint32_t item = 0;
+            if (leader) {
+                if (lane == 0) {
+                    while (k > *reinterpret_cast<volatile uint32_t*>(&s_prod_at) + 1u) __nanosleep(SPIN_NS);
+                    item = tower_item(P, live_pairs, atomicAdd(&P.claim[0], 1u));
+                    ring_put(s_ring, k, item, 1u);
+                }
+                item = __shfl_sync(0xffffffffu, item, 0);
+            } else {
+                if (lane == 0) item = ring_get(s_ring, k);
+                item = __shfl_sync(0xffffffffu, item, 0);
+            }
+            if (item == ITEM_END) break;
             const int pos = item & 0xff, tp = (item >> 8) & 0xffff, L = item >> 24;
-            if (tp < live_pairs && L > P.first_level && P.flags && lane < 9) {
+            if (L > P.first_level && P.flags && lane < 9) {
                 int src;
                 if (tap_valid(pos, lane, src)) {
                     const uint32_t* fl = P.flags + (((size_t)(L - 1) * P.n_pairs + tp) * NPOS + src) * 2 + rank;
                     const long long t0 = clock64();
                     while (ld_acquire_gpu(fl) != P.epoch) {
                         __nanosleep(32);
-                        // the producer of this flag is not resident (co-residency assumption broken): fail the
-                        // launch instead of hanging the GPU
+                        // cannot happen (an item's inputs were claimed before it by pairs that are running): fail the launch
+                        // instead of hanging the GPU if it ever does
                         if ((unsigned long long)(clock64() - t0) > WATCHDOG_CYCLES) __trap();
                     }
                 }
             }
             __syncwarp();
-            if (lane == 0) st_release_cta_shared(&s_deps_ok, (uint32_t)k + 1);
+            if (lane == 0) st_release_cta_shared(&s_deps_ok, k + 1u);
         }
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- epilogue (TMEM -> HBM) + publish
         const int q = warp & 3;
-        uint32_t j = 0;
-        for (int k = 0; k < TOWER_MAX_ITEMS; ++k) {
-            const uint32_t item = __ldg(&sched[k]);
-            if (item == SCHED_END) break;
+        for (uint32_t k = 0;; ++k) {
+            uint32_t item = 0;
+            if (lane == 0) item = ring_get(s_ring, k);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item == ITEM_END) break;
             const int pos = item & 0xff, tp = (item >> 8) & 0xffff, L = item >> 24;
-            if (tp >= live_pairs) continue;
             const int tile = 2 * tp + (int)rank;
-            const uint32_t acc = j & 1, acc_phase = (j >> 1) & 1;
-            ++j;
+            const uint32_t acc = k & 1, acc_phase = (k >> 1) & 1;
             const bool odd = L >= 2 && (L & 1) == 0;           // second conv of a residual block
             const bool last = L == NLAYERS && P.fuse_heads;    // its output only feeds the three 1x1 head convolutions
             __nv_bfloat16* out = (odd || L == 0) ? P.act0 : P.act1;
-            const float* bias = s_bias + L * C;
             const size_t row_off = ((size_t)pos * P.bpad + (size_t)tile * BLOCK_M + q * 32 + lane) * C;
             if (last) {
                 // the tower's output row never leaves the SM: bias + residual + ReLU in fp32, then the three 1x1 head
                 // filters as dot products over the row this thread holds
-                if (P.flags) while (ld_acquire_cta_shared(&s_deps_ok) <= (uint32_t)k) __nanosleep(SPIN_NS);
+                if (P.flags) while (ld_acquire_cta_shared(&s_deps_ok) <= k) __nanosleep(SPIN_NS);
                 float h[3];
-                epilogue_heads(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C, bias, s_hw, out + row_off, &acc_full[acc], acc_phase, P.wait_hint, h);
+                epilogue_heads(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C, P.bias_g + L * C, P.head_w, out + row_off, &acc_full[acc],
+                               acc_phase, P.wait_hint, h);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
@@ -501,17 +572,17 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             // dependencies are: fetch them while the MMAs still run
             uint4 res[4][4];
             if (odd) {
-                if (P.flags) while (ld_acquire_cta_shared(&s_deps_ok) <= (uint32_t)k) __nanosleep(SPIN_NS);
+                if (P.flags) while (ld_acquire_cta_shared(&s_deps_ok) <= k) __nanosleep(SPIN_NS);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(out + row_off + c * 32);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) res[c][j] = ld_cg_v4(rp + j);
+                    ld_cg_v8(out + row_off + c * 32, res[c][0], res[c][1]);
+                    ld_cg_v8(out + row_off + c * 32 + 16, res[c][2], res[c][3]);
                 }
             }
             if (P.wait_hint) mbar_wait_hint(&acc_full[acc], acc_phase, P.wait_hint); else mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C;
+            const int bias0 = L * C;
 #pragma unroll
             for (int c = 0; c < C / 32; ++c) {
                 uint32_t v[32];
@@ -542,8 +613,8 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
 #pragma unroll
                     for (int h = 0; h < 4; ++h) {
                         const int e = j * 8 + h * 2;
-                        float x0 = __uint_as_float(v[e]) + bias[c * 32 + e];
-                        float x1 = __uint_as_float(v[e + 1]) + bias[c * 32 + e + 1];
+                        float x0 = __uint_as_float(v[e]) + P.bias[bias0 + c * 32 + e];
+                        float x1 = __uint_as_float(v[e + 1]) + P.bias[bias0 + c * 32 + e + 1];
                         if (odd) {
                             const uint32_t r = (&res[c & 3][j].x)[h];
                             x0 += __uint_as_float(r << 16);
@@ -557,13 +628,11 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                     outv[j] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                 }
                 if (odd && c + 4 < C / 32) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(out + row_off + (c + 4) * 32);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) res[c & 3][j] = ld_cg_v4(rp + j);
+                    ld_cg_v8(out + row_off + (c + 4) * 32, res[c & 3][0], res[c & 3][1]);
+                    ld_cg_v8(out + row_off + (c + 4) * 32 + 16, res[c & 3][2], res[c & 3][3]);
                 }
-                uint4* op = reinterpret_cast<uint4*>(out + row_off + c * 32);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) op[j] = outv[j];
+                st_v8(out + row_off + c * 32, outv[0], outv[1]);
+                st_v8(out + row_off + c * 32 + 16, outv[2], outv[3]);
             }
             // publish: the barrier orders all 128 threads' stores before the (cumulative) gpu-scope release
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -577,6 +646,15 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+    // the last pair to leave rewinds the list for the next launch on this stream
+    if (leader && threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&P.claim[1], 1u) == (gridDim.x >> 1) - 1u) {
+            P.claim[0] = 0u;
+            P.claim[1] = 0u;
+            __threadfence();
+        }
     }
 }
 
@@ -813,15 +891,15 @@ heads_legal_kernel(const float* __restrict__ head_in, HeadWeights H, az::View V,
             const int g = slot / V.K;
             const int t = 2 * g + (V.game_ply[g] & 1);
             const uint32_t node = V.leaf_node[slot];
-            const size_t gi = (size_t)t * V.NC + node;
-            E = (int)(V.node_info[gi] & 0xffffu);
-            e0 = (size_t)t * V.EC + V.node_edge_off[gi];
-            codes = V.edge_code + e0;
+            const az::NodeHead h = az::load_head(&V.nodes[(size_t)t * V.NC + node]);
+            E = (int)(h.info & 0xffffu);
+            e0 = (size_t)t * V.EC + h.edge_off;
+            codes = nullptr;                       // read from the leaf's edge records below
         }
         float lg[3] = {-INFINITY, -INFINITY, -INFINITY};
         float m = -INFINITY;
         for (int i = lane, kk = 0; i < E && kk < 3; i += 32, ++kk) {
-            const int code = codes[i];
+            const int code = lookahead ? codes[i] : V.edges[e0 + i].link.code;
             float acc = __ldg(H.plb + code);
 #pragma unroll
             for (int j = 0; j < 61; ++j) acc += in[j] * __ldg(H.plt + j * 554 + code);   // 61 independent gathers in flight
@@ -836,7 +914,7 @@ heads_legal_kernel(const float* __restrict__ head_in, HeadWeights H, az::View V,
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         for (int i = lane, kk = 0; i < E && kk < 3; i += 32, ++kk) {
             lg[kk] = expf(lg[kk] - m) / sum;
-            if (!lookahead) V.edge_P[e0 + i] = lg[kk];
+            if (!lookahead) V.edges[e0 + i].stat.P = lg[kk];
         }
         // ---- value
         float hv[8];
@@ -923,15 +1001,14 @@ struct Network {
     HeadWeights heads{};
     CUtensorMap map_act[2], map_w, map_stem_in, map_stem_w;
     bool have_weights = false;
-    uint32_t* sched = nullptr;         // per-layer form: [18][clusters][TOWER_MAX_ITEMS]
-    int sched_tiles = -1, sched_grid = 0;
-    uint32_t* tower_sched = nullptr;   // [clusters][TOWER_MAX_ITEMS]
-    uint32_t* tower_flags = nullptr;   // [19][n_pairs][30][2]
-    int tower_pairs = -1, tower_grid = 0;
+    uint32_t* tower_flags = nullptr;   // [19][n_pairs][30][2] epoch stamps of the published items
+    uint32_t* tower_claim = nullptr;   // [2] next item of the running launch's list, pairs that have left it
+    int tower_pairs = -1;
+    TowerParams tower_params;          // the kernel's parameter block; its `bias` is the host copy of the folded biases
+    uint8_t pos_order[32];
     uint32_t epoch = 0;
-    bool cooperative = true;           // fused form: launched with cudaLaunchAttributeCooperative (all CTA pairs resident or none)
-    bool per_layer = false;            // false: tower_tc_kernel (one data-flow ordered launch for the 18 layers, default);
-                                       // true: the same kernel launched once per layer (MCAZ_TOWER=layers, or no co-residency)
+    bool per_layer = false;            // false: tower_tc_kernel (one data-flow ordered launch for all levels, default);
+                                       // true: the same kernel launched once per level (MCAZ_TOWER=layers)
     // profiling (az_profile_network)
     unsigned long long* stats = nullptr;   // MCAZ_TOWER_STATS=1: [grid][8] wait-cycle counters of the last tower launch
     bool profiling = false;
@@ -991,23 +1068,20 @@ int network_create(az_engine* e) {
     if (int rc = make_map_3d(&N->map_stem_w, N->stem_w, STEM_K, C, 9, STEM_K, C / 2, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
     MCAZ_CUDA(cudaFuncSetAttribute(tower_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_SMEM));
     {
-        // Default: the fused data-flow tower, provided every CTA pair of its grid can be resident at once (its
-        // flag waits assume that).  MCAZ_TOWER=layers forces one launch per layer.
-        const char* m = getenv("MCAZ_TOWER");
+        const char* m = getenv("MCAZ_TOWER");      // "layers": one launch per level (bit-identical; for tests and per-level profiles)
         N->per_layer = m && std::strcmp(m, "layers") == 0;
-        if (!N->per_layer) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(2 * (num_sms() / 2)); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = TOWER_SMEM;
-            cudaLaunchAttribute attr;
-            attr.id = cudaLaunchAttributeClusterDimension;
-            attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-            cfg.attrs = &attr; cfg.numAttrs = 1;
-            int max_clusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&max_clusters, tower_tc_kernel, &cfg) != cudaSuccess || max_clusters < num_sms() / 2) {
-                cudaGetLastError();
-                N->per_layer = true;
-            }
+        // positions with the most valid taps first: the list's long items lead each (level, tile pair) run
+        int taps_of[NPOS], order[NPOS];
+        for (int pos = 0; pos < NPOS; ++pos) {
+            const int r = pos / 5, c = pos % 5;
+            taps_of[pos] = ((r == 0 || r == 5) ? 2 : 3) * ((c == 0 || c == 4) ? 2 : 3);
+            order[pos] = pos;
         }
+        std::stable_sort(order, order + NPOS, [&](int a, int b) { return taps_of[a] > taps_of[b]; });
+        std::memset(N->pos_order, 0, sizeof(N->pos_order));
+        for (int i = 0; i < NPOS; ++i) N->pos_order[i] = (uint8_t)order[i];
+        MCAZ_CUDA(cudaMalloc(&N->tower_claim, 2 * sizeof(uint32_t)));
+        MCAZ_CUDA(cudaMemset(N->tower_claim, 0, 2 * sizeof(uint32_t)));
     }
     return net_alloc_acts(e, std::min(std::max(e->v.G * e->v.K, e->v.row_cap), MAX_CHUNK_BOARDS));   // grows on demand (network_forward batches)
 }
@@ -1022,9 +1096,8 @@ void network_destroy(az_engine* e) {
     if (N->stem_in) cudaFree(N->stem_in);
     if (N->head_in) cudaFree(N->head_in);
     if (N->head_pool) cudaFree(N->head_pool);
-    if (N->sched) cudaFree(N->sched);
-    if (N->tower_sched) cudaFree(N->tower_sched);
     if (N->tower_flags) cudaFree(N->tower_flags);
+    if (N->tower_claim) cudaFree(N->tower_claim);
     if (N->stats) cudaFree(N->stats);
     for (auto& ev : N->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     delete N;
@@ -1040,53 +1113,14 @@ int network_set_weights(az_engine* e, const float* flat) {
     prep_heads_kernel<<<64, 256, 0, e->stream>>>(flat, N->heads);
     MCAZ_CHECK_LAUNCH();
     e->launches += 3;
+    MCAZ_CUDA(cudaMemcpyAsync(N->tower_params.bias, N->bias, sizeof(N->tower_params.bias), cudaMemcpyDeviceToHost, e->stream));
+    MCAZ_CUDA(cudaStreamSynchronize(e->stream));       // the tower takes the biases in its parameter block
     N->have_weights = true;
     return MCAZ_OK;
 }
 
-// Per-layer form: longest-processing-time-first assignment of each layer's work items (position x tile pair,
-// weighted by the number of valid taps) to the CTA pairs; one table per layer, same kernel.
-static int build_schedule(az_engine* e, int n_pairs) {
-    Network* N = e->net;
-    const int clusters = std::max(1, std::min(num_sms() / 2, n_pairs * NPOS));
-    if (N->sched_tiles == n_pairs && N->sched_grid == 2 * clusters) return MCAZ_OK;
-    struct Item { uint32_t code; int weight; };
-    std::vector<Item> items;
-    for (int pos = 0; pos < NPOS; ++pos) {
-        const int r = pos / 5, c = pos % 5;
-        const int taps = ((r == 0 || r == 5) ? 2 : 3) * ((c == 0 || c == 4) ? 2 : 3);
-        for (int tp = 0; tp < n_pairs; ++tp) items.push_back({(uint32_t)pos | ((uint32_t)tp << 8), taps});
-    }
-    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.weight > b.weight; });
-    std::vector<int> load(clusters, 0), count(clusters, 0);
-    const size_t per_layer = (size_t)clusters * TOWER_MAX_ITEMS;
-    std::vector<uint32_t> table(per_layer * NLEVELS, SCHED_END);
-    for (const Item& it : items) {
-        int best = -1;
-        for (int c = 0; c < clusters; ++c)
-            if (count[c] < TOWER_MAX_ITEMS - 1 && (best < 0 || load[c] < load[best])) best = c;
-        if (best < 0) return fail(MCAZ_ECAPACITY, "conv schedule: too many items per CTA pair");
-        for (int L = 0; L < NLEVELS; ++L)
-            table[L * per_layer + (size_t)best * TOWER_MAX_ITEMS + count[best]] = it.code | ((uint32_t)L << 24);
-        count[best]++;
-        load[best] += it.weight;
-    }
-    if (N->sched) cudaFree(N->sched);
-    N->sched = nullptr;
-    MCAZ_CUDA(cudaMalloc(&N->sched, table.size() * sizeof(uint32_t)));
-    MCAZ_CUDA(cudaMemcpyAsync(N->sched, table.data(), table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
-    MCAZ_CUDA(cudaStreamSynchronize(e->stream));
-    N->sched_tiles = n_pairs;
-    N->sched_grid = 2 * clusters;
-    return MCAZ_OK;
-}
-
-// Data-flow schedule of the whole tower: items in (layer, tile pair, position) order, each given to the
-// CTA pair with the least accumulated work (list scheduling).  Every pair therefore walks the layers in
-// order and the tile pairs in ascending order within a layer, so an item's inputs -- produced one layer
-// earlier at the same place of that order -- are normally long finished when it starts.
 // MCAZ_DEBUG_TOWER (timing experiments, results are then wrong): bit 0 = the last level stores its activations like
-// any other instead of taking the head convolutions, bit 1 = no stem level in the schedule.
+// any other instead of taking the head convolutions, bit 1 = no stem level in the list.
 // Only in builds made with -DMCAZ_TIMING_EXPERIMENTS (never the shipped library): there the environment also sets the L2
 // group size and the epilogue's wait hint.
 #ifdef MCAZ_TIMING_EXPERIMENTS
@@ -1105,57 +1139,16 @@ static constexpr int tower_debug() { return 0; }
 static constexpr int env_or(const char*, int dflt) { return dflt; }
 #endif
 
-static int build_tower_schedule(az_engine* e, int n_pairs) {
+// Epoch flags of the published items, one per (level, tile pair, position, CTA of the pair).
+static int tower_flags_for(az_engine* e, int n_pairs) {
     Network* N = e->net;
-    const int clusters = std::max(1, std::min(num_sms() / 2, n_pairs * NPOS));
-    if (N->tower_pairs == n_pairs && N->tower_grid == 2 * clusters) return MCAZ_OK;
-    int taps_of[NPOS];
-    std::vector<int> order;
-    for (int pos = 0; pos < NPOS; ++pos) {
-        const int r = pos / 5, c = pos % 5;
-        taps_of[pos] = ((r == 0 || r == 5) ? 2 : 3) * ((c == 0 || c == 4) ? 2 : 3);
-        order.push_back(pos);
-    }
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return taps_of[a] > taps_of[b]; });
-    // One schedule per number of live tile pairs (the dense leaf batch of az_search shrinks and grows; the kernel reads
-    // the row count on the device and picks the table built for exactly that many pairs).
-    // Groups of tile pairs go through all 18 layers one after the other, so a group's ping-pong buffers stay
-    // resident in the 126 MB L2 from layer to layer: at most 12 pairs per group (3072 boards, 2 x 47 MB), split
-    // evenly (16 pairs -> 8 + 8).  Small groups leave too few items per layer to hide the waits on the previous
-    // layer (measured on 2 800-row batches: groups of <= 4 pairs 1.40 ms, <= 6: 1.27, <= 8: 1.17, <= 12: 1.165, 16: 1.19).
-    const int group_max = env_or("MCAZ_TOWER_GROUP", 12);
-    const size_t per_table = (size_t)clusters * TOWER_MAX_ITEMS;
-    std::vector<uint32_t> table(per_table * n_pairs, SCHED_END);
-    for (int live = 1; live <= n_pairs; ++live) {
-        std::vector<long long> load(clusters, 0);
-        std::vector<int> count(clusters, 0);
-        uint32_t* tab = table.data() + (size_t)(live - 1) * per_table;
-        const int n_groups = (live + group_max - 1) / group_max;
-        for (int gi = 0; gi < n_groups; ++gi) {
-            const int g0 = (int)((long long)live * gi / n_groups), g1 = (int)((long long)live * (gi + 1) / n_groups);
-            for (int L = tower_debug() & 2 ? 1 : 0; L < NLEVELS; ++L)       // level 0 = stem: nine K = 16 MMAs at most, its cost is the epilogue
-                for (int tp = g0; tp < g1; ++tp)
-                    for (int pos : order) {
-                        int best = 0;
-                        for (int c = 1; c < clusters; ++c)
-                            if (load[c] < load[best]) best = c;
-                        if (count[best] >= TOWER_MAX_ITEMS - 1) return fail(MCAZ_ECAPACITY, "tower schedule: too many items per CTA pair");
-                        tab[(size_t)best * TOWER_MAX_ITEMS + count[best]++] = (uint32_t)pos | ((uint32_t)tp << 8) | ((uint32_t)L << 24);
-                        load[best] += L == 0 ? 1 : taps_of[pos];
-                    }
-        }
-    }
-    if (N->tower_sched) cudaFree(N->tower_sched);
+    if (N->tower_pairs == n_pairs) return MCAZ_OK;
     if (N->tower_flags) cudaFree(N->tower_flags);
-    N->tower_sched = nullptr; N->tower_flags = nullptr;
-    MCAZ_CUDA(cudaMalloc(&N->tower_sched, table.size() * sizeof(uint32_t)));
+    N->tower_flags = nullptr;
     const size_t n_flags = (size_t)NLEVELS * n_pairs * NPOS * 2;
     MCAZ_CUDA(cudaMalloc(&N->tower_flags, n_flags * sizeof(uint32_t)));
     MCAZ_CUDA(cudaMemsetAsync(N->tower_flags, 0, n_flags * sizeof(uint32_t), e->stream));
-    MCAZ_CUDA(cudaMemcpyAsync(N->tower_sched, table.data(), table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
-    MCAZ_CUDA(cudaStreamSynchronize(e->stream));
     N->tower_pairs = n_pairs;
-    N->tower_grid = 2 * clusters;
     N->epoch = 0;
     return MCAZ_OK;
 }
@@ -1203,10 +1196,16 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
         N->events_used++;
         cudaEventRecord(ev0, st);
     }
-    TowerParams T;
-    T.bias = N->bias; T.act0 = N->act[0]; T.act1 = N->act[1]; T.head_w = N->heads.hw4; T.head_in = N->head_in;
-    T.bpad = bpad; T.n_pairs = n_pairs; T.count = count; T.row_base = (uint32_t)row_base;
-    T.first_level = (tower_debug() & 2) ? 1 : 0; T.fuse_heads = (tower_debug() & 1) ? 0 : 1;
+    TowerParams& T = N->tower_params;     // 20 KB parameter block, passed by value; the biases in it are set by network_set_weights
+    std::memcpy(T.pos_order, N->pos_order, sizeof(T.pos_order));
+    T.bias_g = N->bias; T.act0 = N->act[0]; T.act1 = N->act[1]; T.head_w = reinterpret_cast<const float4*>(N->heads.hw4); T.head_in = N->head_in;
+    T.bpad = bpad; T.n_pairs = n_pairs; T.count = count; T.row_base = (uint32_t)row_base; T.claim = N->tower_claim;
+    T.first_level = (tower_debug() & 2) ? 1 : 0; T.n_levels = NLEVELS - T.first_level; T.fuse_heads = (tower_debug() & 1) ? 0 : 1;
+    // Groups of tile pairs go through all levels one after the other, so a group's ping-pong buffers stay resident in the
+    // 126 MB L2 from level to level: at most 12 pairs per group (3072 boards, 2 x 47 MB), split evenly (16 pairs -> 8 + 8).
+    // Small groups leave too few items per level to hide the waits on the previous level (measured on 2 800-row batches:
+    // groups of <= 4 pairs 1.40 ms, <= 6: 1.27, <= 8: 1.17, <= 12: 1.165, 16: 1.19).
+    T.group_max = env_or("MCAZ_TOWER_GROUP", GROUP_MAX_PAIRS);
     {
         static int want_stats = -1;
         if (want_stats < 0) { const char* ss = getenv("MCAZ_TOWER_STATS"); want_stats = ss && atoi(ss) > 0; }
@@ -1217,40 +1216,19 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
         T.stats = N->stats;
     }
     T.wait_hint = (uint32_t)env_or("MCAZ_WAIT_HINT", 2000);     // A/B on one box: 267.2 -> 266.1 ms per 200 batches; 20000 ns: 266.8
+    const int grid = 2 * std::max(1, std::min(num_sms() / 2, n_pairs * NPOS));
     if (N->per_layer) {
-        if (int rc = build_schedule(e, n_pairs)) return rc;
-        T.flags = nullptr; T.epoch = 0; T.sched_stride = 0;
-        const size_t per_layer = (size_t)(N->sched_grid / 2) * TOWER_MAX_ITEMS;
-        for (int L = 0; L < NLEVELS; ++L) {
-            T.sched = N->sched + L * per_layer;
-            tower_tc_kernel<<<N->sched_grid, CONV_THREADS, TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in,
-                                                                             N->map_stem_w, T);
+        T.flags = nullptr; T.epoch = 0; T.n_levels = 1;
+        for (int L = (tower_debug() & 2) ? 1 : 0; L < NLEVELS; ++L) {
+            T.first_level = L;
+            tower_tc_kernel<<<grid, CONV_THREADS, TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in, N->map_stem_w, T);
             MCAZ_CHECK_LAUNCH();
         }
         e->launches += NLEVELS - 1;
     } else {
-        if (int rc = build_tower_schedule(e, n_pairs)) return rc;
-        T.sched = N->tower_sched; T.flags = N->tower_flags; T.epoch = ++N->epoch;
-        T.sched_stride = (size_t)(N->tower_grid / 2) * TOWER_MAX_ITEMS;
-        // The CTA pairs of this launch wait on one another's flags, so they must all be resident at once.  A cooperative
-        // launch makes the hardware guarantee that whatever else runs on the GPU (another engine's stream, the caller's
-        // torch kernels): the grid starts only when all of it fits.  (network_create checked that it can fit at all.)
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(N->tower_grid); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = TOWER_SMEM; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
-        cfg.attrs = attr; cfg.numAttrs = N->cooperative ? 1 : 0;
-        cudaError_t le = cudaLaunchKernelEx(&cfg, tower_tc_kernel, N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in, N->map_stem_w, T);
-        if (le != cudaSuccess && N->cooperative) {
-            // this driver does not take the cooperative attribute together with a cluster launch: engines that share the GPU
-            // with other streams must then not overlap their towers (own_stream engines fall back to one launch per level)
-            cudaGetLastError();
-            N->cooperative = false;
-            if (e->cfg.own_stream) { N->per_layer = true; return forward_chunk(e, tokens, clocks, n, logits, values, search_view, row_base, sched_rows); }
-            cfg.numAttrs = 0;
-            le = cudaLaunchKernelEx(&cfg, tower_tc_kernel, N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in, N->map_stem_w, T);
-        }
-        if (le != cudaSuccess) return fail(MCAZ_ECUDA, std::string("tower launch: ") + cudaGetErrorString(le));
+        if (int rc = tower_flags_for(e, n_pairs)) return rc;
+        T.flags = N->tower_flags; T.epoch = ++N->epoch;
+        tower_tc_kernel<<<grid, CONV_THREADS, TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in, N->map_stem_w, T);
         MCAZ_CHECK_LAUNCH();
     }
     if (ev1) cudaEventRecord(ev1, st);

