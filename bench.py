@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument('--no-plain', action='store_true', help='skip the comparison pass without cache / continuous mode')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-fp8', action='store_true', help='skip the leg that runs the same workload on the opt-in e4m3 tower')
     ap.add_argument('--no-legs', action='store_true', help='N > 1 only: skip the config4 (32768 games x 800 sims/move sharded) and '
                     'loop (self-play + gather + learner step + weight broadcast) legs')
     ap.add_argument('--loop-moves', type=int, default=6, help='moves of self-play per loop iteration in the loop leg')
@@ -358,6 +359,45 @@ def run_ours(args):
                 'steps': n_cont, 'mode': 'continuous (az_selfplay), free_sims 4, eval_cache as the headline; a step = %d network batches' % S}
         sp3.engine.close()
 
+    # the opt-in e4m3 tower (az_config.network = 2) on the same workload: reported beside the bf16 headline, never as it
+    fp8 = None
+    if not args.no_plain and not args.no_fp8:
+        sp4 = BatchedSelfPlay(net, n_games=G, num_simulations=S, seed=1234 + rank, precision='fp8', eval_cache_log2=args.eval_cache,
+                              free_sims=args.free_sims)
+        if not args.no_stagger:
+            sp4.stagger()
+        for _ in range(2):
+            sp4.step()
+        barrier()
+        f0 = sp4.engine.counters()
+        sp4.reset_kernel_timer()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        n_fp8 = max(1, min(args.steps, 3))
+        for _ in range(n_fp8):
+            sp4.step()
+        t1.record()
+        barrier()
+        f1 = sp4.engine.counters()
+        ft = torch.tensor([t0.elapsed_time(t1), float(f1['simulations'] - f0['simulations']), float(f1['evaluations'] - f0['evaluations'])],
+                          dtype=torch.float64, device='cuda')
+        fprof = sp4.kernel_profile(evaluations=f1['evaluations'] - f0['evaluations'])
+        if world > 1:
+            fmax = ft.clone()
+            dist.all_reduce(fmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ft)
+            ft[0] = fmax[0]
+        fp8_peak = 2.0 * pk['tflops']
+        fp8 = {'value': float(ft[1]) / (float(ft[0]) / 1000.0), 'unit': 'sims/s', 'evals_per_second': float(ft[2]) / (float(ft[0]) / 1000.0),
+               'steps': n_fp8, 'dtype': 'e4m3 operands in the 18 tower convolutions (fp32 accumulate, bf16 residual stream, fp32 heads) / f64 tree statistics',
+               'tolerance': 'priors and values within 1e-2 of the fp32 reference network (tests/test_gpu_fp8.py)',
+               'roofline': None if fprof is None else {
+                   'bound': 'tensor', 'kernel': 'tower_tc_kernel<FP8> (tcgen05.mma kind::f8f6f4)', 'achieved': fprof['achieved'], 'unit': 'TFLOP/s',
+                   'ms_per_launch': fprof['ms_per_launch'], 'rows_per_launch': fprof['rows_per_launch'], 'peak': fp8_peak,
+                   'frac': fprof['achieved'] / fp8_peak, 'mma_frac': fprof['achieved_mma'] / fp8_peak,
+                   'peak_source': 'fallback: 2 x the measured sustained bf16 rate (MEASURED_PEAKS.json holds no fp8 figure; nominal dense fp8 is twice bf16)'}}
+        sp4.engine.close()
+
     # N > 1: the two multi-GPU configurations of BASELINE.json beside the headline -- configs[3] at its full size sharded over
     # the ranks, and one iteration of the full loop of configs[4]
     config4 = loop_leg = None
@@ -398,7 +438,7 @@ def run_ours(args):
                                'terminal': terminal_all / max(sims_all, 1),
                                'rows_evaluated_twice_in_one_batch': dup_all / max(sims_all, 1)},
             'roofline': roof, 'tree_roofline': tree, 'without_cache_lockstep': plain, 'continuous_selfplay': cont,
-            'config4': config4, 'loop': loop_leg,
+            'fp8_tower': fp8, 'config4': config4, 'loop': loop_leg,
             'cpu_baseline': cpu, 'dropin_config1': dropin, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
         }
         emit(json.dumps(out))

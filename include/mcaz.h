@@ -133,7 +133,10 @@ typedef struct az_config {
                                   0 = caller supplies noise / picks moves (parity mode)     */
     uint64_t seed;
     mc_rules rules;
-    int32_t network;           /* 0 = external evaluator only; 1 = built-in bf16 tcgen05 net */
+    int32_t network;           /* 0 = external evaluator only; 1 = built-in bf16 tcgen05 net; 2 = the same network with the
+                                  18 tower convolutions on e4m3 operands (fp32 accumulation, per-channel weight scales,
+                                  per-level activation scales calibrated at az_set_weights, bf16 residual stream): about
+                                  twice the evaluations per second, priors and values within 1e-2 of fp32 (opt-in) */
     int32_t leaves_per_step;   /* 1 = the reference's sequential search (bit-exact); K > 1 = K descents per
                                   tree and step kept apart by virtual loss (throughput option for few games;
                                   changes visit counts); leaf batch rows = n_games * K, row = game * K + j   */

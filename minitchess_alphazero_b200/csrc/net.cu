@@ -21,6 +21,7 @@
 // Weights: W[layer 18][tap 9][cout 256][cin 256] bf16 with BatchNorm folded in, 21.2 MB, L2-resident.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 
 #include <algorithm>
 #include <cmath>
@@ -52,6 +53,7 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int STEM_K = 16;         // channels of a one-hot stem row (14 live): one K = 16 MMA, one 32-byte swizzle row
 constexpr int STEM_TILE_BYTES = BLOCK_M * STEM_K * 2;   // 4 KB: 128 boards (or 128 output channels) x 16 channels
 constexpr int CONV_THREADS = 256;                // TMA, MMA, TMEM-alloc, spare + 4 epilogue warps
+constexpr int CALIB_ROWS = 2048;                 // positions of the e4m3 tower's calibration pass (az_set_weights)
 constexpr int MAX_CHUNK_BOARDS = 8192;           // boards per forward pass (32 tile pairs: three L2 groups)
 
 // flat state_dict offsets (floats), exp/policy.py:56-69 order without num_batches_tracked
@@ -138,6 +140,22 @@ __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, 
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// e4m3 x e4m3 -> fp32 (kind::f8f6f4, dense): K = 32 per instruction, twice the multiply-adds of the bf16 form per shared-memory byte
+__device__ __forceinline__ void umma_fp8_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// four floats -> four e4m3 bytes (round to nearest even, saturating at +-448), lowest address first
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+    uint16_t lo, hi;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));     // the first source lands in the upper byte
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+    return (uint32_t)lo | ((uint32_t)hi << 16);
+}
 // commit: arrive on the barrier at this offset in both CTAs of the pair once the MMAs issued so far retire
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -172,6 +190,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
 // both K-major, N >> 3 in [17,23), M >> 4 in [24,29).
 // cta_group::2: one instruction spans the CTA pair, M = 256 boards (128 per CTA), N = 256.
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
+// kind::f8f6f4: A = B = E4M3 (format 0), D = F32; same shape fields
+constexpr uint32_t IDESC_FP8 = (1u << 4) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
+constexpr float E4M3_MAX = 448.0f;
 
 __device__ __forceinline__ bool tap_valid(int pos, int tap, int& src) {
     int row = pos / 5 + tap / 3 - 1, col = pos % 5 + tap % 3 - 1;
@@ -203,7 +224,8 @@ __device__ __forceinline__ bool tap_valid(int pos, int tap, int& src) {
 #define SPIN_NS 40     // back-off of the waits on the dependency watcher: a hot spin costs issue slots and power
 #endif
 constexpr int TOWER_SMEM = STAGES * STAGE_BYTES + 1024 + 256;
-static_assert(TOWER_SMEM <= 227 * 1024, "tower shared memory");
+constexpr int TOWER_SMEM_FP8 = TOWER_SMEM + NLEVELS * C * 4;          // + the dequantisation factors of the e4m3 form
+static_assert(TOWER_SMEM_FP8 <= 227 * 1024, "tower shared memory");
 constexpr unsigned long long WATCHDOG_CYCLES = 20ull * 1000 * 1000 * 1000;   // ~10 s: a dependency that never arrives
 constexpr int ITEM_RING = 16;          // claimed items in flight per CTA (scheduler -> producer / MMA / epilogue); see tower_scheduler
 #ifndef TOWER_GROUP_PAIRS
@@ -235,6 +257,13 @@ struct TowerParams {
                                   // TMA producer: total, waiting for dependencies, waiting for a free stage; MMA issuer: operand wait
                                   // at the first stage of an item, items} in clock cycles; else nullptr
     uint8_t pos_order[32];        // the 30 positions, those with the most valid taps first
+    // ---- e4m3 tower (network = 2): operands of the 18 convolutions in fp8, fp32 accumulation, residual stream in bf16
+    const float* scale_g;         // [19][256] dequantisation factor per level and output channel: weight scale of the channel x
+                                  // activation scale of the level's input (row 0, the stem, is 1)
+    float inv_a[NLEVELS];         // 1 / activation scale of each level's output: what the epilogue multiplies by before rounding to e4m3
+    uint8_t* actq0;               // e4m3 copy of the block inputs x (levels 0, 2, 4, ...): A operand of a block's first convolution
+    uint8_t* actq1;               // e4m3 h between the two convolutions of a block (levels 1, 3, ...); never kept in bf16
+    unsigned int* level_absmax;   // calibration launch (bf16 form): per level the largest activation written, as float bits (values >= 0)
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
@@ -253,13 +282,9 @@ __device__ __forceinline__ uint32_t ld_acquire_cta_shared(const uint32_t* p) {
 __device__ __forceinline__ void st_release_cta_shared(uint32_t* p, uint32_t v) {
     asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint4 ld_cg_v4(const uint4* p) {   // L2-coherent: never a stale L1 line across layers
-    uint4 v;
-    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
-// 256-bit forms (sm_100: LDG.256 / STG.256): a thread's 32 channels of a row are 64 contiguous bytes = two whole 32-byte
-// sectors, so the activation rows travel as full sectors in half as many L2 requests as with 128-bit accesses
+// 256-bit accesses (sm_100: LDG.256 / STG.256; .cg = L2-coherent, never a stale L1 line across levels): a thread's 32 channels of
+// a row are 64 contiguous bytes = two whole 32-byte sectors, so the activation rows travel as full sectors in half as many L2
+// requests as with 128-bit accesses
 __device__ __forceinline__ void ld_cg_v8(const void* p, uint4& a, uint4& b) {
     asm volatile("ld.global.cg.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p) : "memory");
@@ -311,9 +336,11 @@ __device__ __forceinline__ uint32_t tower_item(const TowerParams& P, int live_pa
 // Epilogue of the last level for one accumulator row (this thread's board at one position): 8 chunks of 32 channels.
 // Kept out of line so that its registers do not weigh on the common epilogue.  The residual row is published before
 // the item's MMAs start, so four chunks of it are fetched ahead of the accumulator and refilled as they are used.
-__device__ __noinline__ void epilogue_heads(uint32_t taddr, const float* __restrict__ bias, const float4* __restrict__ hw,
-                                            const __nv_bfloat16* res_row, uint64_t* acc_full, uint32_t acc_phase, uint32_t wait_hint,
-                                            float* h) {
+// (A template over the calling kernel's form: ptxas 12.9 crashes on one out-of-line function shared by several tcgen05 kernels.)
+template <int FORM>
+__device__ __noinline__ void epilogue_heads(uint32_t taddr, const float* __restrict__ bias, const float* __restrict__ scale,
+                                            const float4* __restrict__ hw, const __nv_bfloat16* res_row, uint64_t* acc_full,
+                                            uint32_t acc_phase, uint32_t wait_hint, float* h) {
     uint4 res[4][4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -343,8 +370,10 @@ __device__ __noinline__ void epilogue_heads(uint32_t taddr, const float* __restr
             for (int hh = 0; hh < 4; ++hh) {
                 const int e = j * 8 + hh * 2;
                 const uint32_t r = (&res[c & 3][j].x)[hh];
-                const float x0 = fmaxf(__uint_as_float(v[e]) + __ldg(bias + c * 32 + e) + __uint_as_float(r << 16), 0.f);
-                const float x1 = fmaxf(__uint_as_float(v[e + 1]) + __ldg(bias + c * 32 + e + 1) + __uint_as_float(r & 0xffff0000u), 0.f);
+                float a0 = __uint_as_float(v[e]), a1 = __uint_as_float(v[e + 1]);
+                if (scale) { a0 *= __ldg(scale + c * 32 + e); a1 *= __ldg(scale + c * 32 + e + 1); }      // e4m3 tower: dequantise
+                const float x0 = fmaxf(a0 + __ldg(bias + c * 32 + e) + __uint_as_float(r << 16), 0.f);
+                const float x1 = fmaxf(a1 + __ldg(bias + c * 32 + e + 1) + __uint_as_float(r & 0xffff0000u), 0.f);
                 const float4 w0 = __ldg(hw + c * 32 + e), w1 = __ldg(hw + c * 32 + e + 1);
                 h0 = fmaf(x0, w0.x, h0); h1 = fmaf(x0, w0.y, h1); h2 = fmaf(x0, w0.z, h2);
                 h0 = fmaf(x1, w1.x, h0); h1 = fmaf(x1, w1.y, h1); h2 = fmaf(x1, w1.z, h2);
@@ -358,10 +387,17 @@ __device__ __noinline__ void epilogue_heads(uint32_t taddr, const float* __restr
     h[0] = h0; h[1] = h1; h[2] = h2;
 }
 
+// FP8: the 18 convolutions multiply e4m3 operands (map_q0 / map_q1 / map_wq; the bf16 maps are then unused).  CALIB (bf16 form
+// only): the epilogue also records the largest activation of every level -- the calibration pass of the e4m3 tower.
+template <bool FP8, bool CALIB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
 tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_constant__ CUtensorMap map_act1,
                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_stem_in,
-                const __grid_constant__ CUtensorMap map_stem_w, const __grid_constant__ TowerParams P) {
+                const __grid_constant__ CUtensorMap map_stem_w, const __grid_constant__ CUtensorMap map_q0,
+                const __grid_constant__ CUtensorMap map_q1, const __grid_constant__ CUtensorMap map_wq,
+                const __grid_constant__ TowerParams P) {
+    static_assert(!(FP8 && CALIB), "the calibration pass runs the bf16 form");
+    constexpr int KCHUNK = FP8 ? 128 : BLOCK_K;      // elements of one 128-byte swizzle row = K of one stage
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -370,6 +406,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
     uint64_t* acc_full = bars + 2 * STAGES;
     uint64_t* acc_empty = bars + 2 * STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float* s_scale = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);      // FP8 only: [19][256] (TOWER_SMEM_FP8)
     __shared__ unsigned long long s_ring[ITEM_RING];   // claimed items (written by the leader's scheduler, here and in the peer)
     __shared__ uint32_t s_deps_ok;            // items [0, s_deps_ok) have all their inputs published (written by warp 3)
     __shared__ uint32_t s_prod_at;            // item the TMA producer of this CTA is loading (flow control of the scheduler)
@@ -384,6 +421,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
         live_pairs = (int)min((uint32_t)P.n_pairs, (rows + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
     }
 
+    if (FP8) for (int i = threadIdx.x; i < NLEVELS * C; i += CONV_THREADS) s_scale[i] = __ldg(P.scale_g + i);
     if (threadIdx.x < ITEM_RING) s_ring[threadIdx.x] = 0ull;
     if (threadIdx.x == 0) { s_deps_ok = 0; s_prod_at = 0; }
     if (warp == 1 && lane == 0) {
@@ -421,9 +459,9 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             }
             // level 0 (stem): one-hot rows x folded embedding/conv table, one 16-channel chunk (32-byte rows) per tap;
             // level L >= 1: convolution L - 1 reads act0 (even) / act1 (odd), four chunks per tap
-            const int conv = L - 1, chunks = L == 0 ? 1 : C / BLOCK_K;
-            const CUtensorMap* map_in = L == 0 ? &map_stem_in : ((conv & 1) ? &map_act1 : &map_act0);
-            const CUtensorMap* map_wt = L == 0 ? &map_stem_w : &map_w;
+            const int conv = L - 1, chunks = L == 0 ? 1 : C / KCHUNK;
+            const CUtensorMap* map_in = L == 0 ? &map_stem_in : (FP8 ? ((conv & 1) ? &map_q1 : &map_q0) : ((conv & 1) ? &map_act1 : &map_act0));
+            const CUtensorMap* map_wt = L == 0 ? &map_stem_w : (FP8 ? &map_wq : &map_w);
             const int w_base = L == 0 ? 0 : conv * 9;
             for (int tap = 0; tap < 9; ++tap) {
                 int src;
@@ -436,8 +474,8 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                     if (leader) mbar_expect_tx(&full[s], L == 0 ? 4 * STEM_TILE_BYTES : 2 * STAGE_BYTES);
                     else mbar_arrive_remote(&full[s], 0);
                     uint8_t* st = smem + s * STAGE_BYTES;
-                    tma_load_3d_2sm(st, map_in, &full[s], kc * BLOCK_K, tile * BLOCK_M, src);
-                    tma_load_3d_2sm(st + A_BYTES, map_wt, &full[s], kc * BLOCK_K, (int)rank * (C / 2), w_base + tap);
+                    tma_load_3d_2sm(st, map_in, &full[s], kc * KCHUNK, tile * BLOCK_M, src);
+                    tma_load_3d_2sm(st + A_BYTES, map_wt, &full[s], kc * KCHUNK, (int)rank * (C / 2), w_base + tap);
                 }
             }
         }
@@ -455,7 +493,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             if (item == ITEM_END) break;
             const int pos = item & 0xff;
             const bool stem = (item >> 24) == 0;          // K = 16 per tap: the 14 one-hot channels
-            const int chunks = stem ? 1 : C / BLOCK_K, ksteps = stem ? 1 : BLOCK_K / 16;
+            const int chunks = stem ? 1 : C / KCHUNK, ksteps = stem ? 1 : BLOCK_K / 16;     // 4 instructions of 32 bytes of K per stage
             const uint32_t acc = k & 1;
             const long long t0 = clock64();
             mbar_wait(&acc_empty[acc], ((k >> 1) & 1) ^ 1);
@@ -481,7 +519,8 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
 #pragma unroll
                     for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
                         if (kk < ksteps) {
-                            umma_bf16_2sm(d_tmem, da + 2 * kk, db + 2 * kk, IDESC, accumulate);
+                            if (FP8 && !stem) umma_fp8_2sm(d_tmem, da + 2 * kk, db + 2 * kk, IDESC_FP8, accumulate);
+                            else umma_bf16_2sm(d_tmem, da + 2 * kk, db + 2 * kk, IDESC, accumulate);
                             accumulate = 1;
                         }
                     }
@@ -546,15 +585,19 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             const uint32_t acc = k & 1, acc_phase = (k >> 1) & 1;
             const bool odd = L >= 2 && (L & 1) == 0;           // second conv of a residual block
             const bool last = L == NLAYERS && P.fuse_heads;    // its output only feeds the three 1x1 head convolutions
-            __nv_bfloat16* out = (odd || L == 0) ? P.act0 : P.act1;
+            // bf16 form: x lives in act0 (levels 0, 2, 4, ...), h in act1.  e4m3 form: act0 is the bf16 residual stream x, the
+            // operands are the e4m3 copies actq0 (x) and actq1 (h)
+            __nv_bfloat16* out = (FP8 || odd || L == 0) ? P.act0 : P.act1;
+            const bool write_bf16 = !FP8 || odd || L == 0;
+            uint8_t* outq = FP8 ? ((odd || L == 0) ? P.actq0 : P.actq1) : nullptr;
             const size_t row_off = ((size_t)pos * P.bpad + (size_t)tile * BLOCK_M + q * 32 + lane) * C;
             if (last) {
                 // the tower's output row never leaves the SM: bias + residual + ReLU in fp32, then the three 1x1 head
                 // filters as dot products over the row this thread holds
                 if (P.flags) while (ld_acquire_cta_shared(&s_deps_ok) <= k) __nanosleep(SPIN_NS);
                 float h[3];
-                epilogue_heads(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C, P.bias_g + L * C, P.head_w, out + row_off, &acc_full[acc],
-                               acc_phase, P.wait_hint, h);
+                epilogue_heads<2 * (int)FP8 + (int)CALIB>(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C, P.bias_g + L * C, FP8 ? P.scale_g + L * C : nullptr, P.head_w,
+                               out + row_off, &acc_full[acc], acc_phase, P.wait_hint, h);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
@@ -583,6 +626,8 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C;
             const int bias0 = L * C;
+            const float inv_a = FP8 ? P.inv_a[L] : 0.f;
+            float seen_max = 0.f;
 #pragma unroll
             for (int c = 0; c < C / 32; ++c) {
                 uint32_t v[32];
@@ -607,14 +652,18 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                     }
                 }
                 uint4 outv[4];
+                uint32_t q8[8];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     uint32_t packed[4];
+                    float xq[8];
 #pragma unroll
                     for (int h = 0; h < 4; ++h) {
                         const int e = j * 8 + h * 2;
-                        float x0 = __uint_as_float(v[e]) + P.bias[bias0 + c * 32 + e];
-                        float x1 = __uint_as_float(v[e + 1]) + P.bias[bias0 + c * 32 + e + 1];
+                        float x0 = __uint_as_float(v[e]), x1 = __uint_as_float(v[e + 1]);
+                        if (FP8) { x0 *= s_scale[bias0 + c * 32 + e]; x1 *= s_scale[bias0 + c * 32 + e + 1]; }     // dequantise the accumulator
+                        x0 += P.bias[bias0 + c * 32 + e];
+                        x1 += P.bias[bias0 + c * 32 + e + 1];
                         if (odd) {
                             const uint32_t r = (&res[c & 3][j].x)[h];
                             x0 += __uint_as_float(r << 16);
@@ -622,17 +671,28 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                         }
                         x0 = fmaxf(x0, 0.f);
                         x1 = fmaxf(x1, 0.f);
+                        if (CALIB) seen_max = fmaxf(seen_max, fmaxf(x0, x1));
                         __nv_bfloat162 b2 = __floats2bfloat162_rn(x0, x1);
                         packed[h] = *reinterpret_cast<uint32_t*>(&b2);
+                        xq[2 * h] = x0 * inv_a; xq[2 * h + 1] = x1 * inv_a;
                     }
                     outv[j] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    if (FP8) { q8[2 * j] = pack_e4m3x4(xq[0], xq[1], xq[2], xq[3]); q8[2 * j + 1] = pack_e4m3x4(xq[4], xq[5], xq[6], xq[7]); }
                 }
                 if (odd && c + 4 < C / 32) {
                     ld_cg_v8(out + row_off + (c + 4) * 32, res[c & 3][0], res[c & 3][1]);
                     ld_cg_v8(out + row_off + (c + 4) * 32 + 16, res[c & 3][2], res[c & 3][3]);
                 }
-                st_v8(out + row_off + c * 32, outv[0], outv[1]);
-                st_v8(out + row_off + c * 32 + 16, outv[2], outv[3]);
+                if (write_bf16) {
+                    st_v8(out + row_off + c * 32, outv[0], outv[1]);
+                    st_v8(out + row_off + c * 32 + 16, outv[2], outv[3]);
+                }
+                if (FP8) st_v8(outq + row_off + c * 32, make_uint4(q8[0], q8[1], q8[2], q8[3]), make_uint4(q8[4], q8[5], q8[6], q8[7]));
+            }
+            if (CALIB) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) seen_max = fmaxf(seen_max, __shfl_xor_sync(0xffffffffu, seen_max, o));
+                if (lane == 0) atomicMax(&P.level_absmax[L], __float_as_uint(seen_max));
             }
             // publish: the barrier orders all 128 threads' stores before the (cumulative) gpu-scope release
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -688,6 +748,51 @@ __global__ void prep_stem_kernel(const float* __restrict__ flat, __nv_bfloat16* 
         ws[((size_t)t * C + c) * STEM_K + k] = __float2bfloat16(acc * scale);
     }
     if (t == 0) bias[c] = (sb[c] - mean[c]) * scale + beta[c];
+}
+
+// ---- e4m3 tower: weights.  One block per (output channel, convolution): the folded 3x3x256 filter of the channel over its
+// largest magnitude / 448 (per-output-channel scale, multiplied back onto the fp32 accumulator by the epilogue).
+__global__ void __launch_bounds__(256) prep_tower_fp8_kernel(const float* __restrict__ flat, uint8_t* __restrict__ wq, float* __restrict__ w_scale) {
+    __shared__ float s_max[8];
+    const int n = blockIdx.x, L = blockIdx.y, k = threadIdx.x;
+    const float* base = flat + OFF_TOWER + (size_t)L * TOWER_STRIDE;
+    const float *cw = base, *cb = base + 589824, *gamma = cb + 256, *var = gamma + 768;
+    const float fold = gamma[n] / sqrtf(var[n] + BN_EPS);
+    float w[9], m = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { w[t] = cw[((size_t)n * C + k) * 9 + t] * fold; m = fmaxf(m, fabsf(w[t])); }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((k & 31) == 0) s_max[k >> 5] = m;
+    __syncthreads();
+    m = s_max[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, s_max[i]);
+    const float sc = fmaxf(m, 1e-20f) / E4M3_MAX;
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+        wq[(((size_t)L * 9 + t) * C + n) * C + k] = (uint8_t)__nv_cvt_float_to_fp8(w[t] / sc, __NV_SATFINITE, __NV_E4M3);
+    if (k == 0) w_scale[L * C + n] = sc;
+}
+
+// ---- e4m3 tower: calibration positions.  One thread per position: a uniformly random legal playout from the start position,
+// stopped after (i mod 60) plies or at the end of the game, tokenised like Network.process_observation (exp/policy.py:96-105).
+__global__ void __launch_bounds__(128) calib_positions_kernel(mc_state start, mc_rules rules, int n, uint8_t* __restrict__ tokens) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        mc_state s = start;
+        Philox rng(0x5EEDCA11B8A7E5ull, (uint32_t)i, 0u, 0u);
+        const int plies = i % 60;
+        for (int p = 0; p < plies; ++p) {
+            uint16_t codes[MC_MAX_MOVES];
+            int res;
+            const int E = mc::generate(s, rules, codes, &res);
+            if (res != MC_ONGOING || E <= 0) break;
+            mc_state o;
+            if (mc::step(s, codes[min((int)(rng.uniform() * E), E - 1)], rules, &o) != 0) break;
+            s = o;
+        }
+        float clock;
+        mc::tokenize(s, tokens + (size_t)i * MC_TOKENS, &clock);
+    }
 }
 
 struct HeadWeights {
@@ -968,7 +1073,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int make_map_3d(CUtensorMap* map, void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
-                CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+                CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, int elem_bytes = 2) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -978,10 +1083,11 @@ int make_map_3d(CUtensorMap* map, void* ptr, uint64_t d0, uint64_t d1, uint64_t 
         encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
     cuuint64_t dims[3] = {d0, d1, d2};
-    cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+    cuuint64_t strides[2] = {d0 * (cuuint64_t)elem_bytes, d0 * d1 * (cuuint64_t)elem_bytes};
     cuuint32_t box[3] = {b0, b1, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = encode(map, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptr, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
                         swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(MCAZ_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     return MCAZ_OK;
@@ -1000,6 +1106,17 @@ struct Network {
     float* head_pool = nullptr;
     HeadWeights heads{};
     CUtensorMap map_act[2], map_w, map_stem_in, map_stem_w;
+    // e4m3 tower (az_config.network = 2)
+    bool fp8 = false;
+    bool calibrating = false;          // forward_chunk runs the bf16 form with the per-level maxima on (calibrate_fp8)
+    uint8_t* wq = nullptr;             // [18][9][256][256] e4m3: folded weights over their output channel's scale
+    float* w_scale = nullptr;          // [18][256] that scale (largest |weight| of the channel / 448)
+    float* scale = nullptr;            // [19][256] dequantisation factors the kernel reads (w_scale x activation scale of the level's input)
+    uint8_t* actq[2] = {nullptr, nullptr};   // [30][capacity][256] e4m3 x / h
+    unsigned int* level_absmax = nullptr;    // [19] calibration maxima
+    uint8_t* calib_tokens = nullptr;   // [CALIB_ROWS][60]
+    float act_scale[NLEVELS] = {};     // activation scale of each level's output (calibrated at az_set_weights)
+    CUtensorMap map_q[2], map_wq;
     bool have_weights = false;
     uint32_t* tower_flags = nullptr;   // [19][n_pairs][30][2] epoch stamps of the published items
     uint32_t* tower_claim = nullptr;   // [2] next item of the running launch's list, pairs that have left it
@@ -1035,6 +1152,14 @@ static int net_alloc_acts(az_engine* e, int boards) {
     MCAZ_CUDA(cudaMalloc(&N->head_in, (size_t)cap * HEAD_IN * sizeof(float)));
     MCAZ_CUDA(cudaMemset(N->head_in, 0, (size_t)cap * HEAD_IN * sizeof(float)));
     if (int rc = make_map_3d(&N->map_stem_in, N->stem_in, STEM_K, cap, NPOS, STEM_K, BLOCK_M, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
+    if (N->fp8)
+        for (int i = 0; i < 2; ++i) {
+            if (N->actq[i]) cudaFree(N->actq[i]);
+            N->actq[i] = nullptr;
+            MCAZ_CUDA(cudaMalloc(&N->actq[i], (size_t)NPOS * cap * C));
+            MCAZ_CUDA(cudaMemset(N->actq[i], 0, (size_t)NPOS * cap * C));
+            if (int rc = make_map_3d(&N->map_q[i], N->actq[i], C, cap, NPOS, 128, BLOCK_M, CU_TENSOR_MAP_SWIZZLE_128B, 1)) return rc;
+        }
     N->capacity = cap;
     return MCAZ_OK;
 }
@@ -1066,7 +1191,21 @@ int network_create(az_engine* e) {
     N->heads.hw4 = p;
     if (int rc = make_map_3d(&N->map_w, N->w, C, C, (uint64_t)NLAYERS * 9, BLOCK_K, C / 2)) return rc;
     if (int rc = make_map_3d(&N->map_stem_w, N->stem_w, STEM_K, C, 9, STEM_K, C / 2, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
-    MCAZ_CUDA(cudaFuncSetAttribute(tower_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_SMEM));
+    MCAZ_CUDA(cudaFuncSetAttribute(tower_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_SMEM));
+    N->fp8 = e->cfg.network == 2;
+    if (N->fp8) {
+        MCAZ_CUDA(cudaFuncSetAttribute(tower_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_SMEM));
+        MCAZ_CUDA(cudaFuncSetAttribute(tower_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_SMEM_FP8));
+        MCAZ_CUDA(cudaMalloc(&N->wq, (size_t)NLAYERS * 9 * C * C));
+        MCAZ_CUDA(cudaMalloc(&N->w_scale, (size_t)NLAYERS * C * sizeof(float)));
+        MCAZ_CUDA(cudaMalloc(&N->scale, (size_t)NLEVELS * C * sizeof(float)));
+        MCAZ_CUDA(cudaMalloc(&N->level_absmax, NLEVELS * sizeof(unsigned int)));
+        MCAZ_CUDA(cudaMalloc(&N->calib_tokens, (size_t)CALIB_ROWS * MC_TOKENS));
+        if (int rc = make_map_3d(&N->map_wq, N->wq, C, C, (uint64_t)NLAYERS * 9, 128, C / 2, CU_TENSOR_MAP_SWIZZLE_128B, 1)) return rc;
+    } else {
+        // the e4m3 maps are kernel arguments of every form: give the unused ones valid contents
+        N->map_q[0] = N->map_q[1] = N->map_wq = N->map_w;
+    }
     {
         const char* m = getenv("MCAZ_TOWER");      // "layers": one launch per level (bit-identical; for tests and per-level profiles)
         N->per_layer = m && std::strcmp(m, "layers") == 0;
@@ -1083,7 +1222,7 @@ int network_create(az_engine* e) {
         MCAZ_CUDA(cudaMalloc(&N->tower_claim, 2 * sizeof(uint32_t)));
         MCAZ_CUDA(cudaMemset(N->tower_claim, 0, 2 * sizeof(uint32_t)));
     }
-    return net_alloc_acts(e, std::min(std::max(e->v.G * e->v.K, e->v.row_cap), MAX_CHUNK_BOARDS));   // grows on demand (network_forward batches)
+    return net_alloc_acts(e, std::min(std::max(std::max(e->v.G * e->v.K, e->v.row_cap), N->fp8 ? CALIB_ROWS : 0), MAX_CHUNK_BOARDS));   // grows on demand
 }
 
 void network_destroy(az_engine* e) {
@@ -1098,11 +1237,19 @@ void network_destroy(az_engine* e) {
     if (N->head_pool) cudaFree(N->head_pool);
     if (N->tower_flags) cudaFree(N->tower_flags);
     if (N->tower_claim) cudaFree(N->tower_claim);
+    for (int i = 0; i < 2; ++i) if (N->actq[i]) cudaFree(N->actq[i]);
+    if (N->wq) cudaFree(N->wq);
+    if (N->w_scale) cudaFree(N->w_scale);
+    if (N->scale) cudaFree(N->scale);
+    if (N->level_absmax) cudaFree(N->level_absmax);
+    if (N->calib_tokens) cudaFree(N->calib_tokens);
     if (N->stats) cudaFree(N->stats);
     for (auto& ev : N->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     delete N;
     e->net = nullptr;
 }
+
+static int calibrate_fp8(az_engine* e, const float* flat);
 
 int network_set_weights(az_engine* e, const float* flat) {
     Network* N = e->net;
@@ -1116,6 +1263,7 @@ int network_set_weights(az_engine* e, const float* flat) {
     MCAZ_CUDA(cudaMemcpyAsync(N->tower_params.bias, N->bias, sizeof(N->tower_params.bias), cudaMemcpyDeviceToHost, e->stream));
     MCAZ_CUDA(cudaStreamSynchronize(e->stream));       // the tower takes the biases in its parameter block
     N->have_weights = true;
+    if (N->fp8) return calibrate_fp8(e, flat);
     return MCAZ_OK;
 }
 
@@ -1216,22 +1364,35 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
         T.stats = N->stats;
     }
     T.wait_hint = (uint32_t)env_or("MCAZ_WAIT_HINT", 2000);     // A/B on one box: 267.2 -> 266.1 ms per 200 batches; 20000 ns: 266.8
+    T.scale_g = N->scale; T.actq0 = N->actq[0]; T.actq1 = N->actq[1]; T.level_absmax = N->calibrating ? N->level_absmax : nullptr;
     const int grid = 2 * std::max(1, std::min(num_sms() / 2, n_pairs * NPOS));
+    auto launch = [&]() {
+        if (N->calibrating)
+            tower_tc_kernel<false, true><<<grid, CONV_THREADS, TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in, N->map_stem_w,
+                                                                                N->map_q[0], N->map_q[1], N->map_wq, T);
+        else if (N->fp8)
+            tower_tc_kernel<true, false><<<grid, CONV_THREADS, TOWER_SMEM_FP8, st>>>(N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in,
+                                                                                    N->map_stem_w, N->map_q[0], N->map_q[1], N->map_wq, T);
+        else
+            tower_tc_kernel<false, false><<<grid, CONV_THREADS, TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in,
+                                                                                 N->map_stem_w, N->map_q[0], N->map_q[1], N->map_wq, T);
+    };
     if (N->per_layer) {
         T.flags = nullptr; T.epoch = 0; T.n_levels = 1;
         for (int L = (tower_debug() & 2) ? 1 : 0; L < NLEVELS; ++L) {
             T.first_level = L;
-            tower_tc_kernel<<<grid, CONV_THREADS, TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in, N->map_stem_w, T);
+            launch();
             MCAZ_CHECK_LAUNCH();
         }
         e->launches += NLEVELS - 1;
     } else {
         if (int rc = tower_flags_for(e, n_pairs)) return rc;
         T.flags = N->tower_flags; T.epoch = ++N->epoch;
-        tower_tc_kernel<<<grid, CONV_THREADS, TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in, N->map_stem_w, T);
+        launch();
         MCAZ_CHECK_LAUNCH();
     }
     if (ev1) cudaEventRecord(ev1, st);
+    if (!search_view && !logits) { e->launches += 2; return MCAZ_OK; }      // calibration pass: the tower only
     if (search_view)
     {
         const int grid = std::min(num_sms() * 4, (n + HEADS_WARPS - 1) / HEADS_WARPS);
@@ -1259,6 +1420,46 @@ int network_forward_search(az_engine* e, const az::View& V, float* values) {
         const int m = std::min(chunk, rows - base);
         if (int rc = forward_chunk(e, V.tokens + (size_t)base * MC_TOKENS, V.clocks + base, m, nullptr, values, &V, base, chunk)) return rc;
     }
+    return MCAZ_OK;
+}
+
+// e4m3 tower, at every az_set_weights: (1) the bf16 form runs CALIB_ROWS positions from random playouts and records the largest
+// activation of every level; a level's e4m3 operands are its activations over (1.25 x that maximum / 448), saturating -- a
+// static per-level scale, as emulated in tools/fp8_probe.py; (2) the folded weights go to e4m3 over a per-output-channel
+// scale; (3) the epilogue's dequantisation factors are the products of the two.
+static int calibrate_fp8(az_engine* e, const float* flat) {
+    Network* N = e->net;
+    cudaStream_t st = e->stream;
+    mc_state start;
+    mc_state_from_fen("2nbk/2ppp/5/5/PPP2/KBN2 w 0 1", &start);
+    calib_positions_kernel<<<(CALIB_ROWS + 127) / 128, 128, 0, st>>>(start, e->v.rules, CALIB_ROWS, N->calib_tokens);
+    MCAZ_CHECK_LAUNCH();
+    MCAZ_CUDA(cudaMemsetAsync(N->level_absmax, 0, NLEVELS * sizeof(unsigned int), st));
+    N->calibrating = true;
+    const bool was_profiling = N->profiling;
+    N->profiling = false;
+    const int rc = forward_chunk(e, N->calib_tokens, nullptr, CALIB_ROWS, nullptr, nullptr, nullptr, 0);
+    N->calibrating = false;
+    N->profiling = was_profiling;
+    if (rc) return rc;
+    prep_tower_fp8_kernel<<<dim3(C, NLAYERS), C, 0, st>>>(flat, N->wq, N->w_scale);
+    MCAZ_CHECK_LAUNCH();
+    e->launches += 2;
+    unsigned int absmax[NLEVELS];
+    std::vector<float> w_scale((size_t)NLAYERS * C), scale((size_t)NLEVELS * C, 1.0f);
+    MCAZ_CUDA(cudaMemcpyAsync(absmax, N->level_absmax, sizeof(absmax), cudaMemcpyDeviceToHost, st));
+    MCAZ_CUDA(cudaMemcpyAsync(w_scale.data(), N->w_scale, w_scale.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+    MCAZ_CUDA(cudaStreamSynchronize(st));
+    for (int L = 0; L < NLEVELS; ++L) {
+        float m;
+        std::memcpy(&m, &absmax[L], sizeof(m));
+        N->act_scale[L] = std::max(1.25f * m, 1e-6f) / E4M3_MAX;
+        N->tower_params.inv_a[L] = 1.0f / N->act_scale[L];
+    }
+    for (int L = 1; L < NLEVELS; ++L)              // level L = convolution L - 1 on the output of level L - 1
+        for (int n = 0; n < C; ++n) scale[(size_t)L * C + n] = w_scale[(size_t)(L - 1) * C + n] * N->act_scale[L - 1];
+    MCAZ_CUDA(cudaMemcpyAsync(N->scale, scale.data(), scale.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    MCAZ_CUDA(cudaStreamSynchronize(st));
     return MCAZ_OK;
 }
 

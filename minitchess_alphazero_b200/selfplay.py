@@ -51,7 +51,9 @@ class BatchedSelfPlay:
     hand-written sm_100a network inside libmcaz.so (`az_search` / `az_selfplay`)."""
 
     def __init__(self, network, n_games, num_simulations, cpuct=1.0, tau_change=6, epsilon=0.25, alpha=0.6, seed=0,
-                 **engine_options):
+                 precision='bf16', **engine_options):
+        assert precision in ('bf16', 'fp8'), precision      # 'fp8': the e4m3 tower (az_config.network = 2), opt-in
+        self.precision = precision
         self.n_games, self.num_simulations = int(n_games), int(num_simulations)
         # with leaves_per_step = K every search step runs K descents per tree: size the arenas for all of them
         leaves = int(engine_options.get('leaves_per_step', 1) or 1)
@@ -62,7 +64,7 @@ class BatchedSelfPlay:
             engine_options.setdefault('eval_cache_log2', min(24, max(12, (want - 1).bit_length())))
         self.engine = Engine(n_games, max_sims_per_move=num_simulations * leaves, cpuct=float(cpuct), tau_change=int(tau_change),
                              dirichlet_epsilon=float(epsilon), dirichlet_alpha=float(alpha), seed=int(seed),
-                             device_rng=1, network=1, **engine_options)
+                             device_rng=1, network=2 if precision == 'fp8' else 1, **engine_options)
         self.network = network
         self.weights_version = 0
         self.sync_weights()

@@ -1,0 +1,122 @@
+"""GPU: the e4m3 tower (az_config.network = 2) -- the 18 convolutions on fp8 operands (tcgen05.mma kind::f8f6f4, fp32
+accumulation, per-output-channel weight scales, calibrated per-level activation scales, bf16 residual stream) -- against
+the reference Network's fp32 outputs.  BASELINE.json allows a reduced-precision network 1e-2 on priors and values; the
+tolerance is stated here and checked on three networks: random init (seed 0, the golden fixture), non-trivial BatchNorm
+statistics and gains (golden), and a network the learner has stepped.  It is an opt-in evaluator: bf16 stays the default
+and bench.py's headline."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import rules_c as rc
+from oracle import ref_selfplay as rs
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+def make_engine(net, n_games=256, network=2, **kw):
+    from minitchess_alphazero_b200.engine import Engine
+    from minitchess_alphazero_b200.policy import flatten_state_dict
+    eng = Engine(n_games, max_sims_per_move=kw.pop('max_sims_per_move', 4), network=network, **kw)
+    eng.set_weights(flatten_state_dict(net.state_dict()).numpy())
+    return eng
+
+
+def legal_priors(logits, states):
+    codes, counts, _ = rc.legal_moves(states)
+    out = []
+    for i in range(len(states)):
+        lg = torch.from_numpy(np.ascontiguousarray(logits[i, codes[i, :counts[i]].astype(np.int64)]))
+        out.append(lg.softmax(0).numpy())
+    return out
+
+
+def reference(net, tokens, clocks):
+    with torch.no_grad():
+        p, v = rs.RefNetwork(net.state_dict()).forward(torch.from_numpy(tokens.astype(np.int64)).view(-1, 2, 6, 5),
+                                                       torch.from_numpy(clocks).view(-1, 1))
+    return p.numpy(), v.numpy().reshape(-1)
+
+
+def check_against_fp32(net, label):
+    pos = np.ascontiguousarray(rc.random_positions(31, 6000)[:1500])
+    _, counts, results = rc.legal_moves(pos)
+    pos = np.ascontiguousarray(pos[(results == 0) & (counts > 0)][:1024])
+    tokens, clocks = rc.tokenize(pos)
+    p_ref, v_ref = reference(net, tokens, clocks)
+    eng = make_engine(net, n_games=1024)
+    logits, values = eng.network_forward(tokens, clocks)
+    worst_p = max(np.abs(a - b).max() for a, b in zip(legal_priors(logits, pos), legal_priors(p_ref, pos)))
+    worst_v = np.abs(values - v_ref).max()
+    print('%s: e4m3 tower vs fp32 reference: legal-move priors %.2e, values %.2e (tolerance %.0e)' % (label, worst_p, worst_v, TOL))
+    assert worst_p < TOL and worst_v < TOL, (label, worst_p, worst_v)
+    # deterministic and row independent, like the bf16 form
+    l2, v2 = eng.network_forward(tokens[::-1].copy(), clocks[::-1].copy())
+    assert np.array_equal(l2[::-1], logits) and np.array_equal(v2[::-1], values)
+    l3, v3 = eng.network_forward(tokens[:130], clocks[:130])
+    assert np.array_equal(l3, logits[:130]) and np.array_equal(v3, values[:130])
+    return worst_p, worst_v
+
+
+def test_fp8_tower_random_init_within_tolerance(mcaz_lib):
+    from minitchess_alphazero_b200.policy import Network
+    torch.manual_seed(0)
+    net = Network().eval()
+    check_against_fp32(net, 'seed 0')
+    g = load_golden('network_seed0.npz')                           # the fixture written by the reference's own Network
+    eng = make_engine(net)
+    logits, values = eng.network_forward(g['tokens'].reshape(-1, 60), g['clocks'].reshape(-1))
+    assert np.abs(torch.from_numpy(logits).softmax(-1).numpy() - torch.from_numpy(g['logits']).softmax(-1).numpy()).max() < TOL
+    assert np.abs(values - g['values'].reshape(-1)).max() < TOL
+
+
+def test_fp8_tower_with_batchnorm_statistics_within_tolerance(mcaz_lib):
+    from test_gpu_network import bn_perturbed_net
+    net = bn_perturbed_net()
+    check_against_fp32(net, 'BatchNorm statistics')
+    g = load_golden('network_seed0.npz')
+    eng = make_engine(net)
+    logits, values = eng.network_forward(g['tokens'].reshape(-1, 60), g['clocks'].reshape(-1))
+    assert np.abs(torch.from_numpy(logits).softmax(-1).numpy() - torch.from_numpy(g['logits_bn']).softmax(-1).numpy()).max() < TOL
+    assert np.abs(values - g['values_bn'].reshape(-1)).max() < 2 * TOL
+
+
+def test_fp8_tower_after_learner_steps_within_tolerance(mcaz_lib):
+    """A network the learner has moved: 8 AdamW steps at lr 1e-3 on the golden learner dataset (BatchNorm statistics updated
+    in train mode, weights off their initialisation)."""
+    from minitchess_alphazero_b200.loop import learner_update
+    from minitchess_alphazero_b200.policy import Network
+    from test_learner_golden import golden, pack_tuples
+    g = golden()
+    torch.manual_seed(0)
+    net = Network()
+    learner_update(net, pack_tuples(g['items']), batch_size=32, optim_params={'lr': 1e-3}, device='cuda', order=g['runs']['0.001']['batches'])
+    net = net.cpu().eval()
+    check_against_fp32(net, 'after 8 learner steps')
+
+
+def test_fp8_search_is_self_consistent(mcaz_lib):
+    """The search does not care which evaluator feeds it: with the e4m3 tower the exact cache, free simulations and recycling
+    still leave every visit count as the plain search has it (the network is deterministic and row independent)."""
+    from minitchess_alphazero_b200.policy import Network
+    torch.manual_seed(0)
+    net = Network().eval()
+    G, sims = 200, 24
+    plain = make_engine(net, n_games=G, max_sims_per_move=sims, device_rng=1, seed=5)
+    fast = make_engine(net, n_games=G, max_sims_per_move=sims, device_rng=1, seed=5, eval_cache_log2=18, free_sims=4, recycle=1)
+    bf16 = make_engine(net, n_games=G, network=1, max_sims_per_move=sims, device_rng=1, seed=5)
+    agree = 0
+    for move in range(8):
+        for e in (plain, fast, bf16):
+            e.search(sims)
+        a, b, c = plain.root_stats(), fast.root_stats(), bf16.root_stats()
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)), move
+        if move == 0:
+            agree = (a[1].argmax(1) == c[1].argmax(1)).mean()       # same most-visited move as the bf16 tower in most games
+        for e in (plain, fast, bf16):
+            e.play_device()
+    assert agree > 0.8, agree
+    cf = fast.counters()
+    assert cf['cached_evaluations'] > 0 and cf['simulations'] == 8 * G * sims
