@@ -28,7 +28,8 @@
 extern "C" {
 #endif
 
-#define MCAZ_ABI_VERSION 4   /* 4: az_replay_tuple.weights_version, az_set_weights_version, az_tree_dump, counter 14 */
+#define MCAZ_ABI_VERSION 4   /* 4: az_replay_tuple.weights_version, az_set_weights_version, az_tree_dump, counter 14,
+                                az_config.fp8_convolutions, network = 2 */
 
 /* ---- geometry and action indexing (exp/generate_moves_list.py:5-57, exp/moves_dict.json) */
 #define MC_FILES 5
@@ -168,6 +169,10 @@ typedef struct az_config {
                                   then run a game's simulations back to back inside one launch until one needs the
                                   network and return as soon as no game waits for a row.  The order of a game's simulations
                                   and every number in its tree are unchanged (exp/agent.py:41-45).  Default 0             */
+    int32_t fp8_convolutions;  /* network = 2: how many of the 18 tower convolutions, counted from the first, multiply e4m3
+                                  operands -- an even number (whole residual blocks), the rest run in bf16.  0 = default 12:
+                                  measured, priors and values then stay within 1e-2 of the fp32 network on random-init,
+                                  learner-stepped and BatchNorm-perturbed weights (all 18: 1.2e-2 on the last kind)       */
 } az_config;
 
 void az_default_config(az_config* out);

@@ -44,7 +44,7 @@ class Config(ctypes.Structure):
                 ('seed', ctypes.c_uint64), ('rules', Rules), ('network', ctypes.c_int32),
                 ('leaves_per_step', ctypes.c_int32), ('own_stream', ctypes.c_int32),
                 ('eval_cache_log2', ctypes.c_int32), ('free_sims', ctypes.c_int32), ('recycle', ctypes.c_int32),
-                ('lookahead_rows', ctypes.c_int32)]
+                ('lookahead_rows', ctypes.c_int32), ('fp8_convolutions', ctypes.c_int32)]
 
 
 _lib = None

@@ -602,6 +602,7 @@ void az_default_config(az_config* c) {
     c->free_sims = 0;
     c->recycle = 0;
     c->lookahead_rows = 0;
+    c->fp8_convolutions = 0;
 }
 
 int az_create(const az_config* cfg, az_engine** out) {

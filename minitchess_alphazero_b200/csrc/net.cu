@@ -264,6 +264,7 @@ struct TowerParams {
     uint8_t* actq0;               // e4m3 copy of the block inputs x (levels 0, 2, 4, ...): A operand of a block's first convolution
     uint8_t* actq1;               // e4m3 h between the two convolutions of a block (levels 1, 3, ...); never kept in bf16
     unsigned int* level_absmax;   // calibration launch (bf16 form): per level the largest activation written, as float bits (values >= 0)
+    int fp8_levels;               // levels 1 .. fp8_levels (an even number: whole residual blocks) multiply e4m3 operands, the rest bf16
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
@@ -397,7 +398,6 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                 const __grid_constant__ CUtensorMap map_q1, const __grid_constant__ CUtensorMap map_wq,
                 const __grid_constant__ TowerParams P) {
     static_assert(!(FP8 && CALIB), "the calibration pass runs the bf16 form");
-    constexpr int KCHUNK = FP8 ? 128 : BLOCK_K;      // elements of one 128-byte swizzle row = K of one stage
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -459,9 +459,11 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             }
             // level 0 (stem): one-hot rows x folded embedding/conv table, one 16-channel chunk (32-byte rows) per tap;
             // level L >= 1: convolution L - 1 reads act0 (even) / act1 (odd), four chunks per tap
-            const int conv = L - 1, chunks = L == 0 ? 1 : C / KCHUNK;
-            const CUtensorMap* map_in = L == 0 ? &map_stem_in : (FP8 ? ((conv & 1) ? &map_q1 : &map_q0) : ((conv & 1) ? &map_act1 : &map_act0));
-            const CUtensorMap* map_wt = L == 0 ? &map_stem_w : (FP8 ? &map_wq : &map_w);
+            const bool q8 = FP8 && L >= 1 && L <= P.fp8_levels;       // this level's operands are e4m3: 128 elements per 128-byte row
+            const int kchunk = q8 ? 128 : BLOCK_K;
+            const int conv = L - 1, chunks = L == 0 ? 1 : C / kchunk;
+            const CUtensorMap* map_in = L == 0 ? &map_stem_in : (q8 ? ((conv & 1) ? &map_q1 : &map_q0) : ((conv & 1) ? &map_act1 : &map_act0));
+            const CUtensorMap* map_wt = L == 0 ? &map_stem_w : (q8 ? &map_wq : &map_w);
             const int w_base = L == 0 ? 0 : conv * 9;
             for (int tap = 0; tap < 9; ++tap) {
                 int src;
@@ -474,8 +476,8 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                     if (leader) mbar_expect_tx(&full[s], L == 0 ? 4 * STEM_TILE_BYTES : 2 * STAGE_BYTES);
                     else mbar_arrive_remote(&full[s], 0);
                     uint8_t* st = smem + s * STAGE_BYTES;
-                    tma_load_3d_2sm(st, map_in, &full[s], kc * KCHUNK, tile * BLOCK_M, src);
-                    tma_load_3d_2sm(st + A_BYTES, map_wt, &full[s], kc * KCHUNK, (int)rank * (C / 2), w_base + tap);
+                    tma_load_3d_2sm(st, map_in, &full[s], kc * kchunk, tile * BLOCK_M, src);
+                    tma_load_3d_2sm(st + A_BYTES, map_wt, &full[s], kc * kchunk, (int)rank * (C / 2), w_base + tap);
                 }
             }
         }
@@ -493,7 +495,8 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             if (item == ITEM_END) break;
             const int pos = item & 0xff;
             const bool stem = (item >> 24) == 0;          // K = 16 per tap: the 14 one-hot channels
-            const int chunks = stem ? 1 : C / KCHUNK, ksteps = stem ? 1 : BLOCK_K / 16;     // 4 instructions of 32 bytes of K per stage
+            const bool q8 = FP8 && !stem && (int)(item >> 24) <= P.fp8_levels;
+            const int chunks = stem ? 1 : (q8 ? C / 128 : C / BLOCK_K), ksteps = stem ? 1 : BLOCK_K / 16;     // 4 instructions of 32 bytes of K per stage
             const uint32_t acc = k & 1;
             const long long t0 = clock64();
             mbar_wait(&acc_empty[acc], ((k >> 1) & 1) ^ 1);
@@ -519,7 +522,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
 #pragma unroll
                     for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
                         if (kk < ksteps) {
-                            if (FP8 && !stem) umma_fp8_2sm(d_tmem, da + 2 * kk, db + 2 * kk, IDESC_FP8, accumulate);
+                            if (q8) umma_fp8_2sm(d_tmem, da + 2 * kk, db + 2 * kk, IDESC_FP8, accumulate);
                             else umma_bf16_2sm(d_tmem, da + 2 * kk, db + 2 * kk, IDESC, accumulate);
                             accumulate = 1;
                         }
@@ -587,16 +590,20 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             const bool last = L == NLAYERS && P.fuse_heads;    // its output only feeds the three 1x1 head convolutions
             // bf16 form: x lives in act0 (levels 0, 2, 4, ...), h in act1.  e4m3 form: act0 is the bf16 residual stream x, the
             // operands are the e4m3 copies actq0 (x) and actq1 (h)
-            __nv_bfloat16* out = (FP8 || odd || L == 0) ? P.act0 : P.act1;
-            const bool write_bf16 = !FP8 || odd || L == 0;
-            uint8_t* outq = FP8 ? ((odd || L == 0) ? P.actq0 : P.actq1) : nullptr;
+            // (only where the next level multiplies e4m3; x is always kept in bf16 as well, h only where the next level is bf16)
+            const bool is_x = odd || L == 0;
+            const bool write_q = FP8 && L + 1 <= P.fp8_levels;
+            const bool write_bf16 = is_x || !write_q;
+            __nv_bfloat16* out = is_x ? P.act0 : P.act1;
+            uint8_t* outq = is_x ? P.actq0 : P.actq1;
             const size_t row_off = ((size_t)pos * P.bpad + (size_t)tile * BLOCK_M + q * 32 + lane) * C;
             if (last) {
                 // the tower's output row never leaves the SM: bias + residual + ReLU in fp32, then the three 1x1 head
                 // filters as dot products over the row this thread holds
                 if (P.flags) while (ld_acquire_cta_shared(&s_deps_ok) <= k) __nanosleep(SPIN_NS);
                 float h[3];
-                epilogue_heads<2 * (int)FP8 + (int)CALIB>(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C, P.bias_g + L * C, FP8 ? P.scale_g + L * C : nullptr, P.head_w,
+                epilogue_heads<2 * (int)FP8 + (int)CALIB>(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C, P.bias_g + L * C,
+                                                          (FP8 && L <= P.fp8_levels) ? P.scale_g + L * C : nullptr, P.head_w,
                                out + row_off, &acc_full[acc], acc_phase, P.wait_hint, h);
                 tc_fence_before();
                 __syncwarp();
@@ -677,7 +684,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                         xq[2 * h] = x0 * inv_a; xq[2 * h + 1] = x1 * inv_a;
                     }
                     outv[j] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                    if (FP8) { q8[2 * j] = pack_e4m3x4(xq[0], xq[1], xq[2], xq[3]); q8[2 * j + 1] = pack_e4m3x4(xq[4], xq[5], xq[6], xq[7]); }
+                    if (FP8 && write_q) { q8[2 * j] = pack_e4m3x4(xq[0], xq[1], xq[2], xq[3]); q8[2 * j + 1] = pack_e4m3x4(xq[4], xq[5], xq[6], xq[7]); }
                 }
                 if (odd && c + 4 < C / 32) {
                     ld_cg_v8(out + row_off + (c + 4) * 32, res[c & 3][0], res[c & 3][1]);
@@ -687,7 +694,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                     st_v8(out + row_off + c * 32, outv[0], outv[1]);
                     st_v8(out + row_off + c * 32 + 16, outv[2], outv[3]);
                 }
-                if (FP8) st_v8(outq + row_off + c * 32, make_uint4(q8[0], q8[1], q8[2], q8[3]), make_uint4(q8[4], q8[5], q8[6], q8[7]));
+                if (FP8 && write_q) st_v8(outq + row_off + c * 32, make_uint4(q8[0], q8[1], q8[2], q8[3]), make_uint4(q8[4], q8[5], q8[6], q8[7]));
             }
             if (CALIB) {
 #pragma unroll
@@ -1108,6 +1115,7 @@ struct Network {
     CUtensorMap map_act[2], map_w, map_stem_in, map_stem_w;
     // e4m3 tower (az_config.network = 2)
     bool fp8 = false;
+    int fp8_levels = 0;                // levels 1 .. fp8_levels on e4m3 operands (az_config.fp8_convolutions)
     bool calibrating = false;          // forward_chunk runs the bf16 form with the per-level maxima on (calibrate_fp8)
     uint8_t* wq = nullptr;             // [18][9][256][256] e4m3: folded weights over their output channel's scale
     float* w_scale = nullptr;          // [18][256] that scale (largest |weight| of the channel / 448)
@@ -1194,6 +1202,9 @@ int network_create(az_engine* e) {
     MCAZ_CUDA(cudaFuncSetAttribute(tower_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_SMEM));
     N->fp8 = e->cfg.network == 2;
     if (N->fp8) {
+        const int want = e->cfg.fp8_convolutions;
+        if (want < 0 || want > NLAYERS || (want & 1)) return fail(MCAZ_EINVAL, "az_create: fp8_convolutions must be an even number in [0, 18]");
+        N->fp8_levels = want == 0 ? 12 : want;
         MCAZ_CUDA(cudaFuncSetAttribute(tower_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_SMEM));
         MCAZ_CUDA(cudaFuncSetAttribute(tower_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_SMEM_FP8));
         MCAZ_CUDA(cudaMalloc(&N->wq, (size_t)NLAYERS * 9 * C * C));
@@ -1365,6 +1376,7 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
     }
     T.wait_hint = (uint32_t)env_or("MCAZ_WAIT_HINT", 2000);     // A/B on one box: 267.2 -> 266.1 ms per 200 batches; 20000 ns: 266.8
     T.scale_g = N->scale; T.actq0 = N->actq[0]; T.actq1 = N->actq[1]; T.level_absmax = N->calibrating ? N->level_absmax : nullptr;
+    T.fp8_levels = N->fp8_levels;
     const int grid = 2 * std::max(1, std::min(num_sms() / 2, n_pairs * NPOS));
     auto launch = [&]() {
         if (N->calibrating)
@@ -1456,7 +1468,7 @@ static int calibrate_fp8(az_engine* e, const float* flat) {
         N->act_scale[L] = std::max(1.25f * m, 1e-6f) / E4M3_MAX;
         N->tower_params.inv_a[L] = 1.0f / N->act_scale[L];
     }
-    for (int L = 1; L < NLEVELS; ++L)              // level L = convolution L - 1 on the output of level L - 1
+    for (int L = 1; L <= N->fp8_levels; ++L)       // level L = convolution L - 1 on the output of level L - 1; bf16 levels keep 1
         for (int n = 0; n < C; ++n) scale[(size_t)L * C + n] = w_scale[(size_t)(L - 1) * C + n] * N->act_scale[L - 1];
     MCAZ_CUDA(cudaMemcpyAsync(N->scale, scale.data(), scale.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     MCAZ_CUDA(cudaStreamSynchronize(st));

@@ -14,7 +14,8 @@ from minitchess_alphazero_b200.engine import Engine
 from minitchess_alphazero_b200.policy import Network, flatten_state_dict
 
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-eng = Engine(G, max_sims_per_move=4, network=1)
+FP8 = len(sys.argv) > 2 and sys.argv[2] == 'fp8'
+eng = Engine(G, max_sims_per_move=4, network=2 if FP8 else 1)
 torch.manual_seed(0)
 eng.set_weights(flatten_state_dict(Network().state_dict()).numpy())
 tok = torch.randint(0, 7, (G, 60), dtype=torch.uint8, device='cuda')
@@ -31,7 +32,7 @@ n = L.az_tower_stats(eng._h, _lib.ptr(out), len(out))
 assert n > 0, L.mcaz_last_error()
 st = out[:n].reshape(-1, 8).astype(np.float64)
 lead = st[0::2]
-print('rows %d, %d CTA pairs' % (G, len(lead)))
+print('rows %d, %d CTA pairs%s' % (G, len(lead), ', e4m3 tower' if FP8 else ''))
 print('MMA issuer : %.0f k cycles; waiting for operands (TMA) %.1f %%, for a free accumulator (epilogue) %.1f %%, issuing %.1f %%' % (
     lead[:, 0].mean() / 1e3, 100 * lead[:, 1].sum() / lead[:, 0].sum(), 100 * lead[:, 2].sum() / lead[:, 0].sum(),
     100 * (1 - (lead[:, 1].sum() + lead[:, 2].sum()) / lead[:, 0].sum())))
