@@ -311,10 +311,10 @@ int az_counters(az_engine* e, uint64_t* out);
 int az_network_forward(az_engine* e, const uint8_t* tokens, const float* clocks, int n,
                        float* logits, float* values);
 
-/* Measurement hook: with MCAZ_TOWER_STATS=1 in the environment the tower kernel records, per CTA of its last launch, eight
+/* Measurement hook: with MCAZ_TOWER_STATS=1 in the environment the tower kernel records, per CTA of its last launch, twelve
  * counters {MMA issuer: total cycles, waiting for operands (TMA), waiting for a free accumulator (epilogue); TMA
  * producer: total, waiting for dependencies (previous level), waiting for a free stage; MMA issuer: operand wait at the
- * first stage of a work item, work items}.  Copies up to `capacity` words to `out` (host) and returns the number
+ * first stage of a work item, work items; cycles spent issuing e4m3 stages, their number, the same for bf16 stages}.  Copies up to `capacity` words to `out` (host) and returns the number
  * copied (< 0: error).                                                                                                  */
 int az_tower_stats(az_engine* e, unsigned long long* out, int capacity);
 

@@ -224,7 +224,8 @@ __device__ __forceinline__ bool tap_valid(int pos, int tap, int& src) {
 #define SPIN_NS 40     // back-off of the waits on the dependency watcher: a hot spin costs issue slots and power
 #endif
 constexpr int TOWER_SMEM = STAGES * STAGE_BYTES + 1024 + 256;
-constexpr int TOWER_SMEM_FP8 = TOWER_SMEM + NLEVELS * C * 4;          // + the dequantisation factors of the e4m3 form
+constexpr int TOWER_SMEM_FP8 = TOWER_SMEM;      // the e4m3 form reads its dequantisation factors through L1: a larger carve-out (no L1
+                                                // left for the spilled locals of the issue loops) cost more than the table saved
 static_assert(TOWER_SMEM_FP8 <= 227 * 1024, "tower shared memory");
 constexpr unsigned long long WATCHDOG_CYCLES = 20ull * 1000 * 1000 * 1000;   // ~10 s: a dependency that never arrives
 constexpr int ITEM_RING = 16;          // claimed items in flight per CTA (scheduler -> producer / MMA / epilogue); see tower_scheduler
@@ -406,7 +407,6 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
     uint64_t* acc_full = bars + 2 * STAGES;
     uint64_t* acc_empty = bars + 2 * STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-    float* s_scale = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);      // FP8 only: [19][256] (TOWER_SMEM_FP8)
     __shared__ unsigned long long s_ring[ITEM_RING];   // claimed items (written by the leader's scheduler, here and in the peer)
     __shared__ uint32_t s_deps_ok;            // items [0, s_deps_ok) have all their inputs published (written by warp 3)
     __shared__ uint32_t s_prod_at;            // item the TMA producer of this CTA is loading (flow control of the scheduler)
@@ -421,7 +421,6 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
         live_pairs = (int)min((uint32_t)P.n_pairs, (rows + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
     }
 
-    if (FP8) for (int i = threadIdx.x; i < NLEVELS * C; i += CONV_THREADS) s_scale[i] = __ldg(P.scale_g + i);
     if (threadIdx.x < ITEM_RING) s_ring[threadIdx.x] = 0ull;
     if (threadIdx.x == 0) { s_deps_ok = 0; s_prod_at = 0; }
     if (warp == 1 && lane == 0) {
@@ -482,14 +481,14 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             }
         }
         if (P.stats) {
-            unsigned long long* st = P.stats + (size_t)blockIdx.x * 8;
+            unsigned long long* st = P.stats + (size_t)blockIdx.x * 12;
             st[3] = (unsigned long long)(clock64() - p_start); st[4] = (unsigned long long)p_deps; st[5] = (unsigned long long)p_slot;
         }
     } else if (warp == 1 && lane == 0 && leader) {
         // ---------------------------------------------------------------- MMA issuer (leader CTA)
         uint32_t it = 0;
         const long long m_start = clock64();
-        long long m_full = 0, m_acc = 0, m_first = 0, m_items = 0;
+        long long m_full = 0, m_acc = 0, m_first = 0, m_items = 0, m_issue8 = 0, m_issue16 = 0, m_stages8 = 0, m_stages16 = 0;
         for (uint32_t k = 0;; ++k) {
             const uint32_t item = ring_get(s_ring, k);
             if (item == ITEM_END) break;
@@ -516,6 +515,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                     m_full += waited;
                     if (!accumulate) m_first += waited;       // the item's first stage: dependency stalls and ring refills show up here
                     tc_fence_after();
+                    const long long t2 = clock64();
                     const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
                     const uint64_t da = stem ? umma_desc_sw32(a_addr) : umma_desc(a_addr);
                     const uint64_t db = stem ? umma_desc_sw32(a_addr + A_BYTES) : umma_desc(a_addr + A_BYTES);
@@ -528,14 +528,16 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                         }
                     }
                     umma_commit_2sm(&empty[s]);
+                    if (q8) { m_issue8 += clock64() - t2; ++m_stages8; } else if (!stem) { m_issue16 += clock64() - t2; ++m_stages16; }
                 }
             }
             umma_commit_2sm(&acc_full[acc]);
         }
         if (P.stats) {
-            unsigned long long* st = P.stats + (size_t)blockIdx.x * 8;
+            unsigned long long* st = P.stats + (size_t)blockIdx.x * 12;
             st[0] = (unsigned long long)(clock64() - m_start); st[1] = (unsigned long long)m_full; st[2] = (unsigned long long)m_acc;
             st[6] = (unsigned long long)m_first; st[7] = (unsigned long long)m_items;
+            st[8] = (unsigned long long)m_issue8; st[9] = (unsigned long long)m_stages8; st[10] = (unsigned long long)m_issue16; st[11] = (unsigned long long)m_stages16;
         }
     } else if (warp == 3) {
         // ---------------------------------------------------------------- scheduler (leader) + dependency watcher
@@ -631,9 +633,18 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             }
             if (P.wait_hint) mbar_wait_hint(&acc_full[acc], acc_phase, P.wait_hint); else mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
+#ifdef TOWER_NO_EPILOGUE        // timing experiment only (wrong results): hand the accumulator back unread
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (leader) mbar_arrive(&acc_empty[acc]); else mbar_arrive_remote(&acc_empty[acc], 0); }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 4 && lane == 0 && P.flags) st_release_gpu(P.flags + (((size_t)L * P.n_pairs + tp) * NPOS + pos) * 2 + rank, P.epoch);
+            continue;
+#endif
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C;
             const int bias0 = L * C;
             const float inv_a = FP8 ? P.inv_a[L] : 0.f;
+            const float* scale_l = P.scale_g + bias0;      // e4m3 form: this level's dequantisation factors (1 KB, every thread the same word: L1)
             float seen_max = 0.f;
 #pragma unroll
             for (int c = 0; c < C / 32; ++c) {
@@ -668,7 +679,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                     for (int h = 0; h < 4; ++h) {
                         const int e = j * 8 + h * 2;
                         float x0 = __uint_as_float(v[e]), x1 = __uint_as_float(v[e + 1]);
-                        if (FP8) { x0 *= s_scale[bias0 + c * 32 + e]; x1 *= s_scale[bias0 + c * 32 + e + 1]; }     // dequantise the accumulator
+                        if (FP8) { x0 *= __ldg(scale_l + c * 32 + e); x1 *= __ldg(scale_l + c * 32 + e + 1); }     // dequantise the accumulator
                         x0 += P.bias[bias0 + c * 32 + e];
                         x1 += P.bias[bias0 + c * 32 + e + 1];
                         if (odd) {
@@ -1135,7 +1146,7 @@ struct Network {
     bool per_layer = false;            // false: tower_tc_kernel (one data-flow ordered launch for all levels, default);
                                        // true: the same kernel launched once per level (MCAZ_TOWER=layers)
     // profiling (az_profile_network)
-    unsigned long long* stats = nullptr;   // MCAZ_TOWER_STATS=1: [grid][8] wait-cycle counters of the last tower launch
+    unsigned long long* stats = nullptr;   // MCAZ_TOWER_STATS=1: [grid][12] wait-cycle counters of the last tower launch
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
     size_t events_used = 0;
@@ -1369,8 +1380,8 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
         static int want_stats = -1;
         if (want_stats < 0) { const char* ss = getenv("MCAZ_TOWER_STATS"); want_stats = ss && atoi(ss) > 0; }
         if (want_stats && !N->stats) {
-            MCAZ_CUDA(cudaMalloc(&N->stats, (size_t)num_sms() * 8 * sizeof(unsigned long long)));
-            MCAZ_CUDA(cudaMemset(N->stats, 0, (size_t)num_sms() * 8 * sizeof(unsigned long long)));
+            MCAZ_CUDA(cudaMalloc(&N->stats, (size_t)num_sms() * 12 * sizeof(unsigned long long)));
+            MCAZ_CUDA(cudaMemset(N->stats, 0, (size_t)num_sms() * 12 * sizeof(unsigned long long)));
         }
         T.stats = N->stats;
     }
@@ -1500,7 +1511,7 @@ int network_profile(az_engine* e, int on, double* avg_ms_per_tower, int* n_forwa
 extern "C" int az_tower_stats(az_engine* e, unsigned long long* out, int capacity) {
     if (!e || !e->net || !out) return mcaz::fail(MCAZ_EINVAL, "az_tower_stats: bad argument");
     if (!e->net->stats) return mcaz::fail(MCAZ_ESTATE, "az_tower_stats: run with MCAZ_TOWER_STATS=1");
-    const int n = std::min(capacity, mcaz::num_sms() * 8);
+    const int n = std::min(capacity, mcaz::num_sms() * 12);
     cudaStreamSynchronize(e->stream);
     if (cudaMemcpy(out, e->net->stats, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
         return mcaz::fail(MCAZ_ECUDA, "az_tower_stats: copy failed");

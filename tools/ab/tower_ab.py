@@ -26,8 +26,9 @@ def worker(so):
     rng = np.random.RandomState(0)
     tok_all = rng.randint(0, 7, size=(4096, 60)).astype(np.uint8)
     clk_all = rng.rand(4096).astype(np.float32)
-    for rows in (256, 1024, 2816, 4096):
-        eng = Engine(rows, max_sims_per_move=4, network=1)
+    for rows in (2816, 4096):
+        fp8 = int(os.environ.get('AB_FP8', '0'))
+        eng = Engine(rows, max_sims_per_move=4, network=2, fp8_convolutions=fp8) if fp8 else Engine(rows, max_sims_per_move=4, network=1)
         eng.set_weights(flat)
         tok = torch.from_numpy(tok_all[:rows]).cuda(); clk = torch.from_numpy(clk_all[:rows]).cuda()
         lg = torch.empty(rows, 554, device='cuda'); vl = torch.empty(rows, device='cuda')
@@ -45,18 +46,20 @@ def worker(so):
             fwd()
         ms, cnt, _ = eng.profile_network(False, read=True)
         out['tower_ms_%d' % rows] = round(ms, 4)
+        out['fp8'] = fp8
         if os.environ.get('MCAZ_TOWER_STATS') and rows in (2816, 4096):
             import ctypes
-            buf = np.zeros(148 * 8, dtype=np.uint64)
+            buf = np.zeros(148 * 12, dtype=np.uint64)
             L.az_tower_stats.restype = ctypes.c_int
             k = L.az_tower_stats(eng._h, _lib.ptr(buf), len(buf))
             if k > 0:
-                st = buf[:k].reshape(-1, 8).astype(np.float64)
+                st = buf[:k].reshape(-1, 12).astype(np.float64)
                 lead = st[0::2]
                 out['wait_%d' % rows] = {'operands': round(100 * lead[:, 1].sum() / lead[:, 0].sum(), 1),
                                          'accumulator': round(100 * lead[:, 2].sum() / lead[:, 0].sum(), 1),
                                          'producer_deps': round(100 * st[:, 4].sum() / st[:, 3].sum(), 1),
-                                         'producer_slot': round(100 * st[:, 5].sum() / st[:, 3].sum(), 1)}
+                                         'producer_slot': round(100 * st[:, 5].sum() / st[:, 3].sum(), 1),
+                                         'kcycles': round(lead[:, 0].mean() / 1e3), 'cycles_per_item': round(lead[:, 0].sum() / max(lead[:, 7].sum(), 1))}
         eng.close()
     print('RESULT ' + json.dumps(out))
 

@@ -27,7 +27,7 @@ rng = np.random.RandomState(1)
 def main_sections():
     # ---- stateless rules kernels on positions from random playouts (legal_moves_kernel, apply_kernel, tokenize_kernel, perft_*)
     walkers = np.repeat(rules.states_from_fens([rules.STARTING_FEN]), 65536)
-    for _ in range(12):
+    for _ in range(3):
         codes, counts, results = rules.legal_moves(walkers)
         pick = codes[np.arange(len(walkers)), (rng.random_sample(len(walkers)) * np.maximum(counts, 1)).astype(np.int64)]
         nxt, status = rules.apply(walkers, pick)
@@ -39,8 +39,8 @@ def main_sections():
 
     # ---- throughput mode: search_step_kernel<false>, stem_onehot_kernel, tower_tc_kernel, heads_legal_kernel<false>, play_device_kernel,
     # restart_finished_kernel, recycle_kernel (arenas of 3 x sims nodes fill up every other move), prep_* (set_weights)
-    sp = BatchedSelfPlay(net, n_games=G, num_simulations=32, seed=5, node_capacity=3 * 32 + 64, eval_cache_log2=22)
-    for _ in range(6):
+    sp = BatchedSelfPlay(net, n_games=G, num_simulations=32, seed=5, node_capacity=2 * 32 + 64, eval_cache_log2=22)
+    for _ in range(4):
         sp.step()
     sp.run_continuous(8)
     tuples = sp.drain()
@@ -68,7 +68,7 @@ def main_sections():
     ext = Engine(G, max_sims_per_move=16, device_rng=1, seed=2)
     pri = np.full((G, MC_MAX_MOVES), 1.0 / MC_MAX_MOVES, dtype=np.float32)
     val = np.zeros(G, dtype=np.float32)
-    for _ in range(8):
+    for _ in range(3):
         ext.select_expand()
         ext.backup(val, priors=pri)
     ext.close()

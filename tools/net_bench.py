@@ -7,7 +7,8 @@ from minitchess_alphazero_b200 import _lib
 from minitchess_alphazero_b200.engine import Engine
 from minitchess_alphazero_b200.policy import Network, flatten_state_dict
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-eng = Engine(G, max_sims_per_move=4, network=1)
+FP8 = int(sys.argv[3]) if len(sys.argv) > 3 else 0          # number of e4m3 convolutions (0 = the bf16 tower)
+eng = Engine(G, max_sims_per_move=4, network=2, fp8_convolutions=FP8) if FP8 else Engine(G, max_sims_per_move=4, network=1)
 torch.manual_seed(0)
 eng.set_weights(flatten_state_dict(Network().state_dict()).numpy())
 tok = torch.randint(0, 7, (G, 60), dtype=torch.uint8, device='cuda')

@@ -26,11 +26,11 @@ L = _lib.lib()
 for _ in range(20):
     _lib.check(L.az_network_forward(eng._h, _lib.ptr(tok), _lib.ptr(clk), G, _lib.ptr(lg), _lib.ptr(vl)))
 torch.cuda.synchronize()
-out = np.zeros(148 * 8, dtype=np.uint64)
+out = np.zeros(148 * 12, dtype=np.uint64)
 L.az_tower_stats.restype = ctypes.c_int
 n = L.az_tower_stats(eng._h, _lib.ptr(out), len(out))
 assert n > 0, L.mcaz_last_error()
-st = out[:n].reshape(-1, 8).astype(np.float64)
+st = out[:n].reshape(-1, 12).astype(np.float64)
 lead = st[0::2]
 print('rows %d, %d CTA pairs%s' % (G, len(lead), ', e4m3 tower' if FP8 else ''))
 print('MMA issuer : %.0f k cycles; waiting for operands (TMA) %.1f %%, for a free accumulator (epilogue) %.1f %%, issuing %.1f %%' % (
@@ -38,6 +38,8 @@ print('MMA issuer : %.0f k cycles; waiting for operands (TMA) %.1f %%, for a fre
     100 * (1 - (lead[:, 1].sum() + lead[:, 2].sum()) / lead[:, 0].sum())))
 print('MMA issuer : %.1f %% of the operand wait falls on the first stage of a work item (%.0f items per pair, %.0f cycles per item there, %.0f cycles per item in all)' % (
     100 * lead[:, 6].sum() / max(lead[:, 1].sum(), 1), lead[:, 7].mean(), lead[:, 6].sum() / max(lead[:, 7].sum(), 1), lead[:, 0].sum() / max(lead[:, 7].sum(), 1)))
+print('MMA issuer : cycles inside the issue of a stage (4 instructions + commit): e4m3 stages %.0f (%d stages per pair), bf16 stages %.0f (%d)' % (
+    lead[:, 8].sum() / max(lead[:, 9].sum(), 1), lead[:, 9].mean(), lead[:, 10].sum() / max(lead[:, 11].sum(), 1), lead[:, 11].mean()))
 print('TMA producer: %.0f k cycles; waiting for dependencies %.1f %%, for a free stage %.1f %%, issuing %.1f %%' % (
     st[:, 3].mean() / 1e3, 100 * st[:, 4].sum() / st[:, 3].sum(), 100 * st[:, 5].sum() / st[:, 3].sum(),
     100 * (1 - (st[:, 4].sum() + st[:, 5].sum()) / st[:, 3].sum())))
