@@ -539,8 +539,13 @@ def leg_loop(net, rank, world, args, barrier, learner_batches=256):
     dt = time.perf_counter() - t0
     c1 = sp.engine.counters()
     phases = ['selfplay', 'gather', 'learner', 'arena', 'broadcast']
+    # the iteration's time is the slowest rank's; the phases are the learner rank's (the other ranks spend the learner's
+    # update waiting in the broadcast)
     t = torch.tensor([dt] + [float(out['seconds'].get(k, 0.0)) for k in phases], dtype=torch.float64, device='cuda')
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.broadcast(t, src=0)
+    t[0] = tmax[0]
     s = torch.tensor([float(c1['simulations'] - c0['simulations'])], dtype=torch.float64, device='cuda')
     dist.all_reduce(s)
     info = torch.tensor([float(out['tuples']), float(out['used']), float(out['stale']), float(len(out['losses'])), float(out['version'])],
