@@ -163,6 +163,15 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                  : "memory");
 }
 
+// One lane of the (converged) warp; the others skip the block.  With the loop control kept warp-wide, ptxas keeps descriptors,
+// addresses and counters in uniform registers and issues UTCHMMA / UTMALDG / UTCBAR straight, instead of wrapping each in a
+// loop that makes a lane's operands uniform -- a single thread running ~90 dependent instructions per stage was what bounded
+// the round-1 tower (640 cycles per stage against 512 cycles of tensor work).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xFFFFFFFF;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -438,102 +447,115 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
-        // ---------------------------------------------------------------- TMA producer (both CTAs)
-        uint32_t it = 0;
-        const long long p_start = clock64();
+    if (warp == 0) {
+        // ---------------------------------------------------------------- TMA producer (both CTAs): the whole warp runs the loop
+        // control, one elected lane issues the loads
+        uint32_t stage = 0, phase = 0;
+        const bool stats = P.stats != nullptr;
+        const long long p_start = stats ? clock64() : 0;
         long long p_deps = 0, p_slot = 0;
         for (uint32_t k = 0;; ++k) {
             const uint32_t item = ring_get(s_ring, k);
             if (item == ITEM_END) break;
-            *reinterpret_cast<volatile uint32_t*>(&s_prod_at) = k;
+            if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&s_prod_at) = k;
             const int pos = item & 0xff, tp = (item >> 8) & 0xffff, L = item >> 24;
             const int tile = 2 * tp + (int)rank;
             if (L > P.first_level && P.flags) {
                 // inputs published? (warp 3 polls the global flags ahead of us)
-                const long long t0 = clock64();
+                const long long t0 = stats ? clock64() : 0;
                 while (ld_acquire_cta_shared(&s_deps_ok) <= k) __nanosleep(SPIN_NS);
-                p_deps += clock64() - t0;
+                if (stats) p_deps += clock64() - t0;
                 asm volatile("fence.proxy.async;" ::: "memory");   // order the acquired writes before our TMA reads
             }
             // level 0 (stem): one-hot rows x folded embedding/conv table, one 16-channel chunk (32-byte rows) per tap;
-            // level L >= 1: convolution L - 1 reads act0 (even) / act1 (odd), four chunks per tap
+            // level L >= 1: convolution L - 1 reads act0 (even) / act1 (odd), four chunks per tap (two of 128 e4m3 channels)
             const bool q8 = FP8 && L >= 1 && L <= P.fp8_levels;       // this level's operands are e4m3: 128 elements per 128-byte row
             const int kchunk = q8 ? 128 : BLOCK_K;
             const int conv = L - 1, chunks = L == 0 ? 1 : C / kchunk;
             const CUtensorMap* map_in = L == 0 ? &map_stem_in : (q8 ? ((conv & 1) ? &map_q1 : &map_q0) : ((conv & 1) ? &map_act1 : &map_act0));
             const CUtensorMap* map_wt = L == 0 ? &map_stem_w : (q8 ? &map_wq : &map_w);
             const int w_base = L == 0 ? 0 : conv * 9;
+            const uint32_t tx = L == 0 ? 4 * STEM_TILE_BYTES : 2 * STAGE_BYTES;
+            const int row = pos / 5, col = pos - 5 * row;
+#pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-                int src;
-                if (!tap_valid(pos, tap, src)) continue;
-                for (int kc = 0; kc < chunks; ++kc, ++it) {
-                    const int s = it % STAGES;
-                    const long long t1 = clock64();
-                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
-                    p_slot += clock64() - t1;
-                    if (leader) mbar_expect_tx(&full[s], L == 0 ? 4 * STEM_TILE_BYTES : 2 * STAGE_BYTES);
-                    else mbar_arrive_remote(&full[s], 0);
-                    uint8_t* st = smem + s * STAGE_BYTES;
-                    tma_load_3d_2sm(st, map_in, &full[s], kc * kchunk, tile * BLOCK_M, src);
-                    tma_load_3d_2sm(st + A_BYTES, map_wt, &full[s], kc * kchunk, (int)rank * (C / 2), w_base + tap);
+                const int rr = row + tap / 3 - 1, cc = col + tap % 3 - 1;
+                if (rr < 0 || rr > 5 || cc < 0 || cc > 4) continue;       // the tap falls on zero padding
+                const int src = rr * 5 + cc;
+                for (int kc = 0; kc < chunks; ++kc) {
+                    const long long t1 = stats ? clock64() : 0;
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    if (stats) p_slot += clock64() - t1;
+                    if (elect_one_sync()) {
+                        if (leader) mbar_expect_tx(&full[stage], tx);
+                        else mbar_arrive_remote(&full[stage], 0);
+                        uint8_t* st = smem + stage * STAGE_BYTES;
+                        tma_load_3d_2sm(st, map_in, &full[stage], kc * kchunk, tile * BLOCK_M, src);
+                        tma_load_3d_2sm(st + A_BYTES, map_wt, &full[stage], kc * kchunk, (int)rank * (C / 2), w_base + tap);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
-        if (P.stats) {
+        if (stats && lane == 0) {
             unsigned long long* st = P.stats + (size_t)blockIdx.x * 12;
             st[3] = (unsigned long long)(clock64() - p_start); st[4] = (unsigned long long)p_deps; st[5] = (unsigned long long)p_slot;
         }
-    } else if (warp == 1 && lane == 0 && leader) {
-        // ---------------------------------------------------------------- MMA issuer (leader CTA)
-        uint32_t it = 0;
-        const long long m_start = clock64();
+    } else if (warp == 1 && leader) {
+        // ---------------------------------------------------------------- MMA issuer (leader CTA): warp-wide loop, one elected lane issues
+        uint32_t stage = 0, phase = 0;
+        const bool stats = P.stats != nullptr;
+        const long long m_start = stats ? clock64() : 0;
         long long m_full = 0, m_acc = 0, m_first = 0, m_items = 0, m_issue8 = 0, m_issue16 = 0, m_stages8 = 0, m_stages16 = 0;
+        const uint64_t desc0 = umma_desc(smem_u32(smem)), desc0_sw32 = umma_desc_sw32(smem_u32(smem));
         for (uint32_t k = 0;; ++k) {
             const uint32_t item = ring_get(s_ring, k);
             if (item == ITEM_END) break;
-            const int pos = item & 0xff;
-            const bool stem = (item >> 24) == 0;          // K = 16 per tap: the 14 one-hot channels
-            const bool q8 = FP8 && !stem && (int)(item >> 24) <= P.fp8_levels;
-            const int chunks = stem ? 1 : (q8 ? C / 128 : C / BLOCK_K), ksteps = stem ? 1 : BLOCK_K / 16;     // 4 instructions of 32 bytes of K per stage
+            const int pos = item & 0xff, L = (int)(item >> 24);
+            const bool stem = L == 0;                     // K = 16 per tap: the 14 one-hot channels
+            const bool q8 = FP8 && !stem && L <= P.fp8_levels;
+            const int row = pos / 5, col = pos - 5 * row;
+            const int n_taps = ((row == 0 || row == 5) ? 2 : 3) * ((col == 0 || col == 4) ? 2 : 3);
+            const int n_stages = n_taps * (stem ? 1 : (q8 ? C / 128 : C / BLOCK_K));     // all this role has to know of the item
             const uint32_t acc = k & 1;
-            const long long t0 = clock64();
+            const long long t0 = stats ? clock64() : 0;
             mbar_wait(&acc_empty[acc], ((k >> 1) & 1) ^ 1);
-            m_acc += clock64() - t0;
+            if (stats) { m_acc += clock64() - t0; ++m_items; }
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * C;
             uint32_t accumulate = 0;
-            ++m_items;
-            for (int tap = 0; tap < 9; ++tap) {
-                int src;
-                if (!tap_valid(pos, tap, src)) continue;
-                for (int kc = 0; kc < chunks; ++kc, ++it) {
-                    const int s = it % STAGES;
-                    const long long t1 = clock64();
-                    mbar_wait(&full[s], (it / STAGES) & 1);
-                    const long long waited = clock64() - t1;
-                    m_full += waited;
-                    if (!accumulate) m_first += waited;       // the item's first stage: dependency stalls and ring refills show up here
-                    tc_fence_after();
-                    const long long t2 = clock64();
-                    const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-                    const uint64_t da = stem ? umma_desc_sw32(a_addr) : umma_desc(a_addr);
-                    const uint64_t db = stem ? umma_desc_sw32(a_addr + A_BYTES) : umma_desc(a_addr + A_BYTES);
+            for (int st = 0; st < n_stages; ++st) {
+                const long long t1 = stats ? clock64() : 0;
+                mbar_wait(&full[stage], phase);
+                const long long t2 = stats ? clock64() : 0;
+                tc_fence_after();
+                // descriptors of this stage: start address field + stage * STAGE_BYTES / 16 (A), + A_BYTES / 16 more (B)
+                const uint64_t da = (stem ? desc0_sw32 : desc0) + (uint64_t)(stage * (STAGE_BYTES >> 4));
+                const uint64_t db = da + (uint64_t)(A_BYTES >> 4);
+                if (elect_one_sync()) {
+                    if (stem) {
+                        umma_bf16_2sm(d_tmem, da, db, IDESC, accumulate);
+                    } else if (q8) {
 #pragma unroll
-                    for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
-                        if (kk < ksteps) {
-                            if (q8) umma_fp8_2sm(d_tmem, da + 2 * kk, db + 2 * kk, IDESC_FP8, accumulate);
-                            else umma_bf16_2sm(d_tmem, da + 2 * kk, db + 2 * kk, IDESC, accumulate);
-                            accumulate = 1;
-                        }
+                        for (int kk = 0; kk < 4; ++kk) umma_fp8_2sm(d_tmem, da + 2 * kk, db + 2 * kk, IDESC_FP8, kk ? 1u : accumulate);
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) umma_bf16_2sm(d_tmem, da + 2 * kk, db + 2 * kk, IDESC, kk ? 1u : accumulate);
                     }
-                    umma_commit_2sm(&empty[s]);
-                    if (q8) { m_issue8 += clock64() - t2; ++m_stages8; } else if (!stem) { m_issue16 += clock64() - t2; ++m_stages16; }
+                    umma_commit_2sm(&empty[stage]);
                 }
+                if (stats) {
+                    const long long t3 = clock64();
+                    m_full += t2 - t1;
+                    if (!accumulate) m_first += t2 - t1;      // the item's first stage: dependency stalls and ring refills show up here
+                    if (q8) { m_issue8 += t3 - t2; ++m_stages8; } else if (!stem) { m_issue16 += t3 - t2; ++m_stages16; }
+                }
+                accumulate = 1;
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
-            umma_commit_2sm(&acc_full[acc]);
+            if (elect_one_sync()) umma_commit_2sm(&acc_full[acc]);
         }
-        if (P.stats) {
+        if (stats && lane == 0) {
             unsigned long long* st = P.stats + (size_t)blockIdx.x * 12;
             st[0] = (unsigned long long)(clock64() - m_start); st[1] = (unsigned long long)m_full; st[2] = (unsigned long long)m_acc;
             st[6] = (unsigned long long)m_first; st[7] = (unsigned long long)m_items;
