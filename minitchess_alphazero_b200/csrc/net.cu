@@ -275,6 +275,7 @@ struct TowerParams {
     uint8_t* actq1;               // e4m3 h between the two convolutions of a block (levels 1, 3, ...); never kept in bf16
     unsigned int* level_absmax;   // calibration launch (bf16 form): per level the largest activation written, as float bits (values >= 0)
     int fp8_levels;               // levels 1 .. fp8_levels (an even number: whole residual blocks) multiply e4m3 operands, the rest bf16
+    float l2_budget;              // bytes of the L2's persisting set-aside the activations may fill (0: none granted)
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
@@ -304,6 +305,37 @@ __device__ __forceinline__ void st_v8(void* p, const uint4& a, const uint4& b) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
 }
+
+// ---- L2 residency of the activation ping-pong buffers.  A group's activations are written at one level and read back at the
+// next: traffic that should live and die in the L2.  Plain stores do not achieve that -- ncu: 740 MB written to and 565 MB read
+// from HBM per 2816-row launch, against 27 MB of algorithmic bytes -- because the L2 replaces lines least-recently-used and a
+// working set that cycles just above its capacity is LRU's worst case.  So the activation stores of the first `l2_positions`
+// output positions carry an evict_last policy (createpolicy): those lines stay in the L2's persisting set-aside
+// (cudaLimitPersistingL2CacheSize, sized in network_create) from level to level and launch to launch, get overwritten in place
+// and never travel; the positions that would not fit keep the normal policy.  The split is by position, so it is the same lines
+// every time (a fractional policy picks lines by a hash the program cannot align with the set-aside).  TOWER_L2_MODE 0 = plain stores.
+#ifndef TOWER_L2_MODE
+#define TOWER_L2_MODE 1
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_v8_hint(void* p, const uint4& a, const uint4& b, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;"
+                 ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "l"(pol) : "memory");
+}
+#if TOWER_L2_MODE
+#define ST_ACT(p, a, b) st_v8_hint(p, a, b, l2pol)
+#else
+#define ST_ACT(p, a, b) st_v8(p, a, b)
+#endif
 
 // ---- claimed work items: a ring of 64-bit slots per CTA, slot k % ITEM_RING = (item << 32) | (k + 1).  One aligned
 // 64-bit store publishes an item (item and sequence number can never be seen apart), to this CTA and to its peer.
@@ -430,6 +462,17 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
         live_pairs = (int)min((uint32_t)P.n_pairs, (rows + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
     }
 
+#if TOWER_L2_MODE
+    // output positions whose rows stay in the persisting part of the L2: as many as the set-aside holds of one group's two buffers
+    int l2_positions = 0;
+    {
+        const int n_groups = max(1, (live_pairs + P.group_max - 1) / P.group_max);
+        const int group_pairs = (live_pairs + n_groups - 1) / n_groups;
+        const float per_position = (float)max(group_pairs, 1) * (float)(2 * BLOCK_M) * (float)(C * 2 * 2);    // both buffers, bf16
+        l2_positions = min(NPOS, (int)(P.l2_budget / per_position));
+    }
+    const uint64_t l2pol_last = l2_policy_evict_last(), l2pol_normal = l2_policy_evict_normal();
+#endif
     if (threadIdx.x < ITEM_RING) s_ring[threadIdx.x] = 0ull;
     if (threadIdx.x == 0) { s_deps_ok = 0; s_prod_at = 0; }
     if (warp == 1 && lane == 0) {
@@ -621,6 +664,9 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             __nv_bfloat16* out = is_x ? P.act0 : P.act1;
             uint8_t* outq = is_x ? P.actq0 : P.actq1;
             const size_t row_off = ((size_t)pos * P.bpad + (size_t)tile * BLOCK_M + q * 32 + lane) * C;
+#if TOWER_L2_MODE
+            const uint64_t l2pol = pos < l2_positions ? l2pol_last : l2pol_normal;
+#endif
             if (last) {
                 // the tower's output row never leaves the SM: bias + residual + ReLU in fp32, then the three 1x1 head
                 // filters as dot products over the row this thread holds
@@ -724,10 +770,10 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                     ld_cg_v8(out + row_off + (c + 4) * 32 + 16, res[c & 3][2], res[c & 3][3]);
                 }
                 if (write_bf16) {
-                    st_v8(out + row_off + c * 32, outv[0], outv[1]);
-                    st_v8(out + row_off + c * 32 + 16, outv[2], outv[3]);
+                    ST_ACT(out + row_off + c * 32, outv[0], outv[1]);
+                    ST_ACT(out + row_off + c * 32 + 16, outv[2], outv[3]);
                 }
-                if (FP8 && write_q) st_v8(outq + row_off + c * 32, make_uint4(q8[0], q8[1], q8[2], q8[3]), make_uint4(q8[4], q8[5], q8[6], q8[7]));
+                if (FP8 && write_q) ST_ACT(outq + row_off + c * 32, make_uint4(q8[0], q8[1], q8[2], q8[3]), make_uint4(q8[4], q8[5], q8[6], q8[7]));
             }
             if (CALIB) {
 #pragma unroll
@@ -1137,6 +1183,7 @@ int make_map_3d(CUtensorMap* map, void* ptr, uint64_t d0, uint64_t d1, uint64_t 
 
 struct Network {
     int capacity = 0;   // boards the activation buffers hold (multiple of 128)
+    size_t l2_persist_bytes = 0;       // persisting set-aside of the L2 granted to this context (activation stores, TOWER_L2_MODE)
     __nv_bfloat16 *act[2] = {nullptr, nullptr};
     __nv_bfloat16* w = nullptr;        // [18][9][256][256]
     float* bias = nullptr;             // [18][256]
@@ -1212,6 +1259,21 @@ int network_create(az_engine* e) {
     if (major != 10) return fail(MCAZ_ENODEV, "the built-in network needs an sm_100 GPU (tcgen05/TMEM/TMA)");
     Network* N = new Network();
     e->net = N;
+#if TOWER_L2_MODE
+    {   // evict_last lines live in the persisting set-aside of the L2 (a limit of the CUDA context: all the device allows, 79 of
+        // 126 MB on a B200; other kernels of the process keep the rest and whatever part of the set-aside is not in use)
+        int max_persist = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        size_t want = (size_t)max_persist;
+#ifdef MCAZ_TIMING_EXPERIMENTS
+        if (const char* pm = getenv("MCAZ_L2_PERSIST_MB")) want = std::min(want, (size_t)atoi(pm) << 20);
+#endif
+        size_t have = 0;
+        if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize);
+        cudaGetLastError();                 // a device without the feature (MIG slice): no set-aside, every store keeps the normal policy
+        N->l2_persist_bytes = have;
+    }
+#endif
     MCAZ_CUDA(cudaMalloc(&N->w, (size_t)NLAYERS * 9 * C * C * sizeof(__nv_bfloat16)));
     MCAZ_CUDA(cudaMalloc(&N->bias, (size_t)NLEVELS * C * sizeof(float)));
     MCAZ_CUDA(cudaMalloc(&N->stem_w, (size_t)9 * C * STEM_K * sizeof(__nv_bfloat16)));
@@ -1272,6 +1334,9 @@ int network_create(az_engine* e) {
 void network_destroy(az_engine* e) {
     Network* N = e->net;
     if (!N) return;
+#if TOWER_L2_MODE
+    if (N->l2_persist_bytes) cudaCtxResetPersistingL2Cache();      // the freed buffers' lines need not persist
+#endif
     for (int i = 0; i < 2; ++i) if (N->act[i]) cudaFree(N->act[i]);
     if (N->w) cudaFree(N->w);
     if (N->bias) cudaFree(N->bias);
@@ -1410,6 +1475,7 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
     T.wait_hint = (uint32_t)env_or("MCAZ_WAIT_HINT", 2000);     // A/B on one box: 267.2 -> 266.1 ms per 200 batches; 20000 ns: 266.8
     T.scale_g = N->scale; T.actq0 = N->actq[0]; T.actq1 = N->actq[1]; T.level_absmax = N->calibrating ? N->level_absmax : nullptr;
     T.fp8_levels = N->fp8_levels;
+    T.l2_budget = (float)env_or("MCAZ_L2_BUDGET_PCT", 100) / 100.f * (float)N->l2_persist_bytes;
     const int grid = 2 * std::max(1, std::min(num_sms() / 2, n_pairs * NPOS));
     auto launch = [&]() {
         if (N->calibrating)

@@ -59,8 +59,12 @@ def main_sections():
     eng.play(c[live, 0], game_ids=live)                # play_kernel
     tok = torch.randint(0, 7, (G, 60), dtype=torch.uint8, device='cuda')
     eng.network_forward(tok.cpu().numpy(), np.random.rand(G).astype(np.float32))   # heads_kernel (all 554 logits)
-    if len(tuples):
-        collate_device(tuples[:4096])                  # collate_kernel
+    if len(tuples) < 4096:                             # few games finish in so few moves: tuples of the current positions
+        from minitchess_alphazero_b200.engine import REPLAY_DTYPE
+        tuples = np.zeros(4096, dtype=REPLAY_DTYPE)
+        tuples['observation'] = np.resize(states, 4096)
+        tuples['n_legal'] = 1
+    collate_device(tuples[:4096])                      # collate_kernel
     sample_root_noise(1, 0.6, 9, 65536)                # sample_root_noise_kernel
     eng.close()
 
