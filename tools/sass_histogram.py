@@ -15,7 +15,8 @@ for line in text.splitlines():
     m = re.search(r'Function : (\S+)', line)
     if m:
         name = subprocess.run(['c++filt', m.group(1)], capture_output=True, text=True).stdout.strip()
-        name = re.sub(r'\(.*', '', name).replace('mcaz::(anonymous namespace)::', '').replace('mcaz::', '')
+        name = name.replace('(anonymous namespace)::', '').replace('mcaz::', '').replace('void ', '')
+        name = re.sub(r'\(.*', '', name)
         kernels[name] = collections.Counter()
         continue
     m = re.match(r'\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+(?:\.[A-Z0-9_]+)*)', line)
