@@ -49,6 +49,8 @@ def parse_args():
                          'sims-per-move network batches); lockstep: az_search + az_play_device, one move in every game per step')
     ap.add_argument('--eval-cache', type=int, default=24, help='log2 entries of the exact evaluation cache (0 = off)')
     ap.add_argument('--free-sims', type=int, default=0, help='descents per game and launch (0 = library default)')
+    ap.add_argument('--defer-rows', type=int, default=-1, help='az_config.defer_rows (a short last tile pair of a batch waits for the '
+                    'next batch); -1 = the default of BatchedSelfPlay (192), 0 = off')
     ap.add_argument('--no-stagger', action='store_true', help='start all games from the start position instead of spreading '
                     'them over the plies of a game (see BatchedSelfPlay.stagger)')
     ap.add_argument('--no-plain', action='store_true', help='skip the comparison pass without cache / continuous mode')
@@ -218,6 +220,8 @@ def run_ours(args):
     net = Network().eval()
     builtin = True
     opts = {'eval_cache_log2': args.eval_cache, 'free_sims': args.free_sims}
+    if args.defer_rows >= 0:
+        opts['defer_rows'] = args.defer_rows
     sp = BatchedSelfPlay(net, n_games=G, num_simulations=S, seed=1234 + rank, **opts)
     eng = sp.engine
     continuous = args.mode == 'continuous'

@@ -28,8 +28,8 @@
 extern "C" {
 #endif
 
-#define MCAZ_ABI_VERSION 4   /* 4: az_replay_tuple.weights_version, az_set_weights_version, az_tree_dump, counter 14,
-                                az_config.fp8_convolutions, network = 2 */
+#define MCAZ_ABI_VERSION 5   /* 4: az_replay_tuple.weights_version, az_set_weights_version, az_tree_dump, counter 14,
+                                az_config.fp8_convolutions, network = 2;  5: az_config.defer_rows, counters 15-16 */
 
 /* ---- geometry and action indexing (exp/generate_moves_list.py:5-57, exp/moves_dict.json) */
 #define MC_FILES 5
@@ -173,6 +173,13 @@ typedef struct az_config {
                                   operands -- an even number (whole residual blocks), the rest run in bf16.  0 = default 12:
                                   measured, priors and values then stay within 1e-2 of the fp32 network on random-init,
                                   learner-stepped and BatchNorm-perturbed weights (all 18: 1.2e-2 on the last kind)       */
+    int32_t defer_rows;        /* > 0 (az_selfplay; built-in network, leaves_per_step = 1, no look-ahead rows): the network works
+                                  on tile pairs of 256 rows, so a dense batch of 3841 leaves costs as much as one of 4096.
+                                  When the last tile pair of a batch would hold at most defer_rows rows (and is not the only
+                                  one), those leaves are left out of the pass and take rows of the next batch instead: their
+                                  games wait one launch longer, nothing else changes -- the order of a game's simulations and
+                                  every number in its tree are what they are without it (exp/agent.py:41-45).  az_search
+                                  (lock-step: a game has no launch to spare) never defers.  Default 0 = off                */
 } az_config;
 
 void az_default_config(az_config* out);
@@ -302,8 +309,9 @@ int az_collate(const az_replay_tuple* tuples, int n, float* pi, int64_t* tokens,
  * [10] tree levels descended and [11] edges read on the way (bytes-per-simulation accounting),
  * [12] nodes dropped by the recycler (recycle = 1), [13] network rows whose position was already in the
  * evaluation cache when they were stored (evaluated more than once within one batch),
- * [14] replay tuples dropped because the replay queue was full (whole games; see az_drain_replay).      */
-#define AZ_NUM_COUNTERS 15
+ * [14] replay tuples dropped because the replay queue was full (whole games; see az_drain_replay),
+ * [15] leaf rows a network pass left to the next batch and [16] passes that did so (az_config.defer_rows).  */
+#define AZ_NUM_COUNTERS 17
 int az_counters(az_engine* e, uint64_t* out);
 
 /* Stand-alone network forward (exp/policy.py:71-80) on n positions with the engine's weights:

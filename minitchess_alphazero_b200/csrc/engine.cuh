@@ -37,6 +37,7 @@ struct az_engine {
     int parity = 0;                        // row counter of the last search launch
     int lookahead_rows = 0;                // look-ahead rows per batch (cfg.lookahead_rows when the cache is on)
     uint32_t* d_pending = nullptr;         // [2] games waiting for a network row after a launch
+    int defer_rows = 0;                    // cfg.defer_rows where it applies (built-in network, one leaf per step, no look-ahead rows)
     // az_profile_tree: CUDA events around every search_step_kernel launch
     bool tree_profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tree_events;

@@ -40,7 +40,7 @@ constexpr int MAX_LEAVES = 16;                // leaves_per_step limit
 // LEAF_CACHED: a new position whose priors and value were found in the exact evaluation cache -- the
 // simulation is complete without a network row, like a terminal one.
 enum LeafKind : uint8_t { LEAF_NONE = 0, LEAF_EVAL = 1, LEAF_TERMINAL = 2, LEAF_COLLISION = 3, LEAF_CACHED = 4 };
-enum Counter : int { C_SIMS = 0, C_EVALS, C_TERMINAL, C_MOVES, C_GAMES, C_NODES, C_EDGES, C_LAUNCHES, C_COLLISIONS, C_CACHED, C_DEPTH, C_PATH_EDGES, C_RECYCLED, C_DUP_ROWS, C_REPLAY_DROPPED };
+enum Counter : int { C_SIMS = 0, C_EVALS, C_TERMINAL, C_MOVES, C_GAMES, C_NODES, C_EDGES, C_LAUNCHES, C_COLLISIONS, C_CACHED, C_DEPTH, C_PATH_EDGES, C_RECYCLED, C_DUP_ROWS, C_REPLAY_DROPPED, C_DEFERRED_ROWS, C_TRIMMED_BATCHES };
 enum ErrorBit : int { ERR_NODE_CAP = 1, ERR_EDGE_CAP = 2, ERR_HASH_CAP = 4, ERR_DEPTH = 8, ERR_ILLEGAL = 16 };
 
 struct alignas(16) Board4 { uint32_t x, y, z, w; };
@@ -111,6 +111,11 @@ struct View {
     mc_state* row_state;            // [row_cap] position of a look-ahead row (row_slot = -1); the policy head generates its moves
     uint32_t* seen; uint32_t seen_mask;   // tag per cache slot: this position was queued or evaluated (skip it as a child)
     uint32_t* pending_count;        // [2] games that ended this launch waiting for a network row or with budget left (per parity)
+    // deferred rows (az_config.defer_rows): the pass evaluates whole tile pairs; a short tail of the batch waits for the next one
+    uint32_t* row_eff;              // [2] rows of the batch the pass evaluates (cap_rows_kernel; valid when defer_thr > 0)
+    int32_t* slot_row;              // [S] row the slot's pending leaf took
+    int defer_thr;                  // > 0: the pass of THIS launch's batch leaves out a last tile pair of <= defer_thr rows
+    int check_deferred;             // 1: the pass of the previous batch did so -- a leaf whose row it left out takes a new row
     // caller-supplied root noise of a chained search (az_search_noise): block [noise_budget][G][MC_MAX_MOVES]
     const double* noise_block; int noise_budget;
     // replay recording of the device move choice
@@ -232,6 +237,13 @@ MC_HD void count(const View& V, int which, unsigned long long n) {
 
 MC_HD Board4 board_of(const mc_state& s) { return Board4{s.pl0, s.pl1, s.pl2, s.white}; }
 MC_HD mc_state state_of(const Board4& b, uint32_t meta) { return mc_state{b.x, b.y, b.z, b.w, meta}; }
+
+// Rows of a dense batch of `count` rows that the network pass evaluates: all of them, or -- when the last tile pair (256 rows)
+// would hold at most `thr` rows and is not the only one -- the whole tile pairs only.
+MC_HD uint32_t rows_to_run(uint32_t count, uint32_t thr) {
+    const uint32_t r = count & 255u;
+    return (thr != 0u && count > 256u && r != 0u && r <= thr) ? count - r : count;
+}
 
 MC_HD uint32_t hash_state(const mc_state& s) {
     uint32_t h = s.pl0 * 0x9E3779B1u;
@@ -658,7 +670,7 @@ __device__ __forceinline__ uint32_t expand_warp(const View& V, int slot, int t, 
     int row = slot;
     const bool needs_net = !terminal && !hit;
     if (needs_net && V.compact) {
-        if (lane == 0) { row = (int)atomicAdd(&V.row_count[V.parity], 1u); V.row_slot[row] = slot; }
+        if (lane == 0) { row = (int)atomicAdd(&V.row_count[V.parity], 1u); V.row_slot[row] = slot; if (V.slot_row) V.slot_row[slot] = row; }
         row = __shfl_sync(0xffffffffu, row, 0);
     }
     if (needs_net) write_network_row(V, row, lane, s, st, white);

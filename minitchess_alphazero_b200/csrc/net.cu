@@ -1037,7 +1037,7 @@ heads_legal_kernel(const float* __restrict__ head_in, HeadWeights H, az::View V,
                    int row_base, int chunk_rows) {
     // rows of the batch: dense (row -> slot through row_slot, az_search) or one row per slot with a needs_eval mask;
     // this launch covers rows [row_base, row_base + chunk_rows) of it, which sit in act rows [0, chunk_rows)
-    const int total = V.compact ? min((int)__ldg(V.row_count + V.parity), V.row_cap) : V.G * V.K;
+    const int total = V.compact ? min((int)__ldg((V.defer_thr > 0 ? V.row_eff : V.row_count) + V.parity), V.row_cap) : V.G * V.K;
     const int n_rows = max(0, min(chunk_rows, total - row_base));
     __shared__ float s_in[HEADS_WARPS][96];
     __shared__ uint16_t s_codes[LOOKAHEAD ? HEADS_WARPS : 1][az::CACHE_MAX_E];
@@ -1435,7 +1435,9 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
     const int n_pairs = (plan + 2 * BLOCK_M - 1) / (2 * BLOCK_M), bpad = N->capacity;
     cudaStream_t st = e->stream;
     // dense leaf batch of az_search: the number of live rows is only known on the device
-    const uint32_t* count = (search_view && search_view->compact) ? search_view->row_count + search_view->parity : nullptr;
+    // (az_config.defer_rows: the rows the pass evaluates, cap_rows_kernel -- a short last tile pair waits for the next batch)
+    const uint32_t* count = (search_view && search_view->compact)
+                                ? (search_view->defer_thr > 0 ? search_view->row_eff : search_view->row_count) + search_view->parity : nullptr;
     {
         const long long squares = (long long)n * NPOS;                           // one thread per (board, square)
         int grid = (int)std::max<long long>(1, std::min<long long>((squares + 255) / 256, (long long)num_sms() * 8));

@@ -58,6 +58,9 @@ class BatchedSelfPlay:
         # with leaves_per_step = K every search step runs K descents per tree: size the arenas for all of them
         leaves = int(engine_options.get('leaves_per_step', 1) or 1)
         engine_options.setdefault('recycle', 1)       # games only move forward here: plies behind them can be dropped
+        if leaves == 1 and not engine_options.get('lookahead_rows'):
+            # continuous self-play: a short last tile pair of a batch (<= 224 of 256 rows) waits for the next batch
+            engine_options.setdefault('defer_rows', 224)
         if leaves == 1:
             # exact evaluation cache sized for a few moves' worth of evaluations (192 B per entry; 4096 x 200 -> 2^23 = 1.6 GB)
             want = max(1, self.n_games * self.num_simulations * 8)

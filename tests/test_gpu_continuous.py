@@ -136,6 +136,35 @@ def test_continuous_selfplay_plays_the_same_games_as_lockstep(net):
     assert c['moves'] * sims <= c['simulations'] + G * sims           # every move was preceded by its simulations
 
 
+def test_deferred_rows_change_nothing(net):
+    """az_config.defer_rows (az_selfplay): the network pass only runs whole tile pairs (256 rows); a short last pair's leaves
+    wait for the next batch.  Their games lose a launch, nothing else: continuous self-play plays the same games as the plain
+    lock-step search, move for move and visit count for visit count (the replay tuples carry pi), and az_search never defers."""
+    from collections import Counter
+    G, sims = 600, 6                                                 # batches of 300 .. 600 rows: two or three tile pairs
+    lock = make(net, G, sims, seed=21, eval_cache_log2=14, defer_rows=255)
+    for _ in range(62):                                              # every slot finishes its first game (<= 60 plies)
+        lock.search(sims)
+        lock.play_device()
+    assert lock.counters()['trimmed_batches'] == 0                   # lock-step: a game has no launch to spare
+    want = Counter(finished_games(lock.drain_replay()))
+    assert sum(want.values()) >= G
+    for thr in (255, 160):
+        cont = make(net, G, sims, seed=21, eval_cache_log2=14, free_sims=3, recycle=1, defer_rows=thr)
+        got = Counter()
+        for _ in range(40):
+            cont.selfplay(64, sims)
+            got.update(finished_games(cont.drain_replay()))
+            if all(got[k] >= n for k, n in want.items()):
+                break
+        missing = [k for k, n in want.items() if got[k] < n]
+        assert not missing, '%d of %d lock-step games were not reproduced (defer_rows %d)' % (len(missing), len(want), thr)
+        c = cont.counters()
+        assert c['trimmed_batches'] > 0 and c['deferred_rows'] >= c['trimmed_batches']
+        assert c['simulations'] == c['evaluations'] + c['terminal_leaves'] + c['cached_evaluations']
+        assert c['moves'] * sims <= c['simulations'] + G * sims
+
+
 def test_selfplay_argument_checks(net):
     from minitchess_alphazero_b200._lib import McazError
     eng = make(net, 8, 8)
