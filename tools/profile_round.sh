@@ -39,4 +39,11 @@ page ${TAG}_all
 ncu --set full --clock-control none -k "regex:search_step_kernel|heads_legal_kernel" -s 2 -c 6 -f -o $O/${TAG}_lookahead \
     python tools/all_kernels.py 4096 lookahead > $O/${TAG}_ncu_lookahead.log 2>&1
 page ${TAG}_lookahead
+# wait statistics of the tower (bf16 at 4096 / 2816 / 256 rows, e4m3 at 2816), the host-buffer step by phase, the drop-in's move by phase
+for r in 4096 2816 256; do MCAZ_TOWER_STATS=1 python tools/tower_stats.py $r; done > $O/${TAG}_tower_wait_stats.txt 2>&1
+MCAZ_TOWER_STATS=1 python tools/tower_stats.py 2816 fp8 >> $O/${TAG}_tower_wait_stats.txt 2>&1
+python tools/e2e_phases.py > $O/${TAG}_e2e_phases.txt 2>&1
+python tools/dropin_profile.py 36 > $O/${TAG}_dropin_profile.txt 2>&1
+python tools/kernel_table.py $O/${TAG}_hot_raw.csv $O/${TAG}_tower4096_raw.csv $O/${TAG}_tower2816_raw.csv $O/${TAG}_tower2816_fp8_raw.csv $O/${TAG}_lookahead_raw.csv \
+    $O/${TAG}_all_raw.csv > $O/${TAG}_kernel_table.md
 ls -la $O | grep ${TAG}_
