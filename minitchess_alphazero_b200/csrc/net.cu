@@ -451,6 +451,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
     __shared__ unsigned long long s_ring[ITEM_RING];   // claimed items (written by the leader's scheduler, here and in the peer)
     __shared__ uint32_t s_deps_ok;            // items [0, s_deps_ok) have all their inputs published (written by warp 3)
     __shared__ uint32_t s_prod_at;            // item the TMA producer of this CTA is loading (flow control of the scheduler)
+    __shared__ __align__(16) float s_scale[FP8 ? C : 4];   // e4m3 form: the dequantisation factors of the level the epilogue is working on
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -645,6 +646,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- epilogue (TMEM -> HBM) + publish
         const int q = warp & 3;
+        int scale_level = -1;
         for (uint32_t k = 0;; ++k) {
             uint32_t item = 0;
             if (lane == 0) item = ring_get(s_ring, k);
@@ -712,7 +714,15 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C;
             const int bias0 = L * C;
             const float inv_a = FP8 ? P.inv_a[L] : 0.f;
-            const float* scale_l = P.scale_g + bias0;      // e4m3 form: this level's dequantisation factors (1 KB, every thread the same word: L1)
+            if (FP8 && L != scale_level) {
+                // e4m3 form: this level's 256 dequantisation factors go through shared memory (64 broadcast LDS.128 per row instead of
+                // 256 L1 loads: the epilogue, with half the main loop to hide under, bounds the e4m3 levels).  The four warps walk the
+                // same items; the previous item's reads are behind its closing barrier.
+                const int t = (int)threadIdx.x - 128;
+                reinterpret_cast<float2*>(s_scale)[t] = __ldg(reinterpret_cast<const float2*>(P.scale_g + bias0) + t);
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                scale_level = L;
+            }
             float seen_max = 0.f;
 #pragma unroll
             for (int c = 0; c < C / 32; ++c) {
@@ -743,13 +753,22 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                 for (int j = 0; j < 4; ++j) {
                     uint32_t packed[4];
                     float xq[8];
+                    float sc[8];
+                    if (FP8) {
+                        const float4 sa = *reinterpret_cast<const float4*>(&s_scale[c * 32 + j * 8]), sb = *reinterpret_cast<const float4*>(&s_scale[c * 32 + j * 8 + 4]);
+                        sc[0] = sa.x; sc[1] = sa.y; sc[2] = sa.z; sc[3] = sa.w; sc[4] = sb.x; sc[5] = sb.y; sc[6] = sb.z; sc[7] = sb.w;
+                    }
 #pragma unroll
                     for (int h = 0; h < 4; ++h) {
                         const int e = j * 8 + h * 2;
                         float x0 = __uint_as_float(v[e]), x1 = __uint_as_float(v[e + 1]);
-                        if (FP8) { x0 *= __ldg(scale_l + c * 32 + e); x1 *= __ldg(scale_l + c * 32 + e + 1); }     // dequantise the accumulator
-                        x0 += P.bias[bias0 + c * 32 + e];
-                        x1 += P.bias[bias0 + c * 32 + e + 1];
+                        if (FP8) {      // dequantise the accumulator and add the bias in one rounding (factor 1 on the bf16 levels: the plain sum)
+                            x0 = fmaf(x0, sc[2 * h], P.bias[bias0 + c * 32 + e]);
+                            x1 = fmaf(x1, sc[2 * h + 1], P.bias[bias0 + c * 32 + e + 1]);
+                        } else {
+                            x0 += P.bias[bias0 + c * 32 + e];
+                            x1 += P.bias[bias0 + c * 32 + e + 1];
+                        }
                         if (odd) {
                             const uint32_t r = (&res[c & 3][j].x)[h];
                             x0 += __uint_as_float(r << 16);
