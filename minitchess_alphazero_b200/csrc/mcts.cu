@@ -235,6 +235,20 @@ __global__ void cap_rows_kernel(View V) {
     if (eff < count) { V.counters[az::C_DEFERRED_ROWS] += count - eff; V.counters[az::C_TRIMMED_BATCHES] += 1; }      // (one thread, stream-ordered)
 }
 
+// Network input of the look-ahead rows of a batch (row_slot = -1: queued by position only, queue_children): a warp per row,
+// lane = board cell, the same code that writes a leaf's own row (write_network_row).
+__global__ void __launch_bounds__(128) tokenize_lookahead_kernel(View V) {
+    const int rows = min((int)V.row_count[V.parity], V.row_cap), lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+        if (V.row_slot[r] >= 0) continue;
+#if defined(__CUDA_ARCH__)
+        const mc_state s = V.row_state[r];
+        az::write_network_row(V, r, lane, s, mc::sets_of(s), mc::white_to_move(s));
+#endif
+    }
+}
+
 // A search that ends while look-ahead rows are queued never evaluates them: take their tags back, so that a later
 // expansion queues those positions again instead of meeting each of them as a miss.
 __global__ void __launch_bounds__(256) untag_rows_kernel(View V) {
@@ -959,6 +973,11 @@ static int run_search(az_engine* e, int n_batches, int new_budget, bool async, i
                 }
                 break;
             }
+        }
+        if (V.spec_rows > 0) {                        // look-ahead rows were queued by position: their tokens and clocks
+            tokenize_lookahead_kernel<<<std::max(1, std::min((V.row_cap + 3) / 4, num_sms() * 4)), 128, 0, e->stream>>>(V);
+            MCAZ_CHECK_LAUNCH();
+            e->launches++;
         }
         if (int rc = network_forward_search(e, V, e->d_values)) return rc;
     }

@@ -479,9 +479,9 @@ __device__ __forceinline__ WarpGen warp_generate(const View& V, const mc_state& 
 template <typename Emit>
 __device__ __forceinline__ void warp_emit_codes(const View& V, const WarpGen& w, Emit&& emit) {
     if (w.emit_n <= 0) return;
-    int k = w.knight ? w.tot_q + w.off_n : w.off_q;
-    mc::emit_square_codes(w.fv, w.white, w.knight, w.tg, w.knight ? w.nb : w.qb, w.pawn, V.rules.promo_multiplicity,
-                          [&](uint16_t c) { emit(k, c); ++k; });
+    const int k = w.knight ? w.tot_q + w.off_n : w.off_q;
+    mc::emit_square_codes_indexed(w.fv, w.white, w.knight, w.tg, w.knight ? w.nb : w.qb, w.pawn, V.rules.promo_multiplicity,
+                                  [&](int place, uint16_t c) { emit(k + place, c); });
 }
 
 // Exact evaluation cache lookup: same (board, side, fullmove, number of legal moves) evaluated before with these
@@ -532,8 +532,9 @@ __device__ __forceinline__ uint32_t seen_tag(const View& V, const mc_state& s) {
 
 // Look-ahead: queue the children of a new node (its E codes start at edge e0) as rows of the batch, unless they were
 // queued or evaluated before or the batch is full.  Lane = child: every lane applies its move, probes the tag table and,
-// if its child is new, writes the child's network row (tokens, clock) and position; the legal moves of such a row are
-// generated later by the policy head, a warp per row, off this tree's critical path.  Nothing of the tree is touched.
+// if its child is new, writes the child's position as a row of the batch; the row's network input (tokens, clock) is made from it
+// by tokenize_lookahead_kernel before the pass, and its legal moves are generated later by the policy head, a warp per row -- both
+// off this tree's critical path.  Nothing of the tree is touched.
 __device__ __forceinline__ void queue_children(const View& V, int lane, const mc_state& s, bool white, size_t e0, int E, bool deep) {
     for (int base = 0; base < E; base += 32) {
         const int i = base + lane;
@@ -573,8 +574,7 @@ __device__ __forceinline__ void queue_children(const View& V, int lane, const mc
         const bool queued = want && rank < take;
         if (queued) {
             const int row = first + rank;
-            mc::tokenize(cs, V.tokens + (size_t)row * MC_TOKENS, &V.clocks[row]);
-            V.row_slot[row] = -1;
+            V.row_slot[row] = -1;                        // tokens and clock of a look-ahead row: tokenize_lookahead_kernel, off this path
             V.row_state[row] = cs;
             V.seen[idx] = tag;
         }
@@ -604,7 +604,6 @@ __device__ __forceinline__ void queue_children(const View& V, int lane, const mc
                     old = got;
                 }
                 if (row < 0) break;                      // batch full
-                mc::tokenize(gs, V.tokens + (size_t)row * MC_TOKENS, &V.clocks[row]);
                 V.row_slot[row] = -1;
                 V.row_state[row] = gs;
                 V.seen[gidx] = gtag;

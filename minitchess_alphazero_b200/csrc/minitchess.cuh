@@ -256,13 +256,13 @@ MC_HD uint32_t legal_targets(const Sets& t, const Guard& g, bool white, int type
 // squares (black sees the board rotated by 180 degrees: view square = 29 - real square).
 // Queen block: code = QBASE[from] + rank of (dir, dist) among on-board targets; knight block
 // likewise after 430.  Both are evaluated arithmetically: no table in memory.
-MC_HD int qdir_dr(int d) { return d < 3 ? 1 : (d < 5 ? 0 : -1); }
-MC_HD int qdir_df(int d) { return d == 0 || d == 3 || d == 5 ? 1 : (d == 1 || d == 6 ? 0 : -1); }
-MC_HD int ndir_dr(int d) { return d < 2 ? 1 : (d < 4 ? -1 : (d < 6 ? 2 : -2)); }
-MC_HD int ndir_df(int d) { return d < 4 ? ((d & 1) ? -2 : 2) : ((d & 1) ? -1 : 1); }
-MC_HD int min_i(int a, int b) { return a < b ? a : b; }
+MC_HD constexpr int qdir_dr(int d) { return d < 3 ? 1 : (d < 5 ? 0 : -1); }
+MC_HD constexpr int qdir_df(int d) { return d == 0 || d == 3 || d == 5 ? 1 : (d == 1 || d == 6 ? 0 : -1); }
+MC_HD constexpr int ndir_dr(int d) { return d < 2 ? 1 : (d < 4 ? -1 : (d < 6 ? 2 : -2)); }
+MC_HD constexpr int ndir_df(int d) { return d < 4 ? ((d & 1) ? -2 : 2) : ((d & 1) ? -1 : 1); }
+MC_HD constexpr int min_i(int a, int b) { return a < b ? a : b; }
 // number of on-board squares from (r,f) along queen direction d
-MC_HD int qreach(int r, int f, int d) {
+MC_HD constexpr int qreach(int r, int f, int d) {
     int dr = qdir_dr(d), df = qdir_df(d);
     int nr = dr > 0 ? 5 - r : (dr < 0 ? r : 5);
     int nf = df > 0 ? 4 - f : (df < 0 ? f : 5);
@@ -274,7 +274,7 @@ MC_HD int qcount(int r, int f) {
     for (int d = 0; d < 8; ++d) n += qreach(r, f, d);
     return n;
 }
-MC_HD bool n_on(int r, int f, int d) {
+MC_HD constexpr bool n_on(int r, int f, int d) {
     int rr = r + ndir_dr(d), ff = f + ndir_df(d);
     return rr >= 0 && rr < 6 && ff >= 0 && ff < 5;
 }
@@ -349,19 +349,19 @@ static_assert(c_qbase(29) - 13 * 29 < 64 && c_nbase(29) < 128, "packing widths")
 constexpr uint64_t QB0 = c_pack_q(0), QB1 = c_pack_q(1), QB2 = c_pack_q(2);
 constexpr uint64_t NB0 = c_pack_n(0), NB1 = c_pack_n(1), NB2 = c_pack_n(2), NB3 = c_pack_n(3);
 }  // namespace detail
-MC_HD int qbase(int fv) {
+MC_HD constexpr int qbase(int fv) {
     const int w = fv >= 20 ? 2 : (fv >= 10 ? 1 : 0);
     const uint64_t v = w == 2 ? detail::QB2 : (w == 1 ? detail::QB1 : detail::QB0);
     return 13 * fv + (int)((v >> (6 * (fv - 10 * w))) & 63u);
 }
-MC_HD int nbase(int fv) {
+MC_HD constexpr int nbase(int fv) {
     const int w = fv >= 27 ? 3 : (fv >= 18 ? 2 : (fv >= 9 ? 1 : 0));
     const uint64_t v = w == 3 ? detail::NB3 : (w == 2 ? detail::NB2 : (w == 1 ? detail::NB1 : detail::NB0));
     return 430 + (int)((v >> (7 * (fv - 9 * w))) & 127u);
 }
 
-// code -> view squares.  Returns false for code >= 554.
-MC_HD bool code_to_view(int code, int& fv, int& tv) {
+// code -> view squares.  Returns false for code >= 554.  The arithmetic definition (host, and the source of the device table below).
+MC_HD constexpr bool code_to_view_arith(int code, int& fv, int& tv) {
     if (code < 0 || code >= MC_NUM_ACTIONS) return false;
     if (code < 430) {
         int s = 0;
@@ -384,6 +384,102 @@ MC_HD bool code_to_view(int code, int& fv, int& tv) {
             }
     }
     return false;
+}
+
+// ---- small tables for the one-warp-per-tree search, where instructions on the critical path count (a thread-per-position kernel is
+// better off with the arithmetic above).  Both are worked out by the compiler from the arithmetic definitions:
+//   CODE_VIEW[code]      = from | to << 8 (view squares): code_to_view in one load instead of ~100 instructions
+//   MOVE_ORDER.rel[f][t] = offset of the move f -> t within f's queen block (or knight block; a pair of squares is never both), 0xFF: none
+//   MOVE_ORDER.less[f][t] = the targets of f (same block) whose codes come before that of t: the place of a move in the sorted list of
+//                          its square is a population count instead of a walk over 8 directions x reach
+namespace detail {
+struct CodeViewTable { uint16_t v[MC_NUM_ACTIONS]; };
+constexpr CodeViewTable make_code_view() {
+    CodeViewTable t{};
+    for (int c = 0; c < MC_NUM_ACTIONS; ++c) {
+        int fv = 0, tv = 0;
+        code_to_view_arith(c, fv, tv);
+        t.v[c] = (uint16_t)(fv | (tv << 8));
+    }
+    return t;
+}
+struct MoveOrderTable { uint8_t rel[30][32]; uint32_t less[30][32]; };
+constexpr MoveOrderTable make_move_order() {
+    MoveOrderTable t{};
+    for (int fv = 0; fv < 30; ++fv) {
+        for (int tv = 0; tv < 32; ++tv) { t.rel[fv][tv] = 0xFF; t.less[fv][tv] = 0u; }
+        const int r = fv / 5, f = fv % 5;
+        uint32_t seen = 0u;
+        int off = 0;
+        for (int d = 0; d < 8; ++d) {                      // queen block: (direction, distance) in the reference's order
+            const int reach = qreach(r, f, d), stride = 5 * qdir_dr(d) + qdir_df(d);
+            int tv = fv;
+            for (int k = 1; k <= reach; ++k) {
+                tv += stride;
+                t.rel[fv][tv] = (uint8_t)off++;
+                t.less[fv][tv] = seen;
+                seen |= 1u << tv;
+            }
+        }
+        seen = 0u; off = 0;
+        for (int d = 0; d < 8; ++d) {                      // knight block
+            if (!n_on(r, f, d)) continue;
+            const int tv = 5 * (r + ndir_dr(d)) + f + ndir_df(d);
+            t.rel[fv][tv] = (uint8_t)off++;
+            t.less[fv][tv] = seen;
+            seen |= 1u << tv;
+        }
+    }
+    return t;
+}
+}  // namespace detail
+#if defined(__CUDACC__)
+static __device__ const detail::CodeViewTable CODE_VIEW_D = detail::make_code_view();
+static __device__ const detail::MoveOrderTable MOVE_ORDER_D = detail::make_move_order();
+#endif
+
+MC_HD bool code_to_view(int code, int& fv, int& tv) {
+#if defined(__CUDA_ARCH__)
+    if (code < 0 || code >= MC_NUM_ACTIONS) return false;
+    const uint32_t v = CODE_VIEW_D.v[code];
+    fv = (int)(v & 0xffu); tv = (int)(v >> 8);
+    return true;
+#else
+    return code_to_view_arith(code, fv, tv);
+#endif
+}
+
+// emit_square_codes with the place of every code within its square's sorted list: emit(place, code), in no particular order.
+// One table row per legal target instead of the walk.
+template <typename Emit>
+MC_HD int emit_square_codes_table(const detail::MoveOrderTable& T, int fv, bool white, uint32_t tg, int base, bool promo_piece, int promo_rep,
+                                  Emit&& emit) {
+    const uint32_t tgv = view_of(tg, white);
+    const uint32_t promo = (promo_piece && promo_rep > 1) ? (tgv & 0x3E000000u) : 0u;      // view squares 25..29: promotions, repeated
+    uint32_t rest = tgv;
+    int n = 0;
+    while (rest) {
+        const int tv = lsb(rest);
+        rest &= rest - 1;
+        const uint32_t less = T.less[fv][tv];
+        const int code = base + (int)T.rel[fv][tv];
+        const int place = popc(tgv & less) + (promo_rep - 1) * popc(promo & less);
+        const int rep = ((promo >> tv) & 1u) ? promo_rep : 1;
+        for (int j = 0; j < rep; ++j) emit(place + j, (uint16_t)code);
+        n += rep;
+    }
+    return n;
+}
+// Device: the table form; host: the walk (tests/host_harness checks the table form against it).
+template <typename Emit>
+MC_HD int emit_square_codes_indexed(int fv, bool white, bool knight, uint32_t tg, int base, bool promo_piece, int promo_rep, Emit&& emit) {
+#if defined(__CUDA_ARCH__)
+    (void)knight;
+    return emit_square_codes_table(MOVE_ORDER_D, fv, white, tg, base, promo_piece, promo_rep, emit);
+#else
+    int place = 0;
+    return emit_square_codes(fv, white, knight, tg, base, promo_piece, promo_rep, [&](uint16_t c) { emit(place, c); ++place; });
+#endif
 }
 
 // (view from, view to) -> code or -1

@@ -45,6 +45,20 @@ void hh_targets_both(const mc_state* s, int n, const mc_rules* rules, uint32_t* 
         }
     }
 }
+// The device tables (CODE_VIEW, MOVE_ORDER) are constexpr products of the arithmetic: the same objects built for the host.
+static const mc::detail::CodeViewTable HH_CODE_VIEW = mc::detail::make_code_view();
+static const mc::detail::MoveOrderTable HH_MOVE_ORDER = mc::detail::make_move_order();
+int hh_code_view_table(int code) { return HH_CODE_VIEW.v[code]; }
+// codes of the moves from view square fv to the (real-square) targets tg, by the walk and by the table form; returns the count of
+// the walk, *n_table gets the count of the table form; out_table[place] = code
+int hh_emit_both(int fv, int white, int knight, uint32_t tg, int promo_piece, int promo_rep, uint16_t* out_walk, uint16_t* out_table, int* n_table) {
+    const int base = knight ? mc::nbase(fv) : mc::qbase(fv);
+    int n = 0;
+    mc::emit_square_codes(fv, white != 0, knight != 0, tg, base, promo_piece != 0, promo_rep, [&](uint16_t c) { out_walk[n++] = c; });
+    *n_table = mc::emit_square_codes_table(HH_MOVE_ORDER, fv, white != 0, tg, base, promo_piece != 0, promo_rep,
+                                           [&](int place, uint16_t c) { out_table[place] = c; });
+    return n;
+}
 int hh_view_to_code(int fv, int tv) { return mc::view_to_code(fv, tv); }
 int hh_code_to_view(int code, int* fv, int* tv) { return mc::code_to_view(code, *fv, *tv) ? 0 : -1; }
 }

@@ -1,6 +1,8 @@
 """CPU: the oracle's rules against the committed golden vectors (made by the reference's own
 exp/environment.py on the shim), the C mailbox against the Python mailbox, and the host build
 of the product's bitboard header against both."""
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -173,3 +175,40 @@ def test_tokeniser_matches_golden(host_rules):
     for i, r in enumerate(rows):
         assert t0[i].tolist() == r['tokens'] and t1[i].tolist() == r['tokens'], r['fen']
         assert k0[i].tobytes().hex() == r['clock_f32_hex'] and k1[i].tobytes().hex() == r['clock_f32_hex']
+
+
+def test_search_tables_match_the_arithmetic(host_rules):
+    """The two tables the one-warp-per-tree search reads on the device (csrc/minitchess.cuh: CODE_VIEW, MOVE_ORDER) are constexpr
+    products of the arithmetic definitions; the same objects built for the host must reproduce code_to_view for all 554 codes and
+    the walk of emit_square_codes -- code by code, place by place -- for random target sets, both blocks, both colours and
+    repeated promotion codes (promo_multiplicity 4)."""
+    fv, tv = ctypes.c_int(), ctypes.c_int()
+    for code in range(554):
+        assert host_rules.hh_code_to_view(code, ctypes.byref(fv), ctypes.byref(tv)) == 0
+        assert host_rules.hh_code_view_table(code) == fv.value | (tv.value << 8)
+        assert host_rules.hh_view_to_code(fv.value, tv.value) == code
+    rng = np.random.RandomState(11)
+    walk = np.zeros(256, dtype=np.uint16)
+    table = np.zeros(256, dtype=np.uint16)
+    n_table = ctypes.c_int()
+    checked = 0
+    for square in range(30):
+        for knight in (0, 1):
+            for white in (0, 1):
+                # every target a piece on this view square can have in its block (view squares), as a real-square set
+                reach = 0
+                for t in range(30):
+                    c = host_rules.hh_view_to_code(square, t)
+                    if c >= 0 and (c >= 430) == bool(knight):
+                        reach |= 1 << (t if white else 29 - t)
+                for trial in range(24):
+                    tg = reach & int(rng.randint(0, 1 << 30)) if trial else reach
+                    for promo_piece, rep in ((0, 1), (1, 1), (1, 4)):
+                        if knight and promo_piece:
+                            continue
+                        walk[:] = 0xffff; table[:] = 0xfffe
+                        n = host_rules.hh_emit_both(square, white, knight, ctypes.c_uint32(tg), promo_piece, rep, vp(walk), vp(table), ctypes.byref(n_table))
+                        assert n == n_table.value, (square, knight, white, hex(tg), promo_piece, rep)
+                        assert np.array_equal(walk[:n], table[:n]), (square, knight, white, hex(tg), promo_piece, rep)
+                        checked += n
+    assert checked > 30000
