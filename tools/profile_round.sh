@@ -33,10 +33,10 @@ page ${TAG}_tower2816_fp8
 # every other kernel of the library at working sizes (two launches of each are enough: -c counts all matching launches)
 python tools/all_kernels.py > $O/${TAG}_all_kernels.log 2>&1 || exit 1
 ncu --set full --clock-control none \
-    -k "regex:legal_moves_kernel|apply_kernel|tokenize_kernel|perft|play_device_kernel|restart_finished_kernel|recycle_kernel|root_stats_kernel|game_states_kernel|node_stats_kernel|reset_games_kernel|reset_trees_kernel|set_positions_kernel|play_kernel|heads_kernel|collate_kernel|sample_root_noise_kernel|select_expand_kernel|backup_kernel|untag_rows_kernel|prep_|calib_positions" \
+    -k "regex:legal_moves_kernel|apply_kernel|tokenize_kernel|perft|play_device_kernel|restart_finished_kernel|recycle_kernel|root_stats_kernel|game_states_kernel|node_stats_kernel|reset_games_kernel|reset_trees_kernel|set_positions_kernel|play_kernel|heads_kernel|collate_kernel|sample_root_noise_kernel|select_expand_kernel|backup_kernel|untag_rows_kernel|cap_rows_kernel|prep_|calib_positions" \
     -c 90 -f -o $O/${TAG}_all python tools/all_kernels.py > $O/${TAG}_ncu_all.log 2>&1
 page ${TAG}_all
-ncu --set full --clock-control none -k "regex:search_step_kernel|heads_legal_kernel" -s 2 -c 6 -f -o $O/${TAG}_lookahead \
+ncu --set full --clock-control none -k "regex:search_step_kernel|heads_legal_kernel|tokenize_lookahead_kernel" -s 3 -c 9 -f -o $O/${TAG}_lookahead \
     python tools/all_kernels.py 4096 lookahead > $O/${TAG}_ncu_lookahead.log 2>&1
 page ${TAG}_lookahead
 # wait statistics of the tower (bf16 at 4096 / 2816 / 256 rows, e4m3 at 2816), the host-buffer step by phase, the drop-in's move by phase
