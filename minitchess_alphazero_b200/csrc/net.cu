@@ -53,6 +53,10 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int STEM_K = 16;         // channels of a one-hot stem row (14 live): one K = 16 MMA, one 32-byte swizzle row
 constexpr int STEM_TILE_BYTES = BLOCK_M * STEM_K * 2;   // 4 KB: 128 boards (or 128 output channels) x 16 channels
 constexpr int CONV_THREADS = 256;                // TMA, MMA, TMEM-alloc, spare + 4 epilogue warps
+// The e4m3 form runs TWO sets of four epilogue warps, one per TMEM accumulator buffer (items alternate between them): an e4m3 item's
+// main loop is half as long as a bf16 one and no longer hides a 256 x 256 epilogue, so each set gets two item times for its item.
+__host__ __device__ constexpr int tower_epilogue_sets(bool fp8) { return fp8 ? 2 : 1; }
+__host__ __device__ constexpr int tower_threads(bool fp8) { return 128 + 128 * tower_epilogue_sets(fp8); }
 constexpr int CALIB_ROWS = 2048;                 // positions of the e4m3 tower's calibration pass (az_set_weights)
 constexpr int MAX_CHUNK_BOARDS = 8192;           // boards per forward pass (32 tile pairs: three L2 groups)
 
@@ -384,9 +388,10 @@ template <int FORM>
 __device__ __noinline__ void epilogue_heads(uint32_t taddr, const float* __restrict__ bias, const float* __restrict__ scale,
                                             const float4* __restrict__ hw, const __nv_bfloat16* res_row, uint64_t* acc_full,
                                             uint32_t acc_phase, uint32_t wait_hint, float* h) {
-    uint4 res[4][4];
+    constexpr int RD = (FORM & 2) ? 2 : 4;       // chunks of the residual row fetched ahead (the e4m3 form's 384 threads have 168 registers each)
+    uint4 res[RD][4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < RD; ++c) {
         ld_cg_v8(res_row + c * 32, res[c][0], res[c][1]);
         ld_cg_v8(res_row + c * 32 + 16, res[c][2], res[c][3]);
     }
@@ -412,7 +417,7 @@ __device__ __noinline__ void epilogue_heads(uint32_t taddr, const float* __restr
 #pragma unroll
             for (int hh = 0; hh < 4; ++hh) {
                 const int e = j * 8 + hh * 2;
-                const uint32_t r = (&res[c & 3][j].x)[hh];
+                const uint32_t r = (&res[c & (RD - 1)][j].x)[hh];
                 float a0 = __uint_as_float(v[e]), a1 = __uint_as_float(v[e + 1]);
                 if (scale) { a0 *= __ldg(scale + c * 32 + e); a1 *= __ldg(scale + c * 32 + e + 1); }      // e4m3 tower: dequantise
                 const float x0 = fmaxf(a0 + __ldg(bias + c * 32 + e) + __uint_as_float(r << 16), 0.f);
@@ -422,9 +427,9 @@ __device__ __noinline__ void epilogue_heads(uint32_t taddr, const float* __restr
                 h0 = fmaf(x1, w1.x, h0); h1 = fmaf(x1, w1.y, h1); h2 = fmaf(x1, w1.z, h2);
             }
         }
-        if (c + 4 < C / 32) {
-            ld_cg_v8(res_row + (c + 4) * 32, res[c & 3][0], res[c & 3][1]);
-            ld_cg_v8(res_row + (c + 4) * 32 + 16, res[c & 3][2], res[c & 3][3]);
+        if (c + RD < C / 32) {
+            ld_cg_v8(res_row + (c + RD) * 32, res[c & (RD - 1)][0], res[c & (RD - 1)][1]);
+            ld_cg_v8(res_row + (c + RD) * 32 + 16, res[c & (RD - 1)][2], res[c & (RD - 1)][3]);
         }
     }
     h[0] = h0; h[1] = h1; h[2] = h2;
@@ -433,7 +438,7 @@ __device__ __noinline__ void epilogue_heads(uint32_t taddr, const float* __restr
 // FP8: the 18 convolutions multiply e4m3 operands (map_q0 / map_q1 / map_wq; the bf16 maps are then unused).  CALIB (bf16 form
 // only): the epilogue also records the largest activation of every level -- the calibration pass of the e4m3 tower.
 template <bool FP8, bool CALIB>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tower_threads(FP8), 1)
 tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_constant__ CUtensorMap map_act1,
                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_stem_in,
                 const __grid_constant__ CUtensorMap map_stem_w, const __grid_constant__ CUtensorMap map_q0,
@@ -451,7 +456,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
     __shared__ unsigned long long s_ring[ITEM_RING];   // claimed items (written by the leader's scheduler, here and in the peer)
     __shared__ uint32_t s_deps_ok;            // items [0, s_deps_ok) have all their inputs published (written by warp 3)
     __shared__ uint32_t s_prod_at;            // item the TMA producer of this CTA is loading (flow control of the scheduler)
-    __shared__ __align__(16) float s_scale[FP8 ? C : 4];   // e4m3 form: the dequantisation factors of the level the epilogue is working on
+    __shared__ __align__(16) float s_scale_all[FP8 ? 2 * C : 4];   // e4m3 form: the dequantisation factors of the level each epilogue set is working on
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -646,12 +651,17 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- epilogue (TMEM -> HBM) + publish
         const int q = warp & 3;
+        constexpr int SETS = tower_epilogue_sets(FP8), RD = FP8 ? 2 : 4;
+        const int set = SETS == 2 ? (warp - 4) >> 2 : 0; // this warp's epilogue set: it takes the items of accumulator buffer `set` (e4m3 form)
+        const int bar_done = 1 + set, bar_scale = 3 + set;        // named barriers of the set's 128 threads
+        float* s_scale = s_scale_all + (FP8 ? set * C : 0);
         int scale_level = -1;
         for (uint32_t k = 0;; ++k) {
             uint32_t item = 0;
             if (lane == 0) item = ring_get(s_ring, k);
             item = __shfl_sync(0xffffffffu, item, 0);
             if (item == ITEM_END) break;
+            if (SETS == 2 && (int)(k & 1) != set) continue;       // the other set's item
             const int pos = item & 0xff, tp = (item >> 8) & 0xffff, L = item >> 24;
             const int tile = 2 * tp + (int)rank;
             const uint32_t acc = k & 1, acc_phase = (k >> 1) & 1;
@@ -685,18 +695,18 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                 }
                 float* hin = P.head_in + ((size_t)tile * BLOCK_M + q * 32 + lane) * HEAD_IN;
                 hin[pos] = h[0]; hin[NPOS + pos] = h[1]; hin[2 * NPOS + 1 + pos] = h[2];
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (warp == 4 && lane == 0 && P.flags)
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_done) : "memory");
+                if (q == 0 && lane == 0 && P.flags)
                     st_release_gpu(P.flags + (((size_t)L * P.n_pairs + tp) * NPOS + pos) * 2 + rank, P.epoch);
                 continue;
             }
             // residual rows (this block's input, written two layers back) are published once the item's
             // dependencies are: fetch them while the MMAs still run
-            uint4 res[4][4];
+            uint4 res[RD][4];
             if (odd) {
                 if (P.flags) while (ld_acquire_cta_shared(&s_deps_ok) <= k) __nanosleep(SPIN_NS);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < RD; ++c) {
                     ld_cg_v8(out + row_off + c * 32, res[c][0], res[c][1]);
                     ld_cg_v8(out + row_off + c * 32 + 16, res[c][2], res[c][3]);
                 }
@@ -707,8 +717,8 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { if (leader) mbar_arrive(&acc_empty[acc]); else mbar_arrive_remote(&acc_empty[acc], 0); }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (warp == 4 && lane == 0 && P.flags) st_release_gpu(P.flags + (((size_t)L * P.n_pairs + tp) * NPOS + pos) * 2 + rank, P.epoch);
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_done) : "memory");
+            if (q == 0 && lane == 0 && P.flags) st_release_gpu(P.flags + (((size_t)L * P.n_pairs + tp) * NPOS + pos) * 2 + rank, P.epoch);
             continue;
 #endif
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C;
@@ -718,9 +728,9 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                 // e4m3 form: this level's 256 dequantisation factors go through shared memory (64 broadcast LDS.128 per row instead of
                 // 256 L1 loads: the epilogue, with half the main loop to hide under, bounds the e4m3 levels).  The four warps walk the
                 // same items; the previous item's reads are behind its closing barrier.
-                const int t = (int)threadIdx.x - 128;
+                const int t = ((int)threadIdx.x - 128) & 127;
                 reinterpret_cast<float2*>(s_scale)[t] = __ldg(reinterpret_cast<const float2*>(P.scale_g + bias0) + t);
-                asm volatile("bar.sync 2, 128;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_scale) : "memory");
                 scale_level = L;
             }
             float seen_max = 0.f;
@@ -770,7 +780,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                             x1 += P.bias[bias0 + c * 32 + e + 1];
                         }
                         if (odd) {
-                            const uint32_t r = (&res[c & 3][j].x)[h];
+                            const uint32_t r = (&res[c & (RD - 1)][j].x)[h];
                             x0 += __uint_as_float(r << 16);
                             x1 += __uint_as_float(r & 0xffff0000u);
                         }
@@ -784,9 +794,9 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                     outv[j] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                     if (FP8 && write_q) { q8[2 * j] = pack_e4m3x4(xq[0], xq[1], xq[2], xq[3]); q8[2 * j + 1] = pack_e4m3x4(xq[4], xq[5], xq[6], xq[7]); }
                 }
-                if (odd && c + 4 < C / 32) {
-                    ld_cg_v8(out + row_off + (c + 4) * 32, res[c & 3][0], res[c & 3][1]);
-                    ld_cg_v8(out + row_off + (c + 4) * 32 + 16, res[c & 3][2], res[c & 3][3]);
+                if (odd && c + RD < C / 32) {
+                    ld_cg_v8(out + row_off + (c + RD) * 32, res[c & (RD - 1)][0], res[c & (RD - 1)][1]);
+                    ld_cg_v8(out + row_off + (c + RD) * 32 + 16, res[c & (RD - 1)][2], res[c & (RD - 1)][3]);
                 }
                 if (write_bf16) {
                     ST_ACT(out + row_off + c * 32, outv[0], outv[1]);
@@ -800,8 +810,8 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
                 if (lane == 0) atomicMax(&P.level_absmax[L], __float_as_uint(seen_max));
             }
             // publish: the barrier orders all 128 threads' stores before the (cumulative) gpu-scope release
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (warp == 4 && lane == 0 && P.flags)
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_done) : "memory");
+            if (q == 0 && lane == 0 && P.flags)
                 st_release_gpu(P.flags + (((size_t)L * P.n_pairs + tp) * NPOS + pos) * 2 + rank, P.epoch);
         }
     }
@@ -1500,13 +1510,13 @@ static int forward_chunk(az_engine* e, const uint8_t* tokens, const float* clock
     const int grid = 2 * std::max(1, std::min(num_sms() / 2, n_pairs * NPOS));
     auto launch = [&]() {
         if (N->calibrating)
-            tower_tc_kernel<false, true><<<grid, CONV_THREADS, TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in, N->map_stem_w,
+            tower_tc_kernel<false, true><<<grid, tower_threads(false), TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in, N->map_stem_w,
                                                                                 N->map_q[0], N->map_q[1], N->map_wq, T);
         else if (N->fp8)
-            tower_tc_kernel<true, false><<<grid, CONV_THREADS, TOWER_SMEM_FP8, st>>>(N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in,
+            tower_tc_kernel<true, false><<<grid, tower_threads(true), TOWER_SMEM_FP8, st>>>(N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in,
                                                                                     N->map_stem_w, N->map_q[0], N->map_q[1], N->map_wq, T);
         else
-            tower_tc_kernel<false, false><<<grid, CONV_THREADS, TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in,
+            tower_tc_kernel<false, false><<<grid, tower_threads(false), TOWER_SMEM, st>>>(N->map_act[0], N->map_act[1], N->map_w, N->map_stem_in,
                                                                                  N->map_stem_w, N->map_q[0], N->map_q[1], N->map_wq, T);
     };
     if (N->per_layer) {
