@@ -55,7 +55,10 @@ constexpr int STEM_TILE_BYTES = BLOCK_M * STEM_K * 2;   // 4 KB: 128 boards (or 
 constexpr int CONV_THREADS = 256;                // TMA, MMA, TMEM-alloc, spare + 4 epilogue warps
 // The e4m3 form runs TWO sets of four epilogue warps, one per TMEM accumulator buffer (items alternate between them): an e4m3 item's
 // main loop is half as long as a bf16 one and no longer hides a 256 x 256 epilogue, so each set gets two item times for its item.
-__host__ __device__ constexpr int tower_epilogue_sets(bool fp8) { return fp8 ? 2 : 1; }
+#ifndef TOWER_BF16_SETS
+#define TOWER_BF16_SETS 1      // measured: two sets in the bf16 form too -- see profiles/r02_fp8_epilogue_ab.txt
+#endif
+__host__ __device__ constexpr int tower_epilogue_sets(bool fp8) { return fp8 ? 2 : TOWER_BF16_SETS; }
 __host__ __device__ constexpr int tower_threads(bool fp8) { return 128 + 128 * tower_epilogue_sets(fp8); }
 constexpr int CALIB_ROWS = 2048;                 // positions of the e4m3 tower's calibration pass (az_set_weights)
 constexpr int MAX_CHUNK_BOARDS = 8192;           // boards per forward pass (32 tile pairs: three L2 groups)
@@ -388,7 +391,7 @@ template <int FORM>
 __device__ __noinline__ void epilogue_heads(uint32_t taddr, const float* __restrict__ bias, const float* __restrict__ scale,
                                             const float4* __restrict__ hw, const __nv_bfloat16* res_row, uint64_t* acc_full,
                                             uint32_t acc_phase, uint32_t wait_hint, float* h) {
-    constexpr int RD = (FORM & 2) ? 2 : 4;       // chunks of the residual row fetched ahead (the e4m3 form's 384 threads have 168 registers each)
+    constexpr int RD = tower_epilogue_sets((FORM & 2) != 0) == 2 ? 2 : 4;       // chunks of the residual row fetched ahead (the e4m3 form's 384 threads have 168 registers each)
     uint4 res[RD][4];
 #pragma unroll
     for (int c = 0; c < RD; ++c) {
@@ -651,7 +654,7 @@ tower_tc_kernel(const __grid_constant__ CUtensorMap map_act0, const __grid_const
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- epilogue (TMEM -> HBM) + publish
         const int q = warp & 3;
-        constexpr int SETS = tower_epilogue_sets(FP8), RD = FP8 ? 2 : 4;
+        constexpr int SETS = tower_epilogue_sets(FP8), RD = SETS == 2 ? 2 : 4;
         const int set = SETS == 2 ? (warp - 4) >> 2 : 0; // this warp's epilogue set: it takes the items of accumulator buffer `set` (e4m3 form)
         const int bar_done = 1 + set, bar_scale = 3 + set;        // named barriers of the set's 128 threads
         float* s_scale = s_scale_all + (FP8 ? set * C : 0);
