@@ -338,6 +338,7 @@ class BatchedAlphaZeroAgent:
         self._rng = rng if rng is not None else np.random
         self._fingerprint = None
         self._all = np.arange(self.n_games, dtype=np.int32)
+        self._stats_buffers = None                              # page-locked read-back buffers of select_actions_packed
 
     @property
     def policy(self):
@@ -366,7 +367,15 @@ class BatchedAlphaZeroAgent:
         self._sync_weights()
         eng.set_positions(states, trees=1 - (states['meta'] & 1).astype(np.int32))   # white to move -> tree 0
         eng.search(self._num_simulations)
-        codes, visits, _, n_legal = eng.root_stats(want_q=False)
+        if self._stats_buffers is None:                         # read the root statistics back into page-locked memory, kept between calls
+            import torch
+            shape = (self.n_games, MC_MAX_MOVES)
+            self._stats_pinned = (torch.empty(shape, dtype=torch.int16).pin_memory(), torch.empty(shape, dtype=torch.int32).pin_memory(),
+                                  torch.empty(self.n_games, dtype=torch.int32).pin_memory())
+            self._stats_buffers = (self._stats_pinned[0].numpy().view(np.uint16), self._stats_pinned[1].numpy().view(np.uint32),
+                                   self._stats_pinned[2].numpy())
+        codes, visits, _, n_legal = eng.root_stats(want_q=False, out=self._stats_buffers)
+        codes = codes.copy()                                    # returned to the caller: not a view of the reused buffer
         n_legal = np.maximum(n_legal, 0)
         n = self.n_games
         E = np.maximum(n_legal, 1)

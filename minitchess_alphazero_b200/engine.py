@@ -205,10 +205,20 @@ class Engine:
         self._check(self._L.az_selfplay(self._h, int(n_steps), int(sims_per_move)))
 
     # ------------------------------------------------------------------ read-back
-    def root_stats(self, game_ids=None, want_q=True):
-        """-> codes uint16[n,M], visits uint32[n,M], q float64[n,M] or None, n_legal int32[n] (-1: not visited)."""
+    def root_stats(self, game_ids=None, want_q=True, out=None):
+        """-> codes uint16[n,M], visits uint32[n,M], q float64[n,M] or None, n_legal int32[n] (-1: not visited).
+        `out` = (codes, visits, n_legal) arrays to fill instead of fresh ones (with want_q=False) -- page-locked buffers kept by the
+        caller make the read-back an asynchronous copy instead of a staged one into freshly mapped pages."""
         ids = self._ids(game_ids)
         n = self.n_games if ids is None else len(ids)
+        if out is not None:
+            assert not want_q, 'out= carries no Q buffer'
+            codes, visits, n_legal = out
+            assert codes.shape == (n, MC_MAX_MOVES) and codes.dtype == np.uint16 and codes.flags.c_contiguous
+            assert visits.shape == (n, MC_MAX_MOVES) and visits.dtype == np.uint32 and visits.flags.c_contiguous
+            assert n_legal.shape == (n,) and n_legal.dtype == np.int32
+            self._check(self._L.az_root_stats(self._h, ptr(ids), n, ptr(codes), ptr(visits), None, ptr(n_legal)))
+            return codes, visits, None, n_legal
         codes = np.zeros((n, MC_MAX_MOVES), dtype=np.uint16)
         visits = np.zeros((n, MC_MAX_MOVES), dtype=np.uint32)
         q = np.zeros((n, MC_MAX_MOVES), dtype=np.float64) if want_q else None
