@@ -154,14 +154,18 @@ def _cpu_worker(args):
     return n_sims, n_moves, dt
 
 
-def cpu_reference_sample(sims, seconds, processes, threads):
-    """Runs the oracle port of the reference self-play on `processes` host processes for ~`seconds`."""
+def cpu_reference_sample(sims, seconds, processes, threads, pool=None):
+    """Runs the oracle port of the reference self-play on `processes` host processes for ~`seconds`.  `pool`: a pool of that many
+    spawned workers kept between samples (the reference arm: its workers import torch once, not once per step)."""
     import multiprocessing as mp
-    if processes == 1:
-        res = [_cpu_worker((0, sims, seconds, threads))]
+    jobs = [(i, sims, seconds, threads) for i in range(processes)]
+    if pool is not None:
+        res = pool.map(_cpu_worker, jobs, chunksize=1)
+    elif processes == 1:
+        res = [_cpu_worker(jobs[0])]
     else:
-        with mp.get_context('spawn').Pool(processes) as pool:
-            res = pool.map(_cpu_worker, [(i, sims, seconds, threads) for i in range(processes)])
+        with mp.get_context('spawn').Pool(processes) as own:
+            res = own.map(_cpu_worker, jobs, chunksize=1)
     total_sims = sum(r[0] for r in res)
     wall = max(r[2] for r in res)
     return total_sims / wall, sum(r[1] for r in res) / wall, wall
@@ -173,16 +177,24 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
-    per_step = max(2.0, 2.0 * args.sims * 0.017)      # about two moves per process per step
-    per_step = min(per_step, 20.0)
-    for _ in range(args.warmup):
-        cpu_reference_sample(args.sims, min(per_step, 3.0), procs, 1)
-    t0 = time.perf_counter()
-    sims_s = []
-    for _ in range(args.steps):
-        s, _, _ = cpu_reference_sample(args.sims, per_step, procs, 1)
-        sims_s.append(s)
-    dt = time.perf_counter() - t0
+    # about two moves per process per step, shortened so that warm-up + steps stay within ~3 minutes of samples
+    per_step = min(max(2.0, 2.0 * args.sims * 0.017), 20.0)
+    per_step = max(2.0, min(per_step, 170.0 / max(1, args.steps + args.warmup)))
+    import multiprocessing as mp
+    pool = mp.get_context('spawn').Pool(procs) if procs > 1 else None
+    try:
+        for _ in range(args.warmup):
+            cpu_reference_sample(args.sims, min(per_step, 3.0), procs, 1, pool)
+        t0 = time.perf_counter()
+        sims_s = []
+        for _ in range(args.steps):
+            s, _, _ = cpu_reference_sample(args.sims, per_step, procs, 1, pool)
+            sims_s.append(s)
+        dt = time.perf_counter() - t0
+    finally:
+        if pool is not None:
+            pool.close()
+            pool.join()
     value = sum(sims_s) / len(sims_s)
     sample = '%d processes x 1 torch thread, each playing self-play moves at %d sims/move for %.1f s per step' % (procs, args.sims, per_step)
     emit(json.dumps({
