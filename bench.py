@@ -546,7 +546,7 @@ def leg_loop(net, rank, world, args, barrier, learner_batches=256):
     sp = BatchedSelfPlay(net, n_games=G, num_simulations=S, seed=777 + rank, eval_cache_log2=args.eval_cache)
     sp.stagger()
     kw = dict(batch_size=32, optim_params={'lr': 0.2}, max_batches=learner_batches)
-    iteration(sp, net, 2, **dict(kw, max_batches=8))                 # warm-up: every phase once
+    iteration(sp, net, 2, **dict(kw, max_batches=16))                # warm-up: every phase once (16 mini-batches: the learner's step is captured as a CUDA graph here and kept)
     barrier()
     c0 = sp.engine.counters()
     t0 = time.perf_counter()
@@ -570,7 +570,7 @@ def leg_loop(net, rank, world, args, barrier, learner_batches=256):
     sp.engine.close()
     sec = {k: float(v) for k, v in zip(phases, t[1:].tolist())}
     return {'workload': 'BASELINE.json configs[4]: self-play on %d GPUs (%d games x %d sims/move each, %d moves) -> replay all_gather -> '
-                        'learner update on rank 0 (AdamW lr 0.2, batch 32, first %d mini-batches) -> NCCL weight broadcast -> engines reload'
+                        'learner update on rank 0 (AdamW lr 0.2, batch 32, first %d mini-batches, each step one CUDA graph replay) -> NCCL weight broadcast -> engines reload'
                         % (world, G, S, args.loop_moves, learner_batches),
             'seconds_per_iteration': float(t[0]), 'seconds': sec, 'selfplay_sims_per_second': float(s[0]) / max(sec['selfplay'], 1e-9),
             'tuples_gathered': int(info[0]), 'tuples_used': int(info[1]), 'stale_dropped': int(info[2]), 'learner_steps': int(info[3]),

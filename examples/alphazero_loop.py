@@ -28,6 +28,7 @@ def main():
     ap.add_argument('--iterations', type=int, default=3)
     ap.add_argument('--batch-size', type=int, default=32)
     ap.add_argument('--lr', type=float, default=0.2)
+    ap.add_argument('--eager-learner', action='store_true', help='launch the learner step kernel by kernel instead of replaying its CUDA graph')
     a = ap.parse_args()
     local = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -40,7 +41,7 @@ def main():
     sp = BatchedSelfPlay(net, n_games=a.games, num_simulations=a.sims, seed=100 + int(os.environ.get('RANK', '0')))
     for it in range(a.iterations):
         t0 = time.perf_counter()
-        out = iteration(sp, net, a.moves, batch_size=a.batch_size, optim_params={'lr': a.lr})
+        out = iteration(sp, net, a.moves, batch_size=a.batch_size, optim_params={'lr': a.lr}, graph=False if a.eager_learner else None)
         torch.cuda.synchronize()
         if int(os.environ.get('RANK', '0')) == 0:
             loss = sum(out['losses']) / len(out['losses']) if out['losses'] else float('nan')

@@ -28,8 +28,9 @@
 extern "C" {
 #endif
 
-#define MCAZ_ABI_VERSION 5   /* 4: az_replay_tuple.weights_version, az_set_weights_version, az_tree_dump, counter 14,
-                                az_config.fp8_convolutions, network = 2;  5: az_config.defer_rows, counters 15-16 */
+#define MCAZ_ABI_VERSION 6   /* 4: az_replay_tuple.weights_version, az_set_weights_version, az_tree_dump, counter 14,
+                                az_config.fp8_convolutions, network = 2;  5: az_config.defer_rows, counters 15-16;
+                                6: counter 17 (second-stage compaction of recycle = 1) */
 
 /* ---- geometry and action indexing (exp/generate_moves_list.py:5-57, exp/moves_dict.json) */
 #define MC_FILES 5
@@ -158,7 +159,11 @@ typedef struct az_config {
                                   new nodes are compacted: nodes whose ply is not greater than the game's current
                                   position (other than that position) can never be reached again -- their ply is part
                                   of the key -- so no result changes, and node_capacity = 0 then derives a 5x smaller
-                                  arena (6 x max_sims_per_move + 64).  For engines whose positions only move forward
+                                  arena (6 x max_sims_per_move + 64).  A tree that is still too full after that (deep trees
+                                  under sharp priors keep most of their nodes) is compacted again down to the nodes its
+                                  edges reach from the current position, for as many levels as fit beside the coming
+                                  search: what is dropped there (counter 17) is expanded anew if the search comes back
+                                  to it -- the call goes on instead of failing with MCAZ_ECAPACITY.  For engines whose positions only move forward
                                   (az_play / az_play_device / az_selfplay); leave 0 when az_set_positions may jump back
                                   to an earlier position of a kept tree (the per-agent facade).  Default 0              */
     int32_t lookahead_rows;    /* > 0 (needs eval_cache_log2 > 0, leaves_per_step = 1): for engines with few games.  A pass
@@ -310,8 +315,10 @@ int az_collate(const az_replay_tuple* tuples, int n, float* pi, int64_t* tokens,
  * [12] nodes dropped by the recycler (recycle = 1), [13] network rows whose position was already in the
  * evaluation cache when they were stored (evaluated more than once within one batch),
  * [14] replay tuples dropped because the replay queue was full (whole games; see az_drain_replay),
- * [15] leaf rows a network pass left to the next batch and [16] passes that did so (az_config.defer_rows).  */
-#define AZ_NUM_COUNTERS 17
+ * [15] leaf rows a network pass left to the next batch and [16] passes that did so (az_config.defer_rows),
+ * [17] nodes dropped by the second-stage compaction of recycle = 1 (not provably unreachable: 0 as long as the
+ * trees fit their arenas under the exact rule).                                                               */
+#define AZ_NUM_COUNTERS 18
 int az_counters(az_engine* e, uint64_t* out);
 
 /* Stand-alone network forward (exp/policy.py:71-80) on n positions with the engine's weights:

@@ -14,7 +14,7 @@ MC_TOKENS = 60
 AZ_NUM_PARAMS = 10693458
 AZ_NUM_BN_STATS = 9734
 AZ_NUM_WEIGHT_FLOATS = AZ_NUM_PARAMS + AZ_NUM_BN_STATS
-AZ_NUM_COUNTERS = 17
+AZ_NUM_COUNTERS = 18
 
 STATE_DTYPE = np.dtype([('pl0', '<u4'), ('pl1', '<u4'), ('pl2', '<u4'), ('white', '<u4'), ('meta', '<u4')])
 RESULT_STRINGS = {0: '*', 1: '1-0', 2: '0-1', 3: '1/2-1/2'}
@@ -26,7 +26,7 @@ class McazError(RuntimeError):
         self.code = code
 
 
-ABI_VERSION = 5      # MCAZ_ABI_VERSION of include/mcaz.h
+ABI_VERSION = 6      # MCAZ_ABI_VERSION of include/mcaz.h
 
 
 class Rules(ctypes.Structure):

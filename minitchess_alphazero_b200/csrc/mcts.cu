@@ -455,6 +455,12 @@ __global__ void __launch_bounds__(256) restart_finished_kernel(View V, mc_state 
 // could not take `need_nodes` / `need_edges` more.  Order-preserving, so every block of data only moves towards
 // the front; the hash-table region serves as the old -> new index map and is rebuilt afterwards.  Runs between
 // searches (no simulation pending).
+// Networks with sharp priors grow deep trees, and a deep node outlives many moves under that rule; the reference's dicts
+// grow without bound there.  A tree that still cannot take the search after the exact compaction is compacted a second
+// time (stage 2, counted in C_EVICTED) down to what its edges reach from the game's current position, level by level for as
+// many levels as fit beside the coming search; links into a level that was cut read "never taken" again.  A node dropped
+// there is expanded anew when the search comes back to it -- the one place where a tree may differ from the reference's,
+// taken instead of failing the call with MCAZ_ECAPACITY.
 MC_HD int ply_of_meta(uint32_t meta) { return 2 * (int)((meta >> 16) & 0xffu) + ((meta & 1u) ? 0 : 1); }
 
 constexpr int RECYCLE_THREADS = 256;
@@ -464,15 +470,62 @@ __global__ void __launch_bounds__(RECYCLE_THREADS) recycle_kernel(View V, int ne
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int WARPS = RECYCLE_THREADS / 32;
     for (int t = blockIdx.x; t < 2 * V.G; t += gridDim.x) {
+      for (int stage = 1; stage <= 2; ++stage) {
         const uint32_t n = V.tree_nodes[t], m = V.tree_edges[t];
         __syncthreads();                                    // everyone has read the counters of this tree
-        if (n + (uint32_t)need_nodes <= (uint32_t)V.NC && m + (uint32_t)need_edges <= (uint32_t)V.EC) continue;
+        // stage 1 runs on the worst case of 40 edges per new node (the exact rule costs no result); stage 2, which may, only
+        // when the nodes cannot fit or the edges cannot at twice this tree's own mean fan-out
+        const uint32_t want_edges = stage == 1 ? (uint32_t)need_edges
+                                               : min((uint32_t)need_edges, (uint32_t)need_nodes * (2u * ((m + n) / max(n, 1u)) + 4u));
+        if (n + (uint32_t)need_nodes <= (uint32_t)V.NC && m + want_edges <= (uint32_t)V.EC) break;
         const int g = t >> 1;
         const mc_state cur = V.game_state[g];
         const int cur_ply = ply_of_meta(cur.meta);
         const size_t nb = (size_t)t * V.NC, eb = (size_t)t * V.EC;
         uint32_t* map = V.ht + (size_t)t * V.HC;            // [0, NC): old node -> new node; [NC, 2 NC): where new node j's edges were (HC >= 2 NC)
         uint32_t* old_off_of = map + V.NC;
+        uint32_t cutoff = 0;
+        if (stage == 2) {
+            // marks in map[]: 1 on the current position, then level by level (an edge leads one ply down) level + 1 on the children
+            // of the nodes of a level -- for as long as the levels fit what the arena can keep beside the coming search
+            const uint32_t keep_nodes = (uint32_t)V.NC - min((uint32_t)V.NC, (uint32_t)need_nodes);
+            const uint32_t keep_edges = (uint32_t)V.EC - min((uint32_t)V.EC, want_edges);
+            for (uint32_t i = tid; i < n; i += RECYCLE_THREADS) {
+                const az::Board4 board = az::load_board(&V.nodes[nb + i]);
+                const uint32_t meta = V.nodes[nb + i].head.meta;
+                map[i] = (meta == cur.meta && board.x == cur.pl0 && board.y == cur.pl1 && board.z == cur.pl2 && board.w == cur.white) ? 1u : 0u;
+            }
+            uint32_t kept_n = 0, kept_e = 0;
+            for (uint32_t level = 1;; ++level) {
+                __syncthreads();                            // the marks of this level are written, s_scan is free
+                uint32_t a = 0, b = 0;
+                for (uint32_t i = tid; i < n; i += RECYCLE_THREADS)
+                    if (map[i] == level) {
+                        const uint32_t info = V.nodes[nb + i].head.info;
+                        ++a;
+                        b += (info & az::INFO_TERMINAL) ? 0u : (info & 0xffffu);
+                    }
+                a = __reduce_add_sync(0xffffffffu, a);
+                b = __reduce_add_sync(0xffffffffu, b);
+                if (lane == 0) { s_scan[warp][0] = a; s_scan[warp][1] = b; }
+                __syncthreads();
+                a = 0; b = 0;
+                for (int w = 0; w < WARPS; ++w) { a += s_scan[w][0]; b += s_scan[w][1]; }
+                if (a == 0 || kept_n + a > keep_nodes || kept_e + b > keep_edges) break;      // this level and everything below it go
+                kept_n += a; kept_e += b; cutoff = level;
+                for (uint32_t i = tid; i < n; i += RECYCLE_THREADS) {
+                    if (map[i] != level) continue;
+                    const az::NodeHead h = az::load_head(&V.nodes[nb + i]);
+                    if (h.info & az::INFO_TERMINAL) continue;
+                    const uint32_t E = h.info & 0xffffu;
+                    for (uint32_t k = 0; k < E; ++k) {
+                        const uint32_t child = V.edges[eb + h.edge_off + k].link.child;
+                        if (child != az::NONE) map[child] = level + 1u;
+                    }
+                }
+            }
+            __syncthreads();
+        }
         if (tid == 0) { s_tot[0] = 0; s_tot[1] = 0; }
         __syncthreads();
         // ---- pass 1: node headers (chunks of 256 nodes: read, scan, barrier, write).  The scan over the edge counts gives
@@ -484,7 +537,8 @@ __global__ void __launch_bounds__(RECYCLE_THREADS) recycle_kernel(View V, int ne
             if (i < n) {
                 board = az::load_board(&V.nodes[nb + i]); head = az::load_head(&V.nodes[nb + i]);
                 const int ply = ply_of_meta(head.meta);
-                live = ply > cur_ply || (head.meta == cur.meta && board.x == cur.pl0 && board.y == cur.pl1 && board.z == cur.pl2 && board.w == cur.white);
+                live = stage == 2 ? (map[i] != 0u && map[i] <= cutoff)
+                                  : ply > cur_ply || (head.meta == cur.meta && board.x == cur.pl0 && board.y == cur.pl1 && board.z == cur.pl2 && board.w == cur.white);
             }
             const uint32_t E = live && !(head.info & az::INFO_TERMINAL) ? (head.info & 0xffffu) : 0u;
             // block-wide exclusive scan of (live, E)
@@ -532,9 +586,9 @@ __global__ void __launch_bounds__(RECYCLE_THREADS) recycle_kernel(View V, int ne
                 if (i < E) {
                     az::Edge* e = &V.edges[eb + new_off + i];
                     uint32_t child = lk[k].child, child_off = 0;
-                    if (child != az::NONE) {                  // children are deeper: always live; their headers are final since pass 1
-                        child = map[child];
-                        child_off = V.nodes[nb + child].head.edge_off;
+                    if (child != az::NONE) {                  // children are deeper: live under the exact rule, their headers final since pass 1;
+                        child = map[child];                   // stage 2 may have cut the child's level: the link is then as never taken
+                        child_off = child != az::NONE ? V.nodes[nb + child].head.edge_off : 0u;
                     }
                     *reinterpret_cast<uint4*>(&e->stat) = make_uint4((uint32_t)__double2loint(st[k].Q), (uint32_t)__double2hiint(st[k].Q), st[k].N, __float_as_uint(st[k].P));
                     *reinterpret_cast<uint4*>(&e->link) = make_uint4(child, child_off, lk[k].child_info, (uint32_t)lk[k].code | ((uint32_t)lk[k].vl << 16));
@@ -549,7 +603,7 @@ __global__ void __launch_bounds__(RECYCLE_THREADS) recycle_kernel(View V, int ne
             V.tree_root[t] = (r != az::NONE && r < n) ? map[r] : az::NONE;
             V.tree_nodes[t] = n_live;
             V.tree_edges[t] = m_live;
-            atomicAdd(&V.counters[az::C_RECYCLED], (unsigned long long)(n - n_live));
+            atomicAdd(&V.counters[stage == 2 ? az::C_EVICTED : az::C_RECYCLED], (unsigned long long)(n - n_live));
         }
         __syncthreads();
         uint32_t* tab = V.ht + (size_t)t * V.HC;
@@ -562,6 +616,7 @@ __global__ void __launch_bounds__(RECYCLE_THREADS) recycle_kernel(View V, int ne
             while (atomicCAS(&tab[h], 0u, i + 1u) != 0u) h = (h + 1u) & mask;
         }
         __syncthreads();
+      }
     }
 }
 

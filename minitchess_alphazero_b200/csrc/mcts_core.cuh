@@ -40,7 +40,7 @@ constexpr int MAX_LEAVES = 16;                // leaves_per_step limit
 // LEAF_CACHED: a new position whose priors and value were found in the exact evaluation cache -- the
 // simulation is complete without a network row, like a terminal one.
 enum LeafKind : uint8_t { LEAF_NONE = 0, LEAF_EVAL = 1, LEAF_TERMINAL = 2, LEAF_COLLISION = 3, LEAF_CACHED = 4 };
-enum Counter : int { C_SIMS = 0, C_EVALS, C_TERMINAL, C_MOVES, C_GAMES, C_NODES, C_EDGES, C_LAUNCHES, C_COLLISIONS, C_CACHED, C_DEPTH, C_PATH_EDGES, C_RECYCLED, C_DUP_ROWS, C_REPLAY_DROPPED, C_DEFERRED_ROWS, C_TRIMMED_BATCHES };
+enum Counter : int { C_SIMS = 0, C_EVALS, C_TERMINAL, C_MOVES, C_GAMES, C_NODES, C_EDGES, C_LAUNCHES, C_COLLISIONS, C_CACHED, C_DEPTH, C_PATH_EDGES, C_RECYCLED, C_DUP_ROWS, C_REPLAY_DROPPED, C_DEFERRED_ROWS, C_TRIMMED_BATCHES, C_EVICTED };
 enum ErrorBit : int { ERR_NODE_CAP = 1, ERR_EDGE_CAP = 2, ERR_HASH_CAP = 4, ERR_DEPTH = 8, ERR_ILLEGAL = 16 };
 
 struct alignas(16) Board4 { uint32_t x, y, z, w; };

@@ -16,7 +16,7 @@ from ._lib import (AZ_NUM_COUNTERS, AZ_NUM_WEIGHT_FLOATS, MC_MAX_MOVES, MC_NUM_A
 
 COUNTER_NAMES = ('simulations', 'evaluations', 'terminal_leaves', 'moves', 'games_finished', 'nodes', 'edges',
                  'kernel_launches', 'collisions', 'cached_evaluations', 'path_depth', 'path_edges', 'recycled_nodes', 'duplicate_rows',
-                 'replay_dropped', 'deferred_rows', 'trimmed_batches')
+                 'replay_dropped', 'deferred_rows', 'trimmed_batches', 'evicted_nodes')
 
 REPLAY_DTYPE = np.dtype([('observation', STATE_DTYPE), ('n_legal', '<u2'), ('action', '<u2'), ('reward', 'i1'),
                          ('pad', 'u1', 3), ('weights_version', '<u4'), ('codes', '<u2', MC_MAX_MOVES), ('pi', '<f4', MC_MAX_MOVES)])

@@ -18,6 +18,7 @@ app/base.py:195-196 (commented out in the reference, hence off by default).
 """
 import copy
 import time
+import weakref
 
 import torch
 import torch.distributed as dist
@@ -27,20 +28,105 @@ from .policy import flatten_state_dict
 from .selfplay import collate_device
 
 
+_GRAPHED = weakref.WeakKeyDictionary()      # network -> (key, optimizer, _GraphedStep): the captured step is kept between updates
+
+
+class _GraphedStep:
+    """One optimiser step (forward, loss, backward, AdamW) of `learner_update` captured as a CUDA graph over static batch buffers.
+    At batch 32 the step is ~200 small kernels and bound by their launches from Python; replayed as one graph it costs its GPU time.
+    The three warm-up steps PyTorch asks for before a capture run on the real parameters, so parameters, BatchNorm buffers and
+    the optimiser state are put back afterwards: the update takes exactly the steps the eager loop takes."""
+
+    def __init__(self, model, optimizer, channels, clock, pi, reward, batch_size):
+        B = batch_size
+        self.channels = channels.new_zeros((B,) + tuple(channels.shape[1:]))
+        self.clock = clock.new_zeros((B,) + tuple(clock.shape[1:]))
+        self.pi = pi.new_zeros((B,) + tuple(pi.shape[1:]))
+        self.reward = reward.new_zeros((B,) + tuple(reward.shape[1:]))
+        self.load(channels, clock, pi, reward, torch.arange(B, device=channels.device))
+        tensors = list(model.parameters()) + list(model.buffers())
+        saved = [t.detach().clone() for t in tensors]
+        # parameters that took an eager step before carry gradient-accumulation nodes of the default stream: expected here
+        quiet = getattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch', None)
+        if quiet is not None:
+            quiet(False)
+        side = torch.cuda.Stream()                                      # warm-up and capture on one stream
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                optimizer.zero_grad(set_to_none=True)
+                self._loss(model).backward()
+                optimizer.step()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph, stream=side):
+            self.loss = self._loss(model)
+            self.loss.backward()
+            optimizer.step()
+        with torch.no_grad():
+            for t, v in zip(tensors, saved):
+                t.copy_(v)
+        _reset(optimizer)
+
+    def _loss(self, model):
+        p, v = model((self.channels, self.clock))
+        return ((v - self.reward) ** 2 - (self.pi * p.log_softmax(-1)).sum(1, keepdim=True)).mean()     # exp/learner.py:89
+
+    def load(self, channels, clock, pi, reward, idx):
+        torch.index_select(channels, 0, idx, out=self.channels)
+        torch.index_select(clock, 0, idx, out=self.clock)
+        torch.index_select(pi, 0, idx, out=self.pi)
+        torch.index_select(reward, 0, idx, out=self.reward)
+
+    def step(self, channels, clock, pi, reward, idx):
+        self.load(channels, clock, pi, reward, idx)
+        self.graph.replay()
+        return self.loss.detach().clone()
+
+
+def _reset(optimizer):
+    """The optimiser as `torch.optim.AdamW(...)` leaves it before its first step (exp/learner.py:73 builds a new one per update)."""
+    with torch.no_grad():
+        for state in optimizer.state.values():
+            for v in state.values():
+                if torch.is_tensor(v):
+                    v.zero_()
+
+
 def learner_update(network, tuples, batch_size=32, epochs=1, optim_params=None, device='cuda', generator=None, max_batches=None,
-                   order=None):
+                   order=None, graph=None):
     """One `update` over the given replay tuples (packed az_replay_tuple records, or the four tensors `collate_fn` returns).
     Returns the list of mini-batch losses.  `order`: an explicit list of index lists (one per mini-batch) instead of a fresh
-    shuffle -- the parity test replays the batches the reference's DataLoader drew."""
-    optim_params = optim_params or {'lr': 0.2}                       # app/learner.py:69
+    shuffle -- the parity test replays the batches the reference's DataLoader drew.  `graph`: replay the step of full
+    mini-batches as one CUDA graph (default: on a CUDA device when the update has at least 16 of them); short batches and
+    `graph=False` take the same step launched kernel by kernel.  The captured step and its optimiser stay with the network
+    between updates (same parameters, batch size and optimiser arguments): a later update starts from a zeroed optimiser
+    state, which is what a new AdamW starts from."""
+    optim_params = dict(optim_params or {'lr': 0.2})                 # app/learner.py:69
     if isinstance(tuples, (list, tuple)) and len(tuples) == 4 and all(torch.is_tensor(t) for t in tuples):
         pi, channels, clock, reward = (t.to(device) for t in tuples)  # already collated (exp/learner.py:23-41 layout)
     else:
         pi, channels, clock, reward = collate_device(tuples, device=device)
     model = network.train().to(device)
-    optimizer = torch.optim.AdamW(model.parameters(), **optim_params)  # exp/learner.py:73
     n = pi.shape[0]
-    losses = []
+    on_cuda = torch.device(device).type == 'cuda'
+    planned = (len(order) if order is not None else epochs * (n // batch_size))
+    if max_batches is not None:
+        planned = min(planned, max_batches)
+    if graph is None:
+        graph = on_cuda and planned >= 16
+    optimizer = graphed = key = None
+    if graph:
+        optim_params.setdefault('capturable', True)
+        key = (batch_size, repr(sorted(optim_params.items())), tuple(p.data_ptr() for p in model.parameters()))
+        kept = _GRAPHED.get(network)
+        if kept is not None and kept[0] == key:
+            optimizer, graphed = kept[1], kept[2]
+            _reset(optimizer)
+    if optimizer is None:
+        optimizer = torch.optim.AdamW(model.parameters(), **optim_params)  # exp/learner.py:73
+    losses = []                                                       # device scalars: one read-back at the end, not one per step
     for _ in range(epochs):
         if order is None:
             perm = torch.randperm(n, device=device, generator=generator)
@@ -52,14 +138,20 @@ def learner_update(network, tuples, batch_size=32, epochs=1, optim_params=None, 
                 continue
             if max_batches is not None and len(losses) >= max_batches:
                 break
+            if graph and idx.numel() == batch_size:
+                if graphed is None:
+                    graphed = _GraphedStep(model, optimizer, channels, clock, pi, reward, batch_size)
+                    _GRAPHED[network] = (key, optimizer, graphed)
+                losses.append(graphed.step(channels, clock, pi, reward, idx))
+                continue
             p, v = model((channels[idx], clock[idx]))
             loss = ((v - reward[idx]) ** 2 - (pi[idx] * p.log_softmax(-1)).sum(1, keepdim=True)).mean()
             optimizer.zero_grad()
             loss.backward()
             optimizer.step()
-            losses.append(float(loss.detach()))
+            losses.append(loss.detach())
     network.eval()
-    return losses
+    return torch.stack(losses).tolist() if losses else []
 
 
 def iteration(selfplay, network, n_moves, learner_rank=0, max_tuples=None, arena_games_per_side=0, arena_simulations=None,

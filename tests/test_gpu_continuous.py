@@ -193,6 +193,7 @@ def test_recycling_unreachable_plies_changes_nothing(net):
             e.play_device()
     ck, cs, ct = keep.counters(), small.counters(), tight.counters()
     assert ck['recycled_nodes'] == 0 and cs['recycled_nodes'] > 0 and ct['recycled_nodes'] > cs['recycled_nodes']
+    assert cs['evicted_nodes'] == 0                                           # the exact rule was enough: nothing else was dropped
     assert ck['games_finished'] == cs['games_finished'] == ct['games_finished'] >= G
     assert ck['nodes'] == cs['nodes'] == ct['nodes']
     from collections import Counter                                            # same games (games that end in one launch
@@ -203,6 +204,38 @@ def test_recycling_unreachable_plies_changes_nothing(net):
     for _ in range(8):
         cont.selfplay(10 * sims, sims)
     assert cont.counters()['games_finished'] >= G and cont.counters()['recycled_nodes'] > 0
+
+
+def test_sharp_priors_fall_back_to_edge_reachable_compaction(net):
+    """A network with sharp priors grows deep trees, and a deep node stays ahead of the game for many moves: the exact rule
+    keeps it, the reference's dicts simply grow, and a 6x arena overflowed in the third iteration of examples/alphazero_loop.py
+    (MCAZ_ECAPACITY).  The second-stage compaction keeps what the tree's edges reach from the current position: the search
+    goes on, the drop is counted (counter 17), every search still runs all its simulations and the games end."""
+    import copy
+    sharp = copy.deepcopy(net)
+    with torch.no_grad():
+        sharp.plinear.weight.mul_(80.0)
+        sharp.plinear.bias.mul_(80.0)
+    G, sims = 64, 50
+    eng = make(sharp, G, sims, seed=5, recycle=1, eval_cache_log2=15, node_capacity=sims * 5 // 2)
+    before = 0
+    for move in range(70):
+        eng.search(sims)
+        c = eng.counters()
+        states, results = eng.game_states()
+        assert c['simulations'] - before == sims * int((results == 0).sum()), move     # every running game spent its whole budget
+        before = c['simulations']
+        codes, visits, q, n_legal = eng.root_stats()
+        live = n_legal > 0
+        assert (visits.sum(1)[live] >= sims - 1).all(), move
+        eng.play_device()
+    c = eng.counters()
+    assert c['evicted_nodes'] > 0 and c['games_finished'] >= G
+    # continuous self-play on the default recycled arena with the same network
+    cont = make(sharp, G, sims, seed=5, recycle=1, eval_cache_log2=15)
+    for _ in range(8):
+        cont.selfplay(10 * sims, sims)
+    assert cont.counters()['games_finished'] >= G
 
 
 def test_more_games_than_one_network_pass(net):

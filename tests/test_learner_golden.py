@@ -80,9 +80,11 @@ def test_learner_update_matches_reference_update_cpu(lr):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('graph', [False, True])
 @pytest.mark.parametrize('lr', ['0.2', '0.001'])
-def test_learner_update_on_packed_tuples_matches_reference_update_gpu(mcaz_lib, lr):
-    """The same through the device collate (az_collate) and cuDNN/cuBLAS fp32 (TF32 off for the comparison)."""
+def test_learner_update_on_packed_tuples_matches_reference_update_gpu(mcaz_lib, lr, graph):
+    """The same through the device collate (az_collate) and cuDNN/cuBLAS fp32 (TF32 off for the comparison), with the step
+    launched kernel by kernel and replayed as one CUDA graph (what long updates do by default)."""
     from minitchess_alphazero_b200.loop import learner_update
     from minitchess_alphazero_b200.policy import Network
     g = golden()
@@ -93,7 +95,7 @@ def test_learner_update_on_packed_tuples_matches_reference_update_gpu(mcaz_lib, 
     torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
     try:
         losses = learner_update(net, pack_tuples(g['items']), batch_size=g['batch_size'], optim_params={'lr': run['lr']},
-                                device='cuda', order=run['batches'])
+                                device='cuda', order=run['batches'], graph=graph)
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
     # A convolution bias that feeds a BatchNorm in train mode has a gradient of exactly zero (the batch mean absorbs it); what
