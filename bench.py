@@ -286,10 +286,11 @@ def run_ours(args):
     cached = c1['cached_evaluations'] - c0['cached_evaluations']
     terminal = c1['terminal_leaves'] - c0['terminal_leaves']
     dup = c1['duplicate_rows'] - c0['duplicate_rows']
-    tot = torch.tensor([sims, evals, moves, cached, terminal, dup], dtype=torch.float64, device='cuda')
+    evicted = c1['evicted_nodes']             # since creation: nodes the second-stage compaction dropped (0 = every tree is the reference's)
+    tot = torch.tensor([sims, evals, moves, cached, terminal, dup, evicted], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(tot)
-    sims_all, evals_all, moves_all, cached_all, terminal_all, dup_all = (float(x) for x in tot.tolist())
+    sims_all, evals_all, moves_all, cached_all, terminal_all, dup_all, evicted_all = (float(x) for x in tot.tolist())
     value = sims_all / (ms / 1000.0)
 
     # roofline of the dominant kernel: the network tower (tensor-bound), from the rows it actually evaluated
@@ -478,7 +479,8 @@ def run_ours(args):
             'positions_per_second': moves_all / (ms / 1000.0), 'evals_per_second': evals_all / (ms / 1000.0),
             'sims_breakdown': {'network_rows': evals_all / max(sims_all, 1), 'cache_hits': cached_all / max(sims_all, 1),
                                'terminal': terminal_all / max(sims_all, 1),
-                               'rows_evaluated_twice_in_one_batch': dup_all / max(sims_all, 1)},
+                               'rows_evaluated_twice_in_one_batch': dup_all / max(sims_all, 1),
+                               'tree_nodes_evicted_by_the_inexact_compaction': int(evicted_all)},
             'roofline': roof, 'tree_roofline': tree, 'without_cache_lockstep': plain, 'continuous_selfplay': cont,
             'fp8_tower': fp8, 'config4': config4, 'loop': loop_leg,
             'cpu_baseline': cpu, 'dropin_config1': dropin, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
