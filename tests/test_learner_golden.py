@@ -108,3 +108,30 @@ def test_learner_update_on_packed_tuples_matches_reference_update_gpu(mcaz_lib, 
     # Likewise the one- and two-element BatchNorm parameters of the heads at any lr: the comparison takes the tensors with at
     # least 1024 elements (the convolution and linear weights: 10.68 of the 10.69 M parameters), where a step is small against the sum.
     check(run, losses, net, later_tol=2e-2, sum_tol=2e-2 if lr == '0.001' else float('inf'), skip=('layers.0.bias',), min_numel=1024)
+
+
+@pytest.mark.gpu
+def test_captured_step_is_reused_and_starts_like_a_new_optimizer(mcaz_lib):
+    """The CUDA graph of the step stays with the network.  A second update on the same network (weights put back to the golden
+    run's start) replays the same graph from a zeroed optimiser state and must reproduce the reference's losses again."""
+    import copy
+    from minitchess_alphazero_b200 import loop
+    from minitchess_alphazero_b200.policy import Network
+    g = golden()
+    run = g['runs']['0.001']
+    torch.manual_seed(g['seed'])
+    net = Network()
+    start = copy.deepcopy(net.state_dict())
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        kw = dict(batch_size=g['batch_size'], optim_params={'lr': run['lr']}, device='cuda', order=run['batches'], graph=True)
+        first = loop.learner_update(net, pack_tuples(g['items']), **kw)
+        kept = loop._GRAPHED[net][2]
+        net.load_state_dict(start)
+        second = loop.learner_update(net, pack_tuples(g['items']), **kw)
+        assert loop._GRAPHED[net][2] is kept
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    check(run, second, net, later_tol=2e-2, sum_tol=2e-2, skip=('layers.0.bias',), min_numel=1024)
+    assert max(abs(a - b) for a, b in zip(first, second)) <= 2e-2
