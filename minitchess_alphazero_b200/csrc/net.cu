@@ -52,7 +52,6 @@ constexpr int B_BYTES = (C / 2) * BLOCK_K * 2;   // 16 KB: this CTA's half of th
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int STEM_K = 16;         // channels of a one-hot stem row (14 live): one K = 16 MMA, one 32-byte swizzle row
 constexpr int STEM_TILE_BYTES = BLOCK_M * STEM_K * 2;   // 4 KB: 128 boards (or 128 output channels) x 16 channels
-constexpr int CONV_THREADS = 256;                // TMA, MMA, TMEM-alloc, spare + 4 epilogue warps
 // The e4m3 form runs TWO sets of four epilogue warps, one per TMEM accumulator buffer (items alternate between them): an e4m3 item's
 // main loop is half as long as a bf16 one and no longer hides a 256 x 256 epilogue, so each set gets two item times for its item.
 #ifndef TOWER_BF16_SETS
@@ -308,7 +307,7 @@ __device__ __forceinline__ void ld_cg_v8(const void* p, uint4& a, uint4& b) {
     asm volatile("ld.global.cg.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p) : "memory");
 }
-__device__ __forceinline__ void st_v8(void* p, const uint4& a, const uint4& b) {
+[[maybe_unused]] __device__ __forceinline__ void st_v8(void* p, const uint4& a, const uint4& b) {      // TOWER_L2_MODE 0
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
 }
