@@ -649,6 +649,10 @@ int engine_check_errors(az_engine* e) {
     if (flag & az::ERR_HASH_CAP) msg += " hash table full";
     if (flag & az::ERR_DEPTH) msg += " path deeper than MAX_DEPTH";
     if (flag & az::ERR_ILLEGAL) msg += " illegal move or bad game id in az_play";
+    if (flag & 7)
+        msg += e->cfg.recycle ? " (a tree needs more than node_capacity even after compaction: raise az_config.node_capacity)"
+                              : " (trees are kept whole: reset them per episode -- az_reset_games / az_reset_trees, the reference's "
+                                "MonteCarloInit callback -- or raise az_config.node_capacity / max_sims_per_move)";
     return fail((flag & az::ERR_ILLEGAL) && !(flag & 7) ? MCAZ_EINVAL : MCAZ_ECAPACITY, msg);
 }
 
