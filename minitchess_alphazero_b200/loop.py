@@ -115,7 +115,8 @@ def learner_update(network, tuples, batch_size=32, epochs=1, optim_params=None, 
     if max_batches is not None:
         planned = min(planned, max_batches)
     if graph is None:
-        graph = on_cuda and planned >= 16
+        graph = planned >= 16
+    graph = bool(graph) and on_cuda
     optimizer = graphed = key = None
     if graph:
         optim_params.setdefault('capturable', True)
